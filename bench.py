@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the FCAM hot path (BASELINE.json metric: caption-face pairs/sec of the word-region +
+sentence loss fwd+bwd; margin-head samples/sec reported beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N = 1 : BASELINE configs[1] -- words_loss + sent_loss forward + backward (both gradients),
+        B=128 captions x 128 faces, T=22 words (BERT flavour), R=14x14 regions, D=256, fp32 inputs.
+N > 1 : launched by torchrun, one rank per GPU; every rank keeps 128 faces + 128 captions, the
+        captions are all-gathered (NCCL) and each rank computes its [128, 128*N] block of the
+        global score matrix ("weak": fixed local batch, global batch 128*N).
+One JSON line is printed by rank 0.  `--impl reference` times the CPU port of the reference's
+PyTorch implementation (oracle/ref_port.py) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import synth  # noqa: E402
+
+B_LOCAL, T, IH, IW, D = 128, 22, 14, 14, 256
+R = IH * IW
+GAMMAS = (4.0, 5.0, 10.0)
+HEAD = dict(B=512, Din=512, C=10177, s=30.0, m=0.5, gamma=2.0)
+FLOPS_PER_PAIR = 12 * T * R * D          # fwd 4TRD + bwd 8TRD (both gradients)
+L2_BYTES = 126 * 2 ** 20
+
+
+def make_args():
+    ns = types.SimpleNamespace
+    return ns(en_type="BERT", bert_words_num=T + 2, CUDA=True, device="cuda",
+              TRAIN=ns(SMOOTH=ns(GAMMA1=GAMMAS[0], GAMMA2=GAMMAS[1], GAMMA3=GAMMAS[2])))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # "under load" = samples in the upper half of the observed power range
+            thr = (max(power) + min(power)) / 2 if power else 0
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            self.result = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU port of the reference implementation
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(ctx, words, img, txt, cid, n_caps=None):
+    """One fwd+bwd of words_loss + sent_loss with the reference's op sequence on CPU.
+    n_caps < B restricts the per-caption loop to the first n_caps captions (bounded sample)."""
+    from oracle import ref_port as P
+    B = ctx.shape[0]
+    c = torch.from_numpy(ctx).clone().requires_grad_(True)
+    w = torch.from_numpy(words).clone().requires_grad_(True)
+    a = torch.from_numpy(img).clone().requires_grad_(True)
+    b = torch.from_numpy(txt).clone().requires_grad_(True)
+    labels = torch.arange(B)
+    t0 = time.perf_counter()
+    c_ref = c.view(B, IH, IW, D).permute(0, 3, 1, 2)
+    w_ref = w.transpose(1, 2)
+    if n_caps is None or n_caps >= B:
+        l0, l1, _ = P.words_loss_port(c_ref, w_ref, labels, None, *GAMMAS)
+        pairs = B * B
+    else:
+        # the reference's cost is linear in the caption loop: run n_caps iterations of it
+        cols = []
+        for i in range(n_caps):
+            word = w_ref[i, :, :T].unsqueeze(0).contiguous().repeat(B, 1, 1)
+            wctx, _ = P.attention_port(word, c_ref, GAMMAS[0])
+            row = P._cos(word.transpose(1, 2).contiguous().view(B * T, -1),
+                         wctx.transpose(1, 2).contiguous().view(B * T, -1)).view(B, T)
+            cols.append(torch.log(row.mul(GAMMAS[1]).exp().sum(dim=1, keepdim=True)))
+        sim = torch.cat(cols, 1) * GAMMAS[2]
+        l0 = torch.nn.functional.cross_entropy(sim, torch.arange(B) % n_caps)
+        l1 = torch.nn.functional.cross_entropy(sim.t(), torch.arange(n_caps))
+        pairs = B * n_caps
+    s0, s1 = P.sent_loss_port(a, b, labels, cid, GAMMAS[2])
+    (l0 + l1 + s0 + s1).backward()
+    return time.perf_counter() - t0, pairs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = B_LOCAL
+    ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100)
+    img, txt, cid = synth.sentence_inputs(B, D, seed=100)
+    # size the per-step sample so that the whole run stays within ~3 minutes
+    t_probe, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps=8)
+    per_cap = t_probe / 8
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_caps = int(max(4, min(B, budget / max(per_cap, 1e-6))))
+    for _ in range(args.warmup):
+        cpu_reference_step(ctx, words, img, txt, cid, n_caps)
+    times, pairs = [], 0
+    for _ in range(args.steps):
+        dt, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = pairs / (ms * 1e-3)
+    sample = (f"{n_caps} of {B} captions x {B} faces per step ({pairs} pairs), T={T}, R={R}, D={D}, fwd+bwd both "
+              f"gradients, + sent_loss B={B}")
+    line = {
+        "impl": "reference", "metric": "fcam_words+sent_loss_fwd_bwd_pairs_per_sec", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: words_loss+sent_loss fwd+bwd B=128 T=22 R=196 D=256 (bounded sample)",
+                   "global_batch": B, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from text_guided_face_recognition_b200 import _lib, ops
+    from text_guided_face_recognition_b200 import distributed as tdist
+    from text_guided_face_recognition_b200.models import losses, metrics
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    margs = make_args()
+    B = B_LOCAL
+    Bg = B * world
+    precision = ops.default_precision()
+
+    # rotating input sets so that every step reads inputs that are not L2 resident
+    bytes_per_set = 4 * (B * R * D + B * T * D + 2 * B * D)
+    n_sets = max(2, int(np.ceil(2.0 * L2_BYTES / bytes_per_set)))
+    sets, host_sets = [], []
+    for k in range(n_sets):
+        ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100 + 17 * k + 1000 * rank)
+        img, txt, cid = synth.sentence_inputs(B, D, seed=100 + 17 * k + 1000 * rank)
+        if k < 2:
+            host_sets.append(tuple(torch.from_numpy(a).pin_memory() for a in (ctx, words, img, txt)))
+        sets.append(tuple(torch.from_numpy(a).to(dev).requires_grad_(True) for a in (ctx, words, img, txt)))
+    labels = torch.arange(B, device=dev)
+    cid_dev = torch.arange(B, device=dev) + rank * B       # distinct classes: mask path runs, nothing masked
+
+    def step(c, w, a, b):
+        for t in (c, w, a, b):
+            t.grad = None
+        c_ref = c.view(B, IH, IW, D).permute(0, 3, 1, 2)
+        if world == 1:
+            l0, l1, _ = losses.words_loss(c_ref, w.transpose(1, 2), labels, None, None, B, margs)
+            s0, s1 = losses.sent_loss(a, b, labels, cid_dev, B, margs)
+        else:
+            l0, l1, _ = tdist.words_loss_sharded(c, w, None, *GAMMAS, precision=precision)
+            s0, s1 = tdist.sent_loss_sharded(a, b, cid_dev, GAMMAS[2])
+        total = l0 + l1 + s0 + s1
+        total.backward()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(*sets[k % n_sets])
+    barrier()
+    ops.launch_counter.n = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for k in range(args.steps):
+            step(*sets[(args.warmup + k) % n_sets])
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.launch_counter.n
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms = ms_total / args.steps
+    pairs = B * Bg * world                         # all ranks' [B, Bg] blocks = Bg^2
+    value = pairs / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST inputs (pinned) + D2H of the losses
+    def e2e_step(hs, ds):
+        with torch.no_grad():
+            for h, d_ in zip(hs, ds):
+                d_.copy_(h, non_blocking=True)
+        return step(*ds).detach().cpu()
+
+    for k in range(2):
+        e2e_step(host_sets[k % 2], sets[k % 2])
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        e2e_step(host_sets[k % 2], sets[k % 2])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_ms /= args.steps
+    e2e = {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": bytes_per_set,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+
+    line = {
+        "metric": "fcam_words+sent_loss_fwd_bwd_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if precision == _lib.PREC_FP32 else "f16-operand/f32-accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"configs[1]: words_loss+sent_loss fwd+bwd (both gradients), {B} faces x {Bg} captions "
+                               f"per rank, T={T}, R={R}, D={D}",
+                   "global_batch": Bg, "local_batch": B, "parallelism": f"row-sharded x{world}",
+                   "precision": "fp32-simt" if precision == _lib.PREC_FP32 else "tcgen05",
+                   "l2": f"rotating {n_sets} input sets ({n_sets * bytes_per_set >> 20} MiB > 126 MiB L2)"},
+        "clocks": clk.result, "e2e": e2e, "gpu_launches": launches,
+    }
+
+    if rank == 0:
+        # ---- dominant kernel: word-region backward, timed alone with CUDA events on the launch stream
+        pk = peaks()
+        c, w = sets[0][0].detach(), sets[1][1].detach()
+        wall = torch.cat([w] * world) if world > 1 else w
+        gsim = torch.randn(B, Bg, device=dev) / Bg
+        dctx = torch.empty(B, R, D, device=dev)
+        dwords = torch.empty(Bg, T, D, device=dev)
+        lib = _lib.load()
+        wsb = lib.tgfr_wordregion_workspace_bytes(B, Bg, T, R, D, precision)
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def bwd_call():
+            _lib.check(lib.tgfr_wordregion_bwd(c.data_ptr(), *c.stride(), wall.data_ptr(), *wall.stride(), 0, B, Bg,
+                                               T, R, D, *GAMMAS, 1e-8, gsim.data_ptr(), dctx.data_ptr(),
+                                               dwords.data_ptr(), precision, ws.data_ptr(), wsb, st), "bwd")
+        flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
+        ks = []
+        for k in range(3 + max(3, min(args.steps, 10))):
+            flush.zero_()
+            e0.record()
+            bwd_call()
+            e1.record()
+            torch.cuda.synchronize()
+            if k >= 3:
+                ks.append(e0.elapsed_time(e1))
+        k_ms = sum(ks) / len(ks)
+        flops = 8 * T * R * D * B * Bg
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                            "frac": achieved / pk["tf_burst"], "traffic": None, "kernel": "wordregion_bwd",
+                            "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
+                            "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
+                            "step_frac_of_peak": FLOPS_PER_PAIR * B * Bg / (ms * 1e-3) / 1e12 / pk["tf_sus"]}
+
+        # ---- margin head (BASELINE configs[2]) reported beside the headline metric
+        h = HEAD
+        xn, wn, lab = synth.margin_inputs(h["B"], h["Din"], h["C"], seed=100)
+        head = metrics.ArcMarginProduct(h["Din"], h["C"], s=h["s"], m=h["m"]).to(dev)
+        with torch.no_grad():
+            head.weight.copy_(torch.from_numpy(wn))
+        x = torch.from_numpy(xn).to(dev).requires_grad_(True)
+        labt = torch.from_numpy(lab).to(dev)
+        crit = losses.FocalLoss(gamma=h["gamma"])
+
+        def head_step():
+            x.grad = None
+            head.weight.grad = None
+            crit(head(x, labt), labt).backward()
+        for _ in range(3):
+            head_step()
+        torch.cuda.synchronize()
+        hs = []
+        for _ in range(max(3, min(args.steps, 10))):
+            flush.zero_()
+            e0.record()
+            head_step()
+            e1.record()
+            torch.cuda.synchronize()
+            hs.append(e0.elapsed_time(e1))
+        h_ms = sum(hs) / len(hs)
+        hflops = 6 * h["Din"] * h["C"] * h["B"]
+        line["margin_head"] = {"metric": "arcface_focal_fwd_bwd_samples_per_sec", "value": h["B"] / (h_ms * 1e-3),
+                               "unit": "samples/s", "ms_per_step": h_ms, "config": h,
+                               "tflops": hflops / (h_ms * 1e-3) / 1e12,
+                               "frac_of_tensor_peak": hflops / (h_ms * 1e-3) / 1e12 / pk["tf_burst"]}
+
+        # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100)
+            img, txt, cid = synth.sentence_inputs(B, D, seed=100)
+            cpu_reference_step(ctx, words, img, txt, cid, n_caps=4)          # warm-up
+            t_used, n_pairs, n_caps = 0.0, 0, 32
+            while t_used < 10.0:
+                dt, p = cpu_reference_step(ctx, words, img, txt, cid, n_caps=n_caps)
+                t_used += dt
+                n_pairs += p
+            line["cpu_baseline"] = {"value": n_pairs / t_used, "unit": "pairs/s", "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": f"{n_pairs} pairs ({n_caps} of {B} captions x {B} faces per pass), "
+                                              f"{t_used:.1f} s of oracle/ref_port.py on the host"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/*
+ * tgfr_b200.h -- C ABI of libtgfr_b200.so: the FCAM contrastive-loss / margin-head hot path of
+ * Mahedi-61/Text_Guided_Face_Recognition, written for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI layer: its boundary is Python symbols.  Every
+ * entry point below replaces the device work of one of those symbols and is what the Python
+ * mirror in text_guided_face_recognition_b200/models/ binds with ctypes.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - float tensors are fp32, label/class-id tensors int64, caption lengths int32;
+ *   - strides are in ELEMENTS; "canonical" layouts are ctx [Bc,R,D], words [Bq,T,D];
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *   - every function returns 0 on success, a negative TGFR_E_* code on failure, and never
+ *     falls back to a CPU path; tgfr_last_error() returns a static description.
+ *   - functions are re-entrant per device (no global mutable state besides the error string).
+ */
+#ifndef TGFR_B200_H_
+#define TGFR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGFR_OK 0
+#define TGFR_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define TGFR_E_CUDA (-2)      /* CUDA runtime error (see tgfr_last_error) */
+#define TGFR_E_WORKSPACE (-3) /* workspace too small */
+#define TGFR_E_ARCH (-4)      /* device is not sm_100 */
+
+/* precision selector of the word-region kernels */
+#define TGFR_PREC_FP32 0      /* SIMT fp32 everywhere (bit-for-bit deterministic forward) */
+#define TGFR_PREC_TC 1        /* tcgen05 tensor-core contractions, fp32 accumulate/statistics */
+
+int tgfr_version(void);
+const char* tgfr_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x), else TGFR_E_ARCH. */
+int tgfr_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Word-region attention loss.  Replaces models/attention.py:10-43 (func_attention) as called
+ * B times from models/losses.py:73-114 (words_loss): all Bc x Bq (face, caption) pairs at once.
+ *   sim[b, i] = gamma3 * log sum_t exp(gamma2 * cos(q_it, W_bit))           (losses.py:104-122)
+ * cap_lens: int32 [Bq] (LSTM path, losses.py:82) or NULL (all captions use T words).
+ * attn_diag: optional [Bc, T, R]; row b receives A2 of pair (b, b + diag_off) (losses.py:97),
+ *            zero-filled beyond the caption's length; NULL to skip.
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
+                        const float* words, int64_t w_sb, int64_t w_st, int64_t w_sd,
+                        const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D,
+                        float gamma1, float gamma2, float gamma3, float eps,
+                        float* sim, float* attn_diag, int diag_off,
+                        int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradients of sum(gsim * sim): dctx [Bc,R,D] and dwords [Bq,T,D] (contiguous, OVERWRITTEN;
+ * either may be NULL to skip it -- the reference's training scripts only need dctx because the
+ * text side is detached, utils/dataset_utils.py:42-46).  Recomputes the attention on chip. */
+int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
+                        const float* words, int64_t w_sb, int64_t w_st, int64_t w_sd,
+                        const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D,
+                        float gamma1, float gamma2, float gamma3, float eps,
+                        const float* gsim, float* dctx, float* dwords,
+                        int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Bytes of scratch the two calls above need for the given shape/precision (0 is possible). */
+size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int precision);
+
+/* Stand-alone func_attention(query, context, gamma1) for B independent (query, context) pairs
+ * (models/attention.py:10-43): wc [B,T,D] canonical, attn [B,T,R]. */
+int tgfr_attention_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
+                       const float* query, int64_t q_sb, int64_t q_st, int64_t q_sd,
+                       int B, int T, int R, int D, float gamma1,
+                       float* wc, float* attn, void* stream);
+/* Backward of the above for upstream gradients g_wc [B,T,D] and g_attn [B,T,R] (either may be
+ * NULL): dctx [B,R,D], dquery [B,T,D], both contiguous and overwritten. */
+int tgfr_attention_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
+                       const float* query, int64_t q_sb, int64_t q_st, int64_t q_sd,
+                       int B, int T, int R, int D, float gamma1,
+                       const float* g_wc, const float* g_attn,
+                       float* dctx, float* dquery, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cosine score matrix.  Replaces models/losses.py:38-48 (sent_loss), :338-343 (global_loss) and
+ * :292-294 (ClipLoss.get_logits).
+ *   normalise != 0: scores[i,j] = scale * <x_i,y_j> / max(|x_i||y_j|, eps);  else scale*<x_i,y_j>.
+ * class_ids_x/_y (int64, may be NULL): entries with class_ids_x[i]==class_ids_y[j] and
+ * (i + diag_off) != j are set to -inf (losses.py:20-30, 47-48).  xnorm/ynorm: outputs [Bx]/[By]
+ * kept for the backward pass.
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_cosine_scores_fwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr,
+                           int Bx, int By, int D, float scale, int normalise, float eps,
+                           const int64_t* class_ids_x, const int64_t* class_ids_y, int diag_off,
+                           float* scores, float* xnorm, float* ynorm, void* stream);
+/* dx [Bx,D], dy [By,D] (contiguous, overwritten; either may be NULL) from gscores [Bx,By]. */
+int tgfr_cosine_scores_bwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr,
+                           int Bx, int By, int D, float scale, int normalise, float eps,
+                           const float* xnorm, const float* ynorm, const float* gscores,
+                           float* dx, float* dy, void* workspace, size_t workspace_bytes, void* stream);
+size_t tgfr_cosine_workspace_bytes(int Bx, int By, int D);
+
+/* ------------------------------------------------------------------------------------------
+ * Two-direction cross entropy over a [Bx,By] score block whose row b is paired with column
+ * b + diag_off (nn.CrossEntropyLoss x2 at losses.py:49-53, 128-132, 348-350).
+ * stats layout (floats): rowlse[Bx] | colmax[By] | colsum[By] | diag[Bx].  A rank that holds a
+ * row block of the global matrix all-gathers colmax/colsum and combines them before _finish.
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_pair_ce_stats(const float* scores, int Bx, int By, int diag_off,
+                       float* rowlse, float* colmax, float* colsum, float* diag, void* stream);
+/* losses[0] = sum_b (rowlse[b] - diag[b]) * inv_b ; collse[j] = colmax[j] + log(colsum[j]);
+ * losses[1] = sum over this rank's diagonal columns of (collse[b+diag_off] - diag[b]) * inv_b. */
+int tgfr_pair_ce_finish(const float* rowlse, const float* colmax, const float* colsum,
+                        const float* diag, int Bx, int By, int diag_off, float inv_b,
+                        float* losses, float* collse, void* stream);
+/* gscores = (g0 * (softmax_row - I) + g1 * (softmax_col - I)) * inv_b; g0/g1 are DEVICE scalars. */
+int tgfr_pair_ce_bwd(const float* scores, const float* rowlse, const float* collse,
+                     const float* g0, const float* g1, int Bx, int By, int diag_off, float inv_b,
+                     float* gscores, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Margin heads.  cos = normalize(x) . normalize(w_c): models/metrics.py:44, models/magface.py:92-94.
+ * w_sc / w_sk: element strides of weight along the class / feature axis
+ *   (ArcMarginProduct.weight [C,Din]: w_sc=Din, w_sk=1;  MagLinear.weight [Din,C]: w_sc=1, w_sk=C).
+ * class_off: first class id owned by this rank (class-sharded partial FC); labels are global.
+ * ------------------------------------------------------------------------------------------ */
+/* out[b,c] = s * cos[b,c]  (clamp_cos != 0: cos clamped to [-1,1] first, magface.py:94);
+ * xnorm[B], wnorm[C] receive the raw L2 norms. */
+int tgfr_cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
+                        int B, int C, int Din, float s, int clamp_cos,
+                        float* out, int64_t out_sr, float* xnorm, float* wnorm, void* stream);
+/* ArcFace margin on the label column, in place (metrics.py:45-57); cos_t[B] keeps the target
+ * cosine (NaN if the label is not owned by this rank). */
+int tgfr_arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, int C,
+                          int class_off, float s, float m, int easy_margin, float* cos_t, void* stream);
+/* dx [B,Din], dw (same strides as w) from glogits [B,C]; dx may be NULL. dx/dw overwritten. */
+int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
+                        const float* xnorm, const float* wnorm, const int64_t* labels,
+                        const float* cos_t, const float* glogits, int64_t g_sr,
+                        int B, int C, int Din, int class_off, float s, float m, int easy_margin,
+                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream);
+size_t tgfr_margin_workspace_bytes(int B, int C, int Din);
+
+/* MagFace: cos_m[b,c] from cos_s (= scale*cos) and per-row margins (magface.py:95-106). */
+int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale,
+                        int easy_margin, float* cos_m_s, void* stream);
+/* Given upstream g_cos, g_cosm (either may be NULL): gtotal[b,c] (gradient w.r.t. scale*cos) and
+ * gmargin[b] (gradient w.r.t. the per-row margin). */
+int tgfr_mag_margin_bwd(const float* cos_s, const float* margin, const float* g_cos, const float* g_cosm,
+                        int B, int C, float scale, int easy_margin, float* gtotal, float* gmargin,
+                        void* stream);
+/* Backward of tgfr_cos_logits_fwd alone (no label margin): dx, dw from gout [B,C]. */
+int tgfr_cos_logits_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
+                        const float* xnorm, const float* wnorm, const float* out, int64_t out_sr,
+                        const float* gout, int64_t g_sr, int B, int C, int Din, float s, int clamp_cos,
+                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise cross entropy over dense logits [B,C] (nn.CrossEntropyLoss inside FocalLoss,
+ * losses.py:319-325, and F.cross_entropy at magface.py:135).  Online softmax, one pass.
+ * rowmax/rowsum: per-row max and sum exp(l - max) of THIS rank's class shard; tgt[b] = logit of
+ * the label column (0 if not owned).
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_ce_rows_stats(const float* logits, int64_t sr, const int64_t* labels, int B, int C,
+                       int class_off, float* rowmax, float* rowsum, float* tgt, void* stream);
+/* out[0] = logp = mean_b(rowmax + log rowsum - tgt); out[1] = focal loss (1-exp(-logp))^gamma*logp;
+ * out[2] = d focal / d logp.  lse[b] = rowmax + log(rowsum). */
+int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt, int B, float gamma,
+                      float* out, float* lse, void* stream);
+/* glogits[b,c] = coef * gout * (exp(l - lse[b]) - [c == label_b]) / B; coef, gout DEVICE scalars
+ * (either may be NULL = 1). */
+int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse,
+                     const float* coef, const float* gout, int B, int C, int class_off,
+                     float* glogits, int64_t g_sr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGFR_B200_H_ */

@@ -141,3 +141,31 @@ def test_mag_head(golden_dir, name):
     dx, dw = O.mag_head_grads(g["x"], g["weight"], g["label"], g_loss=1.0, g_lossg=float(g["lam_g"]), **kw)
     assert rel(dx, g["dx"]) < RTOL_GRAD
     assert rel(dw, g["dweight"]) < RTOL_GRAD
+
+
+def test_ref_port_matches_golden(golden_dir):
+    """oracle/ref_port.py (the CPU-baseline arm) reproduces the real reference's numbers."""
+    import torch
+    from oracle import ref_port as P
+    g = load(golden_dir, "wordregion_lstm_ragged")
+    B, T, ih, iw = int(g["B"]), int(g["T"]), int(g["ih"]), int(g["iw"])
+    c = torch.from_numpy(g["ctx"]).clone().requires_grad_(True)
+    w = torch.from_numpy(g["words"]).clone().requires_grad_(True)
+    g1, g2, g3 = (float(v) for v in g["gammas"])
+    l0, l1, att = P.words_loss_port(c.view(B, ih, iw, -1).permute(0, 3, 1, 2), w.transpose(1, 2), torch.arange(B),
+                                    [int(v) for v in g["cap_lens"]], g1, g2, g3)
+    assert abs(l0.item() - float(g["loss0"])) < 1e-6 * abs(float(g["loss0"]))
+    assert abs(l1.item() - float(g["loss1"])) < 1e-6 * abs(float(g["loss1"]))
+    (float(g["w0"]) * l0 + float(g["w1"]) * l1).backward()
+    assert rel(c.grad.numpy(), g["dctx"]) < 1e-6
+    assert rel(w.grad.numpy(), g["dwords"]) < 1e-6
+    s = load(golden_dir, "sentence_collisions")
+    a = torch.from_numpy(s["img"]).clone().requires_grad_(True)
+    b = torch.from_numpy(s["txt"]).clone().requires_grad_(True)
+    s0, s1 = P.sent_loss_port(a, b, torch.arange(a.shape[0]), s["class_ids"], float(s["gamma3"]))
+    assert abs(s0.item() - float(s["sent_loss0"])) < 1e-6 and abs(s1.item() - float(s["sent_loss1"])) < 1e-6
+    h = load(golden_dir, "arc_small")
+    x = torch.from_numpy(h["x"])
+    out, loss = P.arc_focal_port(x, torch.from_numpy(h["weight"]), torch.from_numpy(h["label"]), float(h["s"]),
+                                 float(h["m"]), float(h["gamma"]), bool(h["easy"]))
+    assert np.max(np.abs(out.numpy() - h["logits"])) < 1e-5 and abs(loss.item() - float(h["loss"])) < 1e-5

@@ -1,0 +1,221 @@
+// extern "C" surface of libtgfr_b200.so (declared in include/tgfr_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tgfr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// wordregion_simt.cu
+int wordregion_fwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
+                        const int32_t*, int, int, int, int, int, float, float, float, float, float*, float*, int,
+                        cudaStream_t);
+int wordregion_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
+                        const int32_t*, int, int, int, int, int, float, float, float, float, const float*, float*,
+                        float*, cudaStream_t);
+int attention_fwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
+                       int, int, float, float*, float*, cudaStream_t);
+int attention_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
+                       int, int, float, const float*, const float*, float*, float*, cudaStream_t);
+// wordregion_tc.cu
+size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D);
+int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
+                      const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t,
+                      cudaStream_t);
+// dense_simt.cu
+int cosine_scores_fwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const int64_t*,
+                      const int64_t*, int, float*, float*, float*, cudaStream_t);
+size_t cosine_workspace_bytes(int, int, int);
+int cosine_scores_bwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const float*,
+                      const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
+int pair_ce_stats(const float*, int, int, int, float*, float*, float*, float*, cudaStream_t);
+int pair_ce_finish(const float*, const float*, const float*, const float*, int, int, int, float, float*, float*,
+                   cudaStream_t);
+int pair_ce_bwd(const float*, const float*, const float*, const float*, const float*, int, int, int, float, float*,
+                cudaStream_t);
+int cos_logits_fwd(const float*, int64_t, const float*, int64_t, int64_t, int, int, int, float, int, float*, int64_t,
+                   float*, float*, cudaStream_t);
+int arc_margin_apply(float*, int64_t, const int64_t*, int, int, int, float, float, int, float*, cudaStream_t);
+size_t margin_workspace_bytes(int, int, int);
+int margin_bwd(const float*, int64_t, const float*, int64_t, int64_t, const float*, const float*, const int64_t*,
+               const float*, const float*, int64_t, int, int, int, int, float, float, int, float*, float*, void*,
+               size_t, cudaStream_t);
+int mag_margin_fwd(const float*, const float*, int, int, float, int, float*, cudaStream_t);
+int mag_margin_bwd(const float*, const float*, const float*, const float*, int, int, float, int, float*, float*,
+                   cudaStream_t);
+int ce_rows_stats(const float*, int64_t, const int64_t*, int, int, int, float*, float*, float*, cudaStream_t);
+int focal_finish(const float*, const float*, const float*, int, float, float*, float*, cudaStream_t);
+int ce_rows_bwd(const float*, int64_t, const int64_t*, const float*, const float*, const float*, int, int, int,
+                float*, int64_t, cudaStream_t);
+
+}  // namespace tgfr
+
+using namespace tgfr;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int tgfr_version(void) { return 100; }
+const char* tgfr_last_error(void) { return g_err; }
+
+int tgfr_device_check(void) {
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TGFR_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libtgfr_b200 is built for sm_100a only", dev, prop.major, prop.minor);
+    return TGFR_E_ARCH;
+  }
+  return TGFR_OK;
+}
+
+size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int precision) {
+  if (precision == TGFR_PREC_TC) return wordregion_tc_workspace_bytes(Bc, Bq, T, R, D);
+  return 0;
+}
+
+int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* words,
+                        int64_t w_sb, int64_t w_st, int64_t w_sd, const int32_t* cap_lens, int Bc, int Bq, int T,
+                        int R, int D, float gamma1, float gamma2, float gamma3, float eps, float* sim,
+                        float* attn_diag, int diag_off, int precision, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  TGFR_REQUIRE(ctx && words && sim, "wordregion_fwd: NULL tensor");
+  if (precision == TGFR_PREC_TC) {
+    if (int rc = wordregion_fwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,
+                                   gamma1, gamma2, gamma3, eps, sim, workspace, workspace_bytes, ST(stream)))
+      return rc;
+    if (!attn_diag) return TGFR_OK;
+    // the B diagonal attention maps are produced by the fp32 kernel on the matching pairs only
+    const int n = Bc;
+    TGFR_REQUIRE(diag_off >= 0 && diag_off + n <= Bq, "wordregion_fwd: diagonal outside the caption range");
+    return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words + (int64_t)diag_off * w_sb, w_sb, w_st, w_sd, n, T,
+                              R, D, gamma1, reinterpret_cast<float*>(workspace), attn_diag, ST(stream));
+  }
+  TGFR_REQUIRE(precision == TGFR_PREC_FP32, "wordregion_fwd: unknown precision %d", precision);
+  return wordregion_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
+                             gamma2, gamma3, eps, sim, attn_diag, diag_off, ST(stream));
+}
+
+int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* words,
+                        int64_t w_sb, int64_t w_st, int64_t w_sd, const int32_t* cap_lens, int Bc, int Bq, int T,
+                        int R, int D, float gamma1, float gamma2, float gamma3, float eps, const float* gsim,
+                        float* dctx, float* dwords, int precision, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  (void)workspace; (void)workspace_bytes; (void)precision;
+  TGFR_REQUIRE(ctx && words && gsim, "wordregion_bwd: NULL tensor");
+  return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
+                             gamma2, gamma3, eps, gsim, dctx, dwords, ST(stream));
+}
+
+int tgfr_attention_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* query,
+                       int64_t q_sb, int64_t q_st, int64_t q_sd, int B, int T, int R, int D, float gamma1, float* wc,
+                       float* attn, void* stream) {
+  TGFR_REQUIRE(ctx && query, "attention_fwd: NULL tensor");
+  return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, query, q_sb, q_st, q_sd, B, T, R, D, gamma1, wc, attn,
+                            ST(stream));
+}
+
+int tgfr_attention_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* query,
+                       int64_t q_sb, int64_t q_st, int64_t q_sd, int B, int T, int R, int D, float gamma1,
+                       const float* g_wc, const float* g_attn, float* dctx, float* dquery, void* stream) {
+  TGFR_REQUIRE(ctx && query, "attention_bwd: NULL tensor");
+  return attention_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, query, q_sb, q_st, q_sd, B, T, R, D, gamma1, g_wc, g_attn,
+                            dctx, dquery, ST(stream));
+}
+
+int tgfr_cosine_scores_fwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr, int Bx, int By, int D,
+                           float scale, int normalise, float eps, const int64_t* class_ids_x,
+                           const int64_t* class_ids_y, int diag_off, float* scores, float* xnorm, float* ynorm,
+                           void* stream) {
+  TGFR_REQUIRE(x && y && scores, "cosine_scores_fwd: NULL tensor");
+  return cosine_scores_fwd(x, x_sr, y, y_sr, Bx, By, D, scale, normalise, eps, class_ids_x, class_ids_y, diag_off,
+                           scores, xnorm, ynorm, ST(stream));
+}
+
+int tgfr_cosine_scores_bwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr, int Bx, int By, int D,
+                           float scale, int normalise, float eps, const float* xnorm, const float* ynorm,
+                           const float* gscores, float* dx, float* dy, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  TGFR_REQUIRE(x && y && gscores, "cosine_scores_bwd: NULL tensor");
+  return cosine_scores_bwd(x, x_sr, y, y_sr, Bx, By, D, scale, normalise, eps, xnorm, ynorm, gscores, dx, dy,
+                           workspace, workspace_bytes, ST(stream));
+}
+
+size_t tgfr_cosine_workspace_bytes(int Bx, int By, int D) { return cosine_workspace_bytes(Bx, By, D); }
+
+int tgfr_pair_ce_stats(const float* scores, int Bx, int By, int diag_off, float* rowlse, float* colmax,
+                       float* colsum, float* diag, void* stream) {
+  return pair_ce_stats(scores, Bx, By, diag_off, rowlse, colmax, colsum, diag, ST(stream));
+}
+int tgfr_pair_ce_finish(const float* rowlse, const float* colmax, const float* colsum, const float* diag, int Bx,
+                        int By, int diag_off, float inv_b, float* losses, float* collse, void* stream) {
+  return pair_ce_finish(rowlse, colmax, colsum, diag, Bx, By, diag_off, inv_b, losses, collse, ST(stream));
+}
+int tgfr_pair_ce_bwd(const float* scores, const float* rowlse, const float* collse, const float* g0, const float* g1,
+                     int Bx, int By, int diag_off, float inv_b, float* gscores, void* stream) {
+  return pair_ce_bwd(scores, rowlse, collse, g0, g1, Bx, By, diag_off, inv_b, gscores, ST(stream));
+}
+
+int tgfr_cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C,
+                        int Din, float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm,
+                        void* stream) {
+  TGFR_REQUIRE(x && w && out && xnorm && wnorm, "cos_logits_fwd: NULL tensor");
+  return cos_logits_fwd(x, x_sr, w, w_sc, w_sk, B, C, Din, s, clamp_cos, out, out_sr, xnorm, wnorm, ST(stream));
+}
+int tgfr_arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off, float s,
+                          float m, int easy_margin, float* cos_t, void* stream) {
+  TGFR_REQUIRE(logits && labels && cos_t, "arc_margin_apply: NULL tensor");
+  return arc_margin_apply(logits, sr, labels, B, C, class_off, s, m, easy_margin, cos_t, ST(stream));
+}
+int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
+                        const float* wnorm, const int64_t* labels, const float* cos_t, const float* glogits,
+                        int64_t g_sr, int B, int C, int Din, int class_off, float s, float m, int easy_margin,
+                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream) {
+  TGFR_REQUIRE(x && w && xnorm && wnorm && labels && cos_t && glogits, "arc_margin_bwd: NULL tensor");
+  return margin_bwd(x, x_sr, w, w_sc, w_sk, xnorm, wnorm, labels, cos_t, glogits, g_sr, B, C, Din, class_off, s, m,
+                    easy_margin, dx, dw, workspace, workspace_bytes, ST(stream));
+}
+size_t tgfr_margin_workspace_bytes(int B, int C, int Din) { return margin_workspace_bytes(B, C, Din); }
+
+int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale, int easy_margin,
+                        float* cos_m_s, void* stream) {
+  return mag_margin_fwd(cos_s, margin, B, C, scale, easy_margin, cos_m_s, ST(stream));
+}
+int tgfr_mag_margin_bwd(const float* cos_s, const float* margin, const float* g_cos, const float* g_cosm, int B,
+                        int C, float scale, int easy_margin, float* gtotal, float* gmargin, void* stream) {
+  return mag_margin_bwd(cos_s, margin, g_cos, g_cosm, B, C, scale, easy_margin, gtotal, gmargin, ST(stream));
+}
+int tgfr_cos_logits_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
+                        const float* wnorm, const float* out, int64_t out_sr, const float* gout, int64_t g_sr, int B,
+                        int C, int Din, float s, int clamp_cos, float* dx, float* dw, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  (void)out; (void)out_sr; (void)clamp_cos;
+  TGFR_REQUIRE(x && w && xnorm && wnorm && gout, "cos_logits_bwd: NULL tensor");
+  return margin_bwd(x, x_sr, w, w_sc, w_sk, xnorm, wnorm, nullptr, nullptr, gout, g_sr, B, C, Din, 0, s, 0.f, 0, dx,
+                    dw, workspace, workspace_bytes, ST(stream));
+}
+
+int tgfr_ce_rows_stats(const float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off,
+                       float* rowmax, float* rowsum, float* tgt, void* stream) {
+  return ce_rows_stats(logits, sr, labels, B, C, class_off, rowmax, rowsum, tgt, ST(stream));
+}
+int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt, int B, float gamma, float* out,
+                      float* lse, void* stream) {
+  return focal_finish(rowmax, rowsum, tgt, B, gamma, out, lse, ST(stream));
+}
+int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse, const float* coef,
+                     const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, void* stream) {
+  return ce_rows_bwd(logits, sr, labels, lse, coef, gout, B, C, class_off, glogits, g_sr, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,611 @@
+// fp32 SIMT kernels for the dense part of the path: cosine score matrices (sent/global/Clip
+// losses), the two-direction B x B cross entropy, the margin heads (ArcFace / MagFace) and the
+// row-wise cross entropy / focal loss.  The contraction is a strided 64x64x16 register-tiled
+// SGEMM with fused normalisation scales; everything else is bandwidth-bound glue around it.
+#include "common.cuh"
+
+namespace tgfr {
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// row norms: one warp per row, arbitrary strides
+// --------------------------------------------------------------------------------------------
+__global__ void rownorm_kernel(const float* __restrict__ x, int64_t s_row, int64_t s_col, int rows, int cols,
+                               float* __restrict__ norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = x + (int64_t)row * s_row;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = __ldg(p + (int64_t)c * s_col);
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) norm[row] = sqrtf(acc);
+}
+
+// column norms of a row-major [rows, cols] matrix (MagLinear.weight [Din, C]): coalesced over cols
+__global__ void colnorm_kernel(const float* __restrict__ x, int64_t s_row, int rows, int cols,
+                               float* __restrict__ norm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float v = __ldg(x + (int64_t)r * s_row + c);
+    acc = fmaf(v, v, acc);
+  }
+  norm[c] = sqrtf(acc);
+}
+
+int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, float* norm, cudaStream_t st) {
+  if (s_vec == 1 && s_elem != 1) {
+    colnorm_kernel<<<ceil_div(nvec, 256), 256, 0, st>>>(x, s_elem, len, nvec, norm);
+  } else {
+    rownorm_kernel<<<ceil_div(nvec, 8), 256, 0, st>>>(x, s_vec, s_elem, nvec, len, norm);
+  }
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// strided SGEMM:  C[m,n] = epilogue( sum_k A(m,k) * B(k,n) * bk[k] )
+// --------------------------------------------------------------------------------------------
+enum EpiMode {
+  kEpiScale = 0,   // alpha * acc * inv(am[m]) * inv(bn[n])       (am/bn are norms, clamped at norm_eps)
+  kEpiCosine = 1,  // alpha * acc / max(am[m]*bn[n], eps), -inf on class collisions
+  kEpiClamp = 2,   // alpha * clamp(acc * inv(am[m]) * inv(bn[n]), -1, 1)
+};
+
+struct Gemm {
+  const float* A; int64_t sAm, sAk;
+  const float* B; int64_t sBk, sBn;
+  float* C; int64_t sCm, sCn;
+  int M, N, K;
+  float alpha;
+  const float* bk;      // optional norms over k: B(k,n) is divided by max(bk[k], norm_eps)
+  const float* am;      // optional norms over m
+  const float* bn;      // optional norms over n
+  float norm_eps;       // F.normalize eps (1e-12)
+  float eps;            // cosine clamp
+  int mode;
+  const int64_t* ids_m; // optional class ids for the -inf mask (kEpiCosine)
+  const int64_t* ids_n;
+  int diag_off;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+
+__global__ void __launch_bounds__(GT) sgemm_kernel(const Gemm g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (g.sAk == 1), b_nfast = (g.sBn == 1);
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int mm, kk;
+      if (a_kfast) { kk = tid & 15; mm = (tid >> 4) + 16 * i; }
+      else         { mm = tid & 63; kk = (tid >> 6) + 4 * i; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < g.K) ? __ldg(g.A + (int64_t)m * g.sAm + (int64_t)k * g.sAk) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int nn, kk;
+      if (b_nfast) { nn = tid & 63; kk = (tid >> 6) + 4 * i; }
+      else         { kk = tid & 15; nn = (tid >> 4) + 16 * i; }
+      const int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < g.N && k < g.K) {
+        v = __ldg(g.B + (int64_t)k * g.sBk + (int64_t)n * g.sBn);
+        if (g.bk) v /= fmaxf(__ldg(g.bk + k), g.norm_eps);
+      }
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    const float na = g.am ? __ldg(g.am + m) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      const float nb = g.bn ? __ldg(g.bn + n) : 1.f;
+      float v;
+      if (g.mode == kEpiCosine) {
+        v = acc[i][j] / fmaxf(na * nb, g.eps) * g.alpha;
+        if (g.ids_m && g.ids_n && (m + g.diag_off) != n && __ldg(g.ids_m + m) == __ldg(g.ids_n + n)) v = -INFINITY;
+      } else {
+        v = acc[i][j];
+        if (g.am) v /= fmaxf(na, g.norm_eps);
+        if (g.bn) v /= fmaxf(nb, g.norm_eps);
+        if (g.mode == kEpiClamp) v = fminf(fmaxf(v, -1.f), 1.f);
+        v *= g.alpha;
+      }
+      g.C[(int64_t)m * g.sCm + (int64_t)n * g.sCn] = v;
+    }
+  }
+}
+
+int launch_gemm(const Gemm& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return TGFR_OK;
+  const dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+  sgemm_kernel<<<grid, GT, 0, st>>>(g);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// d(normalize(v))/dv projection:  out = (g - <g, v^> v^) / |v|,  one warp per vector
+// --------------------------------------------------------------------------------------------
+__global__ void normalize_bwd_kernel(const float* __restrict__ ghat, int64_t g_sv, const float* __restrict__ v,
+                                     int64_t v_sv, int64_t v_se, const float* __restrict__ norm, float norm_eps,
+                                     int nvec, int len, float* __restrict__ out, int64_t o_sv, int64_t o_se) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nvec) return;
+  const float n = fmaxf(norm[row], norm_eps), inv = 1.f / n;
+  const float* gp = ghat + (int64_t)row * g_sv;
+  const float* vp = v + (int64_t)row * v_sv;
+  float dot = 0.f;
+  for (int c = lane; c < len; c += 32) dot = fmaf(gp[c], __ldg(vp + (int64_t)c * v_se) * inv, dot);
+  dot = warp_sum(dot);
+  float* op = out + (int64_t)row * o_sv;
+  for (int c = lane; c < len; c += 32) {
+    const float vh = __ldg(vp + (int64_t)c * v_se) * inv;
+    op[(int64_t)c * o_se] = (gp[c] - dot * vh) * inv;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// two-direction cross entropy over a [Bx, By] block
+// --------------------------------------------------------------------------------------------
+__global__ void pair_ce_stats_kernel(const float* __restrict__ sc, int Bx, int By, int diag_off,
+                                     float* __restrict__ rowlse, float* __restrict__ colmax,
+                                     float* __restrict__ colsum, float* __restrict__ diag) {
+  __shared__ float scratch[32];
+  const int id = blockIdx.x;
+  const bool is_row = id < Bx;
+  const int n = is_row ? By : Bx;
+  const float* base = is_row ? sc + (int64_t)id * By : sc + (id - Bx);
+  const int64_t stride = is_row ? 1 : By;
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) m = fmaxf(m, base[k * stride]);
+  m = block_max(m, scratch);
+  const float mm = (m == -INFINITY) ? 0.f : m;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += expf(base[k * stride] - mm);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) {
+    if (is_row) {
+      rowlse[id] = mm + logf(s);
+      const int j = id + diag_off;
+      diag[id] = (j >= 0 && j < By) ? sc[(int64_t)id * By + j] : 0.f;
+    } else {
+      colmax[id - Bx] = mm;
+      colsum[id - Bx] = s;
+    }
+  }
+}
+
+__global__ void pair_ce_finish_kernel(const float* __restrict__ rowlse, const float* __restrict__ colmax,
+                                      const float* __restrict__ colsum, const float* __restrict__ diag, int Bx,
+                                      int By, int diag_off, float inv_b, float* __restrict__ losses,
+                                      float* __restrict__ collse) {
+  __shared__ float scratch[32];
+  for (int j = threadIdx.x; j < By; j += blockDim.x) collse[j] = colmax[j] + logf(colsum[j]);
+  __syncthreads();
+  float l0 = 0.f, l1 = 0.f;
+  for (int b = threadIdx.x; b < Bx; b += blockDim.x) {
+    l0 += rowlse[b] - diag[b];
+    const int j = b + diag_off;
+    if (j >= 0 && j < By) l1 += collse[j] - diag[b];
+  }
+  l0 = block_sum(l0, scratch);
+  l1 = block_sum(l1, scratch);
+  if (threadIdx.x == 0) {
+    losses[0] = l0 * inv_b;
+    losses[1] = l1 * inv_b;
+  }
+}
+
+__global__ void pair_ce_bwd_kernel(const float* __restrict__ sc, const float* __restrict__ rowlse,
+                                   const float* __restrict__ collse, const float* __restrict__ g0p,
+                                   const float* __restrict__ g1p, int Bx, int By, int diag_off, float inv_b,
+                                   float* __restrict__ gs) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Bx * By) return;
+  const int b = (int)(idx / By), j = (int)(idx - (int64_t)b * By);
+  const float g0 = g0p ? *g0p : 1.f, g1 = g1p ? *g1p : 1.f;
+  const float s = sc[idx];
+  const float on = (j == b + diag_off) ? 1.f : 0.f;
+  const float pr = expf(s - rowlse[b]), pc = expf(s - collse[j]);
+  gs[idx] = (g0 * (pr - on) + g1 * (pc - on)) * inv_b;
+}
+
+// --------------------------------------------------------------------------------------------
+// row-wise cross entropy over dense logits, focal loss
+// --------------------------------------------------------------------------------------------
+__global__ void ce_rows_stats_kernel(const float* __restrict__ lg, int64_t sr, const int64_t* __restrict__ labels,
+                                     int C, int class_off, float* __restrict__ rowmax, float* __restrict__ rowsum,
+                                     float* __restrict__ tgt) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float* p = lg + (int64_t)b * sr;
+  float m = -INFINITY, s = 0.f;     // online softmax: one pass over the row
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = p[c];
+    if (v > m) { s = s * expf(m - v) + 1.f; m = v; }
+    else       { s += expf(v - m); }
+  }
+  const float bm = block_max(m, scratch);
+  const float bmm = (bm == -INFINITY) ? 0.f : bm;
+  s = (m == -INFINITY) ? 0.f : s * expf(m - bmm);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) {
+    rowmax[b] = bmm;
+    rowsum[b] = s;
+    const int64_t y = labels[b] - class_off;
+    tgt[b] = (y >= 0 && y < C) ? p[y] : 0.f;
+  }
+}
+
+__global__ void focal_finish_kernel(const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                    const float* __restrict__ tgt, int B, float gamma, float* __restrict__ out,
+                                    float* __restrict__ lse) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float l = rowmax[b] + logf(rowsum[b]);
+    lse[b] = l;
+    acc += l - tgt[b];
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) {
+    const float logp = acc / (float)B;          // CrossEntropyLoss(mean), losses.py:322
+    const float pt = expf(-logp);               // :323
+    const float om = 1.f - pt;
+    float loss, dl;
+    if (gamma == 0.f) { loss = logp; dl = 1.f; }
+    else {
+      loss = powf(om, gamma) * logp;            // :324
+      dl = powf(om, gamma) + gamma * powf(om, gamma - 1.f) * pt * logp;
+    }
+    out[0] = logp; out[1] = loss; out[2] = dl;
+  }
+}
+
+__global__ void ce_rows_bwd_kernel(const float* __restrict__ lg, int64_t sr, const int64_t* __restrict__ labels,
+                                   const float* __restrict__ lse, const float* __restrict__ coef,
+                                   const float* __restrict__ gout, int B, int C, int class_off,
+                                   float* __restrict__ gl, int64_t g_sr) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float k = (coef ? *coef : 1.f) * (gout ? *gout : 1.f) / (float)B;
+  const float on = ((int64_t)c + class_off == labels[b]) ? 1.f : 0.f;
+  gl[(int64_t)b * g_sr + c] = k * (expf(lg[(int64_t)b * sr + c] - lse[b]) - on);
+}
+
+// --------------------------------------------------------------------------------------------
+// ArcFace margin on the label column (metrics.py:45-57) and its backward correction
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float arc_phi(float c, float cm, float sm, float th, float mm, int easy, float* dphi) {
+  const float one_m = 1.f - c * c;
+  const float sine = sqrtf(fminf(fmaxf(one_m, 0.f), 1.f));
+  const float phi = c * cm - sine * sm;
+  const bool use = easy ? (c > 0.f) : (c > th);
+  if (dphi) {
+    const bool inside = one_m >= 0.f && one_m <= 1.f;
+    *dphi = use ? (cm + (inside ? c / sine : 0.f) * sm) : 1.f;
+  }
+  return use ? phi : (easy ? c : c - mm);
+}
+
+__global__ void arc_apply_kernel(float* __restrict__ lg, int64_t sr, const int64_t* __restrict__ labels, int B,
+                                 int C, int class_off, float s, float cm, float sm, float th, float mm, int easy,
+                                 float* __restrict__ cos_t) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t y = labels[b] - class_off;
+  if (y < 0 || y >= C) { cos_t[b] = nanf(""); return; }
+  float* p = lg + (int64_t)b * sr + y;
+  const float c = *p / s;
+  cos_t[b] = c;
+  *p = s * arc_phi(c, cm, sm, th, mm, easy, nullptr);
+}
+
+// dXhat[b,:] += k_b * w^_y ; dWhat[y,:] += k_b * x^_b   with k_b = (phi'(cos_t) - 1) * s * g[b,y]
+__global__ void arc_fix_kernel(const float* __restrict__ x, int64_t x_sr, const float* __restrict__ w, int64_t w_sc,
+                               int64_t w_sk, const float* __restrict__ xnorm, const float* __restrict__ wnorm,
+                               const int64_t* __restrict__ labels, const float* __restrict__ cos_t,
+                               const float* __restrict__ g, int64_t g_sr, int C, int Din, int class_off, float s,
+                               float cm, float sm, float th, float mm, int easy, float* __restrict__ dxh,
+                               float* __restrict__ dwh) {
+  const int b = blockIdx.x;
+  const int64_t y = labels[b] - class_off;
+  if (y < 0 || y >= C) return;
+  float dphi;
+  arc_phi(cos_t[b], cm, sm, th, mm, easy, &dphi);
+  const float k = (dphi - 1.f) * s * g[(int64_t)b * g_sr + y];
+  if (k == 0.f) return;
+  const float ix = 1.f / fmaxf(xnorm[b], 1e-12f), iw = 1.f / fmaxf(wnorm[y], 1e-12f);
+  for (int d = threadIdx.x; d < Din; d += blockDim.x) {
+    if (dxh) dxh[(int64_t)b * Din + d] += k * w[y * w_sc + (int64_t)d * w_sk] * iw;
+    atomicAdd(dwh + y * Din + d, k * x[(int64_t)b * x_sr + d] * ix);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// MagFace margin (magface.py:95-106), elementwise over [B, C]
+// --------------------------------------------------------------------------------------------
+__global__ void mag_fwd_kernel(const float* __restrict__ cs, const float* __restrict__ margin, int B, int C,
+                               float scale, int easy, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mar = margin[b];
+  float cm, sm;
+  sincosf(mar, &sm, &cm);
+  const float ct = cs[(int64_t)b * C + c] / scale;
+  const float st = sqrtf(1.f - ct * ct);
+  float v = ct * cm - st * sm;
+  if (easy) v = (ct > 0.f) ? v : ct;
+  else {
+    const float th = cosf(3.14159265358979323846f - mar), mm = sinf(3.14159265358979323846f - mar) * mar;
+    v = (ct > th) ? v : ct - mm;
+  }
+  out[(int64_t)b * C + c] = scale * v;
+}
+
+__global__ void mag_bwd_kernel(const float* __restrict__ cs, const float* __restrict__ margin,
+                               const float* __restrict__ g_cos, const float* __restrict__ g_cosm, int B, int C,
+                               float scale, int easy, float* __restrict__ gtotal, float* __restrict__ gmargin) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float mar = margin[b];
+  float cm, sm;
+  sincosf(mar, &sm, &cm);
+  const float pi = 3.14159265358979323846f;
+  const float th = cosf(pi - mar);
+  const float alt_dm = cosf(pi - mar) * mar - sinf(pi - mar);   // d/dmar (cos - sin(pi-mar)*mar)
+  float gm = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int64_t idx = (int64_t)b * C + c;
+    const float ct = cs[idx] / scale;
+    const float st = sqrtf(1.f - ct * ct);
+    const bool use = easy ? (ct > 0.f) : (ct > th);
+    const float gc = g_cos ? g_cos[idx] : 0.f, gcm = g_cosm ? g_cosm[idx] : 0.f;
+    float dsel_dcos = 1.f, dsel_dm = easy ? 0.f : alt_dm;
+    if (use) {
+      dsel_dcos = cm + (ct / st) * sm;
+      dsel_dm = -ct * sm - st * cm;
+    }
+    // both outputs are scale * f(cos); gtotal is the gradient w.r.t. (scale * cos)
+    gtotal[idx] = gc + (gcm != 0.f ? gcm * dsel_dcos : 0.f);
+    gm += (gcm != 0.f) ? gcm * scale * dsel_dm : 0.f;
+  }
+  gm = block_sum(gm, scratch);
+  if (threadIdx.x == 0) gmargin[b] = gm;
+}
+
+}  // namespace
+
+// ============================================================================================
+// host-side entry points used by capi.cu
+// ============================================================================================
+int cosine_scores_fwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr, int Bx, int By, int D, float scale,
+                      int normalise, float eps, const int64_t* ids_x, const int64_t* ids_y, int diag_off,
+                      float* scores, float* xnorm, float* ynorm, cudaStream_t st) {
+  TGFR_REQUIRE(Bx > 0 && By > 0 && D > 0, "cosine_scores: empty shape");
+  TGFR_REQUIRE(normalise || !(ids_x && ids_y), "cosine_scores: the class-id mask needs normalise != 0");
+  if (normalise) {
+    TGFR_REQUIRE(xnorm && ynorm, "cosine_scores: xnorm/ynorm required when normalise != 0");
+    if (int rc = launch_norms(x, x_sr, 1, Bx, D, xnorm, st)) return rc;
+    if (int rc = launch_norms(y, y_sr, 1, By, D, ynorm, st)) return rc;
+  }
+  Gemm g{};
+  g.A = x; g.sAm = x_sr; g.sAk = 1;
+  g.B = y; g.sBk = 1; g.sBn = y_sr;
+  g.C = scores; g.sCm = By; g.sCn = 1;
+  g.M = Bx; g.N = By; g.K = D; g.alpha = scale; g.norm_eps = 1e-12f; g.eps = eps;
+  if (normalise) { g.mode = kEpiCosine; g.am = xnorm; g.bn = ynorm; }
+  else g.mode = kEpiScale;
+  g.ids_m = ids_x; g.ids_n = ids_y; g.diag_off = diag_off;
+  return launch_gemm(g, st);
+}
+
+size_t cosine_workspace_bytes(int Bx, int By, int D) {
+  return sizeof(float) * ((size_t)Bx * D + (size_t)By * D);
+}
+
+int cosine_scores_bwd(const float* x, int64_t x_sr, const float* y, int64_t y_sr, int Bx, int By, int D, float scale,
+                      int normalise, float eps, const float* xnorm, const float* ynorm, const float* gs, float* dx,
+                      float* dy, void* ws, size_t ws_bytes, cudaStream_t st) {
+  (void)eps;
+  TGFR_REQUIRE(ws_bytes >= cosine_workspace_bytes(Bx, By, D), "cosine_scores_bwd: workspace too small");
+  float* dxh = reinterpret_cast<float*>(ws);
+  float* dyh = dxh + (size_t)Bx * D;
+  if (dx) {
+    Gemm g{};  // dXhat = scale * G . Yhat
+    g.A = gs; g.sAm = By; g.sAk = 1;
+    g.B = y; g.sBk = y_sr; g.sBn = 1;
+    g.C = normalise ? dxh : dx; g.sCm = D; g.sCn = 1;
+    g.M = Bx; g.N = D; g.K = By; g.alpha = scale; g.norm_eps = 1e-12f; g.mode = kEpiScale;
+    g.bk = normalise ? ynorm : nullptr;
+    if (int rc = launch_gemm(g, st)) return rc;
+    if (normalise) {
+      normalize_bwd_kernel<<<ceil_div(Bx, 8), 256, 0, st>>>(dxh, D, x, x_sr, 1, xnorm, 1e-12f, Bx, D, dx, D, 1);
+      TGFR_LAUNCH_OK();
+    }
+  }
+  if (dy) {
+    Gemm g{};  // dYhat = scale * G^T . Xhat
+    g.A = gs; g.sAm = 1; g.sAk = By;
+    g.B = x; g.sBk = x_sr; g.sBn = 1;
+    g.C = normalise ? dyh : dy; g.sCm = D; g.sCn = 1;
+    g.M = By; g.N = D; g.K = Bx; g.alpha = scale; g.norm_eps = 1e-12f; g.mode = kEpiScale;
+    g.bk = normalise ? xnorm : nullptr;
+    if (int rc = launch_gemm(g, st)) return rc;
+    if (normalise) {
+      normalize_bwd_kernel<<<ceil_div(By, 8), 256, 0, st>>>(dyh, D, y, y_sr, 1, ynorm, 1e-12f, By, D, dy, D, 1);
+      TGFR_LAUNCH_OK();
+    }
+  }
+  return TGFR_OK;
+}
+
+int pair_ce_stats(const float* scores, int Bx, int By, int diag_off, float* rowlse, float* colmax, float* colsum,
+                  float* diag, cudaStream_t st) {
+  TGFR_REQUIRE(Bx > 0 && By > 0, "pair_ce_stats: empty shape");
+  pair_ce_stats_kernel<<<Bx + By, 128, 0, st>>>(scores, Bx, By, diag_off, rowlse, colmax, colsum, diag);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int pair_ce_finish(const float* rowlse, const float* colmax, const float* colsum, const float* diag, int Bx, int By,
+                   int diag_off, float inv_b, float* losses, float* collse, cudaStream_t st) {
+  pair_ce_finish_kernel<<<1, 256, 0, st>>>(rowlse, colmax, colsum, diag, Bx, By, diag_off, inv_b, losses, collse);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int pair_ce_bwd(const float* scores, const float* rowlse, const float* collse, const float* g0, const float* g1,
+                int Bx, int By, int diag_off, float inv_b, float* gscores, cudaStream_t st) {
+  const int64_t n = (int64_t)Bx * By;
+  pair_ce_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, rowlse, collse, g0, g1, Bx, By, diag_off,
+                                                                  inv_b, gscores);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C, int Din,
+                   float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm, cudaStream_t st) {
+  TGFR_REQUIRE(B > 0 && C > 0 && Din > 0, "cos_logits: empty shape");
+  if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
+  if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  Gemm g{};
+  g.A = x; g.sAm = x_sr; g.sAk = 1;
+  g.B = w; g.sBk = w_sk; g.sBn = w_sc;
+  g.C = out; g.sCm = out_sr; g.sCn = 1;
+  g.M = B; g.N = C; g.K = Din; g.alpha = s; g.norm_eps = 1e-12f;
+  g.am = xnorm; g.bn = wnorm; g.mode = clamp_cos ? kEpiClamp : kEpiScale;
+  return launch_gemm(g, st);
+}
+
+int arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off, float s, float m,
+                     int easy, float* cos_t, cudaStream_t st) {
+  const float pi = 3.14159265358979323846f;
+  arc_apply_kernel<<<ceil_div(B, 128), 128, 0, st>>>(logits, sr, labels, B, C, class_off, s, cosf(m), sinf(m),
+                                                     cosf(pi - m), sinf(pi - m) * m, easy, cos_t);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+size_t margin_workspace_bytes(int B, int C, int Din) {
+  return sizeof(float) * ((size_t)B * Din + (size_t)C * Din);
+}
+
+// shared by ArcFace (labels != NULL) and the plain cosine head (MagFace)
+int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
+               const float* wnorm, const int64_t* labels, const float* cos_t, const float* g, int64_t g_sr, int B,
+               int C, int Din, int class_off, float s, float m, int easy, float* dx, float* dw, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  TGFR_REQUIRE(ws_bytes >= margin_workspace_bytes(B, C, Din), "margin_bwd: workspace too small");
+  TGFR_REQUIRE(dw != nullptr, "margin_bwd: dw must not be NULL");
+  float* dxh = reinterpret_cast<float*>(ws);
+  float* dwh = dxh + (size_t)B * Din;
+  if (dx) {
+    Gemm a{};  // dXhat[b,:] = s * sum_c g[b,c] w^_c
+    a.A = g; a.sAm = g_sr; a.sAk = 1;
+    a.B = w; a.sBk = w_sc; a.sBn = w_sk;
+    a.C = dxh; a.sCm = Din; a.sCn = 1;
+    a.M = B; a.N = Din; a.K = C; a.alpha = s; a.norm_eps = 1e-12f; a.mode = kEpiScale; a.bk = wnorm;
+    if (int rc = launch_gemm(a, st)) return rc;
+  }
+  {
+    Gemm b{};  // dWhat[c,:] = s * sum_b g[b,c] x^_b
+    b.A = g; b.sAm = 1; b.sAk = g_sr;
+    b.B = x; b.sBk = x_sr; b.sBn = 1;
+    b.C = dwh; b.sCm = Din; b.sCn = 1;
+    b.M = C; b.N = Din; b.K = B; b.alpha = s; b.norm_eps = 1e-12f; b.mode = kEpiScale; b.bk = xnorm;
+    if (int rc = launch_gemm(b, st)) return rc;
+  }
+  if (labels) {
+    const float pi = 3.14159265358979323846f;
+    arc_fix_kernel<<<B, 128, 0, st>>>(x, x_sr, w, w_sc, w_sk, xnorm, wnorm, labels, cos_t, g, g_sr, C, Din, class_off,
+                                      s, cosf(m), sinf(m), cosf(pi - m), sinf(pi - m) * m, easy, dx ? dxh : nullptr,
+                                      dwh);
+    TGFR_LAUNCH_OK();
+  }
+  if (dx) {
+    normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dxh, Din, x, x_sr, 1, xnorm, 1e-12f, B, Din, dx, Din, 1);
+    TGFR_LAUNCH_OK();
+  }
+  normalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dwh, Din, w, w_sc, w_sk, wnorm, 1e-12f, C, Din, dw, w_sc, w_sk);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale, int easy, float* out,
+                   cudaStream_t st) {
+  mag_fwd_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, st>>>(cos_s, margin, B, C, scale, easy, out);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int mag_margin_bwd(const float* cos_s, const float* margin, const float* g_cos, const float* g_cosm, int B, int C,
+                   float scale, int easy, float* gtotal, float* gmargin, cudaStream_t st) {
+  mag_bwd_kernel<<<B, 256, 0, st>>>(cos_s, margin, g_cos, g_cosm, B, C, scale, easy, gtotal, gmargin);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int ce_rows_stats(const float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off, float* rowmax,
+                  float* rowsum, float* tgt, cudaStream_t st) {
+  TGFR_REQUIRE(B > 0 && C > 0, "ce_rows_stats: empty shape");
+  ce_rows_stats_kernel<<<B, 256, 0, st>>>(logits, sr, labels, C, class_off, rowmax, rowsum, tgt);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int focal_finish(const float* rowmax, const float* rowsum, const float* tgt, int B, float gamma, float* out,
+                 float* lse, cudaStream_t st) {
+  focal_finish_kernel<<<1, 256, 0, st>>>(rowmax, rowsum, tgt, B, gamma, out, lse);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse, const float* coef,
+                const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, cudaStream_t st) {
+  ce_rows_bwd_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, st>>>(logits, sr, labels, lse, coef, gout, B, C, class_off,
+                                                                glogits, g_sr);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+}  // namespace tgfr

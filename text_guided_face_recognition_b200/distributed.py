@@ -1,0 +1,285 @@
+"""Sharding of the FCAM hot path over one NVSwitch box: one process per GPU, NCCL via
+torch.distributed.  The reference has no distributed code at all (only
+nn.DataParallel with the losses un-sharded on device 0); this replaces that.
+
+  contrastive losses : every rank owns a row block of faces (its local region / image features never
+                       move), all-gathers the caption-side embeddings (words [B,T,D], sentences
+                       [B,D]) and computes its [B_local, B_global] block of the score matrix.
+                       One all-gather of the per-column (max, sum-exp) pairs closes the column-wise
+                       cross entropy; the backward needs one reduce-scatter of d(words) and only when
+                       the text side requires grad.
+  margin head        : class-sharded partial FC.  Features/labels are all-gathered over the data
+                       parallel batch, each rank holds W[c0:c1, :], the softmax statistics are
+                       all-reduced (max, then sum-exp and target logit), dX is reduce-scattered.
+
+The collective plumbing below (gather/scatter autograd functions, statistic merging, class ranges)
+is device agnostic so that the N>1 logic is unit-tested with gloo on CPU; the arithmetic on each
+rank's block always goes through libtgfr_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import ptr, stream_ptr
+
+__all__ = [
+    "all_gather_rows", "merge_column_stats", "class_range", "words_loss_sharded", "sent_loss_sharded",
+    "ShardedArcMarginProduct", "sharded_focal_ce",
+]
+
+
+def _world(group):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+# ---------------------------------------------------------------------------------------------
+# differentiable all-gather along dim 0 (backward: reduce-scatter of the gradient)
+# ---------------------------------------------------------------------------------------------
+class _AllGatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        n, _ = _world(group)
+        x = x.contiguous()
+        out = torch.empty((n * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        ctx.group = group
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, _ = _world(ctx.group)
+        g = g.contiguous()
+        out = torch.empty((ctx.rows,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        if g.is_cuda:
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=ctx.group)
+        else:  # gloo (CPU tests) has no reduce_scatter: all-reduce then slice
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+            r = dist.get_rank(ctx.group)
+            out.copy_(g[r * ctx.rows:(r + 1) * ctx.rows])
+        return out, None
+
+
+def all_gather_rows(x, group=None):
+    """[B_local, ...] -> [world * B_local, ...]; equal B_local on every rank."""
+    if x.requires_grad:
+        return _AllGatherRows.apply(x, group)
+    with torch.no_grad():
+        return _AllGatherRows.apply(x, group)
+
+
+def merge_column_stats(colmax, colsum, group=None):
+    """Combine per-rank column (max, sum exp(s - max)) pairs of a row-sharded score matrix.
+    Returns the global (max, sum) per column."""
+    n, _ = _world(group)
+    both = torch.stack([colmax, colsum]).contiguous()                # [2, By]
+    gathered = torch.empty((n,) + tuple(both.shape), dtype=both.dtype, device=both.device)
+    dist.all_gather_into_tensor(gathered, both, group=group)
+    maxes, sums = gathered[:, 0], gathered[:, 1]                     # [n, By]
+    gmax = maxes.max(dim=0).values
+    gsum = (sums * torch.exp(maxes - gmax)).sum(dim=0)
+    return gmax, gsum
+
+
+def class_range(num_classes, world, rank):
+    """[c0, c1) owned by `rank`: the first (num_classes % world) ranks get one extra class."""
+    base, extra = divmod(num_classes, world)
+    c0 = rank * base + min(rank, extra)
+    return c0, c0 + base + (1 if rank < extra else 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# two-direction cross entropy over a row block [B_local, B_global] of the global score matrix
+# ---------------------------------------------------------------------------------------------
+class _PairCESharded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, group):
+        _lib.ensure_device(scores.device)
+        n, rank = _world(group)
+        scores = scores.contiguous()
+        Bx, By = scores.shape
+        off = rank * Bx
+        dev = scores.device
+        stats = torch.empty(2 * Bx + 2 * By, dtype=torch.float32, device=dev)
+        rowlse, colmax, colsum, diag = stats[:Bx], stats[Bx:Bx + By], stats[Bx + By:Bx + 2 * By], stats[Bx + 2 * By:]
+        st = stream_ptr()
+        ops._call("tgfr_pair_ce_stats", scores.data_ptr(), Bx, By, off, rowlse.data_ptr(), colmax.data_ptr(),
+                  colsum.data_ptr(), diag.data_ptr(), st)
+        gmax, gsum = merge_column_stats(colmax, colsum, group)
+        gmax, gsum = gmax.contiguous(), gsum.contiguous()
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        collse = torch.empty(By, dtype=torch.float32, device=dev)
+        ops._call("tgfr_pair_ce_finish", rowlse.data_ptr(), gmax.data_ptr(), gsum.data_ptr(), diag.data_ptr(),
+                  Bx, By, off, 1.0 / By, losses.data_ptr(), collse.data_ptr(), stream_ptr())
+        dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(scores, stats, collse)
+        ctx.off = off
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        scores, stats, collse = ctx.saved_tensors
+        Bx, By = scores.shape
+        g = torch.stack([g0.float().reshape(()), g1.float().reshape(())]).contiguous()
+        gs = torch.empty_like(scores)
+        ops._call("tgfr_pair_ce_bwd", scores.data_ptr(), stats.data_ptr(), collse.data_ptr(), g[0:].data_ptr(),
+                  g[1:].data_ptr(), Bx, By, ctx.off, 1.0 / By, gs.data_ptr(), stream_ptr())
+        return gs, None
+
+
+def words_loss_sharded(feats, words, cap_lens, gamma1, gamma2, gamma3, group=None, precision=None,
+                       want_attn=False):
+    """Row-sharded words_loss.  feats [B_local,R,D] (this rank's faces), words [B_local,T,D]
+    (this rank's captions), cap_lens int [B_local] or None.  Returns the GLOBAL (loss0, loss1) over
+    the world*B_local batch -- identical on every rank -- and this rank's diagonal attention maps.
+    Backward gives the exact gradient of the global loss w.r.t. the local tensors."""
+    n, rank = _world(group)
+    words_all = all_gather_rows(words, group)
+    lens_all = None
+    if cap_lens is not None:
+        lens_all = all_gather_rows(cap_lens.to(device=feats.device, dtype=torch.int32), group)
+    sim, attn = ops.wordregion_sim(feats, words_all, lens_all, gamma1, gamma2, gamma3, 1e-8, precision,
+                                   want_attn, rank * feats.shape[0])
+    loss0, loss1 = _PairCESharded.apply(sim, group)
+    return loss0, loss1, attn
+
+
+def sent_loss_sharded(img, txt, class_ids, gamma3, group=None, eps=1e-8):
+    """Row-sharded sent_loss / global_loss (class_ids=None).  img, txt: [B_local, D]."""
+    n, rank = _world(group)
+    txt_all = all_gather_rows(txt, group)
+    ids_x = ids_y = None
+    if class_ids is not None:
+        ids_x = class_ids.to(device=img.device, dtype=torch.int64).contiguous().view(-1)
+        ids_y = all_gather_rows(ids_x, group)
+    scores = _CosineScoresOff.apply(img.float(), txt_all.float(), float(gamma3), float(eps), ids_x, ids_y,
+                                    rank * img.shape[0])
+    return _PairCESharded.apply(scores, group)
+
+
+class _CosineScoresOff(torch.autograd.Function):
+    """ops._CosineScores with a diagonal offset (row b of the block pairs with column b + off)."""
+
+    @staticmethod
+    def forward(ctx, x, y, scale, eps, ids_x, ids_y, off):
+        _lib.ensure_device(x.device)
+        x, y = x.contiguous(), y.contiguous()
+        Bx, D = x.shape
+        By = y.shape[0]
+        scores = torch.empty((Bx, By), dtype=torch.float32, device=x.device)
+        xn = torch.empty(Bx, dtype=torch.float32, device=x.device)
+        yn = torch.empty(By, dtype=torch.float32, device=x.device)
+        ops._call("tgfr_cosine_scores_fwd", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), Bx, By, D,
+                  scale, 1, eps, ptr(ids_x), ptr(ids_y), off, scores.data_ptr(), xn.data_ptr(), yn.data_ptr(),
+                  stream_ptr())
+        ctx.save_for_backward(x, y, xn, yn)
+        ctx.cfg = (scale, eps)
+        return scores
+
+    @staticmethod
+    def backward(ctx, gs):
+        x, y, xn, yn = ctx.saved_tensors
+        scale, eps = ctx.cfg
+        Bx, D = x.shape
+        By = y.shape[0]
+        gs = gs.float().contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        lib = _lib.load()
+        wsb = lib.tgfr_cosine_workspace_bytes(Bx, By, D)
+        ws = ops._workspace(wsb, x.device)
+        ops._call("tgfr_cosine_scores_bwd", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), Bx, By, D,
+                  scale, 1, eps, xn.data_ptr(), yn.data_ptr(), gs.data_ptr(), ptr(dx), ptr(dy), ptr(ws), wsb,
+                  stream_ptr())
+        return dx, dy, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# class-sharded margin head with a fused, never-gathered softmax cross entropy
+# ---------------------------------------------------------------------------------------------
+class _FocalCESharded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, gamma, class_off, group):
+        _lib.ensure_device(logits.device)
+        logits = logits.contiguous()
+        B, C = logits.shape
+        dev = logits.device
+        stats = torch.empty(4 * B, dtype=torch.float32, device=dev)
+        rowmax, rowsum, tgt, lse = stats[:B], stats[B:2 * B], stats[2 * B:3 * B], stats[3 * B:]
+        ops._call("tgfr_ce_rows_stats", logits.data_ptr(), logits.stride(0), target.data_ptr(), B, C, class_off,
+                  rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), stream_ptr())
+        gmax = rowmax.clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+        pack = torch.stack([rowsum * torch.exp(rowmax - gmax), tgt]).contiguous()
+        dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+        gsum, gtgt = pack[0].contiguous(), pack[1].contiguous()
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        ops._call("tgfr_focal_finish", gmax.data_ptr(), gsum.data_ptr(), gtgt.data_ptr(), B, gamma, out.data_ptr(),
+                  lse.data_ptr(), stream_ptr())
+        ctx.save_for_backward(logits, target, stats, out)
+        ctx.class_off = class_off
+        return out[1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, stats, out = ctx.saved_tensors
+        B, C = logits.shape
+        lse = stats[3 * B:]
+        gout = gout.float().reshape(1).contiguous()
+        gl = torch.empty((B, C), dtype=torch.float32, device=logits.device)
+        ops._call("tgfr_ce_rows_bwd", logits.data_ptr(), logits.stride(0), target.data_ptr(), lse.data_ptr(),
+                  out[2:].data_ptr(), gout.data_ptr(), B, C, ctx.class_off, gl.data_ptr(), gl.stride(0),
+                  stream_ptr())
+        return gl, None, None, None, None
+
+
+def sharded_focal_ce(logits_shard, target_all, gamma, class_off, group=None):
+    """Focal loss of the batch-mean CE over class-sharded logits [B_global, C_local]."""
+    target_all = target_all.view(-1).to(device=logits_shard.device, dtype=torch.int64).contiguous()
+    return _FocalCESharded.apply(logits_shard.float(), target_all, float(gamma), int(class_off), group)
+
+
+class ShardedArcMarginProduct(torch.nn.Module):
+    """ArcMarginProduct with the class dimension split over the process group (partial FC).
+
+    `weight` holds rows [c0, c1) of the reference's [out_features, in_features] parameter;
+    load_full_weight / full_weight convert from / to the reference's state_dict tensor.
+    forward(input_local, label_local) -> (logits_shard [B_global, C_local], labels_all);
+    loss(input_local, label_local, gamma) runs the fused focal cross entropy without ever
+    materialising the [B, C] logits on one device.
+    """
+
+    def __init__(self, in_features, out_features, s=30.0, m=0.50, easy_margin=False, group=None):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.s, self.m, self.easy_margin, self.group = s, m, easy_margin, group
+        n, rank = _world(group)
+        self.c0, self.c1 = class_range(out_features, n, rank)
+        full = torch.empty(out_features, in_features)
+        gen = torch.Generator().manual_seed(100)          # identical init on every rank, then slice
+        bound = (6.0 / (in_features + out_features)) ** 0.5
+        full.uniform_(-bound, bound, generator=gen)
+        self.weight = torch.nn.Parameter(full[self.c0:self.c1].clone())
+
+    @torch.no_grad()
+    def load_full_weight(self, full):
+        self.weight.copy_(full[self.c0:self.c1])
+
+    @torch.no_grad()
+    def full_weight(self):
+        n, _ = _world(self.group)
+        parts = [None] * n
+        dist.all_gather_object(parts, self.weight.detach().cpu(), group=self.group)
+        return torch.cat(parts, 0)
+
+    def forward(self, input, label):
+        x_all = all_gather_rows(input, self.group)
+        lab_all = all_gather_rows(label.view(-1).to(device=input.device, dtype=torch.int64), self.group)
+        logits = ops.arc_logits(x_all, self.weight, lab_all, self.s, self.m, self.easy_margin, self.c0)
+        return logits, lab_all
+
+    def loss(self, input, label, gamma=2.0):
+        logits, lab_all = self.forward(input, label)
+        return sharded_focal_ce(logits, lab_all, gamma, self.c0, self.group)

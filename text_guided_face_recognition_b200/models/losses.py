@@ -1,0 +1,234 @@
+"""Mirror of the reference's models/losses.py for the FCAM hot path.
+
+Same names and call signatures as the reference; the arithmetic runs in
+libtgfr_b200.so.  Hot-path symbols: cosine_similarity, sent_loss, words_loss, ClipLoss,
+FocalLoss, global_loss.  KL_loss / clip_loss / cross_entropy / CMPLoss are small PyTorch
+pass-throughs kept so that `from models.losses import ...` lines of the reference drivers work;
+WordRegionAlignment is never instantiated by the reference and raises.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ._backend import ops
+from .attention import func_attention  # noqa: F401  (re-exported like the reference, losses.py:5)
+
+
+def _gammas(args):
+    sm = args.TRAIN.SMOOTH
+    return float(sm.GAMMA1), float(sm.GAMMA2), float(sm.GAMMA3)
+
+
+def _require_arange(labels, n, what):
+    """The reference always passes labels = arange(batch) (prepare_labels); the fused B x B cross
+    entropy pairs row b with column b.  Checked once per labels tensor (one device sync)."""
+    key = (labels.data_ptr(), labels._version, n)
+    if _require_arange.seen.get("key") == key:
+        return
+    if labels.numel() != n or not bool((labels.view(-1).cpu() == torch.arange(n)).all()):
+        raise NotImplementedError(f"{what}: only labels == arange(batch_size) is supported")
+    _require_arange.seen["key"] = key
+
+
+_require_arange.seen = {}
+
+
+# ################## Loss for matching text-image ###################
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """Reference models/losses.py:12-16: sum(x1*x2) / max(|x1||x2|, eps), squeezed.
+
+    Inside words_loss this computation is fused into the word-region kernel; the free function
+    is kept for API parity and evaluates the same formula with PyTorch ops."""
+    w12 = torch.sum(x1 * x2, dim)
+    w1 = torch.norm(x1, 2, dim)
+    w2 = torch.norm(x2, 2, dim)
+    return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, args, eps=1e-8):
+    """Reference models/losses.py:19-57.  Returns (loss0, loss1); (None, None) when labels is None.
+
+    class_ids (numpy or tensor, may be None): same-class off-diagonal pairs are masked to -inf
+    inside the score kernel (losses.py:20-30, 47-48)."""
+    if cnn_code.dim() == 3:
+        if cnn_code.size(0) != 1:
+            raise NotImplementedError("sent_loss: only [B,D] or [1,B,D] inputs are supported")
+        cnn_code, rnn_code = cnn_code[0], rnn_code[0]
+    if cnn_code.shape[0] != batch_size or rnn_code.shape[0] != batch_size:
+        raise RuntimeError(f"sent_loss: batch_size={batch_size} but inputs are {tuple(cnn_code.shape)}, "
+                           f"{tuple(rnn_code.shape)}")
+    ids = None
+    if class_ids is not None:
+        ids = torch.as_tensor(np.asarray(class_ids) if not torch.is_tensor(class_ids) else class_ids)
+        ids = ids.to(device=cnn_code.device, dtype=torch.int64).contiguous().view(-1)
+    g3 = float(args.TRAIN.SMOOTH.GAMMA3)
+    scores = ops.cosine_scores(cnn_code, rnn_code, g3, True, eps, ids, ids)
+    if labels is None:
+        return None, None
+    _require_arange(labels, batch_size, "sent_loss")
+    return ops.pair_ce(scores)
+
+
+def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, args):
+    """Reference models/losses.py:61-135.
+
+    words_emb(query): batch x nef x seq_len; img_features(context): batch x nef x ih x iw.
+    Returns (loss0, loss1, att_maps) with att_maps a list of `batch_size` tensors
+    [1, words_num_i, ih, iw] (attention of caption i over its own image, losses.py:97).
+    class_ids is accepted and ignored exactly like the reference (its mask is commented out,
+    losses.py:75-79, 116-127)."""
+    B = batch_size
+    if img_features.shape[0] != B or words_emb.shape[0] != B:
+        raise RuntimeError(f"words_loss: batch_size={B} but inputs are {tuple(img_features.shape)}, "
+                           f"{tuple(words_emb.shape)}")
+    D, ih, iw = img_features.shape[1], img_features.shape[2], img_features.shape[3]
+    if args.en_type == "BERT":
+        T = int(args.bert_words_num) - 2                       # losses.py:83 (drops [CLS]/[SEP])
+        lens_host = [T] * B
+        lens_dev = None
+    elif args.en_type == "LSTM":
+        lens_host = [int(v) for v in cap_lens.data.tolist()]  # losses.py:70-71, 82
+        T = min(max(lens_host), words_emb.shape[2])
+        lens_dev = cap_lens
+    else:
+        raise UnboundLocalError(f"words_loss: unknown args.en_type {args.en_type!r}")  # reference: words_num unset
+    T = min(T, words_emb.shape[2])
+    g1, g2, g3 = _gammas(args)
+    feats = img_features.permute(0, 2, 3, 1).reshape(B, ih * iw, D)
+    words = words_emb.transpose(1, 2)[:, :T]
+    sim, attn = ops.wordregion_sim(feats, words, lens_dev, g1, g2, g3, 1e-8, None, True, 0)
+    att_maps = []
+    for i in range(B):
+        n = min(lens_host[i], T)
+        att_maps.append(attn[i:i + 1, :n].reshape(1, n, ih, iw))
+    if labels is None:
+        return None, None, att_maps
+    _require_arange(labels, B, "words_loss")
+    loss0, loss1 = ops.pair_ce(sim)
+    return loss0, loss1, att_maps
+
+
+def KL_loss(mu, logvar):
+    """Reference models/losses.py:138-142 (not on the hot path)."""
+    return -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
+
+
+def cross_entropy(preds, targets, reduction='none'):
+    """Soft-target cross entropy, reference models/losses.py:159-165 (not on the hot path)."""
+    loss = (-targets * F.log_softmax(preds, dim=-1)).sum(1)
+    if reduction == "none":
+        return loss
+    elif reduction == "mean":
+        return loss.mean()
+
+
+def clip_loss(text_embeddings, image_embeddings, args):
+    """Soft-target CLIP loss, reference models/losses.py:145-156 (not on the hot path)."""
+    logits = (text_embeddings @ image_embeddings.T) / args.temperature
+    sim = (image_embeddings @ image_embeddings.T + text_embeddings @ text_embeddings.T) / 2
+    targets = F.softmax(sim * args.temperature, dim=-1)
+    both = cross_entropy(logits.T, targets.T) + cross_entropy(logits, targets)
+    return (both / 2.0).mean()
+
+
+class CMPLoss(nn.Module):
+    """Cross-modal projection losses, reference models/losses.py:169-264.  Only built when
+    cfg is_CMP is true (default false); kept as a PyTorch pass-through."""
+
+    def __init__(self, is_CMPM, is_CMPC, num_classes, feature_dim):
+        super().__init__()
+        self.CMPM, self.CMPC = is_CMPM, is_CMPC
+        self.epsilon = 1e-8
+        self.num_classes = num_classes
+        self.W = nn.Parameter(torch.empty(feature_dim, num_classes))
+        nn.init.xavier_uniform_(self.W.data, gain=1)
+
+    def compute_cmpc_loss(self, text_embeddings, image_embeddings, labels):
+        w = self.W / self.W.norm(dim=0)
+        img_n = F.normalize(image_embeddings, dim=1, eps=0)
+        txt_n = F.normalize(text_embeddings, dim=1, eps=0)
+        img_on_txt = (image_embeddings * txt_n).sum(1, keepdim=True) * txt_n
+        txt_on_img = (text_embeddings * img_n).sum(1, keepdim=True) * img_n
+        return F.cross_entropy(img_on_txt @ w, labels) + F.cross_entropy(txt_on_img @ w, labels)
+
+    def compute_cmpm_loss(self, text_embeddings, image_embeddings, labels):
+        same = (labels.view(-1, 1) == labels.view(1, -1)).float()
+        same = same / same.norm(dim=1)
+        log_q = torch.log(same + self.epsilon)
+        i2t = image_embeddings @ F.normalize(text_embeddings, dim=1, eps=0).t()
+        t2i = text_embeddings @ F.normalize(image_embeddings, dim=1, eps=0).t()
+        total = 0.0
+        for proj in (i2t, t2i):
+            logp = F.log_softmax(proj, dim=1)
+            total = total + (logp.exp() * (logp - log_q)).sum(1).mean()
+        return total
+
+    def forward(self, text_embeddings, image_embeddings, labels):
+        cmpc = self.compute_cmpc_loss(text_embeddings, image_embeddings, labels) if self.CMPC else 0.0
+        cmpm = self.compute_cmpm_loss(text_embeddings, image_embeddings, labels) if self.CMPM else 0.0
+        return cmpc + cmpm, cmpc, cmpm
+
+
+class ClipLoss(nn.Module):
+    """Reference models/losses.py:268-309: (CE(scale*img@txt^T) + CE(scale*txt@img^T)) / 2 with
+    labels = arange; features are NOT normalised here."""
+
+    def __init__(self, cache_labels=False):
+        super().__init__()
+        self.cache_labels = cache_labels
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        logits_per_image = ops.cosine_scores(image_features, text_features, logit_scale, False)
+        return logits_per_image, logits_per_image.t()
+
+    def forward(self, text_features, image_features, args, logit_scale=1):
+        logits_per_image, _ = self.get_logits(image_features, text_features, logit_scale)
+        loss_i, loss_t = ops.pair_ce(logits_per_image)
+        return (loss_i + loss_t) / 2
+
+
+class FocalLoss(nn.Module):
+    """Reference models/losses.py:313-325: focal transform of the *batch-mean* cross entropy."""
+
+    def __init__(self, gamma=0, eps=1e-7):
+        super().__init__()
+        self.gamma = gamma
+        self.eps = eps
+
+    def forward(self, input, target):
+        return ops.focal_ce(input, target, self.gamma)
+
+
+def global_loss(cnn_code, rnn_code, eps=1e-8, temp3=10.0):
+    """Reference models/losses.py:329-351: sent_loss without mask, labels = arange, loss0 + loss1."""
+    if cnn_code.dim() == 3:
+        if cnn_code.size(0) != 1:
+            raise NotImplementedError("global_loss: only [B,D] or [1,B,D] inputs are supported")
+        cnn_code, rnn_code = cnn_code[0], rnn_code[0]
+    scores = ops.cosine_scores(cnn_code, rnn_code, temp3, True, eps)
+    loss0, loss1 = ops.pair_ce(scores)
+    return loss0 + loss1
+
+
+class WordRegionAlignment(nn.Module):
+    """Reference models/losses.py:355-424; never instantiated there (the is_WRA branch is `pass`,
+    src/train_encoders_bert.py:286-287).  Out of scope."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("WordRegionAlignment is disabled in the reference and out of scope")

@@ -1,0 +1,420 @@
+"""torch.autograd bindings of the C-ABI kernels (one Function per differentiable operator).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every FLOP of the
+hot path runs in libtgfr_b200.so.  Nothing here falls back to eager PyTorch math.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
+
+__all__ = [
+    "default_precision", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
+    "mag_logits", "func_attention_canonical", "launch_counter",
+]
+
+
+class _LaunchCounter:
+    """Counts C-ABI calls (each issues >= 1 kernel); bench.py reports it as gpu_launches."""
+    n = 0
+
+
+launch_counter = _LaunchCounter
+
+
+def default_precision() -> int:
+    """TGFR_WORDREGION_PRECISION = fp32 | tc  (default: tc when built)."""
+    v = os.environ.get("TGFR_WORDREGION_PRECISION", "fp32").lower()
+    return PREC_TC if v in ("tc", "tensor", "1") else PREC_FP32
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+# kernels launched by one call of each entry point (memsets not counted)
+_KERNELS_PER_CALL = {
+    "tgfr_wordregion_fwd": 1, "tgfr_wordregion_bwd": 1, "tgfr_attention_fwd": 1, "tgfr_attention_bwd": 1,
+    "tgfr_cosine_scores_fwd": 3, "tgfr_cosine_scores_bwd": 4, "tgfr_pair_ce_stats": 1, "tgfr_pair_ce_finish": 1,
+    "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
+    "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
+    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1,
+}
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    _LaunchCounter.n += _KERNELS_PER_CALL.get(name, 1)
+    check(getattr(lib, name)(*args), name)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device) if nbytes else None
+
+
+# ---------------------------------------------------------------------------------------------
+# word-region similarity matrix
+# ---------------------------------------------------------------------------------------------
+class _WordRegionSim(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, words, cap_lens, g1, g2, g3, eps, precision, want_attn, diag_off):
+        # feats [Bc,R,D], words [Bq,T,D] -- arbitrary strides; cap_lens int32 [Bq] or None
+        _lib.ensure_device(feats.device)
+        Bc, R, D = feats.shape
+        Bq, T, _ = words.shape
+        sim = torch.empty((Bc, Bq), dtype=torch.float32, device=feats.device)
+        attn = torch.empty((Bc, T, R), dtype=torch.float32, device=feats.device) if want_attn else None
+        lib = _lib.load()
+        wsb = lib.tgfr_wordregion_workspace_bytes(Bc, Bq, T, R, D, precision)
+        ws = _workspace(wsb, feats.device)
+        _call("tgfr_wordregion_fwd", feats.data_ptr(), *feats.stride(), words.data_ptr(), *words.stride(),
+              ptr(cap_lens), Bc, Bq, T, R, D, g1, g2, g3, eps, sim.data_ptr(), ptr(attn), diag_off,
+              precision, ptr(ws), wsb, stream_ptr())
+        ctx.save_for_backward(feats, words, cap_lens)
+        ctx.cfg = (g1, g2, g3, eps, precision)
+        if attn is not None:
+            ctx.mark_non_differentiable(attn)
+        return sim, attn
+
+    @staticmethod
+    def backward(ctx, gsim, _gattn):
+        feats, words, cap_lens = ctx.saved_tensors
+        g1, g2, g3, eps, precision = ctx.cfg
+        Bc, R, D = feats.shape
+        Bq, T, _ = words.shape
+        need_c, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gsim = _f32(gsim).contiguous()
+        dctx = torch.empty((Bc, R, D), dtype=torch.float32, device=feats.device) if need_c else None
+        dwords = torch.empty((Bq, T, D), dtype=torch.float32, device=feats.device) if need_q else None
+        lib = _lib.load()
+        wsb = lib.tgfr_wordregion_workspace_bytes(Bc, Bq, T, R, D, precision)
+        ws = _workspace(wsb, feats.device)
+        _call("tgfr_wordregion_bwd", feats.data_ptr(), *feats.stride(), words.data_ptr(), *words.stride(),
+              ptr(cap_lens), Bc, Bq, T, R, D, g1, g2, g3, eps, gsim.data_ptr(), ptr(dctx), ptr(dwords),
+              precision, ptr(ws), wsb, stream_ptr())
+        return dctx, dwords, None, None, None, None, None, None, None, None
+
+
+def wordregion_sim(feats, words, cap_lens, g1, g2, g3, eps=1e-8, precision=None, want_attn=True, diag_off=0):
+    """sim [Bc,Bq] (differentiable) and the diagonal attention maps [Bc,T,R] (or None)."""
+    if precision is None:
+        precision = default_precision()
+    if cap_lens is not None:
+        cap_lens = cap_lens.to(device=feats.device, dtype=torch.int32).contiguous()
+    return _WordRegionSim.apply(_f32(feats), _f32(words), cap_lens, float(g1), float(g2), float(g3), float(eps),
+                                int(precision), bool(want_attn), int(diag_off))
+
+
+# ---------------------------------------------------------------------------------------------
+# two-direction cross entropy over a square score matrix (single device)
+# ---------------------------------------------------------------------------------------------
+class _PairCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores):
+        _lib.ensure_device(scores.device)
+        scores = scores.contiguous()
+        Bx, By = scores.shape
+        dev = scores.device
+        stats = torch.empty(2 * Bx + 2 * By, dtype=torch.float32, device=dev)
+        rowlse, colmax, colsum, diag = stats[:Bx], stats[Bx:Bx + By], stats[Bx + By:Bx + 2 * By], stats[Bx + 2 * By:]
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        collse = torch.empty(By, dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        _call("tgfr_pair_ce_stats", scores.data_ptr(), Bx, By, 0, rowlse.data_ptr(), colmax.data_ptr(),
+              colsum.data_ptr(), diag.data_ptr(), st)
+        _call("tgfr_pair_ce_finish", rowlse.data_ptr(), colmax.data_ptr(), colsum.data_ptr(), diag.data_ptr(),
+              Bx, By, 0, 1.0 / Bx, losses.data_ptr(), collse.data_ptr(), st)
+        ctx.save_for_backward(scores, stats, collse)
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        scores, stats, collse = ctx.saved_tensors
+        Bx, By = scores.shape
+        g = torch.stack([_f32(g0).reshape(()), _f32(g1).reshape(())]).contiguous()
+        gs = torch.empty_like(scores)
+        _call("tgfr_pair_ce_bwd", scores.data_ptr(), stats.data_ptr(), collse.data_ptr(), g[0:].data_ptr(),
+              g[1:].data_ptr(), Bx, By, 0, 1.0 / Bx, gs.data_ptr(), stream_ptr())
+        return gs
+
+
+def pair_ce(scores):
+    """(loss0, loss1): CE(scores, arange) and CE(scores^T, arange), mean reduction."""
+    if scores.dim() != 2 or scores.shape[0] != scores.shape[1]:
+        raise ValueError(f"pair_ce expects a square [B,B] matrix, got {tuple(scores.shape)}")
+    return _PairCE.apply(_f32(scores))
+
+
+# ---------------------------------------------------------------------------------------------
+# cosine score matrix (sent_loss / global_loss / ClipLoss)
+# ---------------------------------------------------------------------------------------------
+class _CosineScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, scale, normalise, eps, ids_x, ids_y):
+        _lib.ensure_device(x.device)
+        x, y = x.contiguous(), y.contiguous()
+        Bx, D = x.shape
+        By = y.shape[0]
+        dev = x.device
+        scores = torch.empty((Bx, By), dtype=torch.float32, device=dev)
+        xn = torch.empty(Bx, dtype=torch.float32, device=dev)
+        yn = torch.empty(By, dtype=torch.float32, device=dev)
+        _call("tgfr_cosine_scores_fwd", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), Bx, By, D, scale,
+              int(normalise), eps, ptr(ids_x), ptr(ids_y), 0, scores.data_ptr(), xn.data_ptr(), yn.data_ptr(),
+              stream_ptr())
+        ctx.save_for_backward(x, y, xn, yn)
+        ctx.cfg = (scale, normalise, eps)
+        return scores
+
+    @staticmethod
+    def backward(ctx, gs):
+        x, y, xn, yn = ctx.saved_tensors
+        scale, normalise, eps = ctx.cfg
+        Bx, D = x.shape
+        By = y.shape[0]
+        gs = _f32(gs).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        lib = _lib.load()
+        wsb = lib.tgfr_cosine_workspace_bytes(Bx, By, D)
+        ws = _workspace(wsb, x.device)
+        _call("tgfr_cosine_scores_bwd", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), Bx, By, D, scale,
+              int(normalise), eps, xn.data_ptr(), yn.data_ptr(), gs.data_ptr(), ptr(dx), ptr(dy), ptr(ws), wsb,
+              stream_ptr())
+        return dx, dy, None, None, None, None, None
+
+
+def cosine_scores(x, y, scale, normalise=True, eps=1e-8, ids_x=None, ids_y=None):
+    return _CosineScores.apply(_f32(x), _f32(y), float(scale), bool(normalise), float(eps), ids_x, ids_y)
+
+
+# ---------------------------------------------------------------------------------------------
+# ArcFace logits
+# ---------------------------------------------------------------------------------------------
+class _ArcLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, label, s, m, easy, class_off):
+        _lib.ensure_device(x.device)
+        x = x.contiguous()
+        B, Din = x.shape
+        C = weight.shape[0]
+        dev = x.device
+        out = torch.empty((B, C), dtype=torch.float32, device=dev)
+        xn = torch.empty(B, dtype=torch.float32, device=dev)
+        wn = torch.empty(C, dtype=torch.float32, device=dev)
+        cos_t = torch.empty(B, dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
+              weight.stride(1), B, C, Din, s, 0, out.data_ptr(), out.stride(0), xn.data_ptr(), wn.data_ptr(), st)
+        _call("tgfr_arc_margin_apply", out.data_ptr(), out.stride(0), label.data_ptr(), B, C, class_off, s, m,
+              int(easy), cos_t.data_ptr(), st)
+        ctx.save_for_backward(x, weight, label, xn, wn, cos_t)
+        ctx.cfg = (s, m, easy, class_off)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, label, xn, wn, cos_t = ctx.saved_tensors
+        s, m, easy, class_off = ctx.cfg
+        B, Din = x.shape
+        C = weight.shape[0]
+        g = _f32(g)
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        lib = _lib.load()
+        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
+        ws = _workspace(wsb, x.device)
+        _call("tgfr_arc_margin_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
+              weight.stride(1), xn.data_ptr(), wn.data_ptr(), label.data_ptr(), cos_t.data_ptr(), g.data_ptr(),
+              g.stride(0), B, C, Din, class_off, s, m, int(easy), ptr(dx), dw.data_ptr(), ptr(ws), wsb,
+              stream_ptr())
+        # dw was written with weight's strides; both are [C,Din] contiguous here
+        return dx, dw, None, None, None, None, None
+
+
+def arc_logits(x, weight, label, s, m, easy_margin=False, class_off=0):
+    label = label.view(-1).to(device=x.device, dtype=torch.int64).contiguous()
+    return _ArcLogits.apply(_f32(x), _f32(weight).contiguous(), label, float(s), float(m), bool(easy_margin),
+                            int(class_off))
+
+
+# ---------------------------------------------------------------------------------------------
+# row-wise cross entropy + focal transform of its batch mean
+# ---------------------------------------------------------------------------------------------
+class _FocalCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, gamma):
+        _lib.ensure_device(logits.device)
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        B, C = logits.shape
+        dev = logits.device
+        stats = torch.empty(4 * B, dtype=torch.float32, device=dev)
+        rowmax, rowsum, tgt, lse = stats[:B], stats[B:2 * B], stats[2 * B:3 * B], stats[3 * B:]
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        _call("tgfr_ce_rows_stats", logits.data_ptr(), logits.stride(0), target.data_ptr(), B, C, 0,
+              rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), st)
+        _call("tgfr_focal_finish", rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), B, gamma, out.data_ptr(),
+              lse.data_ptr(), st)
+        ctx.save_for_backward(logits, target, stats, out)
+        return out[1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, stats, out = ctx.saved_tensors
+        B, C = logits.shape
+        lse = stats[3 * B:]
+        gout = _f32(gout).reshape(1).contiguous()
+        gl = torch.empty((B, C), dtype=torch.float32, device=logits.device)
+        _call("tgfr_ce_rows_bwd", logits.data_ptr(), logits.stride(0), target.data_ptr(), lse.data_ptr(),
+              out[2:].data_ptr(), gout.data_ptr(), B, C, 0, gl.data_ptr(), gl.stride(0), stream_ptr())
+        return gl, None, None
+
+
+def focal_ce(logits, target, gamma=0.0):
+    """(1 - exp(-CE))**gamma * CE with CE = mean cross entropy over the batch; gamma=0 -> plain CE."""
+    if logits.dim() != 2:
+        raise ValueError(f"focal_ce expects [B,C] logits, got {tuple(logits.shape)}")
+    target = target.view(-1).to(device=logits.device, dtype=torch.int64).contiguous()
+    return _FocalCE.apply(_f32(logits), target, float(gamma))
+
+
+# ---------------------------------------------------------------------------------------------
+# MagFace logits: (scale*cos, scale*cos(theta+m)) with per-row margins
+# ---------------------------------------------------------------------------------------------
+class _MagLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, margin, scale, easy):
+        _lib.ensure_device(x.device)
+        x = x.contiguous()
+        B, Din = x.shape
+        C = weight.shape[1]                      # MagLinear.weight is [Din, C]
+        dev = x.device
+        cos_s = torch.empty((B, C), dtype=torch.float32, device=dev)
+        cos_m = torch.empty((B, C), dtype=torch.float32, device=dev)
+        xn = torch.empty(B, dtype=torch.float32, device=dev)
+        wn = torch.empty(C, dtype=torch.float32, device=dev)
+        mar = margin.reshape(-1).contiguous()
+        st = stream_ptr()
+        _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(1),
+              weight.stride(0), B, C, Din, scale, 1, cos_s.data_ptr(), cos_s.stride(0), xn.data_ptr(),
+              wn.data_ptr(), st)
+        _call("tgfr_mag_margin_fwd", cos_s.data_ptr(), mar.data_ptr(), B, C, scale, int(easy), cos_m.data_ptr(), st)
+        ctx.save_for_backward(x, weight, mar, cos_s, xn, wn)
+        ctx.cfg = (scale, easy, margin.shape)
+        return cos_s, cos_m
+
+    @staticmethod
+    def backward(ctx, g_cos, g_cosm):
+        x, weight, mar, cos_s, xn, wn = ctx.saved_tensors
+        scale, easy, mshape = ctx.cfg
+        B, Din = x.shape
+        C = weight.shape[1]
+        dev = x.device
+        g_cos = None if g_cos is None else _f32(g_cos).contiguous()
+        g_cosm = None if g_cosm is None else _f32(g_cosm).contiguous()
+        gtotal = torch.empty((B, C), dtype=torch.float32, device=dev)
+        gmar = torch.empty(B, dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        _call("tgfr_mag_margin_bwd", cos_s.data_ptr(), mar.data_ptr(), ptr(g_cos), ptr(g_cosm), B, C, scale,
+              int(easy), gtotal.data_ptr(), gmar.data_ptr(), st)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        lib = _lib.load()
+        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
+        ws = _workspace(wsb, dev)
+        _call("tgfr_cos_logits_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(1),
+              weight.stride(0), xn.data_ptr(), wn.data_ptr(), cos_s.data_ptr(), cos_s.stride(0),
+              gtotal.data_ptr(), gtotal.stride(0), B, C, Din, scale, 1, ptr(dx), dw.data_ptr(), ptr(ws), wsb, st)
+        return dx, dw, gmar.reshape(mshape), None, None
+
+
+def mag_logits(x, weight, margin, scale, easy_margin=True):
+    return _MagLogits.apply(_f32(x), _f32(weight).contiguous(), _f32(margin), float(scale), bool(easy_margin))
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone func_attention on canonical layouts
+# ---------------------------------------------------------------------------------------------
+class _FuncAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, query, g1):
+        # feats [B,R,D], query [B,T,D] (arbitrary strides) -> wc [B,T,D], attn [B,T,R]
+        _lib.ensure_device(feats.device)
+        B, R, D = feats.shape
+        T = query.shape[1]
+        wc = torch.empty((B, T, D), dtype=torch.float32, device=feats.device)
+        attn = torch.empty((B, T, R), dtype=torch.float32, device=feats.device)
+        _call("tgfr_attention_fwd", feats.data_ptr(), *feats.stride(), query.data_ptr(), *query.stride(), B, T, R,
+              D, g1, wc.data_ptr(), attn.data_ptr(), stream_ptr())
+        ctx.save_for_backward(feats, query)
+        ctx.g1 = g1
+        return wc, attn
+
+    @staticmethod
+    def backward(ctx, g_wc, g_attn):
+        feats, query = ctx.saved_tensors
+        B, R, D = feats.shape
+        T = query.shape[1]
+        g_wc = None if g_wc is None else _f32(g_wc).contiguous()
+        g_attn = None if g_attn is None else _f32(g_attn).contiguous()
+        dctx = torch.empty((B, R, D), dtype=torch.float32, device=feats.device) if ctx.needs_input_grad[0] else None
+        dq = torch.empty((B, T, D), dtype=torch.float32, device=feats.device) if ctx.needs_input_grad[1] else None
+        _call("tgfr_attention_bwd", feats.data_ptr(), *feats.stride(), query.data_ptr(), *query.stride(), B, T, R,
+              D, ctx.g1, ptr(g_wc), ptr(g_attn), ptr(dctx), ptr(dq), stream_ptr())
+        return dctx, dq, None
+
+
+def func_attention_canonical(feats, query, gamma1):
+    return _FuncAttention.apply(_f32(feats), _f32(query), float(gamma1))
+
+
+# ---------------------------------------------------------------------------------------------
+# plain cosine logits s * cos(x, w_c) with weight [C, Din] (AddMargin / Sphere / AdaFace heads)
+# ---------------------------------------------------------------------------------------------
+class _CosLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, s, clamp, w_class_dim):
+        _lib.ensure_device(x.device)
+        x = x.contiguous()
+        B, Din = x.shape
+        C = weight.shape[w_class_dim]
+        dev = x.device
+        out = torch.empty((B, C), dtype=torch.float32, device=dev)
+        xn = torch.empty(B, dtype=torch.float32, device=dev)
+        wn = torch.empty(C, dtype=torch.float32, device=dev)
+        _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(w_class_dim),
+              weight.stride(1 - w_class_dim), B, C, Din, s, int(clamp), out.data_ptr(), out.stride(0),
+              xn.data_ptr(), wn.data_ptr(), stream_ptr())
+        ctx.save_for_backward(x, weight, out, xn, wn)
+        ctx.cfg = (s, clamp, w_class_dim)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out, xn, wn = ctx.saved_tensors
+        s, clamp, wd = ctx.cfg
+        B, Din = x.shape
+        C = weight.shape[wd]
+        g = _f32(g).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        lib = _lib.load()
+        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
+        ws = _workspace(wsb, x.device)
+        _call("tgfr_cos_logits_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(wd),
+              weight.stride(1 - wd), xn.data_ptr(), wn.data_ptr(), out.data_ptr(), out.stride(0), g.data_ptr(),
+              g.stride(0), B, C, Din, s, int(clamp), ptr(dx), dw.data_ptr(), ptr(ws), wsb, stream_ptr())
+        return dx, dw, None, None, None
+
+
+def cos_logits(x, weight, s=1.0, clamp=False, w_class_dim=0):
+    """s * normalize(x) @ normalize(weight)^T; weight is [C,Din] (w_class_dim=0) or [Din,C] (=1)."""
+    return _CosLogits.apply(_f32(x), _f32(weight).contiguous(), float(s), bool(clamp), int(w_class_dim))
