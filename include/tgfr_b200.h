@@ -172,6 +172,16 @@ int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, con
                      const float* coef, const float* gout, int B, int C, int class_off,
                      float* glogits, int64_t g_sr, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Self-tests of the tcgen05 / TMA building blocks (used by tests/test_gpu_tc.py only).
+ * tgfr_debug_umma: out[128,N] = A * B^T on one CTA with fp16 operands a (a_mn ? [K,128] : [128,K])
+ * and b (b_mn ? [K,N] : [N,K]); manual_a stages A with the hand-written 128B swizzle.
+ * tgfr_debug_tma_reduce: out[r,c] += 1000 r + c through a swizzled tile and a TMA reduce-add.
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,
+                    void* stream);
+int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,10 @@ int focal_finish(const float*, const float*, const float*, int, float, float*, f
 int ce_rows_bwd(const float*, int64_t, const int64_t*, const float*, const float*, const float*, int, int, int,
                 float*, int64_t, cudaStream_t);
 
+// tc_selftest.cu
+int debug_umma(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
+int debug_tma_reduce(float*, int, int, cudaStream_t);
+
 }  // namespace tgfr
 
 using namespace tgfr;
@@ -216,6 +220,14 @@ int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt
 int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse, const float* coef,
                      const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, void* stream) {
   return ce_rows_bwd(logits, sr, labels, lse, coef, gout, B, C, class_off, glogits, g_sr, ST(stream));
+}
+
+int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,
+                    void* stream) {
+  return debug_umma(a, b, out, N, K, a_mn, b_mn, manual_a, ST(stream));
+}
+int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream) {
+  return debug_tma_reduce(out, rows, cols, ST(stream));
 }
 
 }  // extern "C"
