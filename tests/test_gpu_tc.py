@@ -22,6 +22,9 @@ def _lib():
     (1, 1, 1, 256, 64),
     (0, 1, 0, 256, 128),     # dC GEMM: dS(K-major) x words(MN-major)
     (1, 0, 0, 128, 64),
+    (0, 1, 2, 64, 128),      # A operand staged in TMEM by tcgen05.st (dS / E16 in the backward pass)
+    (0, 1, 2, 256, 128),
+    (0, 0, 2, 128, 256),
 ])
 def test_umma_layouts(a_mn, b_mn, manual_a, N, K):
     L = _lib()
@@ -53,3 +56,49 @@ def test_tma_reduce_add():
     r = torch.arange(rows, dtype=torch.float32)[:, None]
     c = torch.arange(cols, dtype=torch.float32)[None, :]
     assert torch.equal(out.cpu(), init + 1000.0 * r + c)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused tensor-core word-region kernels (TGFR_PREC_TC) vs the fp64 oracle and the fp32 SIMT path
+# fp16 operands / fp32 accumulation: |sim| ~ 30 is reproduced to ~1e-3 absolute, the losses to
+# ~1e-5 relative (contract: 1e-4), see DESIGN.md "numerics".
+# ------------------------------------------------------------------------------------------------
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import synth  # noqa: E402
+from oracle import fcam_oracle as O  # noqa: E402
+
+TC_SIM_ATOL = 5e-3
+TC_LOSS_RTOL = 1e-4
+
+
+@pytest.mark.parametrize("B,T,R,D,flavour,ragged", [
+    (8, 22, 196, 256, "BERT", False),
+    (16, 18, 196, 256, "LSTM", True),
+    (6, 7, 16, 64, "LSTM", True),
+    (5, 30, 49, 128, "BERT", False),
+    (128, 22, 196, 256, "BERT", False),       # BASELINE config 2
+])
+def test_tc_forward_vs_oracle(B, T, R, D, flavour, ragged):
+    from text_guided_face_recognition_b200 import _lib, ops
+    ctx, words, cap = synth.wordregion_inputs(B, T, R, D, flavour, seed=100, ragged=ragged)
+    feats = torch.from_numpy(ctx).cuda()
+    wd = torch.from_numpy(words).cuda()
+    capt = None if cap is None else torch.from_numpy(cap).cuda()
+    sim, attn = ops.wordregion_sim(feats, wd, capt, 4.0, 5.0, 10.0, precision=_lib.PREC_TC)
+    sim32, attn32 = ops.wordregion_sim(feats, wd, capt, 4.0, 5.0, 10.0, precision=_lib.PREC_FP32)
+    torch.cuda.synchronize()
+    ref, ref_att = O.wordregion_sim(ctx, words, cap, 4.0, 5.0, 10.0)
+    got = sim.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.max(np.abs(got - ref)) < TC_SIM_ATOL, np.max(np.abs(got - ref))
+    assert np.max(np.abs(sim32.cpu().numpy() - ref)) < 2e-4
+    l0, l1 = ops.pair_ce(sim)
+    r0, r1 = O.pair_ce(ref)
+    assert abs(l0.item() - r0) < TC_LOSS_RTOL * r0 and abs(l1.item() - r1) < TC_LOSS_RTOL * r1
+    # the diagonal attention maps come from the fp32 kernel in both modes
+    assert torch.equal(attn, attn32)
+    for i, a in enumerate(ref_att):
+        assert np.max(np.abs(attn[i, : a.shape[0]].cpu().numpy() - a)) < 1e-5

@@ -22,8 +22,8 @@ int wordregion_fwd_simt(const float*, int64_t, int64_t, int64_t, const float*, i
 int wordregion_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                         const int32_t*, int, int, int, int, int, float, float, float, float, const float*, float*,
                         float*, cudaStream_t);
-int attention_fwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
-                       int, int, float, float*, float*, cudaStream_t);
+int attention_fwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
+                       const int32_t*, int, int, int, int, float, float*, float*, cudaStream_t);
 int attention_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
                        int, int, float, const float*, const float*, float*, float*, cudaStream_t);
 // wordregion_tc.cu
@@ -102,8 +102,9 @@ int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
     // the B diagonal attention maps are produced by the fp32 kernel on the matching pairs only
     const int n = Bc;
     TGFR_REQUIRE(diag_off >= 0 && diag_off + n <= Bq, "wordregion_fwd: diagonal outside the caption range");
-    return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words + (int64_t)diag_off * w_sb, w_sb, w_st, w_sd, n, T,
-                              R, D, gamma1, reinterpret_cast<float*>(workspace), attn_diag, ST(stream));
+    return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words + (int64_t)diag_off * w_sb, w_sb, w_st, w_sd,
+                              cap_lens ? cap_lens + diag_off : nullptr, n, T, R, D, gamma1, nullptr, attn_diag,
+                              ST(stream));
   }
   TGFR_REQUIRE(precision == TGFR_PREC_FP32, "wordregion_fwd: unknown precision %d", precision);
   return wordregion_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
@@ -125,8 +126,8 @@ int tgfr_attention_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t
                        int64_t q_sb, int64_t q_st, int64_t q_sd, int B, int T, int R, int D, float gamma1, float* wc,
                        float* attn, void* stream) {
   TGFR_REQUIRE(ctx && query, "attention_fwd: NULL tensor");
-  return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, query, q_sb, q_st, q_sd, B, T, R, D, gamma1, wc, attn,
-                            ST(stream));
+  return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, query, q_sb, q_st, q_sd, nullptr, B, T, R, D, gamma1, wc,
+                            attn, ST(stream));
 }
 
 int tgfr_attention_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* query,

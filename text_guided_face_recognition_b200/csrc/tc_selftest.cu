@@ -30,14 +30,25 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     mbar_init(&bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
   const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
-  if (manual_a) {
+  if (manual_a == 2) {
+    // A operand in TMEM: lane = row, 32-bit column j holds halfs (2j, 2j+1) of that row (a_g is [128][K])
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a_g + (size_t)tid * K);
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src[c0 + j];
+      tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  } else if (manual_a) {
     // thread k owns row k of A_g[K][128]: two 64-half panels of K rows each
     if (tid < K) {
       const uint4* src = reinterpret_cast<const uint4*>(a_g + (size_t)tid * 128);
@@ -49,6 +60,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   __syncthreads();
   if (tid == 0) {
+    tc_fence_after();
     mbar_arrive_expect_tx(&bar_load, (manual_a ? 0u : a_bytes) + b_bytes);
     if (!manual_a) {
       if (!a_mn) for (int kc = 0; kc < K / 64; ++kc) tma_load_3d(sa + kc * (128 * 128), &tmap_a, &bar_load, kc * 64, 0, 0);
@@ -65,7 +77,8 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       else       ad = make_smem_desc(smem_u32(sa) + k16 * 2048, K * 128, 1024);
       if (!b_mn) bd = make_smem_desc(smem_u32(sb) + (k16 >> 2) * (N * 128) + (k16 & 3) * 32, 16, 1024);
       else       bd = make_smem_desc(smem_u32(sb) + k16 * 2048, K * 128, 1024);
-      umma_ss(tmem, ad, bd, idesc, k16 > 0);
+      if (manual_a == 2) umma_ts(tmem, tmem + 256 + 8 * k16, bd, idesc, k16 > 0);
+      else umma_ss(tmem, ad, bd, idesc, k16 > 0);
     }
     umma_commit(&bar_mma);
   }
@@ -82,7 +95,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // out[r][c] += f(r, c) through a swizzled fp32 staging tile and cp.reduce.async.bulk.tensor
@@ -115,7 +128,8 @@ tma_reduce_selftest_kernel(const __grid_constant__ CUtensorMap tmap_out, int row
 int debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,
                cudaStream_t st) {
   TGFR_REQUIRE(N % 64 == 0 && N >= 64 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, "debug_umma: bad N/K");
-  TGFR_REQUIRE(!manual_a || (a_mn && K <= 128), "debug_umma: manual_a needs a_mn and K <= 128");
+  TGFR_REQUIRE(manual_a != 1 || (a_mn && K <= 128), "debug_umma: manual_a=1 needs a_mn and K <= 128");
+  TGFR_REQUIRE(manual_a != 2 || (!a_mn && N <= 256), "debug_umma: manual_a=2 (A in TMEM) needs a K-major A");
   CUtensorMap ta, tb;
   if (!a_mn) { if (int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, K, 128, 1, 64, 128, 1)) return rc; }
   else       { if (int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, 128, K, 1, 64, K, 1)) return rc; }

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) wr_fwd_kernel(const Params p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qs = p.D + 4;
   int Ti = p.T;
-  if (MODE == kLoss && p.cap_lens) Ti = min(max(p.cap_lens[i], 1), p.T);
+  if (p.cap_lens) Ti = min(max(p.cap_lens[i], 1), p.T);
   const float* cb = p.ctx + (int64_t)b * p.csb;
 
   load_rows<TP>(s.q, p.words + (int64_t)i * p.wsb, p.wst, p.wsd, Ti, p.D);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 2) wr_fwd_kernel(const Params p) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int d = lane + 32 * k;
-        if (d < p.D) p.wc[((int64_t)b * p.T + t) * p.D + d] = wu[j][k] * invz;
+        if (d < p.D && p.wc) p.wc[((int64_t)b * p.T + t) * p.D + d] = wu[j][k] * invz;
       }
       if (lane == 0) s.z[t] = zs[j];
     } else {
@@ -520,15 +520,16 @@ int wordregion_bwd_simt(const float* ctx, int64_t csb, int64_t csr, int64_t csd,
 }
 
 int attention_fwd_simt(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* query, int64_t qsb,
-                       int64_t qst, int64_t qsd, int B, int T, int R, int D, float g1, float* wc, float* attn,
-                       cudaStream_t st) {
+                       int64_t qst, int64_t qsd, const int32_t* cap_lens, int B, int T, int R, int D, float g1,
+                       float* wc, float* attn, cudaStream_t st) {
   Params p{};
   p.ctx = ctx; p.csb = csb; p.csr = csr; p.csd = csd;
   p.words = query; p.wsb = qsb; p.wst = qst; p.wsd = qsd;
+  p.cap_lens = cap_lens;
   p.Bc = B; p.Bq = B; p.T = T; p.R = R; p.D = D; p.g1 = g1; p.g2 = 1.f; p.g3 = 1.f; p.eps = 1e-8f;
   p.wc = wc; p.attn = attn;
   if (int rc = check_shape(p)) return rc;
-  TGFR_REQUIRE(wc != nullptr, "attention_fwd: wc must not be NULL");
+  TGFR_REQUIRE(wc != nullptr || attn != nullptr, "attention_fwd: no output requested");
   return dispatch_fwd<kAttention>(p, st);
 }
 

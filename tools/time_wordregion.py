@@ -1,0 +1,16 @@
+import sys, torch, numpy as np
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import synth
+from text_guided_face_recognition_b200 import _lib, ops
+B,T,R,D=128,22,196,256
+ctx,words,_=synth.wordregion_inputs(B,T,R,D,'BERT',100)
+f=torch.from_numpy(ctx).cuda(); w=torch.from_numpy(words).cuda()
+for prec,name in ((_lib.PREC_TC,'tc'),(_lib.PREC_FP32,'fp32')):
+    for _ in range(3): ops.wordregion_sim(f,w,None,4.,5.,10.,precision=prec,want_attn=False)
+    torch.cuda.synchronize()
+    e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ops.wordregion_sim(f,w,None,4.,5.,10.,precision=prec,want_attn=False)
+    e1.record(); torch.cuda.synchronize()
+    ms=e0.elapsed_time(e1)/10
+    print(name,'fwd ms',ms,'TFLOP/s (alg 4TRD)',4*T*R*D*B*B/ms/1e9)
