@@ -102,3 +102,33 @@ def test_tc_forward_vs_oracle(B, T, R, D, flavour, ragged):
     assert torch.equal(attn, attn32)
     for i, a in enumerate(ref_att):
         assert np.max(np.abs(attn[i, : a.shape[0]].cpu().numpy() - a)) < 1e-5
+
+
+TC_GRAD_RTOL = 1e-3      # contract for the TF32-class path; emulation of the fp16-operand pipeline gives ~4e-4
+
+
+@pytest.mark.parametrize("B,T,R,D,flavour,ragged", [
+    (8, 22, 196, 256, "BERT", False),
+    (16, 18, 196, 256, "LSTM", True),
+    (6, 7, 16, 64, "LSTM", True),
+    (5, 30, 49, 128, "BERT", False),
+    (7, 12, 130, 192, "LSTM", True),
+    (32, 22, 196, 256, "BERT", False),
+])
+def test_tc_backward_vs_oracle(B, T, R, D, flavour, ragged):
+    from text_guided_face_recognition_b200 import _lib, ops
+    ctx, words, cap = synth.wordregion_inputs(B, T, R, D, flavour, seed=100, ragged=ragged)
+    feats = torch.from_numpy(ctx).cuda().requires_grad_(True)
+    wd = torch.from_numpy(words).cuda()                     # text side detached, as in the reference's scripts
+    capt = None if cap is None else torch.from_numpy(cap).cuda()
+    sim, _ = ops.wordregion_sim(feats, wd, capt, 4.0, 5.0, 10.0, precision=_lib.PREC_TC, want_attn=False)
+    l0, l1 = ops.pair_ce(sim)
+    (l0 + l1).backward()
+    torch.cuda.synchronize()
+    got = feats.grad.cpu().numpy()
+    assert np.isfinite(got).all()
+    ref, _ = O.words_loss_grads(ctx, words, None, cap, 4.0, 5.0, 10.0)
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err < TC_GRAD_RTOL, err
+    worst = max(np.linalg.norm(got[b] - ref[b]) / np.linalg.norm(ref[b]) for b in range(B))
+    assert worst < 2 * TC_GRAD_RTOL, worst

@@ -31,6 +31,9 @@ size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D);
 int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                       const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t,
                       cudaStream_t);
+int wordregion_bwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
+                      const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, void*, size_t,
+                      cudaStream_t);
 // dense_simt.cu
 int cosine_scores_fwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const int64_t*,
                       const int64_t*, int, float*, float*, float*, cudaStream_t);
@@ -116,8 +119,20 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         int R, int D, float gamma1, float gamma2, float gamma3, float eps, const float* gsim,
                         float* dctx, float* dwords, int precision, void* workspace, size_t workspace_bytes,
                         void* stream) {
-  (void)workspace; (void)workspace_bytes; (void)precision;
   TGFR_REQUIRE(ctx && words && gsim, "wordregion_bwd: NULL tensor");
+  if (precision == TGFR_PREC_TC) {
+    // d ctx on the tensor cores; d words (never needed by the reference's training scripts, whose text side is
+    // detached) still comes from the fp32 kernel
+    if (dctx) {
+      if (int rc = wordregion_bwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,
+                                     gamma1, gamma2, gamma3, gsim, dctx, workspace, workspace_bytes, ST(stream)))
+        return rc;
+    }
+    if (!dwords) return TGFR_OK;
+    return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
+                               gamma2, gamma3, eps, gsim, nullptr, dwords, ST(stream));
+  }
+  TGFR_REQUIRE(precision == TGFR_PREC_FP32, "wordregion_bwd: unknown precision %d", precision);
   return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
                              gamma2, gamma3, eps, gsim, dctx, dwords, ST(stream));
 }

@@ -317,6 +317,446 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward (d ctx): recompute S / E / Wu, then
+//   epi-2   dW^[w,:] = sigma * dcos_w (q^_w - cos_w w^_w)  -> fp16 -> shared memory (over the E tile)
+//   GEMM-3  dE^[r,w] = <c_r, dW^_w>                          (same shape as GEMM-1, B = dW^)
+//   epi-3   dS = A1 (dA1 - sum_t A1 dA1), dA1 = g1 E^ dE^, E^ = E / |Wu_w|   (thread-local), written as
+//           fp16 A operands *in TMEM*, in place over the S / dE^ accumulators they were computed from
+//   GEMM-5/6  dC[r, d] = sum_w dS[r,w] q_w[d] + E^[r,w] dW^_w[d]   A from TMEM (lanes = regions),
+//           B = MN-major views of the resident Q tile and of the dW^ tile, accumulated in the TMEM
+//           columns the packed operands freed; 64 features per block, two rounds of four blocks
+//   drain   TMEM -> registers (x 1/sigma) -> swizzled fp32 staging -> TMA reduce-add into d ctx
+// sigma is a per-unit power of two that keeps the fp16 gradient operands in the normal range.
+// ---------------------------------------------------------------------------------------------
+enum BarB { bCFull = 0, bQFull, bSFull, bEFull, bWuFull, bDwFull, bDeFull, bDsFull, bDc0, bDc1, bDr0, bDr1, bNum };
+
+struct TcBwdParams {
+  const float* qnorm;    // [Bq*Tp]
+  const int* lens;       // [Bq]
+  const float* gsim;     // [Bc, Bq]
+  int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
+  uint32_t c_panel, q_panel, e_panel, off_q, off_x, off_misc;
+  float k1, k2, g1, g23;   // g23 = gamma2 * gamma3
+};
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void grp_bar_sync(int tile) {
+  if (tile == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+  else asm volatile("bar.sync 3, 128;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
+wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
+                 const __grid_constant__ CUtensorMap tm_dc, const TcBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_c = smem;
+  uint8_t* s_q = smem + p.off_q;
+  uint8_t* s_x = smem + p.off_x;               // E (GEMM-2) then dW^ (GEMM-3 / GEMM-6); 1 KB of zeros follows it
+  uint8_t* misc = smem + p.off_misc;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+  float* sigma_s = reinterpret_cast<float*>(misc + 136);
+  float2* part = reinterpret_cast<float2*>(misc + 256);      // [128] half-1 partials, then (ca, cb)
+  float* exs = reinterpret_cast<float*>(misc + 256 + 1024);  // [128]
+  float* invnw = exs + 128;                                  // [128] 1/|Wu_w| (0 for padding words)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
+  const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.total_units / gridDim.x);
+  const int kchunks = p.D >> 6;
+
+  if (tid == 0) {
+    mbar_init(&bars[bCFull], 1);
+    mbar_init(&bars[bQFull], 1);
+    mbar_init(&bars[bSFull], 1);
+    mbar_init(&bars[bEFull], kEpiThreads);
+    mbar_init(&bars[bWuFull], 1);
+    mbar_init(&bars[bDwFull], kEpiThreads);
+    mbar_init(&bars[bDeFull], 1);
+    mbar_init(&bars[bDsFull], kEpiThreads);
+    mbar_init(&bars[bDc0], 1);
+    mbar_init(&bars[bDc1], 1);
+    mbar_init(&bars[bDr0], kEpiThreads);
+    mbar_init(&bars[bDr1], kEpiThreads);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_c);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_dc);
+  }
+  // Operand tiles are read a few rows beyond what TMA / the epilogue write (K and N padding of the
+  // MMA shapes); those rows only ever multiply zeros, but they must hold finite values.
+  for (uint32_t k = tid; k < (p.off_misc >> 4); k += kThreadsTC) reinterpret_cast<uint4*>(smem)[k] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int prev_b = -1, n = 0;
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G, g = u - b * p.G;
+        if (n > 0) mbar_wait(&bars[bDr1], (n - 1) & 1);   // previous unit fully drained: Q / X / C are free
+        if (b != prev_b) {
+          mbar_arrive_expect_tx(&bars[bCFull], kchunks * p.c_panel);
+          for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[bCFull], kc * 64, 0, b);
+          prev_b = b;
+        }
+        mbar_arrive_expect_tx(&bars[bQFull], kchunks * p.q_panel);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[bQFull], kc * 64, g * p.nw_rows, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);   // S, dE^
+      const uint32_t idesc2 = make_idesc_f16(128, p.D, true, true);     // Wu
+      const uint32_t idesc5 = make_idesc_f16(128, 64, false, true);     // dC blocks: A in TMEM, B MN-major
+      const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_x = smem_u32(s_x);
+      int prev_b = -1, n = 0, m = -1;
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G;
+        if (b != prev_b) {
+          ++m;
+          mbar_wait(&bars[bCFull], m & 1);
+          prev_b = b;
+        }
+        mbar_wait(&bars[bQFull], n & 1);
+        tc_fence_after();
+        // GEMM-1: S_t = C_t . Q^T
+        for (int t = 0; t < p.n_tiles; ++t)
+          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
+            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
+          }
+        umma_commit(&bars[bSFull]);
+        // GEMM-2: Wu = E^T . C
+        mbar_wait(&bars[bEFull], n & 1);
+        tc_fence_after();
+        for (int j = 0; j < (p.Rp >> 4); ++j) {
+          const uint64_t ad = make_smem_desc(a_x + j * 2048, p.e_panel, 1024);
+          const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
+          umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
+        }
+        umma_commit(&bars[bWuFull]);
+        // GEMM-3: dE^_t = C_t . dW^^T
+        mbar_wait(&bars[bDwFull], n & 1);
+        tc_fence_after();
+        for (int t = 0; t < p.n_tiles; ++t)
+          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
+            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(a_x + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+            umma_ss(tmem + 256 + t * 128, ad, bd, idesc1, k16 > 0);
+          }
+        umma_commit(&bars[bDeFull]);
+        // GEMM-5/6: dC blocks, two rounds of (2 tiles x 2 feature quarters)
+        mbar_wait(&bars[bDsFull], n & 1);
+        for (int round = 0; round < (kchunks + 1) / 2; ++round) {
+          if (round == 1) mbar_wait(&bars[bDr0], n & 1);     // round-0 accumulators have been read
+          tc_fence_after();
+          for (int t = 0; t < p.n_tiles; ++t)
+            for (int qq = 0; qq < 2; ++qq) {
+              const int quarter = 2 * round + qq;
+              if (quarter >= kchunks) continue;
+              const uint32_t dcol = tmem + (qq ? 256 : 0) + t * 128 + 64;
+              for (int k16 = 0; k16 < 8; ++k16) {
+                const uint64_t bx = make_smem_desc(a_x + quarter * p.q_panel + k16 * 2048, p.q_panel, 1024);
+                umma_ts(dcol, tmem + 256 + t * 128 + 8 * k16, bx, idesc5, k16 > 0);      // E^ . dW^
+              }
+              for (int k16 = 0; k16 < 8; ++k16) {
+                const uint64_t bq = make_smem_desc(a_q + quarter * p.q_panel + k16 * 2048, p.q_panel, 1024);
+                umma_ts(dcol, tmem + t * 128 + 8 * k16, bq, idesc5, true);                // dS . Q
+              }
+            }
+          umma_commit(&bars[round == 0 ? bDc0 : bDc1]);
+        }
+        if (kchunks <= 2) umma_commit(&bars[bDc1]);
+        // the next unit's GEMM-1 overwrites the accumulator holes: wait until they are drained
+        mbar_wait(&bars[bDr1], n & 1);
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int tile = (warp - 2) >> 2;
+    const int quarter_w = warp & 3;
+    const int lrow = quarter_w * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quarter_w * 32) << 16;
+    const int r = tile * 128 + lrow;
+    const bool warp_has_rows = tile < p.n_tiles && (tile * 128 + quarter_w * 32) < p.Rp;
+    const int dhalf = p.D >> 1;
+    const int gtid = tid - 64 - tile * 128;         // 0..127 inside the tile group
+    int n = 0;
+    for (int u = u0; u < u1; ++u, ++n) {
+      const int b = u / p.G, g = u - b * p.G;
+      // per-unit power-of-two scale from the largest |d loss / d sim| of the unit's captions
+      float gmax = 0.f;
+      for (int c = 0; c < p.nc; ++c) {
+        const int i = g * p.nc + c;
+        if (i < p.Bq) gmax = fmaxf(gmax, fabsf(__ldg(p.gsim + (int64_t)b * p.Bq + i)));
+      }
+      const float sigma = (gmax > 0.f) ? exp2f(floorf(log2f(4096.f / (p.g23 * gmax)))) : 1.f;
+      const float inv_sigma = 1.f / sigma;
+
+      // ---------------- epi-1: word softmax, E -> shared memory ----------------
+      mbar_wait(&bars[bSFull], n & 1);
+      tc_fence_after();
+      if (warp_has_rows) {
+        for (int c = 0; c < p.nc; ++c) {
+          const int i = g * p.nc + c;
+          const int len = (i < p.Bq) ? __ldg(p.lens + i) : 0;      // missing captions: zero columns
+          uint32_t v[32];
+          const uint32_t col = tmem + t_lane + tile * 128 + c * p.Tp;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (8 * j < p.Tp) tmem_ld8(col + 8 * j, v + 8 * j);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (t < len) mx = fmaxf(mx, __uint_as_float(v[t]));
+          float sum = 0.f, e[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            e[t] = (t < len) ? fast_exp2((__uint_as_float(v[t]) - mx) * kLog2e) : 0.f;
+            sum += e[t];
+          }
+          const float inv = 1.f / sum;
+          const bool live_row = r < p.R;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) e[t] = (t < len && live_row) ? fast_exp2(p.k1 * (e[t] * inv) - p.k1) : 0.f;
+          if (r < p.Rp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (8 * j < p.Tp) {
+                const int w0 = c * p.Tp + 8 * j;
+                uint4 pk;
+                pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
+                pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
+                pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
+                pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
+                *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
+              }
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[bEFull]);
+
+      // ---------------- epi-2: cosine, softmax over words, dW^ -> shared memory ----------------
+      mbar_wait(&bars[bWuFull], n & 1);
+      tc_fence_after();
+      const int w = lrow;
+      const int cw = w / p.Tp, tw = w - cw * p.Tp;
+      const int iw = g * p.nc + cw;
+      const bool valid = (w < p.nw_rows) && (iw < p.Bq) && (tw < __ldg(p.lens + min(iw, p.Bq - 1)));
+      const int64_t qrow = (int64_t)min(iw, p.Bq - 1) * p.Tp + tw;
+      float dot = 0.f, n2 = 0.f;
+      for (int ch = 0; ch < (dhalf >> 5); ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
+        tmem_ld_wait();
+        const int d0 = tile * dhalf + 32 * ch;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (d0 >> 6) * p.q_panel +
+                                                           sw128_offset(w, ((d0 & 63) >> 3) + cc));
+          const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 qf = __half22float2(qh[k]);
+            const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
+            dot = fmaf(qf.x, w0, dot);
+            dot = fmaf(qf.y, w1, dot);
+            n2 = fmaf(w0, w0, n2);
+            n2 = fmaf(w1, w1, n2);
+          }
+        }
+      }
+      if (tile == 1) part[w] = make_float2(dot, n2);
+      epi_bar_sync();
+      float cosv = 0.f, nW = 1.f, nq = 1.f;
+      if (tile == 0) {
+        float ex = 0.f;
+        if (valid) {
+          const float2 o = part[w];
+          dot += o.x;
+          n2 += o.y;
+          nW = fmaxf(sqrtf(n2), 1e-30f);
+          nq = fmaxf(__ldg(p.qnorm + qrow), 1e-30f);
+          cosv = dot / (nq * nW);
+          ex = fast_exp2(p.k2 * cosv);
+        }
+        exs[w] = ex;
+      }
+      epi_bar_sync();
+      if (tile == 0) {
+        float ca = 0.f, cb = 0.f, inw = 0.f;
+        if (valid) {
+          float ssum = 0.f;
+          for (int tt = 0; tt < p.Tp; ++tt) ssum += exs[cw * p.Tp + tt];
+          const float dcos = __ldg(p.gsim + (int64_t)b * p.Bq + iw) * p.g23 * (exs[w] / ssum) * sigma;
+          ca = dcos / nq;                 // multiplies q_w
+          cb = dcos * cosv / nW;          // multiplies Wu_w
+          inw = 1.f / nW;
+        }
+        part[w] = make_float2(ca, cb);
+        invnw[w] = inw;
+      }
+      epi_bar_sync();
+      {
+        const float2 cab = part[w];
+        for (int ch = 0; ch < (dhalf >> 5); ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
+          tmem_ld_wait();
+          const int d0 = tile * dhalf + 32 * ch;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = (d0 >> 6) * p.q_panel + sw128_offset(w, ((d0 & 63) >> 3) + cc);
+            const uint4 qv = *reinterpret_cast<const uint4*>(s_q + off);
+            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 qf = __half22float2(qh[k]);
+              const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
+              o[k] = valid ? pack_half2(cab.x * qf.x - cab.y * w0, cab.x * qf.y - cab.y * w1) : 0u;
+            }
+            if (w < p.nw_rows) *reinterpret_cast<uint4*>(s_x + off) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[bDwFull]);
+
+      // ---------------- epi-3: dS and E^ as fp16 A operands, in place in TMEM ----------------
+      mbar_wait(&bars[bDeFull], n & 1);
+      tc_fence_after();
+      if (warp_has_rows) {
+        const uint32_t s_base = tmem + t_lane + tile * 128;
+        const uint32_t e_base = tmem + t_lane + 256 + tile * 128;
+        for (int c = 0; c < p.nc; ++c) {
+          const int i = g * p.nc + c;
+          const bool cap_ok = i < p.Bq;
+          const int len = cap_ok ? __ldg(p.lens + i) : 0;
+          uint32_t vs[32], vd[32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (8 * j < p.Tp) {
+              tmem_ld8(s_base + c * p.Tp + 8 * j, vs + 8 * j);
+              tmem_ld8(e_base + c * p.Tp + 8 * j, vd + 8 * j);
+            }
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (t < len) mx = fmaxf(mx, __uint_as_float(vs[t]));
+          float sum = 0.f, a1[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            a1[t] = (t < len) ? fast_exp2((__uint_as_float(vs[t]) - mx) * kLog2e) : 0.f;
+            sum += a1[t];
+          }
+          const float inv = (len > 0) ? 1.f / sum : 0.f;
+          const bool live_row = r < p.R;
+          float inner = 0.f, eh[32], da[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            a1[t] *= inv;
+            const float ehat = (t < len && live_row) ? fast_exp2(p.k1 * a1[t] - p.k1) * invnw[c * p.Tp + (t < p.Tp ? t : 0)] : 0.f;
+            eh[t] = ehat;
+            da[t] = p.g1 * ehat * __uint_as_float(vd[t]);
+            if (!(t < len && live_row)) da[t] = 0.f;
+            inner = fmaf(a1[t], da[t], inner);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (8 * j < p.Tp) {
+              uint32_t ds[4], ee[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int t0 = 8 * j + 2 * k;
+                ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
+                ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
+              }
+              tmem_st4(s_base + ((c * p.Tp) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
+              tmem_st4(e_base + ((c * p.Tp) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+            }
+        }
+        // zero the K padding (words nw..127) of both operands
+        for (int col = p.nw_rows >> 1; col < 64; col += 4) {
+          tmem_st4(s_base + col, 0u, 0u, 0u, 0u);
+          tmem_st4(e_base + col, 0u, 0u, 0u, 0u);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[bDsFull]);
+
+      // ---------------- drain: dC blocks -> staging -> TMA reduce-add ----------------
+      for (int round = 0; round < 2; ++round) {
+        mbar_wait(&bars[round == 0 ? bDc0 : bDc1], n & 1);
+        tc_fence_after();
+        // staging: tile group 0 uses the (dead) Q panels of this round, group 1 the dW^ panels
+        // (the first KB of X is the K-padding alias of Q's last panel and must stay a valid fp16 tile)
+        uint8_t* stage = (tile == 0 ? s_q : s_x + 1024) + (2 * round) * p.q_panel;
+        if (tile < p.n_tiles && 2 * round < kchunks && gmax > 0.f) {
+          for (int qq = 0; qq < 2; ++qq) {
+            const int quarter = 2 * round + qq;
+            if (quarter >= kchunks) break;
+            const uint32_t dcol = tmem + t_lane + (qq ? 256 : 0) + tile * 128 + 64;
+            for (int hb = 0; hb < 2; ++hb) {
+              uint32_t v[32];
+              if (warp_has_rows) {
+                tmem_ld32(dcol + 32 * hb, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                  float4 o;
+                  o.x = __uint_as_float(v[4 * c16 + 0]) * inv_sigma;
+                  o.y = __uint_as_float(v[4 * c16 + 1]) * inv_sigma;
+                  o.z = __uint_as_float(v[4 * c16 + 2]) * inv_sigma;
+                  o.w = __uint_as_float(v[4 * c16 + 3]) * inv_sigma;
+                  *reinterpret_cast<float4*>(stage + sw128_offset(lrow, c16)) = o;
+                }
+              }
+              fence_proxy_async();
+              grp_bar_sync(tile);
+              if (gtid == 0) {
+                tma_reduce_add_3d(&tm_dc, stage, quarter * 64 + 32 * hb, tile * 128, b);
+                tma_commit_group();
+                tma_wait_group_read<0>();
+              }
+              grp_bar_sync(tile);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[round == 0 ? bDr0 : bDr1]);
+      }
+    }
+    if (gtid == 0) tma_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 struct TcPlan {
   int Tp, Rp, nc, G, nw_rows, n_tiles;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
@@ -350,7 +790,89 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   return TGFR_OK;
 }
 
+struct TcBwdPlan {
+  int Tp, Rp, c_rows, nc, G, nw_rows, n_tiles;
+  uint32_t c_panel, q_panel, e_panel, off_q, off_x, off_misc, smem_bytes;
+};
+
+int make_bwd_plan(int Bq, int T, int R, int D, TcBwdPlan* pl) {
+  TGFR_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "wordregion(tc): D=%d must be 64, 128, 192 or 256", D);
+  TGFR_REQUIRE(R >= 1 && R <= 256, "wordregion(tc): R=%d regions (max 256)", R);
+  TGFR_REQUIRE(T >= 1 && T <= 32, "wordregion(tc): T=%d words (max 32)", T);
+  const int kch = D / 64;
+  pl->Tp = (T + 7) & ~7;
+  pl->Rp = (R + 15) & ~15;
+  pl->c_rows = (R + 7) & ~7;
+  pl->n_tiles = (pl->Rp + 127) / 128;
+  pl->c_panel = (uint32_t)pl->c_rows * 128u;
+  pl->e_panel = (uint32_t)pl->Rp * 128u;
+  for (int nc = 128 / pl->Tp; nc >= 1; --nc) {
+    const uint32_t q_panel = (uint32_t)nc * pl->Tp * 128u;
+    uint32_t q_bytes = kch * q_panel, x_bytes = kch * q_panel + 1024;
+    if (q_bytes < 16384) q_bytes = 16384;                       // drain staging box
+    if (x_bytes < 2 * pl->e_panel) x_bytes = 2 * pl->e_panel;
+    if (x_bytes < 16384 + 1024) x_bytes = 16384 + 1024;
+    const uint32_t off_q = kch * pl->c_panel, off_x = off_q + q_bytes, off_misc = off_x + x_bytes;
+    const uint32_t total = off_misc + 4096 + 1024;
+    if (total <= 232448) {
+      pl->nc = nc; pl->nw_rows = nc * pl->Tp; pl->q_panel = q_panel;
+      pl->off_q = off_q; pl->off_x = off_x; pl->off_misc = off_misc; pl->smem_bytes = total;
+      pl->G = (Bq + nc - 1) / nc;
+      return TGFR_OK;
+    }
+  }
+  set_error("wordregion(tc): no caption grouping fits in shared memory (T=%d R=%d D=%d)", T, R, D);
+  return TGFR_E_INVALID;
+}
+
 }  // namespace
+
+int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* words, int64_t wsb,
+                      int64_t wst, int64_t wsd, const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D, float g1,
+                      float g2, float g3, const float* gsim, float* dctx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcPlan fp;
+  if (int rc = make_plan(Bc, Bq, T, R, D, &fp)) return rc;     // workspace layout is shared with the forward
+  TcBwdPlan pl;
+  if (int rc = make_bwd_plan(Bq, T, R, D, &pl)) return rc;
+  TGFR_REQUIRE(ws != nullptr && ws_bytes >= fp.ws_total, "wordregion(tc): workspace too small (%zu < %zu)", ws_bytes,
+               fp.ws_total);
+  TGFR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "wordregion(tc): workspace must be 256-byte aligned");
+  TGFR_REQUIRE((reinterpret_cast<uintptr_t>(dctx) & 15) == 0, "wordregion(tc): dctx must be 16-byte aligned");
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  __half* c16 = reinterpret_cast<__half*>(base + fp.ws_c16);
+  __half* q16 = reinterpret_cast<__half*>(base + fp.ws_q16);
+  float* qnorm = reinterpret_cast<float*>(base + fp.ws_qnorm);
+  int* lens = reinterpret_cast<int*>(base + fp.ws_lens);
+
+  const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
+  wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc, Bq,
+                                                               T, pl.Tp, R, D, c16, q16, qnorm, lens);
+  TGFR_LAUNCH_OK();
+  TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
+
+  CUtensorMap tm_c, tm_q, tm_dc;
+  if (int rc = make_tmap_3d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, pl.c_rows, 1)) return rc;
+  if (int rc = make_tmap_3d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * pl.Tp, 1, 64, pl.nw_rows, 1))
+    return rc;
+  if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 128, 1)) return rc;
+
+  TcBwdParams p{};
+  p.qnorm = qnorm; p.lens = lens; p.gsim = gsim;
+  p.Bc = Bc; p.Bq = Bq; p.Tp = pl.Tp; p.R = R; p.Rp = pl.Rp; p.D = D; p.nc = pl.nc; p.G = pl.G;
+  p.nw_rows = pl.nw_rows; p.n_tiles = pl.n_tiles; p.total_units = Bc * pl.G;
+  p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
+  p.off_q = pl.off_q; p.off_x = pl.off_x; p.off_misc = pl.off_misc;
+  p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g1 = g1; p.g23 = g2 * g3;
+
+  int dev = 0, sms = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_units < sms ? p.total_units : sms;
+  TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+  wr_tc_bwd_kernel<<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, tm_dc, p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
 
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
   TcPlan pl;
