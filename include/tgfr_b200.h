@@ -181,6 +181,9 @@ int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, con
 int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,
                     void* stream);
 int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream);
+/* Phase trace of the tensor-core word-region kernels: dev_buf = int64[16*32] (or NULL to switch
+ * it off); CTA 0 stamps clock64() per pipeline phase of its first 16 units (tools/trace_wordregion.py). */
+int tgfr_debug_set_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

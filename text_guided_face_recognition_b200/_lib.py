@@ -49,6 +49,7 @@ SIGNATURES = {
     "tgfr_ce_rows_bwd": (I, [P, L, P, P, P, P, I, I, I, P, L, P]),
     "tgfr_debug_umma": (I, [P, P, P, I, I, I, I, I, P]),
     "tgfr_debug_tma_reduce": (I, [P, I, I, P]),
+    "tgfr_debug_set_trace": (I, [P]),
 }
 
 _lib = None

@@ -34,6 +34,7 @@ int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int
 int wordregion_bwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                       const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, void*, size_t,
                       cudaStream_t);
+int wordregion_tc_set_trace(void*);
 // dense_simt.cu
 int cosine_scores_fwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const int64_t*,
                       const int64_t*, int, float*, float*, float*, cudaStream_t);
@@ -242,6 +243,7 @@ int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int 
                     void* stream) {
   return debug_umma(a, b, out, N, K, a_mn, b_mn, manual_a, ST(stream));
 }
+int tgfr_debug_set_trace(void* dev_buf) { return wordregion_tc_set_trace(dev_buf); }
 int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream) {
   return debug_tma_reduce(out, rows, cols, ST(stream));
 }

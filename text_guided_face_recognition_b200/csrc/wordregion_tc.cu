@@ -44,6 +44,14 @@ struct TcParams {
   float k1, k2, g3;
 };
 
+// optional phase trace (tgfr_debug_set_trace): clock64 stamps of CTA 0's first units
+__device__ long long* g_trace = nullptr;
+#define TGFR_TRACE(n, ev)                                                      \
+  do {                                                                         \
+    long long* _t = g_trace;                                                   \
+    if (_t && blockIdx.x == 0 && (n) < 16) _t[(n) * 32 + (ev)] = clock64();    \
+  } while (0)
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -101,6 +109,7 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+template <int TP>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -172,6 +181,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           prev_b = b;
         }
         mbar_wait(&bars[kQFull], n & 1);
+        TGFR_TRACE(n, 17);
         tc_fence_after();
         for (int t = 0; t < p.n_tiles; ++t) {
           for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
@@ -183,7 +193,9 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         umma_commit(&bars[kQEmpty]);
         umma_commit(&bars[kSFull]);
         mbar_wait(&bars[kEFull], n & 1);
+        TGFR_TRACE(n, 18);
         mbar_wait(&bars[kWuEmpty], (n & 1) ^ 1);
+        TGFR_TRACE(n, 19);
         tc_fence_after();
         for (int j = 0; j < (p.Rp >> 4); ++j) {
           const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
@@ -207,44 +219,45 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       const int b = u / p.G, g = u - b * p.G;
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
       mbar_wait(&bars[kSFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 2);
       tc_fence_after();
       if (warp_has_rows) {
         for (int c = 0; c < p.nc; ++c) {
           const int i = g * p.nc + c;
           if (i >= p.Bq) break;
           const int len = __ldg(p.lens + i);
-          uint32_t v[32];
-          const uint32_t col = tmem + t_lane + tile * 128 + c * p.Tp;
+          uint32_t v[TP];
+          const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (8 * j < p.Tp) tmem_ld8(col + 8 * j, v + 8 * j);
+          for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
           tmem_ld_wait();
-          float mx = -INFINITY;
+          float e[TP];
+          float mx = -1e30f;
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < len) mx = fmaxf(mx, __uint_as_float(v[t]));
+          for (int t = 0; t < TP; ++t) {
+            e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
+            mx = fmaxf(mx, e[t]);
+          }
+          const float nmx = -mx * kLog2e;
           float sum = 0.f;
-          float e[32];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            e[t] = (t < len) ? fast_exp2((__uint_as_float(v[t]) - mx) * kLog2e) : 0.f;
+          for (int t = 0; t < TP; ++t) {
+            e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
             sum += e[t];
           }
-          const float inv = 1.f / sum;
+          const float kinv = p.k1 / sum, nk1 = -p.k1;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = (t < len) ? fast_exp2(p.k1 * (e[t] * inv) - p.k1) : 0.f;
+          for (int t = 0; t < TP; ++t) e[t] = fast_exp2(fmaf(e[t], kinv, nk1));
           if (r < p.Rp) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (8 * j < p.Tp) {
-                const int w0 = c * p.Tp + 8 * j;
-                uint4 pk;
-                pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
-                pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
-                pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
-                pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
-                *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
-              }
+            for (int j = 0; j < TP / 8; ++j) {
+              const int w0 = c * TP + 8 * j;
+              uint4 pk;
+              pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
+              pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
+              pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
+              pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
+              *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
             }
           }
         }
@@ -252,12 +265,14 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[kEFull]);
+      if (tid == 64) TGFR_TRACE(n, 3);
 
       // ---------------- epi-2: cosine, exp, log-sum ----------------
       mbar_wait(&bars[kWuFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 4);
       tc_fence_after();
       const int w = lrow;
-      const int c = w / p.Tp, t = w - c * p.Tp;
+      const int c = w / TP, t = w - c * TP;
       const int i = g * p.nc + c;
       const bool valid = (w < p.nw_rows) && (i < p.Bq) && (t < __ldg(p.lens + min(i, p.Bq - 1)));
       const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
@@ -286,6 +301,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(&bars[kWuEmpty]);
+      if (tid == 64) TGFR_TRACE(n, 5);
       part_d[tile * 128 + w] = dot;
       part_n[tile * 128 + w] = n2;
       epi_bar_sync();
@@ -303,7 +319,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         const int ii = g * p.nc + w;
         if (ii < p.Bq) {
           float s = 0.f;
-          for (int tt = 0; tt < p.Tp; ++tt) s += exs[w * p.Tp + tt];
+          for (int tt = 0; tt < TP; ++tt) s += exs[w * TP + tt];
           p.sim[(int64_t)b * p.Bq + ii] = p.g3 * logf(s);
         }
       }
@@ -349,6 +365,7 @@ __device__ __forceinline__ void grp_bar_sync(int tile) {
   else asm volatile("bar.sync 3, 128;" ::: "memory");
 }
 
+template <int TP>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_dc, const TcBwdParams p) {
@@ -431,6 +448,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           prev_b = b;
         }
         mbar_wait(&bars[bQFull], n & 1);
+        TGFR_TRACE(n, 17);
         tc_fence_after();
         // GEMM-1: S_t = C_t . Q^T
         for (int t = 0; t < p.n_tiles; ++t)
@@ -442,6 +460,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         umma_commit(&bars[bSFull]);
         // GEMM-2: Wu = E^T . C
         mbar_wait(&bars[bEFull], n & 1);
+        TGFR_TRACE(n, 18);
         tc_fence_after();
         for (int j = 0; j < (p.Rp >> 4); ++j) {
           const uint64_t ad = make_smem_desc(a_x + j * 2048, p.e_panel, 1024);
@@ -451,6 +470,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         umma_commit(&bars[bWuFull]);
         // GEMM-3: dE^_t = C_t . dW^^T
         mbar_wait(&bars[bDwFull], n & 1);
+        TGFR_TRACE(n, 19);
         tc_fence_after();
         for (int t = 0; t < p.n_tiles; ++t)
           for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
@@ -461,6 +481,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         umma_commit(&bars[bDeFull]);
         // GEMM-5/6: dC blocks, two rounds of (2 tiles x 2 feature quarters)
         mbar_wait(&bars[bDsFull], n & 1);
+        TGFR_TRACE(n, 20);
         for (int round = 0; round < (kchunks + 1) / 2; ++round) {
           if (round == 1) mbar_wait(&bars[bDr0], n & 1);     // round-0 accumulators have been read
           tc_fence_after();
@@ -479,10 +500,12 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
               }
             }
           umma_commit(&bars[round == 0 ? bDc0 : bDc1]);
+          TGFR_TRACE(n, 21 + round);
         }
         if (kchunks <= 2) umma_commit(&bars[bDc1]);
         // the next unit's GEMM-1 overwrites the accumulator holes: wait until they are drained
         mbar_wait(&bars[bDr1], n & 1);
+        TGFR_TRACE(n, 23);
       }
     }
   } else {
@@ -509,55 +532,60 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
       mbar_wait(&bars[bSFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 2);
       tc_fence_after();
       if (warp_has_rows) {
+        const bool live_row = r < p.R;
         for (int c = 0; c < p.nc; ++c) {
           const int i = g * p.nc + c;
           const int len = (i < p.Bq) ? __ldg(p.lens + i) : 0;      // missing captions: zero columns
-          uint32_t v[32];
-          const uint32_t col = tmem + t_lane + tile * 128 + c * p.Tp;
+          uint32_t v[TP];
+          const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (8 * j < p.Tp) tmem_ld8(col + 8 * j, v + 8 * j);
+          for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
           tmem_ld_wait();
-          float mx = -INFINITY;
+          float e[TP];
+          float mx = -1e30f;
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < len) mx = fmaxf(mx, __uint_as_float(v[t]));
-          float sum = 0.f, e[32];
+          for (int t = 0; t < TP; ++t) {
+            e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
+            mx = fmaxf(mx, e[t]);
+          }
+          const float nmx = -mx * kLog2e;
+          float sum = 0.f;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            e[t] = (t < len) ? fast_exp2((__uint_as_float(v[t]) - mx) * kLog2e) : 0.f;
+          for (int t = 0; t < TP; ++t) {
+            e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
             sum += e[t];
           }
-          const float inv = 1.f / sum;
-          const bool live_row = r < p.R;
+          const float kinv = (len > 0) ? p.k1 / sum : 0.f, nk1 = -p.k1;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) e[t] = (t < len && live_row) ? fast_exp2(p.k1 * (e[t] * inv) - p.k1) : 0.f;
+          for (int t = 0; t < TP; ++t) e[t] = (t < len && live_row) ? fast_exp2(fmaf(e[t], kinv, nk1)) : 0.f;
           if (r < p.Rp) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (8 * j < p.Tp) {
-                const int w0 = c * p.Tp + 8 * j;
-                uint4 pk;
-                pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
-                pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
-                pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
-                pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
-                *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
-              }
+            for (int j = 0; j < TP / 8; ++j) {
+              const int w0 = c * TP + 8 * j;
+              uint4 pk;
+              pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
+              pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
+              pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
+              pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
+              *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
+            }
           }
         }
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[bEFull]);
+      if (tid == 64) TGFR_TRACE(n, 3);
 
       // ---------------- epi-2: cosine, softmax over words, dW^ -> shared memory ----------------
       mbar_wait(&bars[bWuFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 4);
       tc_fence_after();
       const int w = lrow;
-      const int cw = w / p.Tp, tw = w - cw * p.Tp;
+      const int cw = w / TP, tw = w - cw * TP;
       const int iw = g * p.nc + cw;
       const bool valid = (w < p.nw_rows) && (iw < p.Bq) && (tw < __ldg(p.lens + min(iw, p.Bq - 1)));
       const int64_t qrow = (int64_t)min(iw, p.Bq - 1) * p.Tp + tw;
@@ -604,7 +632,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         float ca = 0.f, cb = 0.f, inw = 0.f;
         if (valid) {
           float ssum = 0.f;
-          for (int tt = 0; tt < p.Tp; ++tt) ssum += exs[cw * p.Tp + tt];
+          for (int tt = 0; tt < TP; ++tt) ssum += exs[cw * TP + tt];
           const float dcos = __ldg(p.gsim + (int64_t)b * p.Bq + iw) * p.g23 * (exs[w] / ssum) * sigma;
           ca = dcos / nq;                 // multiplies q_w
           cb = dcos * cosv / nW;          // multiplies Wu_w
@@ -640,60 +668,67 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[bDwFull]);
+      if (tid == 64) TGFR_TRACE(n, 5);
 
       // ---------------- epi-3: dS and E^ as fp16 A operands, in place in TMEM ----------------
       mbar_wait(&bars[bDeFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 6);
       tc_fence_after();
       if (warp_has_rows) {
         const uint32_t s_base = tmem + t_lane + tile * 128;
         const uint32_t e_base = tmem + t_lane + 256 + tile * 128;
+        const bool live_row = r < p.R;
         for (int c = 0; c < p.nc; ++c) {
           const int i = g * p.nc + c;
-          const bool cap_ok = i < p.Bq;
-          const int len = cap_ok ? __ldg(p.lens + i) : 0;
-          uint32_t vs[32], vd[32];
+          const int len = (i < p.Bq) ? __ldg(p.lens + i) : 0;
+          uint32_t vs[TP], vd[TP];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (8 * j < p.Tp) {
-              tmem_ld8(s_base + c * p.Tp + 8 * j, vs + 8 * j);
-              tmem_ld8(e_base + c * p.Tp + 8 * j, vd + 8 * j);
-            }
+          for (int j = 0; j < TP / 8; ++j) {
+            tmem_ld8(s_base + c * TP + 8 * j, vs + 8 * j);
+            tmem_ld8(e_base + c * TP + 8 * j, vd + 8 * j);
+          }
           tmem_ld_wait();
-          float mx = -INFINITY;
+          float a1[TP];
+          float mx = -1e30f;
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < len) mx = fmaxf(mx, __uint_as_float(vs[t]));
-          float sum = 0.f, a1[32];
+          for (int t = 0; t < TP; ++t) {
+            a1[t] = (t < len) ? __uint_as_float(vs[t]) : -INFINITY;
+            mx = fmaxf(mx, a1[t]);
+          }
+          const float nmx = -mx * kLog2e;
+          float sum = 0.f;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            a1[t] = (t < len) ? fast_exp2((__uint_as_float(vs[t]) - mx) * kLog2e) : 0.f;
+          for (int t = 0; t < TP; ++t) {
+            a1[t] = fast_exp2(fmaf(a1[t], kLog2e, nmx));
             sum += a1[t];
           }
-          const float inv = (len > 0) ? 1.f / sum : 0.f;
-          const bool live_row = r < p.R;
-          float inner = 0.f, eh[32], da[32];
+          const float inv = (len > 0 && live_row) ? 1.f / sum : 0.f;     // dead rows / captions: a1 = 0 -> dS = E^ = 0
+          const float nk1 = -p.k1;
+          float inner = 0.f, eh[TP], da[TP];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
+          for (int t = 0; t < TP; ++t) {
             a1[t] *= inv;
-            const float ehat = (t < len && live_row) ? fast_exp2(p.k1 * a1[t] - p.k1) * invnw[c * p.Tp + (t < p.Tp ? t : 0)] : 0.f;
-            eh[t] = ehat;
-            da[t] = p.g1 * ehat * __uint_as_float(vd[t]);
-            if (!(t < len && live_row)) da[t] = 0.f;
+            // invnw is 0 for padding words, which zeroes both operands there
+            eh[t] = fast_exp2(fmaf(p.k1, a1[t], nk1)) * invnw[c * TP + t];
+            da[t] = p.g1 * eh[t] * __uint_as_float(vd[t]);
             inner = fmaf(a1[t], da[t], inner);
           }
+          if (!live_row) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (8 * j < p.Tp) {
-              uint32_t ds[4], ee[4];
+            for (int t = 0; t < TP; ++t) eh[t] = 0.f;
+          }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int t0 = 8 * j + 2 * k;
-                ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
-                ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
-              }
-              tmem_st4(s_base + ((c * p.Tp) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
-              tmem_st4(e_base + ((c * p.Tp) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+          for (int j = 0; j < TP / 8; ++j) {
+            uint32_t ds[4], ee[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int t0 = 8 * j + 2 * k;
+              ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
+              ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
             }
+            tmem_st4(s_base + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
+            tmem_st4(e_base + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+          }
         }
         // zero the K padding (words nw..127) of both operands
         for (int col = p.nw_rows >> 1; col < 64; col += 4) {
@@ -704,10 +739,12 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(&bars[bDsFull]);
+      if (tid == 64) TGFR_TRACE(n, 7);
 
       // ---------------- drain: dC blocks -> staging -> TMA reduce-add ----------------
       for (int round = 0; round < 2; ++round) {
         mbar_wait(&bars[round == 0 ? bDc0 : bDc1], n & 1);
+        if (tid == 64) TGFR_TRACE(n, 8 + 2 * round);
         tc_fence_after();
         // staging: tile group 0 uses the (dead) Q panels of this round, group 1 the dW^ panels
         // (the first KB of X is the K-padding alias of Q's last panel and must stay a valid fp16 tile)
@@ -745,6 +782,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive(&bars[round == 0 ? bDr0 : bDr1]);
+        if (tid == 64) TGFR_TRACE(n, 9 + 2 * round);
       }
     }
     if (gtid == 0) tma_wait_group<0>();
@@ -868,9 +906,29 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_units < sms ? p.total_units : sms;
-  TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-  wr_tc_bwd_kernel<<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, tm_dc, p);
+#define TGFR_LAUNCH_BWD(TPV)                                                                                    \
+  case TPV:                                                                                                    \
+    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)pl.smem_bytes));                                                    \
+    wr_tc_bwd_kernel<TPV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, tm_dc, p);                        \
+    break;
+  switch (pl.Tp) {
+    TGFR_LAUNCH_BWD(8)
+    TGFR_LAUNCH_BWD(16)
+    TGFR_LAUNCH_BWD(24)
+    TGFR_LAUNCH_BWD(32)
+    default:
+      set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
+      return TGFR_E_INVALID;
+  }
+#undef TGFR_LAUNCH_BWD
   TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int wordregion_tc_set_trace(void* dev_buf) {
+  long long* p = reinterpret_cast<long long*>(dev_buf);
+  TGFR_CUDA_OK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return TGFR_OK;
 }
 
@@ -917,8 +975,22 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_units < sms ? p.total_units : sms;
-  TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-  wr_tc_fwd_kernel<<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);
+#define TGFR_LAUNCH_FWD(TPV)                                                                                    \
+  case TPV:                                                                                                    \
+    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)pl.smem_bytes));                                                    \
+    wr_tc_fwd_kernel<TPV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);                               \
+    break;
+  switch (pl.Tp) {
+    TGFR_LAUNCH_FWD(8)
+    TGFR_LAUNCH_FWD(16)
+    TGFR_LAUNCH_FWD(24)
+    TGFR_LAUNCH_FWD(32)
+    default:
+      set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
+      return TGFR_E_INVALID;
+  }
+#undef TGFR_LAUNCH_FWD
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }

@@ -1,0 +1,31 @@
+"""Phase trace of the tensor-core word-region kernels (clock64 stamps of CTA 0; see tgfr_debug_set_trace)."""
+import sys, torch, numpy as np
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import synth
+from text_guided_face_recognition_b200 import _lib, ops
+B, T, R, D = 128, 22, 196, 256
+ctx, words, _ = synth.wordregion_inputs(B, T, R, D, 'BERT', 100)
+w = torch.from_numpy(words).cuda()
+f = torch.from_numpy(ctx).cuda().requires_grad_(True)
+lib = _lib.load()
+trace = torch.zeros(16 * 32, dtype=torch.int64, device='cuda')
+def fwd(): return ops.wordregion_sim(f, w, None, 4., 5., 10., precision=_lib.PREC_TC, want_attn=False)[0]
+sim = fwd(); g = torch.randn_like(sim) / B
+sim.backward(g, retain_graph=True); torch.cuda.synchronize()
+names_e = {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 done', 6: 'dE ready', 7: 'epi3 done', 8: 'dC0 ready',
+           9: 'drain0 done', 10: 'dC1 ready', 11: 'drain1 done'}
+names_m = {17: 'Q ready', 18: 'E ready', 19: 'dW ready/WuEmpty', 20: 'dS ready', 21: 'dc0 issued', 22: 'dc1 issued', 23: 'drained'}
+for which in ('fwd', 'bwd'):
+    trace.zero_()
+    _lib.check(lib.tgfr_debug_set_trace(trace.data_ptr()), 'trace')
+    if which == 'fwd': fwd()
+    else: f.grad = None; sim.backward(g, retain_graph=True)
+    torch.cuda.synchronize()
+    _lib.check(lib.tgfr_debug_set_trace(0), 'trace')
+    t = trace.cpu().numpy().reshape(16, 32)
+    base = t[t > 0].min()
+    print('====', which)
+    for n in range(2, 8):
+        evs = sorted((t[n, e] - base, e) for e in range(32) if t[n, e] > 0)
+        print('unit', n, ' '.join(f"{(names_e | names_m).get(e, e)}@{int(c)}" for c, e in evs))
+    print('cycles per unit (epilogue thread):', np.diff(t[2:12, 3]))
