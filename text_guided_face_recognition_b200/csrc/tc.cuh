@@ -217,8 +217,9 @@ typedef CUresult (*PFN_tgfr_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuui
                                          CUtensorMapFloatOOBfill);
 PFN_tgfr_encodeTiled get_encode_tiled();
 
-// rank-3 map over a row-major [d2][d1][d0] tensor (d0 contiguous), box [b2][b1][b0], 128B swizzle.
+// rank-3 map over a row-major [d2][d1][d0] tensor (d0 contiguous), box [b2][b1][b0]; swizzle_bytes is 128
+// (box rows of up to 128 bytes) or 64 (box rows of up to 64 bytes).
 int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
-                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2);
+                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes = 128);
 
 }  // namespace tgfr

@@ -345,7 +345,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 //   drain   TMEM -> registers (x 1/sigma) -> swizzled fp32 staging -> TMA reduce-add into d ctx
 // sigma is a per-unit power of two that keeps the fp16 gradient operands in the normal range.
 // ---------------------------------------------------------------------------------------------
-enum BarB { bCFull = 0, bQFull, bSFull, bEFull, bWuFull, bDwFull, bDeFull, bDsFull, bDc0, bDc1, bDr0, bDr1, bNum };
+enum BarB { bCFull = 0, bQFull, bSFull, bEFull, bWuFull, bDwFull, bDeFull, bDsFull, bDc1, bDc2, bDc3, bDr0, bDr1, bDr2, bDr3, bNum };
 
 struct TcBwdParams {
   const float* qnorm;    // [Bq*Tp]
@@ -360,10 +360,6 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
-__device__ __forceinline__ void grp_bar_sync(int tile) {
-  if (tile == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-  else asm volatile("bar.sync 3, 128;" ::: "memory");
-}
 
 template <int TP>
 __global__ void __launch_bounds__(kThreadsTC, 1)
@@ -377,7 +373,6 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   uint8_t* misc = smem + p.off_misc;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  float* sigma_s = reinterpret_cast<float*>(misc + 136);
   float2* part = reinterpret_cast<float2*>(misc + 256);      // [128] half-1 partials, then (ca, cb)
   float* exs = reinterpret_cast<float*>(misc + 256 + 1024);  // [128]
   float* invnw = exs + 128;                                  // [128] 1/|Wu_w| (0 for padding words)
@@ -396,10 +391,8 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     mbar_init(&bars[bDwFull], kEpiThreads);
     mbar_init(&bars[bDeFull], 1);
     mbar_init(&bars[bDsFull], kEpiThreads);
-    mbar_init(&bars[bDc0], 1);
-    mbar_init(&bars[bDc1], 1);
-    mbar_init(&bars[bDr0], kEpiThreads);
-    mbar_init(&bars[bDr1], kEpiThreads);
+    for (int k = bDc1; k <= bDc3; ++k) mbar_init(&bars[k], 1);
+    for (int k = bDr0; k <= bDr3; ++k) mbar_init(&bars[k], kEpiThreads);
     fence_barrier_init();
     tma_prefetch_desc(&tm_c);
     tma_prefetch_desc(&tm_q);
@@ -421,7 +414,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       int prev_b = -1, n = 0;
       for (int u = u0; u < u1; ++u, ++n) {
         const int b = u / p.G, g = u - b * p.G;
-        if (n > 0) mbar_wait(&bars[bDr1], (n - 1) & 1);   // previous unit fully drained: Q / X / C are free
+        if (n > 0) mbar_wait(&bars[bDr3], (n - 1) & 1);   // previous unit fully drained: Q / X / C are free
         if (b != prev_b) {
           mbar_arrive_expect_tx(&bars[bCFull], kchunks * p.c_panel);
           for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[bCFull], kc * 64, 0, b);
@@ -437,7 +430,6 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     if (lane == 0) {
       const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);   // S, dE^
       const uint32_t idesc2 = make_idesc_f16(128, p.D, true, true);     // Wu
-      const uint32_t idesc5 = make_idesc_f16(128, 64, false, true);     // dC blocks: A in TMEM, B MN-major
       const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_x = smem_u32(s_x);
       int prev_b = -1, n = 0, m = -1;
       for (int u = u0; u < u1; ++u, ++n) {
@@ -479,32 +471,37 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             umma_ss(tmem + 256 + t * 128, ad, bd, idesc1, k16 > 0);
           }
         umma_commit(&bars[bDeFull]);
-        // GEMM-5/6: dC blocks, two rounds of (2 tiles x 2 feature quarters)
+        // GEMM-5/6: four rounds (tile, feature half) of 128-column dC blocks ping-ponging between the two
+        // 128-column holes the packed operands leave free: [64,192) for tile 0, [320,448) for tile 1
         mbar_wait(&bars[bDsFull], n & 1);
         TGFR_TRACE(n, 20);
-        for (int round = 0; round < (kchunks + 1) / 2; ++round) {
-          if (round == 1) mbar_wait(&bars[bDr0], n & 1);     // round-0 accumulators have been read
-          tc_fence_after();
-          for (int t = 0; t < p.n_tiles; ++t)
-            for (int qq = 0; qq < 2; ++qq) {
-              const int quarter = 2 * round + qq;
-              if (quarter >= kchunks) continue;
-              const uint32_t dcol = tmem + (qq ? 256 : 0) + t * 128 + 64;
-              for (int k16 = 0; k16 < 8; ++k16) {
-                const uint64_t bx = make_smem_desc(a_x + quarter * p.q_panel + k16 * 2048, p.q_panel, 1024);
-                umma_ts(dcol, tmem + 256 + t * 128 + 8 * k16, bx, idesc5, k16 > 0);      // E^ . dW^
-              }
-              for (int k16 = 0; k16 < 8; ++k16) {
-                const uint64_t bq = make_smem_desc(a_q + quarter * p.q_panel + k16 * 2048, p.q_panel, 1024);
-                umma_ts(dcol, tmem + t * 128 + 8 * k16, bq, idesc5, true);                // dS . Q
-              }
+        tc_fence_after();
+        for (int rd = 0; rd < 4; ++rd) {
+          const int t = rd & 1, half = rd >> 1;
+          if (rd >= 2) {                                   // the hole's previous block has been drained
+            mbar_wait(&bars[bDr0 + rd - 2], n & 1);
+            tc_fence_after();
+          }
+          const int ncols = min(p.D - half * 128, 128);
+          if (t < p.n_tiles && ncols > 0) {
+            const uint32_t idesc5 = make_idesc_f16(128, ncols, false, true);   // A in TMEM, B MN-major
+            const uint32_t dcol = tmem + (t ? 320 : 64);
+            for (int k16 = 0; k16 < 8; ++k16) {
+              const uint64_t bx = make_smem_desc(a_x + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
+              umma_ts(dcol, tmem + 256 + t * 192 + 8 * k16, bx, idesc5, k16 > 0);      // E^ . dW^
             }
-          umma_commit(&bars[round == 0 ? bDc0 : bDc1]);
-          TGFR_TRACE(n, 21 + round);
+            for (int k16 = 0; k16 < 8; ++k16) {
+              const uint64_t bq = make_smem_desc(a_q + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
+              umma_ts(dcol, tmem + t * 192 + 8 * k16, bq, idesc5, true);                // dS . Q
+            }
+          }
+          if (rd >= 1) {
+            umma_commit(&bars[bDc1 + rd - 1]);
+            TGFR_TRACE(n, 20 + rd);
+          }
         }
-        if (kchunks <= 2) umma_commit(&bars[bDc1]);
         // the next unit's GEMM-1 overwrites the accumulator holes: wait until they are drained
-        mbar_wait(&bars[bDr1], n & 1);
+        mbar_wait(&bars[bDr3], n & 1);
         TGFR_TRACE(n, 23);
       }
     }
@@ -517,7 +514,8 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     const int r = tile * 128 + lrow;
     const bool warp_has_rows = tile < p.n_tiles && (tile * 128 + quarter_w * 32) < p.Rp;
     const int dhalf = p.D >> 1;
-    const int gtid = tid - 64 - tile * 128;         // 0..127 inside the tile group
+    uint8_t* const stage = (tile == 0 ? s_q : s_x + 1024) + ((warp - 2) & 3) * 6144;   // this warp's 3 x 2 KB ring
+    int ring = 0;
     int n = 0;
     for (int u = u0; u < u1; ++u, ++n) {
       const int b = u / p.G, g = u - b * p.G;
@@ -677,8 +675,13 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       if (warp_has_rows) {
         const uint32_t s_base = tmem + t_lane + tile * 128;
         const uint32_t e_base = tmem + t_lane + 256 + tile * 128;
+        // packed fp16 operands: tile 0 in the lower half of its accumulators (captions in ascending order),
+        // tile 1 in the upper half (descending order), so that a thread never overwrites a column it has
+        // not read yet and the free halves [64,192) and [320,448) are contiguous
+        const uint32_t s_pack = s_base + tile * 64, e_pack = e_base + tile * 64;
         const bool live_row = r < p.R;
-        for (int c = 0; c < p.nc; ++c) {
+        for (int cc = 0; cc < p.nc; ++cc) {
+          const int c = tile ? p.nc - 1 - cc : cc;
           const int i = g * p.nc + c;
           const int len = (i < p.Bq) ? __ldg(p.lens + i) : 0;
           uint32_t vs[TP], vd[TP];
@@ -726,14 +729,14 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
               ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
               ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
             }
-            tmem_st4(s_base + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
-            tmem_st4(e_base + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+            tmem_st4(s_pack + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
+            tmem_st4(e_pack + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
           }
         }
         // zero the K padding (words nw..127) of both operands
         for (int col = p.nw_rows >> 1; col < 64; col += 4) {
-          tmem_st4(s_base + col, 0u, 0u, 0u, 0u);
-          tmem_st4(e_base + col, 0u, 0u, 0u, 0u);
+          tmem_st4(s_pack + col, 0u, 0u, 0u, 0u);
+          tmem_st4(e_pack + col, 0u, 0u, 0u, 0u);
         }
         tmem_st_wait();
       }
@@ -741,51 +744,60 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       mbar_arrive(&bars[bDsFull]);
       if (tid == 64) TGFR_TRACE(n, 7);
 
-      // ---------------- drain: dC blocks -> staging -> TMA reduce-add ----------------
-      for (int round = 0; round < 2; ++round) {
-        mbar_wait(&bars[round == 0 ? bDc0 : bDc1], n & 1);
-        if (tid == 64) TGFR_TRACE(n, 8 + 2 * round);
-        tc_fence_after();
-        // staging: tile group 0 uses the (dead) Q panels of this round, group 1 the dW^ panels
-        // (the first KB of X is the K-padding alias of Q's last panel and must stay a valid fp16 tile)
-        uint8_t* stage = (tile == 0 ? s_q : s_x + 1024) + (2 * round) * p.q_panel;
-        if (tile < p.n_tiles && 2 * round < kchunks && gmax > 0.f) {
-          for (int qq = 0; qq < 2; ++qq) {
-            const int quarter = 2 * round + qq;
-            if (quarter >= kchunks) break;
-            const uint32_t dcol = tmem + t_lane + (qq ? 256 : 0) + tile * 128 + 64;
-            for (int hb = 0; hb < 2; ++hb) {
-              uint32_t v[32];
-              if (warp_has_rows) {
-                tmem_ld32(dcol + 32 * hb, v);
-                tmem_ld_wait();
+      // ---------------- drain: dC blocks -> per-warp staging ring -> TMA reduce-add ----------------
+      // Every warp drains 32 lanes x 64 columns of each block through three 2 KB boxes (32 rows x 16 floats,
+      // 64B swizzle) that overlay operand panels 0/1 of Q (warps 2-5) and dW^ (warps 6-9); those panels are
+      // dead once rounds 0 and 1 have retired (bDc1).
+      for (int rd = 0; rd < 4; ++rd) {
+        const int t = rd & 1, half = rd >> 1;
+        if (rd != 1) {
+          mbar_wait(&bars[rd == 0 ? bDc1 : bDc1 + rd - 1], n & 1);
+          tc_fence_after();
+        }
+        if (rd == 0 && tid == 64) TGFR_TRACE(n, 8);
+        const int col0 = half * 128 + tile * 64;             // first feature this warp drains
+        const int row0 = t * 128 + quarter_w * 32;
+        if (t < p.n_tiles && row0 < p.R && col0 < p.D && gmax > 0.f) {
+          const uint32_t dcol = tmem + t_lane + (t ? 320 : 64) + tile * 64;
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(dcol + 32 * ch, v);
+            tmem_ld_wait();
 #pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
-                  float4 o;
-                  o.x = __uint_as_float(v[4 * c16 + 0]) * inv_sigma;
-                  o.y = __uint_as_float(v[4 * c16 + 1]) * inv_sigma;
-                  o.z = __uint_as_float(v[4 * c16 + 2]) * inv_sigma;
-                  o.w = __uint_as_float(v[4 * c16 + 3]) * inv_sigma;
-                  *reinterpret_cast<float4*>(stage + sw128_offset(lrow, c16)) = o;
-                }
+            for (int sub = 0; sub < 2; ++sub) {
+              uint8_t* buf = stage + ring * 2048;
+              if (lane == 0) tma_wait_group_read<2>();       // the box written three stores ago has been read
+              __syncwarp();
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16) {
+                float4 o;
+                o.x = __uint_as_float(v[16 * sub + 4 * c16 + 0]) * inv_sigma;
+                o.y = __uint_as_float(v[16 * sub + 4 * c16 + 1]) * inv_sigma;
+                o.z = __uint_as_float(v[16 * sub + 4 * c16 + 2]) * inv_sigma;
+                o.w = __uint_as_float(v[16 * sub + 4 * c16 + 3]) * inv_sigma;
+                *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = o;
               }
               fence_proxy_async();
-              grp_bar_sync(tile);
-              if (gtid == 0) {
-                tma_reduce_add_3d(&tm_dc, stage, quarter * 64 + 32 * hb, tile * 128, b);
+              __syncwarp();
+              if (lane == 0) {
+                tma_reduce_add_3d(&tm_dc, buf, col0 + 32 * ch + 16 * sub, row0, b);
                 tma_commit_group();
-                tma_wait_group_read<0>();
               }
-              grp_bar_sync(tile);
+              ring = ring == 2 ? 0 : ring + 1;
             }
           }
         }
+        if (rd == 3) {                                        // Q / X are handed back to the producer
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+        }
         tc_fence_before();
-        mbar_arrive(&bars[round == 0 ? bDr0 : bDr1]);
-        if (tid == 64) TGFR_TRACE(n, 9 + 2 * round);
+        mbar_arrive(&bars[bDr0 + rd]);
+        if (tid == 64) TGFR_TRACE(n, 9 + rd);
       }
     }
-    if (gtid == 0) tma_wait_group<0>();
+    if (lane == 0) tma_wait_group<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -847,9 +859,11 @@ int make_bwd_plan(int Bq, int T, int R, int D, TcBwdPlan* pl) {
   for (int nc = 128 / pl->Tp; nc >= 1; --nc) {
     const uint32_t q_panel = (uint32_t)nc * pl->Tp * 128u;
     uint32_t q_bytes = kch * q_panel, x_bytes = kch * q_panel + 1024;
-    if (q_bytes < 16384) q_bytes = 16384;                       // drain staging box
+    if (q_bytes < 24576) q_bytes = 24576;                       // drain staging rings (4 warps x 3 x 2 KB)
     if (x_bytes < 2 * pl->e_panel) x_bytes = 2 * pl->e_panel;
-    if (x_bytes < 16384 + 1024) x_bytes = 16384 + 1024;
+    if (x_bytes < 24576 + 1024) x_bytes = 24576 + 1024;
+    // with more than two feature panels the rings must fit in panels 0/1, which are dead while rounds 2/3 run
+    if (kch > 2 && 2 * q_panel < 24576 + 1024) continue;
     const uint32_t off_q = kch * pl->c_panel, off_x = off_q + q_bytes, off_misc = off_x + x_bytes;
     const uint32_t total = off_misc + 4096 + 1024;
     if (total <= 232448) {
@@ -892,7 +906,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   if (int rc = make_tmap_3d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, pl.c_rows, 1)) return rc;
   if (int rc = make_tmap_3d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * pl.Tp, 1, 64, pl.nw_rows, 1))
     return rc;
-  if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 128, 1)) return rc;
+  if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 16, 32, 1, 64)) return rc;
 
   TcBwdParams p{};
   p.qnorm = qnorm; p.lens = lens; p.gsim = gsim;

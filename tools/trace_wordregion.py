@@ -12,9 +12,9 @@ trace = torch.zeros(16 * 32, dtype=torch.int64, device='cuda')
 def fwd(): return ops.wordregion_sim(f, w, None, 4., 5., 10., precision=_lib.PREC_TC, want_attn=False)[0]
 sim = fwd(); g = torch.randn_like(sim) / B
 sim.backward(g, retain_graph=True); torch.cuda.synchronize()
-names_e = {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 done', 6: 'dE ready', 7: 'epi3 done', 8: 'dC0 ready',
-           9: 'drain0 done', 10: 'dC1 ready', 11: 'drain1 done'}
-names_m = {17: 'Q ready', 18: 'E ready', 19: 'dW ready/WuEmpty', 20: 'dS ready', 21: 'dc0 issued', 22: 'dc1 issued', 23: 'drained'}
+names_e = {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 done', 6: 'dE ready', 7: 'epi3 done', 8: 'dC01 ready',
+           9: 'drain0 done', 10: 'drain1 done', 11: 'drain2 done', 12: 'drain3 done'}
+names_m = {17: 'Q ready', 18: 'E ready', 19: 'dW ready/WuEmpty', 20: 'dS ready', 21: 'dc01 issued', 22: 'dc2 issued', 23: 'dc3 issued'}
 for which in ('fwd', 'bwd'):
     trace.zero_()
     _lib.check(lib.tgfr_debug_set_trace(trace.data_ptr()), 'trace')
