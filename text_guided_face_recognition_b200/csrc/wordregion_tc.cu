@@ -32,7 +32,7 @@ constexpr int kThreadsTC = 320;
 constexpr int kEpiThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
-enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull, kEFull, kWuFull, kWuEmpty, kNumBars };
+enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull, kWuFull, kWuEmpty, kNumBars };
 
 struct TcParams {
   const __half* q16;     // [Bq*Tp, D]
@@ -132,7 +132,8 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     mbar_init(&bars[kCFull], 1);
     mbar_init(&bars[kQFull], 1);
     mbar_init(&bars[kQEmpty], 1);
-    mbar_init(&bars[kSFull], 1);
+    mbar_init(&bars[kSFull0], 1);
+    mbar_init(&bars[kSFull1], 1);
     mbar_init(&bars[kEFull], kEpiThreads);
     mbar_init(&bars[kWuFull], 1);
     mbar_init(&bars[kWuEmpty], kEpiThreads);
@@ -189,9 +190,10 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
             umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
           }
+          if (t == 0) umma_commit(&bars[kSFull0]);       // the tile-0 epilogue group starts while tile 1 runs
         }
         umma_commit(&bars[kQEmpty]);
-        umma_commit(&bars[kSFull]);
+        umma_commit(&bars[kSFull1]);
         mbar_wait(&bars[kEFull], n & 1);
         TGFR_TRACE(n, 18);
         mbar_wait(&bars[kWuEmpty], (n & 1) ^ 1);
@@ -218,7 +220,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     for (int u = u0; u < u1; ++u, ++n) {
       const int b = u / p.G, g = u - b * p.G;
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
-      mbar_wait(&bars[kSFull], n & 1);
+      mbar_wait(&bars[tile == 0 ? kSFull0 : kSFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 2);
       tc_fence_after();
       if (warp_has_rows) {
@@ -268,37 +270,46 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       if (tid == 64) TGFR_TRACE(n, 3);
 
       // ---------------- epi-2: cosine, exp, log-sum ----------------
-      mbar_wait(&bars[kWuFull], n & 1);
-      if (tid == 64) TGFR_TRACE(n, 4);
-      tc_fence_after();
       const int w = lrow;
       const int c = w / TP, t = w - c * TP;
       const int i = g * p.nc + c;
       const bool valid = (w < p.nw_rows) && (i < p.Bq) && (t < __ldg(p.lens + min(i, p.Bq - 1)));
       const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
-      float dot = 0.f, n2 = 0.f;
-      for (int ch = 0; ch < (dhalf >> 5); ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
-        tmem_ld_wait();
-        if (valid) {
-          const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + tile * dhalf + 32 * ch);
+      const int nch = dhalf >> 5;
+      // this thread's half of q_w is fetched before the wait so that its latency hides under GEMM-2
+      uint4 qreg[16];
+      {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + tile * dhalf);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) qreg[k] = (valid && k < 4 * nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&bars[kWuFull], n & 1);
+      if (tid == 64) TGFR_TRACE(n, 4);
+      tc_fence_after();
+      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
+          uint32_t v[32];
+          tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            const uint4 qv = __ldg(qp + cc);
-            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[4 * ch + cc]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 qf = __half22float2(qh[k]);
               const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
               dot = fmaf(qf.x, w0, dot);
-              dot = fmaf(qf.y, w1, dot);
+              dot1 = fmaf(qf.y, w1, dot1);
               n2 = fmaf(w0, w0, n2);
-              n2 = fmaf(w1, w1, n2);
+              n21 = fmaf(w1, w1, n21);
             }
           }
         }
       }
+      dot += dot1;
+      n2 += n21;
       tc_fence_before();
       mbar_arrive(&bars[kWuEmpty]);
       if (tid == 64) TGFR_TRACE(n, 5);
@@ -345,7 +356,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 //   drain   TMEM -> registers (x 1/sigma) -> swizzled fp32 staging -> TMA reduce-add into d ctx
 // sigma is a per-unit power of two that keeps the fp16 gradient operands in the normal range.
 // ---------------------------------------------------------------------------------------------
-enum BarB { bCFull = 0, bQFull, bSFull, bEFull, bWuFull, bDwFull, bDeFull, bDsFull, bDc1, bDc2, bDc3, bDr0, bDr1, bDr2, bDr3, bNum };
+enum BarB { bCFull = 0, bQFull, bSFull0, bSFull1, bEFull, bWuFull, bDwFull, bDeFull0, bDeFull1, bDsFull, bDc1, bDc2, bDc3, bDr0, bDr1, bDr2, bDr3, bNum };
 
 struct TcBwdParams {
   const float* qnorm;    // [Bq*Tp]
@@ -385,11 +396,13 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   if (tid == 0) {
     mbar_init(&bars[bCFull], 1);
     mbar_init(&bars[bQFull], 1);
-    mbar_init(&bars[bSFull], 1);
+    mbar_init(&bars[bSFull0], 1);
+    mbar_init(&bars[bSFull1], 1);
     mbar_init(&bars[bEFull], kEpiThreads);
     mbar_init(&bars[bWuFull], 1);
     mbar_init(&bars[bDwFull], kEpiThreads);
-    mbar_init(&bars[bDeFull], 1);
+    mbar_init(&bars[bDeFull0], 1);
+    mbar_init(&bars[bDeFull1], 1);
     mbar_init(&bars[bDsFull], kEpiThreads);
     for (int k = bDc1; k <= bDc3; ++k) mbar_init(&bars[k], 1);
     for (int k = bDr0; k <= bDr3; ++k) mbar_init(&bars[k], kEpiThreads);
@@ -443,13 +456,15 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         TGFR_TRACE(n, 17);
         tc_fence_after();
         // GEMM-1: S_t = C_t . Q^T
-        for (int t = 0; t < p.n_tiles; ++t)
+        for (int t = 0; t < p.n_tiles; ++t) {
           for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
             const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
             const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
             umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
           }
-        umma_commit(&bars[bSFull]);
+          if (t == 0) umma_commit(&bars[bSFull0]);
+        }
+        umma_commit(&bars[bSFull1]);
         // GEMM-2: Wu = E^T . C
         mbar_wait(&bars[bEFull], n & 1);
         TGFR_TRACE(n, 18);
@@ -464,13 +479,15 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         mbar_wait(&bars[bDwFull], n & 1);
         TGFR_TRACE(n, 19);
         tc_fence_after();
-        for (int t = 0; t < p.n_tiles; ++t)
+        for (int t = 0; t < p.n_tiles; ++t) {
           for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
             const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
             const uint64_t bd = make_smem_desc(a_x + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
             umma_ss(tmem + 256 + t * 128, ad, bd, idesc1, k16 > 0);
           }
-        umma_commit(&bars[bDeFull]);
+          if (t == 0) umma_commit(&bars[bDeFull0]);
+        }
+        umma_commit(&bars[bDeFull1]);
         // GEMM-5/6: four rounds (tile, feature half) of 128-column dC blocks ping-ponging between the two
         // 128-column holes the packed operands leave free: [64,192) for tile 0, [320,448) for tile 1
         mbar_wait(&bars[bDsFull], n & 1);
@@ -529,7 +546,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       const float inv_sigma = 1.f / sigma;
 
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
-      mbar_wait(&bars[bSFull], n & 1);
+      mbar_wait(&bars[tile == 0 ? bSFull0 : bSFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 2);
       tc_fence_after();
       if (warp_has_rows) {
@@ -556,22 +573,32 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
             sum += e[t];
           }
-          const float kinv = (len > 0) ? p.k1 / sum : 0.f, nk1 = -p.k1;
+          const float inv = (len > 0 && live_row) ? 1.f / sum : 0.f, nk1 = -p.k1;
+          uint32_t pa[TP / 2], pe[TP / 2];
 #pragma unroll
-          for (int t = 0; t < TP; ++t) e[t] = (t < len && live_row) ? fast_exp2(fmaf(e[t], kinv, nk1)) : 0.f;
+          for (int t = 0; t < TP; t += 2) {
+            const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
+            e[t] = (t < len && live_row) ? fast_exp2(fmaf(a0, p.k1, nk1)) : 0.f;
+            e[t + 1] = (t + 1 < len && live_row) ? fast_exp2(fmaf(a1, p.k1, nk1)) : 0.f;
+            pa[t >> 1] = pack_half2(a0, a1);
+            pe[t >> 1] = pack_half2(e[t], e[t + 1]);
+          }
+          // A1 and E (fp16) replace the caption's score columns: epi-3 reads them back instead of recomputing
+#pragma unroll
+          for (int j = 0; j < TP / 8; ++j) {
+            tmem_st4(col + 4 * j, pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+            tmem_st4(col + TP / 2 + 4 * j, pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+          }
           if (r < p.Rp) {
 #pragma unroll
             for (int j = 0; j < TP / 8; ++j) {
               const int w0 = c * TP + 8 * j;
-              uint4 pk;
-              pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
-              pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
-              pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
-              pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
-              *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
+              *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
+                  make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
             }
           }
         }
+        tmem_st_wait();
       }
       fence_proxy_async();
       tc_fence_before();
@@ -669,7 +696,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       if (tid == 64) TGFR_TRACE(n, 5);
 
       // ---------------- epi-3: dS and E^ as fp16 A operands, in place in TMEM ----------------
-      mbar_wait(&bars[bDeFull], n & 1);
+      mbar_wait(&bars[tile == 0 ? bDeFull0 : bDeFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 6);
       tc_fence_after();
       if (warp_has_rows) {
@@ -684,42 +711,31 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           const int c = tile ? p.nc - 1 - cc : cc;
           const int i = g * p.nc + c;
           const int len = (i < p.Bq) ? __ldg(p.lens + i) : 0;
+          (void)len;
           uint32_t vs[TP], vd[TP];
 #pragma unroll
           for (int j = 0; j < TP / 8; ++j) {
-            tmem_ld8(s_base + c * TP + 8 * j, vs + 8 * j);
-            tmem_ld8(e_base + c * TP + 8 * j, vd + 8 * j);
+            tmem_ld8(s_base + c * TP + 8 * j, vs + 8 * j);       // [A1 fp16 x TP | E fp16 x TP]
+            tmem_ld8(e_base + c * TP + 8 * j, vd + 8 * j);       // dE^ fp32
           }
           tmem_ld_wait();
-          float a1[TP];
-          float mx = -1e30f;
+          float a1[TP], eh[TP], da[TP];
+          float inner0 = 0.f, inner1 = 0.f;
 #pragma unroll
-          for (int t = 0; t < TP; ++t) {
-            a1[t] = (t < len) ? __uint_as_float(vs[t]) : -INFINITY;
-            mx = fmaxf(mx, a1[t]);
-          }
-          const float nmx = -mx * kLog2e;
-          float sum = 0.f;
-#pragma unroll
-          for (int t = 0; t < TP; ++t) {
-            a1[t] = fast_exp2(fmaf(a1[t], kLog2e, nmx));
-            sum += a1[t];
-          }
-          const float inv = (len > 0 && live_row) ? 1.f / sum : 0.f;     // dead rows / captions: a1 = 0 -> dS = E^ = 0
-          const float nk1 = -p.k1;
-          float inner = 0.f, eh[TP], da[TP];
-#pragma unroll
-          for (int t = 0; t < TP; ++t) {
-            a1[t] *= inv;
-            // invnw is 0 for padding words, which zeroes both operands there
-            eh[t] = fast_exp2(fmaf(p.k1, a1[t], nk1)) * invnw[c * TP + t];
+          for (int t = 0; t < TP; t += 2) {
+            const float2 af = __half22float2(*reinterpret_cast<const __half2*>(&vs[t >> 1]));
+            const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&vs[TP / 2 + (t >> 1)]));
+            const float2 nw = *reinterpret_cast<const float2*>(invnw + c * TP + t);   // 0 for padding words
+            a1[t] = af.x;
+            a1[t + 1] = af.y;
+            eh[t] = ef.x * nw.x;
+            eh[t + 1] = ef.y * nw.y;
             da[t] = p.g1 * eh[t] * __uint_as_float(vd[t]);
-            inner = fmaf(a1[t], da[t], inner);
+            da[t + 1] = p.g1 * eh[t + 1] * __uint_as_float(vd[t + 1]);
+            inner0 = fmaf(a1[t], da[t], inner0);
+            inner1 = fmaf(a1[t + 1], da[t + 1], inner1);
           }
-          if (!live_row) {
-#pragma unroll
-            for (int t = 0; t < TP; ++t) eh[t] = 0.f;
-          }
+          const float inner = inner0 + inner1;
 #pragma unroll
           for (int j = 0; j < TP / 8; ++j) {
             uint32_t ds[4], ee[4];
