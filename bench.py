@@ -36,8 +36,16 @@ B_LOCAL, T, IH, IW, D = 128, 22, 14, 14, 256
 R = IH * IW
 GAMMAS = (4.0, 5.0, 10.0)
 HEAD = dict(B=512, Din=512, C=10177, s=30.0, m=0.5, gamma=2.0)
-FLOPS_PER_PAIR = 12 * T * R * D          # fwd 4TRD + bwd 8TRD (both gradients)
+# fwd 4TRD (2 GEMMs) + bwd 8TRD (4 GEMMs) per pair with both gradients; 10TRD when only the
+# face-side gradient is live, which is what the reference's training scripts run (text side detached,
+# utils/dataset_utils.py:42-46).  Recomputation inside the backward kernel is NOT counted.
+def flops_per_pair(grads):
+    return (12 if grads == "both" else 10) * T * R * D
 L2_BYTES = 126 * 2 ** 20
+
+
+GRADS_DESC = {"both": "face- and text-side gradients",
+              "ctx": "face-side gradient only, text detached as in the reference's training scripts"}
 
 
 def make_args():
@@ -108,13 +116,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: CPU port of the reference implementation
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(ctx, words, img, txt, cid, n_caps=None):
+def cpu_reference_step(ctx, words, img, txt, cid, n_caps=None, grads="both"):
     """One fwd+bwd of words_loss + sent_loss with the reference's op sequence on CPU.
     n_caps < B restricts the per-caption loop to the first n_caps captions (bounded sample)."""
     from oracle import ref_port as P
     B = ctx.shape[0]
     c = torch.from_numpy(ctx).clone().requires_grad_(True)
-    w = torch.from_numpy(words).clone().requires_grad_(True)
+    w = torch.from_numpy(words).clone().requires_grad_(grads == "both")
     a = torch.from_numpy(img).clone().requires_grad_(True)
     b = torch.from_numpy(txt).clone().requires_grad_(True)
     labels = torch.arange(B)
@@ -152,26 +160,27 @@ def run_reference(args):
     ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100)
     img, txt, cid = synth.sentence_inputs(B, D, seed=100)
     # size the per-step sample so that the whole run stays within ~3 minutes
-    t_probe, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps=8)
+    t_probe, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps=8, grads=args.grads)
     per_cap = t_probe / 8
     budget = 150.0 / max(1, args.steps + args.warmup)
     n_caps = int(max(4, min(B, budget / max(per_cap, 1e-6))))
     for _ in range(args.warmup):
-        cpu_reference_step(ctx, words, img, txt, cid, n_caps)
+        cpu_reference_step(ctx, words, img, txt, cid, n_caps, args.grads)
     times, pairs = [], 0
     for _ in range(args.steps):
-        dt, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps)
+        dt, pairs = cpu_reference_step(ctx, words, img, txt, cid, n_caps, args.grads)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = pairs / (ms * 1e-3)
-    sample = (f"{n_caps} of {B} captions x {B} faces per step ({pairs} pairs), T={T}, R={R}, D={D}, fwd+bwd both "
-              f"gradients, + sent_loss B={B}")
+    sample = (f"{n_caps} of {B} captions x {B} faces per step ({pairs} pairs), T={T}, R={R}, D={D}, fwd+bwd "
+              f"({GRADS_DESC[args.grads]}), + sent_loss B={B}")
     line = {
         "impl": "reference", "metric": "fcam_words+sent_loss_fwd_bwd_pairs_per_sec", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: words_loss+sent_loss fwd+bwd B=128 T=22 R=196 D=256 (bounded sample)",
-                   "global_batch": B, "sample": sample},
+        "config": {"workload": f"configs[1]: words_loss+sent_loss fwd+bwd ({GRADS_DESC[args.grads]}), {B} faces x {B} "
+                               f"captions, T={T}, R={R}, D={D} (bounded sample)",
+                   "global_batch": B, "sample": sample, "grads": args.grads},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,7 +221,8 @@ def run_b200(args):
         img, txt, cid = synth.sentence_inputs(B, D, seed=100 + 17 * k + 1000 * rank)
         if k < 2:
             host_sets.append(tuple(torch.from_numpy(a).pin_memory() for a in (ctx, words, img, txt)))
-        sets.append(tuple(torch.from_numpy(a).to(dev).requires_grad_(True) for a in (ctx, words, img, txt)))
+        sets.append(tuple(torch.from_numpy(a).to(dev).requires_grad_(j != 1 or args.grads == "both")
+                          for j, a in enumerate((ctx, words, img, txt))))
     labels = torch.arange(B, device=dev)
     cid_dev = torch.arange(B, device=dev) + rank * B       # distinct classes: mask path runs, nothing masked
 
@@ -285,9 +295,9 @@ def run_b200(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if precision == _lib.PREC_FP32 else "f16-operand/f32-accumulate",
         "data": "synthetic",
-        "config": {"workload": f"configs[1]: words_loss+sent_loss fwd+bwd (both gradients), {B} faces x {Bg} captions "
-                               f"per rank, T={T}, R={R}, D={D}",
-                   "global_batch": Bg, "local_batch": B, "parallelism": f"row-sharded x{world}",
+        "config": {"workload": f"configs[1]: words_loss+sent_loss fwd+bwd ({GRADS_DESC[args.grads]}), {B} faces x {Bg} "
+                               f"captions per rank, T={T}, R={R}, D={D}",
+                   "global_batch": Bg, "local_batch": B, "grads": args.grads, "parallelism": f"row-sharded x{world}",
                    "precision": "fp32-simt" if precision == _lib.PREC_FP32 else "tcgen05",
                    "l2": f"rotating {n_sets} input sets ({n_sets * bytes_per_set >> 20} MiB > 126 MiB L2)"},
         "clocks": clk.result, "e2e": e2e, "gpu_launches": launches,
@@ -300,7 +310,7 @@ def run_b200(args):
         wall = torch.cat([w] * world) if world > 1 else w
         gsim = torch.randn(B, Bg, device=dev) / Bg
         dctx = torch.empty(B, R, D, device=dev)
-        dwords = torch.empty(Bg, T, D, device=dev)
+        dwords = torch.empty(Bg, T, D, device=dev) if args.grads == "both" else None
         lib = _lib.load()
         wsb = lib.tgfr_wordregion_workspace_bytes(B, Bg, T, R, D, precision)
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
@@ -309,7 +319,7 @@ def run_b200(args):
         def bwd_call():
             _lib.check(lib.tgfr_wordregion_bwd(c.data_ptr(), *c.stride(), wall.data_ptr(), *wall.stride(), 0, B, Bg,
                                                T, R, D, *GAMMAS, 1e-8, gsim.data_ptr(), dctx.data_ptr(),
-                                               dwords.data_ptr(), precision, ws.data_ptr(), wsb, st), "bwd")
+                                               _lib.ptr(dwords), precision, ws.data_ptr(), wsb, st), "bwd")
         flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
         ks = []
         for k in range(3 + max(3, min(args.steps, 10))):
@@ -321,13 +331,14 @@ def run_b200(args):
             if k >= 3:
                 ks.append(e0.elapsed_time(e1))
         k_ms = sum(ks) / len(ks)
-        flops = 8 * T * R * D * B * Bg
+        flops = (8 if args.grads == "both" else 6) * T * R * D * B * Bg
         achieved = flops / (k_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                             "frac": achieved / pk["tf_burst"], "traffic": None, "kernel": "wordregion_bwd",
                             "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                             "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
-                            "step_frac_of_peak": FLOPS_PER_PAIR * B * Bg / (ms * 1e-3) / 1e12 / pk["tf_sus"]}
+                            "step_tflops": flops_per_pair(args.grads) * B * Bg / (ms * 1e-3) / 1e12,
+                            "step_frac_of_peak": flops_per_pair(args.grads) * B * Bg / (ms * 1e-3) / 1e12 / pk["tf_sus"]}
 
         # ---- margin head (BASELINE configs[2]) reported beside the headline metric
         h = HEAD
@@ -367,10 +378,10 @@ def run_b200(args):
             torch.set_num_threads(cores)
             ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100)
             img, txt, cid = synth.sentence_inputs(B, D, seed=100)
-            cpu_reference_step(ctx, words, img, txt, cid, n_caps=4)          # warm-up
+            cpu_reference_step(ctx, words, img, txt, cid, n_caps=4, grads=args.grads)          # warm-up
             t_used, n_pairs, n_caps = 0.0, 0, 32
             while t_used < 10.0:
-                dt, p = cpu_reference_step(ctx, words, img, txt, cid, n_caps=n_caps)
+                dt, p = cpu_reference_step(ctx, words, img, txt, cid, n_caps=n_caps, grads=args.grads)
                 t_used += dt
                 n_pairs += p
             line["cpu_baseline"] = {"value": n_pairs / t_used, "unit": "pairs/s", "cores": torch.get_num_threads(),
@@ -390,6 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grads", default="ctx", choices=["ctx", "both"],
+                    help="gradients of the word-region loss: ctx = face side only (the reference's training step), both")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -75,8 +75,9 @@ def merge_column_stats(colmax, colsum, group=None):
     Returns the global (max, sum) per column."""
     n, _ = _world(group)
     both = torch.stack([colmax, colsum]).contiguous()                # [2, By]
-    gathered = torch.empty((n,) + tuple(both.shape), dtype=both.dtype, device=both.device)
+    gathered = torch.empty((n * 2, both.shape[1]), dtype=both.dtype, device=both.device)   # concatenated along dim 0
     dist.all_gather_into_tensor(gathered, both, group=group)
+    gathered = gathered.view(n, 2, both.shape[1])
     maxes, sums = gathered[:, 0], gathered[:, 1]                     # [n, By]
     gmax = maxes.max(dim=0).values
     gsum = (sums * torch.exp(maxes - gmax)).sum(dim=0)

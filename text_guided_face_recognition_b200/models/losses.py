@@ -98,10 +98,12 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size,
     feats = img_features.permute(0, 2, 3, 1).reshape(B, ih * iw, D)
     words = words_emb.transpose(1, 2)[:, :T]
     sim, attn = ops.wordregion_sim(feats, words, lens_dev, g1, g2, g3, 1e-8, None, True, 0)
-    att_maps = []
-    for i in range(B):
-        n = min(lens_host[i], T)
-        att_maps.append(attn[i:i + 1, :n].reshape(1, n, ih, iw))
+    # list of B views [1, words_num_i, ih, iw] (losses.py:97); one unbind instead of B slicing ops
+    maps = attn.reshape(B, 1, T, ih, iw).unbind(0)
+    if all(n >= T for n in lens_host):
+        att_maps = list(maps)
+    else:
+        att_maps = [m[:, :min(n, T)] for m, n in zip(maps, lens_host)]
     if labels is None:
         return None, None, att_maps
     _require_arange(labels, B, "words_loss")

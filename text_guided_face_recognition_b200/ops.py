@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 
 __all__ = [
-    "default_precision", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
+    "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
     "mag_logits", "func_attention_canonical", "launch_counter",
 ]
 
@@ -27,9 +27,9 @@ launch_counter = _LaunchCounter
 
 
 def default_precision() -> int:
-    """TGFR_WORDREGION_PRECISION = fp32 | tc  (default: tc when built)."""
-    v = os.environ.get("TGFR_WORDREGION_PRECISION", "fp32").lower()
-    return PREC_TC if v in ("tc", "tensor", "1") else PREC_FP32
+    """TGFR_WORDREGION_PRECISION = tc (default: tcgen05, fp16 operands / fp32 accumulate) | fp32 (SIMT)."""
+    v = os.environ.get("TGFR_WORDREGION_PRECISION", "tc").lower()
+    return PREC_FP32 if v in ("fp32", "simt", "0") else PREC_TC
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -99,10 +99,20 @@ class _WordRegionSim(torch.autograd.Function):
         return dctx, dwords, None, None, None, None, None, None, None, None
 
 
+def tc_supported(T, R, D) -> bool:
+    """Shapes the tcgen05 kernels take (csrc/wordregion_tc.cu make_plan); others run the fp32 SIMT kernels."""
+    return D % 64 == 0 and 64 <= D <= 256 and 1 <= R <= 256 and 1 <= T <= 32
+
+
 def wordregion_sim(feats, words, cap_lens, g1, g2, g3, eps=1e-8, precision=None, want_attn=True, diag_off=0):
-    """sim [Bc,Bq] (differentiable) and the diagonal attention maps [Bc,T,R] (or None)."""
+    """sim [Bc,Bq] (differentiable) and the diagonal attention maps [Bc,T,R] (or None).
+
+    precision=None: TGFR_WORDREGION_PRECISION (default tc) when the shape fits the tensor-core kernel,
+    else the fp32 SIMT CUDA kernel.  An explicit PREC_TC on an unsupported shape raises."""
     if precision is None:
         precision = default_precision()
+        if precision == PREC_TC and not tc_supported(words.shape[1], feats.shape[1], feats.shape[2]):
+            precision = PREC_FP32
     if cap_lens is not None:
         cap_lens = cap_lens.to(device=feats.device, dtype=torch.int32).contiguous()
     return _WordRegionSim.apply(_f32(feats), _f32(words), cap_lens, float(g1), float(g2), float(g3), float(eps),
