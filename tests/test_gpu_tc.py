@@ -132,3 +132,36 @@ def test_tc_backward_vs_oracle(B, T, R, D, flavour, ragged):
     assert err < TC_GRAD_RTOL, err
     worst = max(np.linalg.norm(got[b] - ref[b]) / np.linalg.norm(ref[b]) for b in range(B))
     assert worst < 2 * TC_GRAD_RTOL, worst
+
+
+@pytest.mark.parametrize("B,T,R,D,flavour,ragged", [
+    (8, 22, 196, 256, "BERT", False),
+    (16, 18, 196, 256, "LSTM", True),
+    (6, 7, 16, 64, "LSTM", True),
+    (5, 30, 49, 128, "BERT", False),
+    (7, 12, 130, 192, "LSTM", True),
+    (32, 22, 196, 256, "BERT", False),
+])
+def test_tc_backward_words_vs_oracle(B, T, R, D, flavour, ragged):
+    """Text-side gradient on the tensor cores (DQ pass), alone and together with the face-side gradient."""
+    from text_guided_face_recognition_b200 import _lib, ops
+    ctx, words, cap = synth.wordregion_inputs(B, T, R, D, flavour, seed=100, ragged=ragged)
+    capt = None if cap is None else torch.from_numpy(cap).cuda()
+    rc, rw = O.words_loss_grads(ctx, words, None, cap, 4.0, 5.0, 10.0)
+    for both in (False, True):
+        feats = torch.from_numpy(ctx).cuda().requires_grad_(both)
+        wd = torch.from_numpy(words).cuda().requires_grad_(True)
+        sim, _ = ops.wordregion_sim(feats, wd, capt, 4.0, 5.0, 10.0, precision=_lib.PREC_TC, want_attn=False)
+        l0, l1 = ops.pair_ce(sim)
+        (l0 + l1).backward()
+        torch.cuda.synchronize()
+        got = wd.grad.cpu().numpy()
+        assert np.isfinite(got).all()
+        err = np.linalg.norm(got - rw) / np.linalg.norm(rw)
+        assert err < TC_GRAD_RTOL, err
+        if cap is not None:                                   # words beyond a caption's length get exactly zero
+            for i in range(B):
+                assert not got[i, int(cap[i]):].any()
+        if both:
+            errc = np.linalg.norm(feats.grad.cpu().numpy() - rc) / np.linalg.norm(rc)
+            assert errc < TC_GRAD_RTOL, errc

@@ -32,8 +32,8 @@ int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int
                       const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t,
                       cudaStream_t);
 int wordregion_bwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
-                      const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, void*, size_t,
-                      cudaStream_t);
+                      const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, float*, void*,
+                      size_t, cudaStream_t);
 int wordregion_tc_set_trace(void*);
 // dense_simt.cu
 int cosine_scores_fwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const int64_t*,
@@ -122,16 +122,8 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         void* stream) {
   TGFR_REQUIRE(ctx && words && gsim, "wordregion_bwd: NULL tensor");
   if (precision == TGFR_PREC_TC) {
-    // d ctx on the tensor cores; d words (never needed by the reference's training scripts, whose text side is
-    // detached) still comes from the fp32 kernel
-    if (dctx) {
-      if (int rc = wordregion_bwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,
-                                     gamma1, gamma2, gamma3, gsim, dctx, workspace, workspace_bytes, ST(stream)))
-        return rc;
-    }
-    if (!dwords) return TGFR_OK;
-    return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
-                               gamma2, gamma3, eps, gsim, nullptr, dwords, ST(stream));
+    return wordregion_bwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
+                             gamma2, gamma3, gsim, dctx, dwords, workspace, workspace_bytes, ST(stream));
   }
   TGFR_REQUIRE(precision == TGFR_PREC_FP32, "wordregion_bwd: unknown precision %d", precision);
   return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,

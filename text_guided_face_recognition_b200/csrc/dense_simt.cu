@@ -77,6 +77,68 @@ struct Gemm {
 
 constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
 
+__device__ __forceinline__ float gemm_epilogue(const Gemm& g, float acc, int m, int n, float na, float nb) {
+  float v;
+  if (g.mode == kEpiCosine) {
+    v = acc / fmaxf(na * nb, g.eps) * g.alpha;
+    if (g.ids_m && g.ids_n && (m + g.diag_off) != n && __ldg(g.ids_m + m) == __ldg(g.ids_n + n)) v = -INFINITY;
+  } else {
+    v = acc;
+    if (g.am) v /= fmaxf(na, g.norm_eps);
+    if (g.bn) v /= fmaxf(nb, g.norm_eps);
+    if (g.mode == kEpiClamp) v = fminf(fmaxf(v, -1.f), 1.f);
+    v *= g.alpha;
+  }
+  return v;
+}
+
+// Latency-bound shapes (the B x B sentence-loss matrices: 2*B*B*D flops on < 1 MB): one warp per 4 x 4 output
+// tile, lanes split K, so that a 128 x 128 product already fills the GPU with 128 CTAs instead of four 64 x 64 tiles.
+__global__ void __launch_bounds__(256) sgemm_small_kernel(const Gemm g) {
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (g.N + 3) >> 2;
+  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int m0 = (tile / tiles_n) << 2, n0 = (tile % tiles_n) << 2;
+  if (m0 >= g.M) return;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k = lane; k < g.K; k += 32) {
+    float a[4], b[4];
+    const float bden = g.bk ? fmaxf(__ldg(g.bk + k), g.norm_eps) : 1.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = (m0 + i < g.M) ? __ldg(g.A + (int64_t)(m0 + i) * g.sAm + (int64_t)k * g.sAk) : 0.f;
+      b[i] = (n0 + i < g.N) ? __ldg(g.B + (int64_t)k * g.sBk + (int64_t)(n0 + i) * g.sBn) : 0.f;
+      if (g.bk) b[i] = b[i] / bden;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = warp_sum(acc[i][j]);
+  if (lane < 16) {
+    const int i = lane >> 2, j = lane & 3;
+    const int m = m0 + i, n = n0 + j;
+    if (m < g.M && n < g.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (ii == i && jj == j) v = acc[ii][jj];
+      const float na = g.am ? __ldg(g.am + m) : 1.f, nb = g.bn ? __ldg(g.bn + n) : 1.f;
+      g.C[(int64_t)m * g.sCm + (int64_t)n * g.sCn] = gemm_epilogue(g, v, m, n, na, nb);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(GT) sgemm_kernel(const Gemm g) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -135,24 +197,19 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(const Gemm g) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
       const float nb = g.bn ? __ldg(g.bn + n) : 1.f;
-      float v;
-      if (g.mode == kEpiCosine) {
-        v = acc[i][j] / fmaxf(na * nb, g.eps) * g.alpha;
-        if (g.ids_m && g.ids_n && (m + g.diag_off) != n && __ldg(g.ids_m + m) == __ldg(g.ids_n + n)) v = -INFINITY;
-      } else {
-        v = acc[i][j];
-        if (g.am) v /= fmaxf(na, g.norm_eps);
-        if (g.bn) v /= fmaxf(nb, g.norm_eps);
-        if (g.mode == kEpiClamp) v = fminf(fmaxf(v, -1.f), 1.f);
-        v *= g.alpha;
-      }
-      g.C[(int64_t)m * g.sCm + (int64_t)n * g.sCn] = v;
+      g.C[(int64_t)m * g.sCm + (int64_t)n * g.sCn] = gemm_epilogue(g, acc[i][j], m, n, na, nb);
     }
   }
 }
 
 int launch_gemm(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return TGFR_OK;
+  if ((int64_t)g.M * g.N <= 512 * 512 && g.K <= 1024) {
+    const int tiles = ceil_div(g.M, 4) * ceil_div(g.N, 4);
+    sgemm_small_kernel<<<ceil_div(tiles, 8), 256, 0, st>>>(g);
+    TGFR_LAUNCH_OK();
+    return TGFR_OK;
+  }
   const dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
   sgemm_kernel<<<grid, GT, 0, st>>>(g);
   TGFR_LAUNCH_OK();

@@ -372,7 +372,11 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
                : "memory");
 }
 
-template <int TP>
+// DQ = false: d ctx (GEMM-5/6 above).  DQ = true: d words -- epi-3 writes dS' = dS + ca_w E^ (the second term is the
+// direct cosine gradient through Wu = E^T C) as fp16 into shared memory in the E layout, GEMM-4
+// dQ[w,d] = sum_r dS'[r,w] c_r[d] reuses GEMM-2's descriptors, and the drain subtracts the direct term in q_w and
+// reduce-adds into the padded [Bq*Tp, D] gradient (tm_dc is then the map of that buffer).
+template <int TP, bool DQ>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_dc, const TcBwdParams p) {
@@ -387,6 +391,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   float2* part = reinterpret_cast<float2*>(misc + 256);      // [128] half-1 partials, then (ca, cb)
   float* exs = reinterpret_cast<float*>(misc + 256 + 1024);  // [128]
   float* invnw = exs + 128;                                  // [128] 1/|Wu_w| (0 for padding words)
+  float* cqs = invnw + 128;                                  // [128] DQ: coefficient of q_w in the direct term
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
@@ -488,33 +493,47 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           if (t == 0) umma_commit(&bars[bDeFull0]);
         }
         umma_commit(&bars[bDeFull1]);
-        // GEMM-5/6: four rounds (tile, feature half) of 128-column dC blocks ping-ponging between the two
-        // 128-column holes the packed operands leave free: [64,192) for tile 0, [320,448) for tile 1
-        mbar_wait(&bars[bDsFull], n & 1);
-        TGFR_TRACE(n, 20);
-        tc_fence_after();
-        for (int rd = 0; rd < 4; ++rd) {
-          const int t = rd & 1, half = rd >> 1;
-          if (rd >= 2) {                                   // the hole's previous block has been drained
-            mbar_wait(&bars[bDr0 + rd - 2], n & 1);
-            tc_fence_after();
+        if constexpr (DQ) {
+          // GEMM-4: dQ[w,d] = sum_r dS'[r,w] c_r[d]  (A = the tile epi-3 wrote, MN-major; B = C, MN-major)
+          mbar_wait(&bars[bDsFull], n & 1);
+          TGFR_TRACE(n, 20);
+          tc_fence_after();
+          for (int j = 0; j < (p.Rp >> 4); ++j) {
+            const uint64_t ad = make_smem_desc(a_x + j * 2048, p.e_panel, 1024);
+            const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
+            umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
           }
-          const int ncols = min(p.D - half * 128, 128);
-          if (t < p.n_tiles && ncols > 0) {
-            const uint32_t idesc5 = make_idesc_f16(128, ncols, false, true);   // A in TMEM, B MN-major
-            const uint32_t dcol = tmem + (t ? 320 : 64);
-            for (int k16 = 0; k16 < 8; ++k16) {
-              const uint64_t bx = make_smem_desc(a_x + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
-              umma_ts(dcol, tmem + 256 + t * 192 + 8 * k16, bx, idesc5, k16 > 0);      // E^ . dW^
+          umma_commit(&bars[bDc1]);
+          TGFR_TRACE(n, 21);
+        } else {
+          // GEMM-5/6: four rounds (tile, feature half) of 128-column dC blocks ping-ponging between the two
+          // 128-column holes the packed operands leave free: [64,192) for tile 0, [320,448) for tile 1
+          mbar_wait(&bars[bDsFull], n & 1);
+          TGFR_TRACE(n, 20);
+          tc_fence_after();
+          for (int rd = 0; rd < 4; ++rd) {
+            const int t = rd & 1, half = rd >> 1;
+            if (rd >= 2) {                                   // the hole's previous block has been drained
+              mbar_wait(&bars[bDr0 + rd - 2], n & 1);
+              tc_fence_after();
             }
-            for (int k16 = 0; k16 < 8; ++k16) {
-              const uint64_t bq = make_smem_desc(a_q + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
-              umma_ts(dcol, tmem + t * 192 + 8 * k16, bq, idesc5, true);                // dS . Q
+            const int ncols = min(p.D - half * 128, 128);
+            if (t < p.n_tiles && ncols > 0) {
+              const uint32_t idesc5 = make_idesc_f16(128, ncols, false, true);   // A in TMEM, B MN-major
+              const uint32_t dcol = tmem + (t ? 320 : 64);
+              for (int k16 = 0; k16 < 8; ++k16) {
+                const uint64_t bx = make_smem_desc(a_x + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
+                umma_ts(dcol, tmem + 256 + t * 192 + 8 * k16, bx, idesc5, k16 > 0);      // E^ . dW^
+              }
+              for (int k16 = 0; k16 < 8; ++k16) {
+                const uint64_t bq = make_smem_desc(a_q + 2 * half * p.q_panel + k16 * 2048, p.q_panel, 1024);
+                umma_ts(dcol, tmem + t * 192 + 8 * k16, bq, idesc5, true);                // dS . Q
+              }
             }
-          }
-          if (rd >= 1) {
-            umma_commit(&bars[bDc1 + rd - 1]);
-            TGFR_TRACE(n, 20 + rd);
+            if (rd >= 1) {
+              umma_commit(&bars[bDc1 + rd - 1]);
+              TGFR_TRACE(n, 20 + rd);
+            }
           }
         }
         // the next unit's GEMM-1 overwrites the accumulator holes: wait until they are drained
@@ -665,6 +684,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         }
         part[w] = make_float2(ca, cb);
         invnw[w] = inw;
+        if constexpr (DQ) cqs[w] = valid ? ca * cosv / nq : 0.f;
       }
       epi_bar_sync();
       {
@@ -696,7 +716,8 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       if (tid == 64) TGFR_TRACE(n, 5);
 
       // ---------------- epi-3: dS and E^ as fp16 A operands, in place in TMEM ----------------
-      mbar_wait(&bars[tile == 0 ? bDeFull0 : bDeFull1], n & 1);
+      // (DQ: the tile written below is GEMM-3's B operand, so every GEMM-3 MMA must have retired)
+      mbar_wait(&bars[(tile == 0 && !DQ) ? bDeFull0 : bDeFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 6);
       tc_fence_after();
       if (warp_has_rows) {
@@ -736,81 +757,158 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             inner1 = fmaf(a1[t + 1], da[t + 1], inner1);
           }
           const float inner = inner0 + inner1;
+          if constexpr (DQ) {
+            if (r < p.Rp) {
 #pragma unroll
-          for (int j = 0; j < TP / 8; ++j) {
-            uint32_t ds[4], ee[4];
+              for (int j = 0; j < TP / 8; ++j) {
+                uint32_t ds[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int t0 = 8 * j + 2 * k;
-              ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
-              ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
+                for (int k = 0; k < 4; ++k) {
+                  const int t0 = 8 * j + 2 * k;
+                  const float ca0 = part[c * TP + t0].x, ca1 = part[c * TP + t0 + 1].x;
+                  const float e0 = live_row ? eh[t0] : 0.f, e1 = live_row ? eh[t0 + 1] : 0.f;
+                  ds[k] = pack_half2(fmaf(ca0, e0, a1[t0] * (da[t0] - inner)), fmaf(ca1, e1, a1[t0 + 1] * (da[t0 + 1] - inner)));
+                }
+                const int w0 = c * TP + 8 * j;
+                *reinterpret_cast<uint4*>(s_x + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
+                    make_uint4(ds[0], ds[1], ds[2], ds[3]);
+              }
             }
-            tmem_st4(s_pack + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
-            tmem_st4(e_pack + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TP / 8; ++j) {
+              uint32_t ds[4], ee[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int t0 = 8 * j + 2 * k;
+                ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
+                ee[k] = pack_half2(eh[t0], eh[t0 + 1]);
+              }
+              tmem_st4(s_pack + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
+              tmem_st4(e_pack + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+            }
           }
         }
-        // zero the K padding (words nw..127) of both operands
-        for (int col = p.nw_rows >> 1; col < 64; col += 4) {
-          tmem_st4(s_pack + col, 0u, 0u, 0u, 0u);
-          tmem_st4(e_pack + col, 0u, 0u, 0u, 0u);
+        if constexpr (!DQ) {
+          // zero the K padding (words nw..127) of both operands
+          for (int col = p.nw_rows >> 1; col < 64; col += 4) {
+            tmem_st4(s_pack + col, 0u, 0u, 0u, 0u);
+            tmem_st4(e_pack + col, 0u, 0u, 0u, 0u);
+          }
         }
         tmem_st_wait();
       }
+      if constexpr (DQ) fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[bDsFull]);
       if (tid == 64) TGFR_TRACE(n, 7);
 
-      // ---------------- drain: dC blocks -> per-warp staging ring -> TMA reduce-add ----------------
-      // Every warp drains 32 lanes x 64 columns of each block through three 2 KB boxes (32 rows x 16 floats,
-      // 64B swizzle) that overlay operand panels 0/1 of Q (warps 2-5) and dW^ (warps 6-9); those panels are
-      // dead once rounds 0 and 1 have retired (bDc1).
-      for (int rd = 0; rd < 4; ++rd) {
-        const int t = rd & 1, half = rd >> 1;
-        if (rd != 1) {
-          mbar_wait(&bars[rd == 0 ? bDc1 : bDc1 + rd - 1], n & 1);
-          tc_fence_after();
-        }
-        if (rd == 0 && tid == 64) TGFR_TRACE(n, 8);
-        const int col0 = half * 128 + tile * 64;             // first feature this warp drains
-        const int row0 = t * 128 + quarter_w * 32;
-        if (t < p.n_tiles && row0 < p.R && col0 < p.D && gmax > 0.f) {
-          const uint32_t dcol = tmem + t_lane + (t ? 320 : 64) + tile * 64;
+      if constexpr (DQ) {
+        // ---------------- drain (DQ): (dQ block - cq_w q_w) / sigma -> staging ring -> TMA reduce-add ----------------
+        mbar_wait(&bars[bDc1], n & 1);
+        if (tid == 64) TGFR_TRACE(n, 8);
+        tc_fence_after();
+        if (gmax > 0.f && quarter_w * 32 < p.nw_rows) {
+          uint8_t* const stage_q = s_x + 1024 + (warp - 2) * 6144;     // the dS' tile is dead once GEMM-4 has retired
+          const bool row_ok = lrow < p.nw_rows;                          // lanes beyond the group hold no words
+          const float cq = cqs[lrow];
+          const int nchq = dhalf >> 5;
 #pragma unroll 1
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < nchq; ++ch) {
+            const int d0 = tile * dhalf + 32 * ch;
             uint32_t v[32];
-            tmem_ld32(dcol + 32 * ch, v);
+            tmem_ld32(tmem + t_lane + 256 + d0, v);
             tmem_ld_wait();
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-              uint8_t* buf = stage + ring * 2048;
-              if (lane == 0) tma_wait_group_read<2>();       // the box written three stores ago has been read
+              uint8_t* buf = stage_q + ring * 2048;
+              if (lane == 0) tma_wait_group_read<2>();
               __syncwarp();
 #pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16) {
-                float4 o;
-                o.x = __uint_as_float(v[16 * sub + 4 * c16 + 0]) * inv_sigma;
-                o.y = __uint_as_float(v[16 * sub + 4 * c16 + 1]) * inv_sigma;
-                o.z = __uint_as_float(v[16 * sub + 4 * c16 + 2]) * inv_sigma;
-                o.w = __uint_as_float(v[16 * sub + 4 * c16 + 3]) * inv_sigma;
-                *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = o;
+              for (int h8 = 0; h8 < 2; ++h8) {
+                const int dd = d0 + 16 * sub + 8 * h8;
+                const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (dd >> 6) * p.q_panel + sw128_offset(lrow, (dd & 63) >> 3));
+                const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 qf = __half22float2(qh[k]);
+                  o[2 * k] = row_ok ? (__uint_as_float(v[16 * sub + 8 * h8 + 2 * k]) - cq * qf.x) * inv_sigma : 0.f;
+                  o[2 * k + 1] = row_ok ? (__uint_as_float(v[16 * sub + 8 * h8 + 2 * k + 1]) - cq * qf.y) * inv_sigma : 0.f;
+                }
+                const int c16 = 2 * h8;
+                *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(buf + lane * 64 + (((c16 + 1) ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(o[4], o[5], o[6], o[7]);
               }
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_reduce_add_3d(&tm_dc, buf, col0 + 32 * ch + 16 * sub, row0, b);
+                tma_reduce_add_3d(&tm_dc, buf, d0 + 16 * sub, g * p.nw_rows + quarter_w * 32, 0);
                 tma_commit_group();
               }
               ring = ring == 2 ? 0 : ring + 1;
             }
           }
         }
-        if (rd == 3) {                                        // Q / X are handed back to the producer
-          if (lane == 0) tma_wait_group_read<0>();
-          __syncwarp();
-        }
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
         tc_fence_before();
-        mbar_arrive(&bars[bDr0 + rd]);
-        if (tid == 64) TGFR_TRACE(n, 9 + rd);
+        mbar_arrive(&bars[bDr3]);
+        if (tid == 64) TGFR_TRACE(n, 12);
+      } else {
+        // ---------------- drain: dC blocks -> per-warp staging ring -> TMA reduce-add ----------------
+        // Every warp drains 32 lanes x 64 columns of each block through three 2 KB boxes (32 rows x 16 floats,
+        // 64B swizzle) that overlay operand panels 0/1 of Q (warps 2-5) and dW^ (warps 6-9); those panels are
+        // dead once rounds 0 and 1 have retired (bDc1).
+        for (int rd = 0; rd < 4; ++rd) {
+          const int t = rd & 1, half = rd >> 1;
+          if (rd != 1) {
+            mbar_wait(&bars[rd == 0 ? bDc1 : bDc1 + rd - 1], n & 1);
+            tc_fence_after();
+          }
+          if (rd == 0 && tid == 64) TGFR_TRACE(n, 8);
+          const int col0 = half * 128 + tile * 64;             // first feature this warp drains
+          const int row0 = t * 128 + quarter_w * 32;
+          if (t < p.n_tiles && row0 < p.R && col0 < p.D && gmax > 0.f) {
+            const uint32_t dcol = tmem + t_lane + (t ? 320 : 64) + tile * 64;
+  #pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+              uint32_t v[32];
+              tmem_ld32(dcol + 32 * ch, v);
+              tmem_ld_wait();
+  #pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                uint8_t* buf = stage + ring * 2048;
+                if (lane == 0) tma_wait_group_read<2>();       // the box written three stores ago has been read
+                __syncwarp();
+  #pragma unroll
+                for (int c16 = 0; c16 < 4; ++c16) {
+                  float4 o;
+                  o.x = __uint_as_float(v[16 * sub + 4 * c16 + 0]) * inv_sigma;
+                  o.y = __uint_as_float(v[16 * sub + 4 * c16 + 1]) * inv_sigma;
+                  o.z = __uint_as_float(v[16 * sub + 4 * c16 + 2]) * inv_sigma;
+                  o.w = __uint_as_float(v[16 * sub + 4 * c16 + 3]) * inv_sigma;
+                  *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = o;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_reduce_add_3d(&tm_dc, buf, col0 + 32 * ch + 16 * sub, row0, b);
+                  tma_commit_group();
+                }
+                ring = ring == 2 ? 0 : ring + 1;
+              }
+            }
+          }
+          if (rd == 3) {                                        // Q / X are handed back to the producer
+            if (lane == 0) tma_wait_group_read<0>();
+            __syncwarp();
+          }
+          tc_fence_before();
+          mbar_arrive(&bars[bDr0 + rd]);
+          if (tid == 64) TGFR_TRACE(n, 9 + rd);
+        }
       }
     }
     if (lane == 0) tma_wait_group<0>();
@@ -826,7 +924,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 struct TcPlan {
   int Tp, Rp, nc, G, nw_rows, n_tiles;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
-  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_total;
+  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_dq, ws_total;
 };
 
 int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
@@ -852,7 +950,8 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   pl->ws_q16 = align_up((size_t)Bc * R * D * 2, 256);
   pl->ws_qnorm = pl->ws_q16 + align_up((size_t)Bq * pl->Tp * D * 2, 256);
   pl->ws_lens = pl->ws_qnorm + align_up((size_t)Bq * pl->Tp * 4, 256);
-  pl->ws_total = pl->ws_lens + align_up((size_t)Bq * 4, 256);
+  pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4, 256);                       // padded fp32 d words [Bq*Tp, D]
+  pl->ws_total = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);
   return TGFR_OK;
 }
 
@@ -877,7 +976,7 @@ int make_bwd_plan(int Bq, int T, int R, int D, TcBwdPlan* pl) {
     uint32_t q_bytes = kch * q_panel, x_bytes = kch * q_panel + 1024;
     if (q_bytes < 24576) q_bytes = 24576;                       // drain staging rings (4 warps x 3 x 2 KB)
     if (x_bytes < 2 * pl->e_panel) x_bytes = 2 * pl->e_panel;
-    if (x_bytes < 24576 + 1024) x_bytes = 24576 + 1024;
+    if (x_bytes < 49152 + 1024) x_bytes = 49152 + 1024;         // DQ drain: 8 warps x 3 x 2 KB over the dead dS' tile
     // with more than two feature panels the rings must fit in panels 0/1, which are dead while rounds 2/3 run
     if (kch > 2 && 2 * q_panel < 24576 + 1024) continue;
     const uint32_t off_q = kch * pl->c_panel, off_x = off_q + q_bytes, off_misc = off_x + x_bytes;
@@ -893,11 +992,23 @@ int make_bwd_plan(int Bq, int T, int R, int D, TcBwdPlan* pl) {
   return TGFR_E_INVALID;
 }
 
+// dwords[i, t, :] = dq_pad[i * Tp + t, :]  (the padded rows t >= T are dropped)
+__global__ void wr_tc_unpad_kernel(const float* __restrict__ dq_pad, float* __restrict__ dwords, int Bq, int T, int Tp, int D) {
+  const int64_t n4 = (int64_t)Bq * T * (D >> 2);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (int64_t)gridDim.x * blockDim.x) {
+    const int d4 = (int)(k % (D >> 2));
+    const int64_t row = k / (D >> 2);
+    const int i = (int)(row / T), t = (int)(row - (int64_t)i * T);
+    reinterpret_cast<float4*>(dwords)[k] = reinterpret_cast<const float4*>(dq_pad)[((int64_t)i * Tp + t) * (D >> 2) + d4];
+  }
+}
+
 }  // namespace
 
 int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* words, int64_t wsb,
                       int64_t wst, int64_t wsd, const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D, float g1,
-                      float g2, float g3, const float* gsim, float* dctx, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      float g2, float g3, const float* gsim, float* dctx, float* dwords, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
   TcPlan fp;
   if (int rc = make_plan(Bc, Bq, T, R, D, &fp)) return rc;     // workspace layout is shared with the forward
   TcBwdPlan pl;
@@ -905,24 +1016,25 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   TGFR_REQUIRE(ws != nullptr && ws_bytes >= fp.ws_total, "wordregion(tc): workspace too small (%zu < %zu)", ws_bytes,
                fp.ws_total);
   TGFR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "wordregion(tc): workspace must be 256-byte aligned");
-  TGFR_REQUIRE((reinterpret_cast<uintptr_t>(dctx) & 15) == 0, "wordregion(tc): dctx must be 16-byte aligned");
+  TGFR_REQUIRE(!dctx || (reinterpret_cast<uintptr_t>(dctx) & 15) == 0, "wordregion(tc): dctx must be 16-byte aligned");
+  TGFR_REQUIRE(!dwords || (reinterpret_cast<uintptr_t>(dwords) & 15) == 0, "wordregion(tc): dwords must be 16-byte aligned");
+  if (!dctx && !dwords) return TGFR_OK;
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   __half* c16 = reinterpret_cast<__half*>(base + fp.ws_c16);
   __half* q16 = reinterpret_cast<__half*>(base + fp.ws_q16);
   float* qnorm = reinterpret_cast<float*>(base + fp.ws_qnorm);
   int* lens = reinterpret_cast<int*>(base + fp.ws_lens);
+  float* dq_pad = reinterpret_cast<float*>(base + fp.ws_dq);
 
   const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
   wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc, Bq,
                                                                T, pl.Tp, R, D, c16, q16, qnorm, lens);
   TGFR_LAUNCH_OK();
-  TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
 
-  CUtensorMap tm_c, tm_q, tm_dc;
+  CUtensorMap tm_c, tm_q;
   if (int rc = make_tmap_3d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, pl.c_rows, 1)) return rc;
   if (int rc = make_tmap_3d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * pl.Tp, 1, 64, pl.nw_rows, 1))
     return rc;
-  if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 16, 32, 1, 64)) return rc;
 
   TcBwdParams p{};
   p.qnorm = qnorm; p.lens = lens; p.gsim = gsim;
@@ -936,23 +1048,49 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_units < sms ? p.total_units : sms;
-#define TGFR_LAUNCH_BWD(TPV)                                                                                    \
+
+#define TGFR_LAUNCH_BWD(TPV, DQV, TM)                                                                          \
   case TPV:                                                                                                    \
-    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)pl.smem_bytes));                                                    \
-    wr_tc_bwd_kernel<TPV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, tm_dc, p);                        \
+    wr_tc_bwd_kernel<TPV, DQV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                     \
     break;
-  switch (pl.Tp) {
-    TGFR_LAUNCH_BWD(8)
-    TGFR_LAUNCH_BWD(16)
-    TGFR_LAUNCH_BWD(24)
-    TGFR_LAUNCH_BWD(32)
-    default:
-      set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
-      return TGFR_E_INVALID;
+  if (dctx) {
+    CUtensorMap tm_dc;
+    TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
+    if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 16, 32, 1, 64)) return rc;
+    switch (pl.Tp) {
+      TGFR_LAUNCH_BWD(8, false, tm_dc)
+      TGFR_LAUNCH_BWD(16, false, tm_dc)
+      TGFR_LAUNCH_BWD(24, false, tm_dc)
+      TGFR_LAUNCH_BWD(32, false, tm_dc)
+      default:
+        set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
+        return TGFR_E_INVALID;
+    }
+    TGFR_LAUNCH_OK();
+  }
+  if (dwords) {
+    CUtensorMap tm_dq;
+    TGFR_CUDA_OK(cudaMemsetAsync(dq_pad, 0, sizeof(float) * (size_t)Bq * pl.Tp * D, st));
+    if (int rc = make_tmap_3d(&tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_pad, D, (uint64_t)Bq * pl.Tp, 1, 16, 32, 1, 64))
+      return rc;
+    switch (pl.Tp) {
+      TGFR_LAUNCH_BWD(8, true, tm_dq)
+      TGFR_LAUNCH_BWD(16, true, tm_dq)
+      TGFR_LAUNCH_BWD(24, true, tm_dq)
+      TGFR_LAUNCH_BWD(32, true, tm_dq)
+      default:
+        set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
+        return TGFR_E_INVALID;
+    }
+    TGFR_LAUNCH_OK();
+    const int64_t n4 = (int64_t)Bq * T * (D >> 2);
+    wr_tc_unpad_kernel<<<(unsigned)((n4 + 255) / 256 < 2048 ? (n4 + 255) / 256 : 2048), 256, 0, st>>>(dq_pad, dwords, Bq, T,
+                                                                                                        pl.Tp, D);
+    TGFR_LAUNCH_OK();
   }
 #undef TGFR_LAUNCH_BWD
-  TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
 
