@@ -29,9 +29,9 @@ extern "C" {
 #define TGFR_E_WORKSPACE (-3) /* workspace too small */
 #define TGFR_E_ARCH (-4)      /* device is not sm_100 */
 
-/* precision selector of the word-region kernels */
+/* precision selector of the word-region kernels and of the margin-head contractions */
 #define TGFR_PREC_FP32 0      /* SIMT fp32 everywhere (bit-for-bit deterministic forward) */
-#define TGFR_PREC_TC 1        /* tcgen05 tensor-core contractions, fp32 accumulate/statistics */
+#define TGFR_PREC_TC 1        /* tcgen05 tensor-core contractions (fp16 operands), fp32 accumulate/statistics */
 
 int tgfr_version(void);
 const char* tgfr_last_error(void);
@@ -124,10 +124,13 @@ int tgfr_pair_ce_bwd(const float* scores, const float* rowlse, const float* coll
  * class_off: first class id owned by this rank (class-sharded partial FC); labels are global.
  * ------------------------------------------------------------------------------------------ */
 /* out[b,c] = s * cos[b,c]  (clamp_cos != 0: cos clamped to [-1,1] first, magface.py:94);
- * xnorm[B], wnorm[C] receive the raw L2 norms. */
+ * xnorm[B], wnorm[C] receive the raw L2 norms.  precision = TGFR_PREC_TC runs the contraction on the
+ * tensor cores and needs tgfr_margin_workspace_bytes(B, C, Din, TGFR_PREC_TC) bytes of 256-byte aligned
+ * workspace (TGFR_PREC_FP32: workspace may be NULL). */
 int tgfr_cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
                         int B, int C, int Din, float s, int clamp_cos,
-                        float* out, int64_t out_sr, float* xnorm, float* wnorm, void* stream);
+                        float* out, int64_t out_sr, float* xnorm, float* wnorm,
+                        int precision, void* workspace, size_t workspace_bytes, void* stream);
 /* ArcFace margin on the label column, in place (metrics.py:45-57); cos_t[B] keeps the target
  * cosine (NaN if the label is not owned by this rank). */
 int tgfr_arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, int C,
@@ -137,8 +140,8 @@ int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_
                         const float* xnorm, const float* wnorm, const int64_t* labels,
                         const float* cos_t, const float* glogits, int64_t g_sr,
                         int B, int C, int Din, int class_off, float s, float m, int easy_margin,
-                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream);
-size_t tgfr_margin_workspace_bytes(int B, int C, int Din);
+                        float* dx, float* dw, int precision, void* workspace, size_t workspace_bytes, void* stream);
+size_t tgfr_margin_workspace_bytes(int B, int C, int Din, int precision);
 
 /* MagFace: cos_m[b,c] from cos_s (= scale*cos) and per-row margins (magface.py:95-106). */
 int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale,
@@ -152,7 +155,7 @@ int tgfr_mag_margin_bwd(const float* cos_s, const float* margin, const float* g_
 int tgfr_cos_logits_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
                         const float* xnorm, const float* wnorm, const float* out, int64_t out_sr,
                         const float* gout, int64_t g_sr, int B, int C, int Din, float s, int clamp_cos,
-                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream);
+                        float* dx, float* dw, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row-wise cross entropy over dense logits [B,C] (nn.CrossEntropyLoss inside FocalLoss,

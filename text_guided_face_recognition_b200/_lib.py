@@ -37,13 +37,13 @@ SIGNATURES = {
     "tgfr_pair_ce_stats": (I, [P, I, I, I, P, P, P, P, P]),
     "tgfr_pair_ce_finish": (I, [P, P, P, P, I, I, I, F, P, P, P]),
     "tgfr_pair_ce_bwd": (I, [P, P, P, P, P, I, I, I, F, P, P]),
-    "tgfr_cos_logits_fwd": (I, [P, L, P, L, L, I, I, I, F, I, P, L, P, P, P]),
+    "tgfr_cos_logits_fwd": (I, [P, L, P, L, L, I, I, I, F, I, P, L, P, P, I, P, Z, P]),
     "tgfr_arc_margin_apply": (I, [P, L, P, I, I, I, F, F, I, P, P]),
-    "tgfr_arc_margin_bwd": (I, [P, L, P, L, L, P, P, P, P, P, L, I, I, I, I, F, F, I, P, P, P, Z, P]),
-    "tgfr_margin_workspace_bytes": (Z, [I, I, I]),
+    "tgfr_arc_margin_bwd": (I, [P, L, P, L, L, P, P, P, P, P, L, I, I, I, I, F, F, I, P, P, I, P, Z, P]),
+    "tgfr_margin_workspace_bytes": (Z, [I, I, I, I]),
     "tgfr_mag_margin_fwd": (I, [P, P, I, I, F, I, P, P]),
     "tgfr_mag_margin_bwd": (I, [P, P, P, P, I, I, F, I, P, P, P]),
-    "tgfr_cos_logits_bwd": (I, [P, L, P, L, L, P, P, P, L, P, L, I, I, I, F, I, P, P, P, Z, P]),
+    "tgfr_cos_logits_bwd": (I, [P, L, P, L, L, P, P, P, L, P, L, I, I, I, F, I, P, P, I, P, Z, P]),
     "tgfr_ce_rows_stats": (I, [P, L, P, I, I, I, P, P, P, P]),
     "tgfr_focal_finish": (I, [P, P, P, I, F, P, P, P]),
     "tgfr_ce_rows_bwd": (I, [P, L, P, P, P, P, I, I, I, P, L, P]),

@@ -47,11 +47,11 @@ int pair_ce_finish(const float*, const float*, const float*, const float*, int, 
 int pair_ce_bwd(const float*, const float*, const float*, const float*, const float*, int, int, int, float, float*,
                 cudaStream_t);
 int cos_logits_fwd(const float*, int64_t, const float*, int64_t, int64_t, int, int, int, float, int, float*, int64_t,
-                   float*, float*, cudaStream_t);
+                   float*, float*, int, void*, size_t, cudaStream_t);
 int arc_margin_apply(float*, int64_t, const int64_t*, int, int, int, float, float, int, float*, cudaStream_t);
-size_t margin_workspace_bytes(int, int, int);
+size_t margin_workspace_bytes(int, int, int, int);
 int margin_bwd(const float*, int64_t, const float*, int64_t, int64_t, const float*, const float*, const int64_t*,
-               const float*, const float*, int64_t, int, int, int, int, float, float, int, float*, float*, void*,
+               const float*, const float*, int64_t, int, int, int, int, float, float, int, float*, float*, int, void*,
                size_t, cudaStream_t);
 int mag_margin_fwd(const float*, const float*, int, int, float, int, float*, cudaStream_t);
 int mag_margin_bwd(const float*, const float*, const float*, const float*, int, int, float, int, float*, float*,
@@ -181,9 +181,11 @@ int tgfr_pair_ce_bwd(const float* scores, const float* rowlse, const float* coll
 
 int tgfr_cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C,
                         int Din, float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm,
-                        void* stream) {
+                        int precision, void* workspace, size_t workspace_bytes, void* stream) {
   TGFR_REQUIRE(x && w && out && xnorm && wnorm, "cos_logits_fwd: NULL tensor");
-  return cos_logits_fwd(x, x_sr, w, w_sc, w_sk, B, C, Din, s, clamp_cos, out, out_sr, xnorm, wnorm, ST(stream));
+  TGFR_REQUIRE(precision == TGFR_PREC_FP32 || precision == TGFR_PREC_TC, "cos_logits_fwd: unknown precision %d", precision);
+  return cos_logits_fwd(x, x_sr, w, w_sc, w_sk, B, C, Din, s, clamp_cos, out, out_sr, xnorm, wnorm, precision, workspace,
+                        workspace_bytes, ST(stream));
 }
 int tgfr_arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off, float s,
                           float m, int easy_margin, float* cos_t, void* stream) {
@@ -193,12 +195,15 @@ int tgfr_arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int 
 int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
                         const float* wnorm, const int64_t* labels, const float* cos_t, const float* glogits,
                         int64_t g_sr, int B, int C, int Din, int class_off, float s, float m, int easy_margin,
-                        float* dx, float* dw, void* workspace, size_t workspace_bytes, void* stream) {
+                        float* dx, float* dw, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   TGFR_REQUIRE(x && w && xnorm && wnorm && labels && cos_t && glogits, "arc_margin_bwd: NULL tensor");
+  TGFR_REQUIRE(precision == TGFR_PREC_FP32 || precision == TGFR_PREC_TC, "arc_margin_bwd: unknown precision %d", precision);
   return margin_bwd(x, x_sr, w, w_sc, w_sk, xnorm, wnorm, labels, cos_t, glogits, g_sr, B, C, Din, class_off, s, m,
-                    easy_margin, dx, dw, workspace, workspace_bytes, ST(stream));
+                    easy_margin, dx, dw, precision, workspace, workspace_bytes, ST(stream));
 }
-size_t tgfr_margin_workspace_bytes(int B, int C, int Din) { return margin_workspace_bytes(B, C, Din); }
+size_t tgfr_margin_workspace_bytes(int B, int C, int Din, int precision) {
+  return margin_workspace_bytes(B, C, Din, precision);
+}
 
 int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale, int easy_margin,
                         float* cos_m_s, void* stream) {
@@ -210,12 +215,13 @@ int tgfr_mag_margin_bwd(const float* cos_s, const float* margin, const float* g_
 }
 int tgfr_cos_logits_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
                         const float* wnorm, const float* out, int64_t out_sr, const float* gout, int64_t g_sr, int B,
-                        int C, int Din, float s, int clamp_cos, float* dx, float* dw, void* workspace,
+                        int C, int Din, float s, int clamp_cos, float* dx, float* dw, int precision, void* workspace,
                         size_t workspace_bytes, void* stream) {
   (void)out; (void)out_sr; (void)clamp_cos;
   TGFR_REQUIRE(x && w && xnorm && wnorm && gout, "cos_logits_bwd: NULL tensor");
+  TGFR_REQUIRE(precision == TGFR_PREC_FP32 || precision == TGFR_PREC_TC, "cos_logits_bwd: unknown precision %d", precision);
   return margin_bwd(x, x_sr, w, w_sc, w_sk, xnorm, wnorm, nullptr, nullptr, gout, g_sr, B, C, Din, 0, s, 0.f, 0, dx,
-                    dw, workspace, workspace_bytes, ST(stream));
+                    dw, precision, workspace, workspace_bytes, ST(stream));
 }
 
 int tgfr_ce_rows_stats(const float* logits, int64_t sr, const int64_t* labels, int B, int C, int class_off,

@@ -2,6 +2,8 @@
 // losses), the two-direction B x B cross entropy, the margin heads (ArcFace / MagFace) and the
 // row-wise cross entropy / focal loss.  The contraction is a strided 64x64x16 register-tiled
 // SGEMM with fused normalisation scales; everything else is bandwidth-bound glue around it.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace tgfr {
@@ -560,11 +562,55 @@ int pair_ce_bwd(const float* scores, const float* rowlse, const float* collse, c
   return TGFR_OK;
 }
 
+// gemm_tc.cu
+bool head_tc_supported(int B, int C, int Din);
+int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, int64_t ldb, int M, int N, int K,
+            float alpha, const float* dscale, int clamp, float* C, int64_t ldc, int splits, cudaStream_t st);
+int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, const float* norm, __half* out,
+                       int ld_out, cudaStream_t st);
+int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st);
+
+namespace {
+struct HeadWs {   // workspace layout of the head calls (fp32 part first, everything 256-byte aligned)
+  size_t dxh, dwh, x16, w16, g16, scale, total;
+  int Dp, Cp;
+};
+HeadWs head_ws(int B, int C, int Din, int precision) {
+  HeadWs h{};
+  h.Dp = (Din + 7) & ~7;
+  h.Cp = (C + 7) & ~7;
+  size_t o = 0;
+  h.dxh = o; o += align_up(sizeof(float) * (size_t)B * Din, 256);
+  h.dwh = o; o += align_up(sizeof(float) * (size_t)C * Din, 256);
+  if (precision == TGFR_PREC_TC) {
+    h.x16 = o; o += align_up(2 * (size_t)B * h.Dp, 256);
+    h.w16 = o; o += align_up(2 * (size_t)C * h.Dp, 256);
+    h.g16 = o; o += align_up(2 * (size_t)B * h.Cp, 256);
+    h.scale = o; o += 256;
+  }
+  h.total = o;
+  return h;
+}
+}  // namespace
+
 int cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C, int Din,
-                   float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm, cudaStream_t st) {
+                   float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm, int precision,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
   TGFR_REQUIRE(B > 0 && C > 0 && Din > 0, "cos_logits: empty shape");
   if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
   if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  if (precision == TGFR_PREC_TC) {
+    TGFR_REQUIRE(head_tc_supported(B, C, Din), "cos_logits(tc): unsupported shape B=%d C=%d Din=%d", B, C, Din);
+    const HeadWs h = head_ws(B, C, Din, precision);
+    TGFR_REQUIRE(ws && ws_bytes >= h.total, "cos_logits(tc): workspace too small (%zu < %zu)", ws_bytes, h.total);
+    TGFR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "cos_logits(tc): workspace must be 256-byte aligned");
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+    __half* x16 = reinterpret_cast<__half*>(base + h.x16);
+    __half* w16 = reinterpret_cast<__half*>(base + h.w16);
+    if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, h.Dp, st)) return rc;
+    if (int rc = head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, h.Dp, st)) return rc;
+    return gemm_tc(x16, 0, h.Dp, w16, 0, h.Dp, B, C, h.Dp, s, nullptr, clamp_cos, out, out_sr, 1, st);
+  }
   Gemm g{};
   g.A = x; g.sAm = x_sr; g.sAk = 1;
   g.B = w; g.sBk = w_sk; g.sBn = w_sc;
@@ -583,20 +629,37 @@ int arc_margin_apply(float* logits, int64_t sr, const int64_t* labels, int B, in
   return TGFR_OK;
 }
 
-size_t margin_workspace_bytes(int B, int C, int Din) {
-  return sizeof(float) * ((size_t)B * Din + (size_t)C * Din);
-}
+size_t margin_workspace_bytes(int B, int C, int Din, int precision) { return head_ws(B, C, Din, precision).total; }
 
 // shared by ArcFace (labels != NULL) and the plain cosine head (MagFace)
 int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const float* xnorm,
                const float* wnorm, const int64_t* labels, const float* cos_t, const float* g, int64_t g_sr, int B,
-               int C, int Din, int class_off, float s, float m, int easy, float* dx, float* dw, void* ws,
-               size_t ws_bytes, cudaStream_t st) {
-  TGFR_REQUIRE(ws_bytes >= margin_workspace_bytes(B, C, Din), "margin_bwd: workspace too small");
+               int C, int Din, int class_off, float s, float m, int easy, float* dx, float* dw, int precision,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+  const HeadWs h = head_ws(B, C, Din, precision);
+  TGFR_REQUIRE(ws && ws_bytes >= h.total, "margin_bwd: workspace too small (%zu < %zu)", ws_bytes, h.total);
+  TGFR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "margin_bwd: workspace must be 256-byte aligned");
   TGFR_REQUIRE(dw != nullptr, "margin_bwd: dw must not be NULL");
-  float* dxh = reinterpret_cast<float*>(ws);
-  float* dwh = dxh + (size_t)B * Din;
-  if (dx) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  float* dxh = reinterpret_cast<float*>(base + h.dxh);
+  float* dwh = reinterpret_cast<float*>(base + h.dwh);
+  if (precision == TGFR_PREC_TC) {
+    TGFR_REQUIRE(head_tc_supported(B, C, Din), "margin_bwd(tc): unsupported shape B=%d C=%d Din=%d", B, C, Din);
+    __half* x16 = reinterpret_cast<__half*>(base + h.x16);
+    __half* w16 = reinterpret_cast<__half*>(base + h.w16);
+    __half* g16 = reinterpret_cast<__half*>(base + h.g16);
+    float* scale = reinterpret_cast<float*>(base + h.scale);
+    if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, h.Dp, st)) return rc;
+    if (int rc = head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, h.Dp, st)) return rc;
+    if (int rc = head_scale_f16(g, g_sr, B, C, scale, g16, h.Cp, st)) return rc;     // g * 2^e as fp16, scale[1] = 2^-e
+    if (dx) {   // dXhat[b,:] = s * sum_c g[b,c] w^_c : A = g16 K-major, B = w^ read MN-major, split over the classes
+      const int tiles = ceil_div(B, 128) * ceil_div(Din, 128);
+      const int splits = tiles >= 148 ? 1 : ceil_div(296, tiles);
+      if (int rc = gemm_tc(g16, 0, h.Cp, w16, 1, h.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
+    }
+    // dWhat[c,:] = s * sum_b g[b,c] x^_b : A = g16 read MN-major, B = x^ read MN-major
+    if (int rc = gemm_tc(g16, 1, h.Cp, x16, 1, h.Dp, C, Din, B, s, scale, 0, dwh, Din, 1, st)) return rc;
+  } else if (dx) {
     Gemm a{};  // dXhat[b,:] = s * sum_c g[b,c] w^_c
     a.A = g; a.sAm = g_sr; a.sAk = 1;
     a.B = w; a.sBk = w_sc; a.sBn = w_sk;
@@ -604,7 +667,7 @@ int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64
     a.M = B; a.N = Din; a.K = C; a.alpha = s; a.norm_eps = 1e-12f; a.mode = kEpiScale; a.bk = wnorm;
     if (int rc = launch_gemm(a, st)) return rc;
   }
-  {
+  if (precision != TGFR_PREC_TC) {
     Gemm b{};  // dWhat[c,:] = s * sum_b g[b,c] x^_b
     b.A = g; b.sAm = 1; b.sAk = g_sr;
     b.B = x; b.sBk = x_sr; b.sBn = 1;

@@ -1,0 +1,268 @@
+// Tensor-core GEMM of the margin heads (TGFR_PREC_TC): C[M,N] (fp32) (+)= alpha * sum_k A(m,k) B(n,k)
+// with fp16 operands staged by TMA and fp32 accumulation in TMEM (tcgen05.mma kind::f16).
+//
+// Three contractions of the head run through it (models/metrics.py:44, its autograd, models/magface.py:92-94):
+//   cos    [B,C]   = x^ . w^T          A = x^ [B,Din] K-major,            B = w^ [C,Din] K-major
+//   dX^    [B,Din] = g  . w^           A = g  [B,C]   K-major,            B = w^ [C,Din] read MN-major (split-K, atomics)
+//   dW^    [C,Din] = g^T. x^           A = g  [B,C]   read MN-major,      B = x^ [B,Din] read MN-major
+// so no operand is ever transposed in memory: the UMMA shared-memory descriptors select the major-ness.
+//
+// One 128 x 128 output tile per CTA, 3-stage TMA pipeline over K in steps of 64 (32 KB per stage), two CTAs per SM
+// so that one CTA's epilogue overlaps the other's main loop.  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// allocator, warps 2-5 epilogue (TMEM -> registers -> warp-private shared-memory transpose -> coalesced row stores,
+// which is what the unaligned row pitch of a [B, 10177] logits matrix needs).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tgfr {
+namespace {
+
+using namespace tc;
+
+constexpr int kGemmThreads = 192;
+constexpr int kStages = 3;
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr uint32_t kTileBytes = kBM * kBK * 2;           // 16 KB per operand per stage
+constexpr uint32_t kStageBytes = 2 * kTileBytes;
+constexpr uint32_t kGemmSmem = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment*/;
+
+struct GemmTcParams {
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  int kt_per_split;      // 64-wide K steps per blockIdx.z
+  float alpha;
+  const float* dscale;   // optional device scalar: alpha is multiplied by dscale[1] (power-of-two gradient scaling)
+  int clamp;             // clamp the accumulator to [-1, 1] before scaling (magface.py:94)
+  int atomic;            // accumulate with atomics (split-K; C pre-zeroed)
+  int a_mn, b_mn;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* accum = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int kt_total = (p.K + kBK - 1) / kBK;
+  const int kt0 = blockIdx.z * p.kt_per_split;
+  const int kt1 = min(kt_total, kt0 + p.kt_per_split);
+  const int nkt = kt1 - kt0;                               // >= 1 by construction of the grid
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % kStages, use = it / kStages;
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kTileBytes;
+        const int k0 = (kt0 + it) * kBK;
+        mbar_arrive_expect_tx(&full[s], kStageBytes);
+        if (p.a_mn) {                                        // memory [K, M]: two panels of 64 M-elements x 64 K-rows
+          tma_load_3d(sa, &tm_a, &full[s], m0, k0, 0);
+          tma_load_3d(sa + 8192, &tm_a, &full[s], m0 + 64, k0, 0);
+        } else {                                             // memory [M, K]: 128 rows x 64 K-elements
+          tma_load_3d(sa, &tm_a, &full[s], k0, m0, 0);
+        }
+        if (p.b_mn) {
+          tma_load_3d(sb, &tm_b, &full[s], n0, k0, 0);
+          tma_load_3d(sb + 8192, &tm_b, &full[s], n0 + 64, k0, 0);
+        } else {
+          tma_load_3d(sb, &tm_b, &full[s], k0, n0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, kBN, p.a_mn != 0, p.b_mn != 0);
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % kStages, use = it / kStages;
+        mbar_wait(&full[s], use & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + s * kStageBytes), b = a + kTileBytes;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint64_t ad = p.a_mn ? make_smem_desc(a + k16 * 2048, 8192, 1024) : make_smem_desc(a + k16 * 32, 16, 1024);
+          const uint64_t bd = p.b_mn ? make_smem_desc(b + k16 * 2048, 8192, 1024) : make_smem_desc(b + k16 * 32, 16, 1024);
+          umma_ss(tmem, ad, bd, idesc, (it | k16) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // epilogue: warp (2..5) owns TMEM lane quarter warp % 4, i.e. rows m0 + 32 q .. + 31
+    const int q = warp & 3;
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    // the operand stages are dead now: warp-private 32 x 33 float transpose buffers live in stage 0
+    float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const int row_base = m0 + q * 32;
+    const float alpha = p.dscale ? p.alpha * __ldg(p.dscale + 1) : p.alpha;
+#pragma unroll 1
+    for (int ch = 0; ch < kBN / 32; ++ch) {
+      const int c0 = n0 + 32 * ch;
+      if (c0 >= p.N) break;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
+        stage[lane * 33 + j] = x * alpha;
+      }
+      __syncwarp();
+      const int col = c0 + lane;
+      if (col < p.N) {
+        const int nrows = min(32, p.M - row_base);
+        for (int rr = 0; rr < nrows; ++rr) {
+          float* dst = p.C + (int64_t)(row_base + rr) * p.ldc + col;
+          const float val = stage[rr * 33 + lane];
+          if (p.atomic) atomicAdd(dst, val);
+          else *dst = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// one warp per vector: out16[v, :] = x_v / max(norm[v], 1e-12) as fp16 (zero padded to ld_out)
+__global__ void normalize_rows_f16_kernel(const float* __restrict__ x, int64_t s_vec, int64_t s_elem, int nvec, int len,
+                                          const float* __restrict__ norm, __half* __restrict__ out, int ld_out) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (v >= nvec) return;
+  const float* src = x + (int64_t)v * s_vec;
+  const float inv = 1.f / fmaxf(__ldg(norm + v), 1e-12f);
+  __half* dst = out + (int64_t)v * ld_out;
+  for (int k = lane; k < ld_out; k += 32) dst[k] = __float2half_rn(k < len ? __ldg(src + (int64_t)k * s_elem) * inv : 0.f);
+}
+
+// weight stored [len, nvec] (vector index contiguous: MagLinear.weight [Din, C]): 32 x 32 tiles through shared memory,
+// norms come from colnorm (already computed); out16 [nvec, ld_out]
+__global__ void normalize_cols_f16_kernel(const float* __restrict__ x, int64_t s_elem, int nvec, int len,
+                                          const float* __restrict__ norm, __half* __restrict__ out, int ld_out) {
+  __shared__ float tile[32][33];
+  const int v0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 256 threads: 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, v = v0 + tx;
+    tile[r][tx] = (k < len && v < nvec) ? __ldg(x + (int64_t)k * s_elem + v) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int v = v0 + r, k = k0 + tx;
+    if (v < nvec && k < ld_out) out[(int64_t)v * ld_out + k] = __float2half_rn(tile[tx][r] / fmaxf(__ldg(norm + v), 1e-12f));
+  }
+}
+
+__global__ void maxabs_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float scratch[32];
+  float m = 0.f;
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(k / cols), c = (int)(k - (int64_t)r * cols);
+    m = fmaxf(m, fabsf(__ldg(g + (int64_t)r * ld + c)));
+  }
+  m = block_max(m, scratch);
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));      // m >= 0: int order = float order
+}
+
+// g16[r, c] = fp16(g[r, c] * 2^e) with 2^e chosen so that the largest entry lands near 2^13; scale[1] = 2^-e
+__global__ void scale_to_f16_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ scale,
+                                    __half* __restrict__ out, int ld_out) {
+  const float mx = scale[0];
+  const float sc = (mx > 0.f) ? exp2f(floorf(log2f(8192.f / mx))) : 1.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) scale[1] = 1.f / sc;
+  const int r = blockIdx.y;
+  const float* src = g + (int64_t)r * ld;
+  __half* dst = out + (int64_t)r * ld_out;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ld_out; c += gridDim.x * blockDim.x)
+    dst[c] = __float2half_rn(c < cols ? __ldg(src + c) * sc : 0.f);
+}
+
+}  // namespace
+
+// ---- host API (used by dense_simt.cu's head entry points when precision == TGFR_PREC_TC) ------------------------
+bool head_tc_supported(int B, int C, int Din) { return B >= 1 && C >= 1 && Din >= 8; }
+
+// fp16 operand: `mn` = 0: memory [rows, K] (K contiguous, pitch ld);  1: memory [K, rows] (rows contiguous, pitch ld)
+static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld) {
+  if (mn) return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, 1, 64, 64, 1, 128, (uint64_t)ld);
+  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, 128, 1, 128, (uint64_t)ld);
+}
+
+int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, int64_t ldb, int M, int N, int K,
+            float alpha, const float* dscale, int clamp, float* C, int64_t ldc, int splits, cudaStream_t st) {
+  CUtensorMap tm_a, tm_b;
+  if (int rc = operand_map(&tm_a, A, a_mn, M, K, lda)) return rc;
+  if (int rc = operand_map(&tm_b, Bm, b_mn, N, K, ldb)) return rc;
+  const int kt_total = (K + kBK - 1) / kBK;
+  if (splits < 1) splits = 1;
+  if (splits > kt_total) splits = kt_total;
+  const int per = (kt_total + splits - 1) / splits;
+  splits = (kt_total + per - 1) / per;                       // no empty split
+  GemmTcParams p{};
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.kt_per_split = per; p.alpha = alpha; p.dscale = dscale; p.clamp = clamp;
+  p.atomic = splits > 1; p.a_mn = a_mn; p.b_mn = b_mn;
+  if (splits > 1) TGFR_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
+  TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+  const dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
+  gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// out16[v, :] = x_v / max(norm[v], 1e-12) for nvec vectors of length len with element strides (s_vec, s_elem)
+int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, const float* norm, __half* out,
+                       int ld_out, cudaStream_t st) {
+  if (s_vec == 1 && s_elem != 1) {        // vector index contiguous ([len, nvec] storage): tiled transpose
+    const dim3 grid((nvec + 31) / 32, (ld_out + 31) / 32);
+    normalize_cols_f16_kernel<<<grid, 256, 0, st>>>(x, s_elem, nvec, len, norm, out, ld_out);
+  } else {
+    normalize_rows_f16_kernel<<<(nvec + 7) / 8, 256, 0, st>>>(x, s_vec, s_elem, nvec, len, norm, out, ld_out);
+  }
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e
+int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st) {
+  TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
+  maxabs_kernel<<<296, 256, 0, st>>>(g, ld, rows, cols, scale);
+  TGFR_LAUNCH_OK();
+  scale_to_f16_kernel<<<dim3((ld_out + 1023) / 1024, rows), 256, 0, st>>>(g, ld, rows, cols, scale, out, ld_out);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+}  // namespace tgfr

@@ -32,6 +32,20 @@ def default_precision() -> int:
     return PREC_FP32 if v in ("fp32", "simt", "0") else PREC_TC
 
 
+def head_precision(Din: int) -> int:
+    """TGFR_HEAD_PRECISION = tc (default: tcgen05 cos-theta / gradient GEMMs, fp16 operands, fp32 accumulate) | fp32."""
+    v = os.environ.get("TGFR_HEAD_PRECISION", "tc").lower()
+    if v in ("fp32", "simt", "0") or Din < 8:
+        return PREC_FP32
+    return PREC_TC
+
+
+def _head_ws(B, C, Din, prec, device):
+    lib = _lib.load()
+    wsb = lib.tgfr_margin_workspace_bytes(B, C, Din, prec)
+    return _workspace(wsb, device), wsb
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.float32 else t.float()
 
@@ -218,18 +232,21 @@ class _ArcLogits(torch.autograd.Function):
         wn = torch.empty(C, dtype=torch.float32, device=dev)
         cos_t = torch.empty(B, dtype=torch.float32, device=dev)
         st = stream_ptr()
+        prec = head_precision(Din)
+        ws, wsb = _head_ws(B, C, Din, prec, dev)
         _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
-              weight.stride(1), B, C, Din, s, 0, out.data_ptr(), out.stride(0), xn.data_ptr(), wn.data_ptr(), st)
+              weight.stride(1), B, C, Din, s, 0, out.data_ptr(), out.stride(0), xn.data_ptr(), wn.data_ptr(),
+              prec, ptr(ws), wsb, st)
         _call("tgfr_arc_margin_apply", out.data_ptr(), out.stride(0), label.data_ptr(), B, C, class_off, s, m,
               int(easy), cos_t.data_ptr(), st)
         ctx.save_for_backward(x, weight, label, xn, wn, cos_t)
-        ctx.cfg = (s, m, easy, class_off)
+        ctx.cfg = (s, m, easy, class_off, prec)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight, label, xn, wn, cos_t = ctx.saved_tensors
-        s, m, easy, class_off = ctx.cfg
+        s, m, easy, class_off, prec = ctx.cfg
         B, Din = x.shape
         C = weight.shape[0]
         g = _f32(g)
@@ -237,12 +254,10 @@ class _ArcLogits(torch.autograd.Function):
             g = g.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
-        lib = _lib.load()
-        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
-        ws = _workspace(wsb, x.device)
+        ws, wsb = _head_ws(B, C, Din, prec, x.device)
         _call("tgfr_arc_margin_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
               weight.stride(1), xn.data_ptr(), wn.data_ptr(), label.data_ptr(), cos_t.data_ptr(), g.data_ptr(),
-              g.stride(0), B, C, Din, class_off, s, m, int(easy), ptr(dx), dw.data_ptr(), ptr(ws), wsb,
+              g.stride(0), B, C, Din, class_off, s, m, int(easy), ptr(dx), dw.data_ptr(), prec, ptr(ws), wsb,
               stream_ptr())
         # dw was written with weight's strides; both are [C,Din] contiguous here
         return dx, dw, None, None, None, None, None
@@ -313,18 +328,20 @@ class _MagLogits(torch.autograd.Function):
         wn = torch.empty(C, dtype=torch.float32, device=dev)
         mar = margin.reshape(-1).contiguous()
         st = stream_ptr()
+        prec = head_precision(Din)
+        ws, wsb = _head_ws(B, C, Din, prec, dev)
         _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(1),
               weight.stride(0), B, C, Din, scale, 1, cos_s.data_ptr(), cos_s.stride(0), xn.data_ptr(),
-              wn.data_ptr(), st)
+              wn.data_ptr(), prec, ptr(ws), wsb, st)
         _call("tgfr_mag_margin_fwd", cos_s.data_ptr(), mar.data_ptr(), B, C, scale, int(easy), cos_m.data_ptr(), st)
         ctx.save_for_backward(x, weight, mar, cos_s, xn, wn)
-        ctx.cfg = (scale, easy, margin.shape)
+        ctx.cfg = (scale, easy, margin.shape, prec)
         return cos_s, cos_m
 
     @staticmethod
     def backward(ctx, g_cos, g_cosm):
         x, weight, mar, cos_s, xn, wn = ctx.saved_tensors
-        scale, easy, mshape = ctx.cfg
+        scale, easy, mshape, prec = ctx.cfg
         B, Din = x.shape
         C = weight.shape[1]
         dev = x.device
@@ -337,12 +354,10 @@ class _MagLogits(torch.autograd.Function):
               int(easy), gtotal.data_ptr(), gmar.data_ptr(), st)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
-        lib = _lib.load()
-        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
-        ws = _workspace(wsb, dev)
+        ws, wsb = _head_ws(B, C, Din, prec, dev)
         _call("tgfr_cos_logits_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(1),
               weight.stride(0), xn.data_ptr(), wn.data_ptr(), cos_s.data_ptr(), cos_s.stride(0),
-              gtotal.data_ptr(), gtotal.stride(0), B, C, Din, scale, 1, ptr(dx), dw.data_ptr(), ptr(ws), wsb, st)
+              gtotal.data_ptr(), gtotal.stride(0), B, C, Din, scale, 1, ptr(dx), dw.data_ptr(), prec, ptr(ws), wsb, st)
         return dx, dw, gmar.reshape(mshape), None, None
 
 
@@ -400,28 +415,28 @@ class _CosLogits(torch.autograd.Function):
         out = torch.empty((B, C), dtype=torch.float32, device=dev)
         xn = torch.empty(B, dtype=torch.float32, device=dev)
         wn = torch.empty(C, dtype=torch.float32, device=dev)
+        prec = head_precision(Din)
+        ws, wsb = _head_ws(B, C, Din, prec, dev)
         _call("tgfr_cos_logits_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(w_class_dim),
               weight.stride(1 - w_class_dim), B, C, Din, s, int(clamp), out.data_ptr(), out.stride(0),
-              xn.data_ptr(), wn.data_ptr(), stream_ptr())
+              xn.data_ptr(), wn.data_ptr(), prec, ptr(ws), wsb, stream_ptr())
         ctx.save_for_backward(x, weight, out, xn, wn)
-        ctx.cfg = (s, clamp, w_class_dim)
+        ctx.cfg = (s, clamp, w_class_dim, prec)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight, out, xn, wn = ctx.saved_tensors
-        s, clamp, wd = ctx.cfg
+        s, clamp, wd, prec = ctx.cfg
         B, Din = x.shape
         C = weight.shape[wd]
         g = _f32(g).contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
-        lib = _lib.load()
-        wsb = lib.tgfr_margin_workspace_bytes(B, C, Din)
-        ws = _workspace(wsb, x.device)
+        ws, wsb = _head_ws(B, C, Din, prec, x.device)
         _call("tgfr_cos_logits_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(wd),
               weight.stride(1 - wd), xn.data_ptr(), wn.data_ptr(), out.data_ptr(), out.stride(0), g.data_ptr(),
-              g.stride(0), B, C, Din, s, int(clamp), ptr(dx), dw.data_ptr(), ptr(ws), wsb, stream_ptr())
+              g.stride(0), B, C, Din, s, int(clamp), ptr(dx), dw.data_ptr(), prec, ptr(ws), wsb, stream_ptr())
         return dx, dw, None, None, None
 
 
