@@ -98,8 +98,9 @@ def test_tc_forward_vs_oracle(B, T, R, D, flavour, ragged):
     l0, l1 = ops.pair_ce(sim)
     r0, r1 = O.pair_ce(ref)
     assert abs(l0.item() - r0) < TC_LOSS_RTOL * r0 and abs(l1.item() - r1) < TC_LOSS_RTOL * r1
-    # the diagonal attention maps come from the fp32 kernel in both modes
-    assert torch.equal(attn, attn32)
+    # the diagonal attention maps come from the fp32 kernels in both modes (the tc path skips the context
+    # contraction and sums the region normaliser in a different order)
+    assert torch.allclose(attn, attn32, rtol=1e-5, atol=1e-8)
     for i, a in enumerate(ref_att):
         assert np.max(np.abs(attn[i, : a.shape[0]].cpu().numpy() - a)) < 1e-5
 

@@ -188,10 +188,9 @@ __global__ void normalize_cols_f16_kernel(const float* __restrict__ x, int64_t s
 __global__ void maxabs_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ out) {
   __shared__ float scratch[32];
   float m = 0.f;
-  const int64_t n = (int64_t)rows * cols;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(k / cols), c = (int)(k - (int64_t)r * cols);
-    m = fmaxf(m, fabsf(__ldg(g + (int64_t)r * ld + c)));
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {        // one row per block pass: coalesced, no index division
+    const float* src = g + (int64_t)r * ld;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(src + c)));
   }
   m = block_max(m, scratch);
   if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));      // m >= 0: int order = float order
@@ -258,7 +257,7 @@ int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e
 int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st) {
   TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
-  maxabs_kernel<<<296, 256, 0, st>>>(g, ld, rows, cols, scale);
+  maxabs_kernel<<<rows < 1184 ? rows : 1184, 256, 0, st>>>(g, ld, rows, cols, scale);
   TGFR_LAUNCH_OK();
   scale_to_f16_kernel<<<dim3((ld_out + 1023) / 1024, rows), 256, 0, st>>>(g, ld, rows, cols, scale, out, ld_out);
   TGFR_LAUNCH_OK();

@@ -200,7 +200,22 @@ __global__ void __launch_bounds__(kThreads, 2) wr_fwd_kernel(const Params p) {
   phase_a<TP>(p, s, cb, Ti);
 
   float wu[NJ][8], zs[NJ];
-  word_gemm<TP>(wu, zs, s.e, cb, p.csr, p.csd, p.R, p.D);
+  if (MODE == kAttention && p.wc == nullptr) {
+    // only the attention maps are wanted (the diagonal maps of the tensor-core path): Z[t] = sum_r E[r,t]
+    // is all that is needed from phase B, the context contraction is skipped
+    const int es = TP + 1;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int t = warp + 8 * j;
+      float z = 0.f;
+      for (int r = lane; r < p.R; r += 32) z += s.e[r * es + t];
+      zs[j] = warp_sum(z);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wu[j][k] = 0.f;
+    }
+  } else {
+    word_gemm<TP>(wu, zs, s.e, cb, p.csr, p.csd, p.R, p.D);
+  }
 
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {

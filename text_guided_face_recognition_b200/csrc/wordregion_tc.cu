@@ -20,6 +20,8 @@
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
 // warps 2-9 = epilogue (4 warps per 128-lane region tile; the two groups split D in epi-2).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -234,19 +236,22 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
           tmem_ld_wait();
           float e[TP];
-          float mx = -1e30f;
+          // four independent max / sum chains: with two warps per scheduler the dependent chain is the cost
+          float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
           for (int t = 0; t < TP; ++t) {
             e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
-            mx = fmaxf(mx, e[t]);
+            mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
           }
+          const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
           const float nmx = -mx * kLog2e;
-          float sum = 0.f;
+          float sump[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int t = 0; t < TP; ++t) {
             e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
-            sum += e[t];
+            sump[t & 3] += e[t];
           }
+          const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
           const float kinv = p.k1 / sum, nk1 = -p.k1;
 #pragma unroll
           for (int t = 0; t < TP; ++t) e[t] = fast_exp2(fmaf(e[t], kinv, nk1));
@@ -286,7 +291,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       mbar_wait(&bars[kWuFull], n & 1);
       if (tid == 64) TGFR_TRACE(n, 4);
       tc_fence_after();
-      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
+      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f, dot2 = 0.f, dot3 = 0.f, n22 = 0.f, n23 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         if (ch < nch) {
@@ -300,16 +305,23 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             for (int k = 0; k < 4; ++k) {
               const float2 qf = __half22float2(qh[k]);
               const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
-              dot = fmaf(qf.x, w0, dot);
-              dot1 = fmaf(qf.y, w1, dot1);
-              n2 = fmaf(w0, w0, n2);
-              n21 = fmaf(w1, w1, n21);
+              if (k & 1) {
+                dot2 = fmaf(qf.x, w0, dot2);
+                dot3 = fmaf(qf.y, w1, dot3);
+                n22 = fmaf(w0, w0, n22);
+                n23 = fmaf(w1, w1, n23);
+              } else {
+                dot = fmaf(qf.x, w0, dot);
+                dot1 = fmaf(qf.y, w1, dot1);
+                n2 = fmaf(w0, w0, n2);
+                n21 = fmaf(w1, w1, n21);
+              }
             }
           }
         }
       }
-      dot += dot1;
-      n2 += n21;
+      dot = (dot + dot1) + (dot2 + dot3);
+      n2 = (n2 + n21) + (n22 + n23);
       tc_fence_before();
       mbar_arrive(&bars[kWuEmpty]);
       if (tid == 64) TGFR_TRACE(n, 5);
@@ -550,8 +562,11 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     const int r = tile * 128 + lrow;
     const bool warp_has_rows = tile < p.n_tiles && (tile * 128 + quarter_w * 32) < p.Rp;
     const int dhalf = p.D >> 1;
-    uint8_t* const stage = (tile == 0 ? s_q : s_x + 1024) + ((warp - 2) & 3) * 6144;   // this warp's 3 x 2 KB ring
-    int ring = 0;
+    // drain boxes (4 KB each): lane quarters 0-2 own two, quarter 3 (half the rows when R <= 224) one -- 28 KB per
+    // warp group, which is what operand panels 0/1 leave free while rounds 2/3 still read panels 2/3
+    uint8_t* const stage = (tile == 0 ? s_q : s_x + 1024) + quarter_w * 8192;
+    const int nbuf = quarter_w == 3 ? 1 : 2;
+    int cur = 0;
     int n = 0;
     for (int u = u0; u < u1; ++u, ++n) {
       const int b = u / p.G, g = u - b * p.G;
@@ -579,19 +594,22 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
           tmem_ld_wait();
           float e[TP];
-          float mx = -1e30f;
+          // four independent max / sum chains: with two warps per scheduler the dependent chain is the cost
+          float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
           for (int t = 0; t < TP; ++t) {
             e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
-            mx = fmaxf(mx, e[t]);
+            mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
           }
+          const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
           const float nmx = -mx * kLog2e;
-          float sum = 0.f;
+          float sump[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int t = 0; t < TP; ++t) {
             e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
-            sum += e[t];
+            sump[t & 3] += e[t];
           }
+          const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
           const float inv = (len > 0 && live_row) ? 1.f / sum : 0.f, nk1 = -p.k1;
           uint32_t pa[TP / 2], pe[TP / 2];
 #pragma unroll
@@ -634,26 +652,31 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       const bool valid = (w < p.nw_rows) && (iw < p.Bq) && (tw < __ldg(p.lens + min(iw, p.Bq - 1)));
       const int64_t qrow = (int64_t)min(iw, p.Bq - 1) * p.Tp + tw;
       float dot = 0.f, n2 = 0.f;
-      for (int ch = 0; ch < (dhalf >> 5); ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
-        tmem_ld_wait();
-        const int d0 = tile * dhalf + 32 * ch;
+      {
+        float dp[4] = {0.f, 0.f, 0.f, 0.f}, np[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < (dhalf >> 5); ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
+          tmem_ld_wait();
+          const int d0 = tile * dhalf + 32 * ch;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (d0 >> 6) * p.q_panel +
-                                                           sw128_offset(w, ((d0 & 63) >> 3) + cc));
-          const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (d0 >> 6) * p.q_panel +
+                                                             sw128_offset(w, ((d0 & 63) >> 3) + cc));
+            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 qf = __half22float2(qh[k]);
-            const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
-            dot = fmaf(qf.x, w0, dot);
-            dot = fmaf(qf.y, w1, dot);
-            n2 = fmaf(w0, w0, n2);
-            n2 = fmaf(w1, w1, n2);
+            for (int k = 0; k < 4; ++k) {
+              const float2 qf = __half22float2(qh[k]);
+              const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
+              dp[(2 * k) & 3] = fmaf(qf.x, w0, dp[(2 * k) & 3]);
+              dp[(2 * k + 1) & 3] = fmaf(qf.y, w1, dp[(2 * k + 1) & 3]);
+              np[(2 * k) & 3] = fmaf(w0, w0, np[(2 * k) & 3]);
+              np[(2 * k + 1) & 3] = fmaf(w1, w1, np[(2 * k + 1) & 3]);
+            }
           }
         }
+        dot = (dp[0] + dp[1]) + (dp[2] + dp[3]);
+        n2 = (np[0] + np[1]) + (np[2] + np[3]);
       }
       if (tile == 1) part[w] = make_float2(dot, n2);
       epi_bar_sync();
@@ -741,7 +764,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           }
           tmem_ld_wait();
           float a1[TP], eh[TP], da[TP];
-          float inner0 = 0.f, inner1 = 0.f;
+          float innerp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int t = 0; t < TP; t += 2) {
             const float2 af = __half22float2(*reinterpret_cast<const __half2*>(&vs[t >> 1]));
@@ -753,10 +776,10 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             eh[t + 1] = ef.y * nw.y;
             da[t] = p.g1 * eh[t] * __uint_as_float(vd[t]);
             da[t + 1] = p.g1 * eh[t + 1] * __uint_as_float(vd[t + 1]);
-            inner0 = fmaf(a1[t], da[t], inner0);
-            inner1 = fmaf(a1[t + 1], da[t + 1], inner1);
+            innerp[t & 2] = fmaf(a1[t], da[t], innerp[t & 2]);
+            innerp[(t & 2) + 1] = fmaf(a1[t + 1], da[t + 1], innerp[(t & 2) + 1]);
           }
-          const float inner = inner0 + inner1;
+          const float inner = (innerp[0] + innerp[1]) + (innerp[2] + innerp[3]);
           if constexpr (DQ) {
             if (r < p.Rp) {
 #pragma unroll
@@ -809,7 +832,10 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         if (tid == 64) TGFR_TRACE(n, 8);
         tc_fence_after();
         if (gmax > 0.f && quarter_w * 32 < p.nw_rows) {
-          uint8_t* const stage_q = s_x + 1024 + (warp - 2) * 6144;     // the dS' tile is dead once GEMM-4 has retired
+          // the dS' tile is dead once GEMM-4 has retired: two 4 KB boxes per warp, one for the last warp (60 KB)
+          uint8_t* const stage_q = s_x + 1024 + (warp - 2) * 8192;
+          const int nbq = warp == 9 ? 1 : 2;
+          int curq = 0;
           const bool row_ok = lrow < p.nw_rows;                          // lanes beyond the group hold no words
           const float cq = cqs[lrow];
           const int nchq = dhalf >> 5;
@@ -819,36 +845,34 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             uint32_t v[32];
             tmem_ld32(tmem + t_lane + 256 + d0, v);
             tmem_ld_wait();
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              uint8_t* buf = stage_q + ring * 2048;
-              if (lane == 0) tma_wait_group_read<2>();
-              __syncwarp();
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                const int dd = d0 + 16 * sub + 8 * h8;
-                const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (dd >> 6) * p.q_panel + sw128_offset(lrow, (dd & 63) >> 3));
-                const __half2* qh = reinterpret_cast<const __half2*>(&qv);
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 qf = __half22float2(qh[k]);
-                  o[2 * k] = row_ok ? (__uint_as_float(v[16 * sub + 8 * h8 + 2 * k]) - cq * qf.x) * inv_sigma : 0.f;
-                  o[2 * k + 1] = row_ok ? (__uint_as_float(v[16 * sub + 8 * h8 + 2 * k + 1]) - cq * qf.y) * inv_sigma : 0.f;
-                }
-                const int c16 = 2 * h8;
-                *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(buf + lane * 64 + (((c16 + 1) ^ ((lane >> 1) & 3)) << 4)) =
-                    make_float4(o[4], o[5], o[6], o[7]);
-              }
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_reduce_add_3d(&tm_dc, buf, d0 + 16 * sub, g * p.nw_rows + quarter_w * 32, 0);
-                tma_commit_group();
-              }
-              ring = ring == 2 ? 0 : ring + 1;
+            uint8_t* const bufq = stage_q + curq * 4096;
+            if (lane == 0) {
+              if (nbq == 2) tma_wait_group_read<1>();
+              else tma_wait_group_read<0>();
             }
+            __syncwarp();
+#pragma unroll
+            for (int h8 = 0; h8 < 4; ++h8) {
+              const int dd = d0 + 8 * h8;
+              const uint4 qv = *reinterpret_cast<const uint4*>(s_q + (dd >> 6) * p.q_panel + sw128_offset(lrow, (dd & 63) >> 3));
+              const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 qf = __half22float2(qh[k]);
+                o[2 * k] = row_ok ? (__uint_as_float(v[8 * h8 + 2 * k]) - cq * qf.x) * inv_sigma : 0.f;
+                o[2 * k + 1] = row_ok ? (__uint_as_float(v[8 * h8 + 2 * k + 1]) - cq * qf.y) * inv_sigma : 0.f;
+              }
+              *reinterpret_cast<float4*>(bufq + sw128_offset(lane, 2 * h8)) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(bufq + sw128_offset(lane, 2 * h8 + 1)) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_3d(&tm_dc, bufq, d0, g * p.nw_rows + quarter_w * 32, 0);
+              tma_commit_group();
+            }
+            curq ^= nbq - 1;
           }
         }
         if (lane == 0) tma_wait_group_read<0>();
@@ -858,9 +882,10 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         if (tid == 64) TGFR_TRACE(n, 12);
       } else {
         // ---------------- drain: dC blocks -> per-warp staging ring -> TMA reduce-add ----------------
-        // Every warp drains 32 lanes x 64 columns of each block through three 2 KB boxes (32 rows x 16 floats,
-        // 64B swizzle) that overlay operand panels 0/1 of Q (warps 2-5) and dW^ (warps 6-9); those panels are
-        // dead once rounds 0 and 1 have retired (bDc1).
+        // Every warp drains 32 lanes x 64 columns of each block through its own 4 KB box (32 rows x 32 floats,
+        // 128B swizzle) that overlays operand panels 0/1 of Q (warps 2-5) and dW^ (warps 6-9); those panels are
+        // dead once rounds 0 and 1 have retired (bDc1).  The two warps of a scheduler alternate, which hides the
+        // wait for the TMA engine to read a box back.
         for (int rd = 0; rd < 4; ++rd) {
           const int t = rd & 1, half = rd >> 1;
           if (rd != 1) {
@@ -872,33 +897,33 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           const int row0 = t * 128 + quarter_w * 32;
           if (t < p.n_tiles && row0 < p.R && col0 < p.D && gmax > 0.f) {
             const uint32_t dcol = tmem + t_lane + (t ? 320 : 64) + tile * 64;
-  #pragma unroll 1
+#pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
               uint32_t v[32];
               tmem_ld32(dcol + 32 * ch, v);
               tmem_ld_wait();
-  #pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
-                uint8_t* buf = stage + ring * 2048;
-                if (lane == 0) tma_wait_group_read<2>();       // the box written three stores ago has been read
-                __syncwarp();
-  #pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) {
-                  float4 o;
-                  o.x = __uint_as_float(v[16 * sub + 4 * c16 + 0]) * inv_sigma;
-                  o.y = __uint_as_float(v[16 * sub + 4 * c16 + 1]) * inv_sigma;
-                  o.z = __uint_as_float(v[16 * sub + 4 * c16 + 2]) * inv_sigma;
-                  o.w = __uint_as_float(v[16 * sub + 4 * c16 + 3]) * inv_sigma;
-                  *reinterpret_cast<float4*>(buf + lane * 64 + ((c16 ^ ((lane >> 1) & 3)) << 4)) = o;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                  tma_reduce_add_3d(&tm_dc, buf, col0 + 32 * ch + 16 * sub, row0, b);
-                  tma_commit_group();
-                }
-                ring = ring == 2 ? 0 : ring + 1;
+              uint8_t* const buf = stage + cur * 4096;
+              if (lane == 0) {                                  // the box written nbuf stores ago has been read
+                if (nbuf == 2) tma_wait_group_read<1>();
+                else tma_wait_group_read<0>();
               }
+              __syncwarp();
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16) {
+                float4 o;
+                o.x = __uint_as_float(v[4 * c16 + 0]) * inv_sigma;
+                o.y = __uint_as_float(v[4 * c16 + 1]) * inv_sigma;
+                o.z = __uint_as_float(v[4 * c16 + 2]) * inv_sigma;
+                o.w = __uint_as_float(v[4 * c16 + 3]) * inv_sigma;
+                *reinterpret_cast<float4*>(buf + sw128_offset(lane, c16)) = o;
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_reduce_add_3d(&tm_dc, buf, col0 + 32 * ch, row0, b);
+                tma_commit_group();
+              }
+              cur ^= nbuf - 1;
             }
           }
           if (rd == 3) {                                        // Q / X are handed back to the producer
@@ -974,11 +999,11 @@ int make_bwd_plan(int Bq, int T, int R, int D, TcBwdPlan* pl) {
   for (int nc = 128 / pl->Tp; nc >= 1; --nc) {
     const uint32_t q_panel = (uint32_t)nc * pl->Tp * 128u;
     uint32_t q_bytes = kch * q_panel, x_bytes = kch * q_panel + 1024;
-    if (q_bytes < 24576) q_bytes = 24576;                       // drain staging rings (4 warps x 3 x 2 KB)
+    if (q_bytes < 28672) q_bytes = 28672;                       // drain boxes (7 x 4 KB per warp group)
     if (x_bytes < 2 * pl->e_panel) x_bytes = 2 * pl->e_panel;
-    if (x_bytes < 49152 + 1024) x_bytes = 49152 + 1024;         // DQ drain: 8 warps x 3 x 2 KB over the dead dS' tile
-    // with more than two feature panels the rings must fit in panels 0/1, which are dead while rounds 2/3 run
-    if (kch > 2 && 2 * q_panel < 24576 + 1024) continue;
+    if (x_bytes < 61440 + 1024) x_bytes = 61440 + 1024;         // DQ drain: 15 x 4 KB over the dead dS' tile
+    // with more than two feature panels the boxes must fit in panels 0/1, which are dead while rounds 2/3 run
+    if (kch > 2 && 2 * q_panel < 28672 + 1024) continue;
     const uint32_t off_q = kch * pl->c_panel, off_x = off_q + q_bytes, off_misc = off_x + x_bytes;
     const uint32_t total = off_misc + 4096 + 1024;
     if (total <= 232448) {
@@ -1047,7 +1072,11 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.total_units < sms ? p.total_units : sms;
+  int grid = p.total_units < sms ? p.total_units : sms;
+  if (const char* dg = getenv("TGFR_DEBUG_GRID")) {             // profiling aid: fewer CTAs -> no L2 contention
+    const int v = atoi(dg);
+    if (v > 0 && v < grid) grid = v;
+  }
 
 #define TGFR_LAUNCH_BWD(TPV, DQV, TM)                                                                          \
   case TPV:                                                                                                    \
@@ -1058,7 +1087,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   if (dctx) {
     CUtensorMap tm_dc;
     TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
-    if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 16, 32, 1, 64)) return rc;
+    if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 32, 1)) return rc;
     switch (pl.Tp) {
       TGFR_LAUNCH_BWD(8, false, tm_dc)
       TGFR_LAUNCH_BWD(16, false, tm_dc)
@@ -1073,7 +1102,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   if (dwords) {
     CUtensorMap tm_dq;
     TGFR_CUDA_OK(cudaMemsetAsync(dq_pad, 0, sizeof(float) * (size_t)Bq * pl.Tp * D, st));
-    if (int rc = make_tmap_3d(&tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_pad, D, (uint64_t)Bq * pl.Tp, 1, 16, 32, 1, 64))
+    if (int rc = make_tmap_3d(&tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_pad, D, (uint64_t)Bq * pl.Tp, 1, 32, 32, 1))
       return rc;
     switch (pl.Tp) {
       TGFR_LAUNCH_BWD(8, true, tm_dq)
@@ -1142,7 +1171,11 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.total_units < sms ? p.total_units : sms;
+  int grid = p.total_units < sms ? p.total_units : sms;
+  if (const char* dg = getenv("TGFR_DEBUG_GRID")) {             // profiling aid: fewer CTAs -> no L2 contention
+    const int v = atoi(dg);
+    if (v > 0 && v < grid) grid = v;
+  }
 #define TGFR_LAUNCH_FWD(TPV)                                                                                    \
   case TPV:                                                                                                    \
     TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
