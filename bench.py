@@ -401,10 +401,19 @@ def run_b200(args):
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         st = torch.cuda.current_stream().cuda_stream
 
+        # the step's backward reads the forward's saved fp16 attention image: produce it with one forward call
+        svb = lib.tgfr_wordregion_saved_bytes(B, Bg, T, R, D, precision) if ops._save_enabled() else 0
+        saved = torch.empty(max(svb, 1), dtype=torch.uint8, device=dev)
+        sim_tmp = torch.empty(B, Bg, device=dev)
+        _lib.check(lib.tgfr_wordregion_fwd(c.data_ptr(), *c.stride(), wall.data_ptr(), *wall.stride(), 0, B, Bg, T, R, D,
+                                           *GAMMAS, 1e-8, sim_tmp.data_ptr(), 0, 0, precision, ws.data_ptr(), wsb,
+                                           saved.data_ptr() if svb else 0, svb, st), "fwd")
+
         def bwd_call():
             _lib.check(lib.tgfr_wordregion_bwd(c.data_ptr(), *c.stride(), wall.data_ptr(), *wall.stride(), 0, B, Bg,
                                                T, R, D, *GAMMAS, 1e-8, gsim.data_ptr(), dctx.data_ptr(),
-                                               _lib.ptr(dwords), precision, ws.data_ptr(), wsb, st), "bwd")
+                                               _lib.ptr(dwords), precision, ws.data_ptr(), wsb,
+                                               saved.data_ptr() if svb else 0, svb, st), "bwd")
         flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
         ks = []
         for k in range(3 + max(3, min(args.steps, 10))):

@@ -51,7 +51,8 @@ int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D,
                         float gamma1, float gamma2, float gamma3, float eps,
                         float* sim, float* attn_diag, int diag_off,
-                        int precision, void* workspace, size_t workspace_bytes, void* stream);
+                        int precision, void* workspace, size_t workspace_bytes,
+                        void* saved, size_t saved_bytes, void* stream);
 
 /* Gradients of sum(gsim * sim): dctx [Bc,R,D] and dwords [Bq,T,D] (contiguous, OVERWRITTEN;
  * either may be NULL to skip it -- the reference's training scripts only need dctx because the
@@ -61,10 +62,16 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D,
                         float gamma1, float gamma2, float gamma3, float eps,
                         const float* gsim, float* dctx, float* dwords,
-                        int precision, void* workspace, size_t workspace_bytes, void* stream);
+                        int precision, void* workspace, size_t workspace_bytes,
+                        const void* saved, size_t saved_bytes, void* stream);
 
 /* Bytes of scratch the two calls above need for the given shape/precision (0 is possible). */
 size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int precision);
+/* Optional forward -> backward buffer (TGFR_PREC_TC): when `saved` (tgfr_wordregion_saved_bytes bytes, 16-byte
+ * aligned) is given to the forward call it stores the fp16 word-softmax / attention image of every pair, and a
+ * backward call that receives the same buffer reads it back instead of recomputing scores and exponentials.
+ * saved = NULL on either side selects the recomputing (memory-lean) path; results agree to fp16 rounding. */
+size_t tgfr_wordregion_saved_bytes(int Bc, int Bq, int T, int R, int D, int precision);
 
 /* Stand-alone func_attention(query, context, gamma1) for B independent (query, context) pairs
  * (models/attention.py:10-43): wc [B,T,D] canonical, attn [B,T,R]. */

@@ -108,6 +108,13 @@ def test_tc_forward_vs_oracle(B, T, R, D, flavour, ragged):
 TC_GRAD_RTOL = 1e-3      # contract for the TF32-class path; emulation of the fp16-operand pipeline gives ~4e-4
 
 
+@pytest.fixture(params=["save", "recompute"])
+def bwd_mode(request, monkeypatch):
+    """The backward either reads the forward's saved fp16 attention image or recomputes it on chip."""
+    monkeypatch.setenv("TGFR_WORDREGION_SAVE", "1" if request.param == "save" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("B,T,R,D,flavour,ragged", [
     (8, 22, 196, 256, "BERT", False),
     (16, 18, 196, 256, "LSTM", True),
@@ -116,7 +123,7 @@ TC_GRAD_RTOL = 1e-3      # contract for the TF32-class path; emulation of the fp
     (7, 12, 130, 192, "LSTM", True),
     (32, 22, 196, 256, "BERT", False),
 ])
-def test_tc_backward_vs_oracle(B, T, R, D, flavour, ragged):
+def test_tc_backward_vs_oracle(B, T, R, D, flavour, ragged, bwd_mode):
     from text_guided_face_recognition_b200 import _lib, ops
     ctx, words, cap = synth.wordregion_inputs(B, T, R, D, flavour, seed=100, ragged=ragged)
     feats = torch.from_numpy(ctx).cuda().requires_grad_(True)
@@ -143,7 +150,7 @@ def test_tc_backward_vs_oracle(B, T, R, D, flavour, ragged):
     (7, 12, 130, 192, "LSTM", True),
     (32, 22, 196, 256, "BERT", False),
 ])
-def test_tc_backward_words_vs_oracle(B, T, R, D, flavour, ragged):
+def test_tc_backward_words_vs_oracle(B, T, R, D, flavour, ragged, bwd_mode):
     """Text-side gradient on the tensor cores (DQ pass), alone and together with the face-side gradient."""
     from text_guided_face_recognition_b200 import _lib, ops
     ctx, words, cap = synth.wordregion_inputs(B, T, R, D, flavour, seed=100, ragged=ragged)

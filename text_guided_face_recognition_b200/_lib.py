@@ -26,9 +26,10 @@ SIGNATURES = {
     "tgfr_version": (I, []),
     "tgfr_last_error": (c_char_p, []),
     "tgfr_device_check": (I, []),
-    "tgfr_wordregion_fwd": (I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, F, F, F, F, P, P, I, I, P, Z, P]),
-    "tgfr_wordregion_bwd": (I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, F, F, F, F, P, P, P, I, P, Z, P]),
+    "tgfr_wordregion_fwd": (I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, F, F, F, F, P, P, I, I, P, Z, P, Z, P]),
+    "tgfr_wordregion_bwd": (I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, F, F, F, F, P, P, P, I, P, Z, P, Z, P]),
     "tgfr_wordregion_workspace_bytes": (Z, [I, I, I, I, I, I]),
+    "tgfr_wordregion_saved_bytes": (Z, [I, I, I, I, I, I]),
     "tgfr_attention_fwd": (I, [P, L, L, L, P, L, L, L, I, I, I, I, F, P, P, P]),
     "tgfr_attention_bwd": (I, [P, L, L, L, P, L, L, L, I, I, I, I, F, P, P, P, P, P]),
     "tgfr_cosine_scores_fwd": (I, [P, L, P, L, I, I, I, F, I, F, P, P, I, P, P, P, P]),

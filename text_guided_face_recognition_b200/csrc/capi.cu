@@ -28,12 +28,13 @@ int attention_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, in
                        int, int, float, const float*, const float*, float*, float*, cudaStream_t);
 // wordregion_tc.cu
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D);
+size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D);
 int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
-                      const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t,
-                      cudaStream_t);
+                      const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t, void*,
+                      size_t, cudaStream_t);
 int wordregion_bwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                       const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, float*, void*,
-                      size_t, cudaStream_t);
+                      size_t, const void*, size_t, cudaStream_t);
 int wordregion_tc_set_trace(void*);
 // dense_simt.cu
 int cosine_scores_fwd(const float*, int64_t, const float*, int64_t, int, int, int, float, int, float, const int64_t*,
@@ -91,16 +92,21 @@ size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int 
   if (precision == TGFR_PREC_TC) return wordregion_tc_workspace_bytes(Bc, Bq, T, R, D);
   return 0;
 }
+size_t tgfr_wordregion_saved_bytes(int Bc, int Bq, int T, int R, int D, int precision) {
+  if (precision == TGFR_PREC_TC) return wordregion_tc_saved_bytes(Bc, Bq, T, R, D);
+  return 0;
+}
 
 int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd, const float* words,
                         int64_t w_sb, int64_t w_st, int64_t w_sd, const int32_t* cap_lens, int Bc, int Bq, int T,
                         int R, int D, float gamma1, float gamma2, float gamma3, float eps, float* sim,
                         float* attn_diag, int diag_off, int precision, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        void* saved, size_t saved_bytes, void* stream) {
   TGFR_REQUIRE(ctx && words && sim, "wordregion_fwd: NULL tensor");
   if (precision == TGFR_PREC_TC) {
     if (int rc = wordregion_fwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,
-                                   gamma1, gamma2, gamma3, eps, sim, workspace, workspace_bytes, ST(stream)))
+                                   gamma1, gamma2, gamma3, eps, sim, workspace, workspace_bytes, saved, saved_bytes,
+                                   ST(stream)))
       return rc;
     if (!attn_diag) return TGFR_OK;
     // the B diagonal attention maps are produced by the fp32 kernel on the matching pairs only
@@ -119,11 +125,12 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         int64_t w_sb, int64_t w_st, int64_t w_sd, const int32_t* cap_lens, int Bc, int Bq, int T,
                         int R, int D, float gamma1, float gamma2, float gamma3, float eps, const float* gsim,
                         float* dctx, float* dwords, int precision, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        const void* saved, size_t saved_bytes, void* stream) {
   TGFR_REQUIRE(ctx && words && gsim, "wordregion_bwd: NULL tensor");
   if (precision == TGFR_PREC_TC) {
     return wordregion_bwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,
-                             gamma2, gamma3, gsim, dctx, dwords, workspace, workspace_bytes, ST(stream));
+                             gamma2, gamma3, gsim, dctx, dwords, workspace, workspace_bytes, saved, saved_bytes,
+                             ST(stream));
   }
   TGFR_REQUIRE(precision == TGFR_PREC_FP32, "wordregion_bwd: unknown precision %d", precision);
   return wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D, gamma1,

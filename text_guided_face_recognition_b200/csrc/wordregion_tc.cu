@@ -41,6 +41,8 @@ struct TcParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
+  uint8_t* saved;        // SAVE: per unit [E tile image: 2 * e_panel bytes][A1 fp16: nc x Rp x Tp], for the backward
+  uint32_t sv_stride;    // bytes per unit
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
   float k1, k2, g3;
@@ -111,7 +113,7 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int TP>
+template <int TP, bool SAVE>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -142,6 +144,10 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tm_c);
     tma_prefetch_desc(&tm_q);
+  }
+  if constexpr (SAVE) {   // the E tile is copied out whole: its never-written padding columns must be defined
+    for (uint32_t k = tid; k < (2 * p.e_panel >> 4); k += kThreadsTC) reinterpret_cast<uint4*>(s_e)[k] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -192,12 +198,16 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
             umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
           }
-          if (t == 0) umma_commit(&bars[kSFull0]);       // the tile-0 epilogue group starts while tile 1 runs
+          if (t == 0) {
+            if constexpr (SAVE) tma_wait_group_read<0>();        // the previous unit's E tile has been copied out
+            umma_commit(&bars[kSFull0]);                         // the tile-0 epilogue group starts while tile 1 runs
+          }
         }
         umma_commit(&bars[kQEmpty]);
         umma_commit(&bars[kSFull1]);
         mbar_wait(&bars[kEFull], n & 1);
         TGFR_TRACE(n, 18);
+
         mbar_wait(&bars[kWuEmpty], (n & 1) ^ 1);
         TGFR_TRACE(n, 19);
         tc_fence_after();
@@ -207,7 +217,12 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
         }
         umma_commit(&bars[kWuFull]);
+        if constexpr (SAVE) {                                    // the E tile (as laid out for GEMM-2) -> saved record
+          bulk_store(p.saved + (int64_t)u * p.sv_stride, s_e, 2 * p.e_panel);
+          tma_commit_group();
+        }
       }
+      if constexpr (SAVE) tma_wait_group<0>();
     }
   } else {
     // ======================================= epilogue =======================================
@@ -228,7 +243,22 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       if (warp_has_rows) {
         for (int c = 0; c < p.nc; ++c) {
           const int i = g * p.nc + c;
-          if (i >= p.Bq) break;
+          if (i >= p.Bq) {
+            if constexpr (SAVE) {                               // missing captions: zero columns for the backward
+              if (r < p.Rp) {
+                uint4* a1dst = reinterpret_cast<uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
+                               ((int64_t)c * p.Rp + r) * (TP / 8);
+#pragma unroll
+                for (int j = 0; j < TP / 8; ++j) {
+                  a1dst[j] = make_uint4(0, 0, 0, 0);
+                  const int w0 = c * TP + 8 * j;
+                  *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
+                }
+              }
+              continue;
+            }
+            break;
+          }
           const int len = __ldg(p.lens + i);
           uint32_t v[TP];
           const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
@@ -252,19 +282,41 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             sump[t & 3] += e[t];
           }
           const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
-          const float kinv = p.k1 / sum, nk1 = -p.k1;
+          const float nk1 = -p.k1;
+          uint32_t pe[TP / 2];
+          if constexpr (SAVE) {
+            // exactly what the backward's epi-1 would put in TMEM: A1 and E as fp16, zero on dead rows / words
+            // (padding words keep E = exp(-g1): the backward multiplies it by 1/|Wu_w| = 0; dead rows are zeroed)
+            const bool live_row = r < p.R;
+            const float inv = live_row ? 1.f / sum : 0.f;
+            uint32_t pa[TP / 2];
 #pragma unroll
-          for (int t = 0; t < TP; ++t) e[t] = fast_exp2(fmaf(e[t], kinv, nk1));
+            for (int t = 0; t < TP; t += 2) {
+              const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
+              pa[t >> 1] = pack_half2(a0, a1);
+              const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
+              pe[t >> 1] = live_row ? pk : 0u;
+            }
+            if (r < p.Rp) {
+              // A1 [caption][row][Tp fp16]: a warp's 32 rows are contiguous in memory (coalesced); E leaves through
+              // the shared-memory tile below (one bulk copy per unit)
+              uint4* a1dst = reinterpret_cast<uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
+                             ((int64_t)c * p.Rp + r) * (TP / 8);
+#pragma unroll
+              for (int j = 0; j < TP / 8; ++j) a1dst[j] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+            }
+          } else {
+            const float kinv = p.k1 / sum;
+#pragma unroll
+            for (int t = 0; t < TP; t += 2)
+              pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
+          }
           if (r < p.Rp) {
 #pragma unroll
             for (int j = 0; j < TP / 8; ++j) {
               const int w0 = c * TP + 8 * j;
-              uint4 pk;
-              pk.x = pack_half2(e[8 * j + 0], e[8 * j + 1]);
-              pk.y = pack_half2(e[8 * j + 2], e[8 * j + 3]);
-              pk.z = pack_half2(e[8 * j + 4], e[8 * j + 5]);
-              pk.w = pack_half2(e[8 * j + 6], e[8 * j + 7]);
-              *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = pk;
+              *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
+                  make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
             }
           }
         }
@@ -374,6 +426,8 @@ struct TcBwdParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   const float* gsim;     // [Bc, Bq]
+  const uint8_t* saved;  // LOAD: the forward's per-unit [E tile image][A1 fp16] records
+  uint32_t sv_stride;    // bytes per unit
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   uint32_t c_panel, q_panel, e_panel, off_q, off_x, off_misc;
   float k1, k2, g1, g23;   // g23 = gamma2 * gamma3
@@ -388,7 +442,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 // direct cosine gradient through Wu = E^T C) as fp16 into shared memory in the E layout, GEMM-4
 // dQ[w,d] = sum_r dS'[r,w] c_r[d] reuses GEMM-2's descriptors, and the drain subtracts the direct term in q_w and
 // reduce-adds into the padded [Bq*Tp, D] gradient (tm_dc is then the map of that buffer).
-template <int TP, bool DQ>
+// LOAD = true: the forward kernel saved the fp16 (A1 | E) image of every unit; GEMM-1 and epi-1 are replaced by
+// reading it back into TMEM / shared memory (no score recomputation, no exponentials).
+template <int TP, bool DQ, bool LOAD>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_dc, const TcBwdParams p) {
@@ -444,15 +500,20 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       int prev_b = -1, n = 0;
       for (int u = u0; u < u1; ++u, ++n) {
         const int b = u / p.G, g = u - b * p.G;
+        if constexpr (LOAD) {   // pull the next unit's saved record towards L2 while this unit runs
+          if (n == 0) bulk_prefetch_l2(p.saved + (int64_t)u * p.sv_stride, p.sv_stride);
+          if (u + 1 < u1) bulk_prefetch_l2(p.saved + (int64_t)(u + 1) * p.sv_stride, p.sv_stride);
+        }
         if (n > 0) mbar_wait(&bars[bDr3], (n - 1) & 1);   // previous unit fully drained: Q / X / C are free
         if (b != prev_b) {
           mbar_arrive_expect_tx(&bars[bCFull], kchunks * p.c_panel);
           for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[bCFull], kc * 64, 0, b);
           prev_b = b;
         }
-        mbar_arrive_expect_tx(&bars[bQFull], kchunks * p.q_panel);
+        mbar_arrive_expect_tx(&bars[bQFull], kchunks * p.q_panel + (LOAD ? 2 * p.e_panel : 0));
         for (int kc = 0; kc < kchunks; ++kc)
           tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[bQFull], kc * 64, g * p.nw_rows, 0);
+        if constexpr (LOAD) bulk_load(s_x, p.saved + (int64_t)u * p.sv_stride, 2 * p.e_panel, &bars[bQFull]);
       }
     }
   } else if (warp == 1) {
@@ -473,17 +534,19 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         TGFR_TRACE(n, 17);
         tc_fence_after();
         // GEMM-1: S_t = C_t . Q^T
-        for (int t = 0; t < p.n_tiles; ++t) {
-          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
-            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
-            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
+        if constexpr (!LOAD) {
+          for (int t = 0; t < p.n_tiles; ++t) {
+            for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
+              const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+              umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
+            }
+            if (t == 0) umma_commit(&bars[bSFull0]);
           }
-          if (t == 0) umma_commit(&bars[bSFull0]);
+          umma_commit(&bars[bSFull1]);
         }
-        umma_commit(&bars[bSFull1]);
-        // GEMM-2: Wu = E^T . C
-        mbar_wait(&bars[bEFull], n & 1);
+        // GEMM-2: Wu = E^T . C   (LOAD: the E tile arrived with the Q tile, straight from the saved record)
+        if constexpr (!LOAD) mbar_wait(&bars[bEFull], n & 1);
         TGFR_TRACE(n, 18);
         tc_fence_after();
         for (int j = 0; j < (p.Rp >> 4); ++j) {
@@ -579,6 +642,45 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       const float sigma = (gmax > 0.f) ? exp2f(floorf(log2f(4096.f / (p.g23 * gmax)))) : 1.f;
       const float inv_sigma = 1.f / sigma;
 
+      if constexpr (LOAD) {
+        // ---------------- epi-1 (LOAD): saved A1 (global) and E (the shared-memory tile) -> TMEM ----------------
+        constexpr int NV = 5;                                      // captions whose A1 is fetched per batch
+        const uint4* a1src = reinterpret_cast<const uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
+                             (int64_t)min(r, p.Rp - 1) * (TP / 8);
+        const int64_t cstride = (int64_t)p.Rp * (TP / 8);          // uint4 per caption
+        for (int c0 = 0; c0 < p.nc; c0 += NV) {
+          uint4 ld[NV][TP / 8];
+#pragma unroll
+          for (int cc = 0; cc < NV; ++cc)
+#pragma unroll
+            for (int j = 0; j < TP / 8; ++j) ld[cc][j] = __ldg(a1src + min(c0 + cc, p.nc - 1) * cstride + j);
+          if (c0 == 0) {
+            // every warp has finished draining the previous unit (TMEM holes, staging boxes over Q / X) ...
+            if (n > 0) mbar_wait(&bars[bDr3], (n - 1) & 1);
+            mbar_wait(&bars[bQFull], n & 1);                       // ... and this unit's E tile has landed
+            if (tid == 64) TGFR_TRACE(n, 2);
+            tc_fence_after();
+          }
+          if (warp_has_rows) {
+#pragma unroll
+            for (int cc = 0; cc < NV; ++cc) {
+              const int c = c0 + cc;
+              if (c < p.nc) {
+                const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
+#pragma unroll
+                for (int j = 0; j < TP / 8; ++j) {
+                  const int w0 = c * TP + 8 * j;
+                  const uint4 ev = *reinterpret_cast<const uint4*>(s_x + (w0 >> 6) * p.e_panel +
+                                                                   sw128_offset(min(r, p.Rp - 1), (w0 & 63) >> 3));
+                  tmem_st4(col + 4 * j, ld[cc][j].x, ld[cc][j].y, ld[cc][j].z, ld[cc][j].w);
+                  tmem_st4(col + TP / 2 + 4 * j, ev.x, ev.y, ev.z, ev.w);
+                }
+              }
+            }
+          }
+        }
+        if (warp_has_rows) tmem_st_wait();
+      } else {
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
       mbar_wait(&bars[tile == 0 ? bSFull0 : bSFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 2);
@@ -637,6 +739,7 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         }
         tmem_st_wait();
       }
+      }  // !LOAD
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[bEFull]);
@@ -980,6 +1083,12 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   return TGFR_OK;
 }
 
+// per-unit record the forward leaves for the backward: the E tile exactly as GEMM-2 reads it (2 x e_panel bytes,
+// 128B-swizzled) followed by A1 as fp16 [nc][Rp][Tp]
+uint32_t saved_unit_bytes(const TcPlan& pl) {
+  return (uint32_t)align_up((size_t)2 * pl.e_panel + (size_t)pl.nc * pl.Rp * pl.Tp * 2, 128);
+}
+
 struct TcBwdPlan {
   int Tp, Rp, c_rows, nc, G, nw_rows, n_tiles;
   uint32_t c_panel, q_panel, e_panel, off_q, off_x, off_misc, smem_bytes;
@@ -1033,7 +1142,7 @@ __global__ void wr_tc_unpad_kernel(const float* __restrict__ dq_pad, float* __re
 int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* words, int64_t wsb,
                       int64_t wst, int64_t wsd, const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D, float g1,
                       float g2, float g3, const float* gsim, float* dctx, float* dwords, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      const void* saved, size_t saved_bytes, cudaStream_t st) {
   TcPlan fp;
   if (int rc = make_plan(Bc, Bq, T, R, D, &fp)) return rc;     // workspace layout is shared with the forward
   TcBwdPlan pl;
@@ -1068,6 +1177,12 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
   p.off_q = pl.off_q; p.off_x = pl.off_x; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g1 = g1; p.g23 = g2 * g3;
+  // the forward's saved (A1 | E) image is usable when both passes tile the captions identically
+  const uint32_t sv_stride = saved_unit_bytes(fp);
+  const bool load = saved != nullptr && pl.nc == fp.nc && pl.Rp == fp.Rp && pl.e_panel == fp.e_panel &&
+                    saved_bytes >= (size_t)p.total_units * sv_stride;
+  p.saved = load ? reinterpret_cast<const uint8_t*>(saved) : nullptr;
+  p.sv_stride = sv_stride;
 
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));
@@ -1078,11 +1193,16 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     if (v > 0 && v < grid) grid = v;
   }
 
-#define TGFR_LAUNCH_BWD(TPV, DQV, TM)                                                                          \
-  case TPV:                                                                                                    \
-    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)pl.smem_bytes));                                                    \
-    wr_tc_bwd_kernel<TPV, DQV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                     \
+#define TGFR_LAUNCH_BWD1(TPV, DQV, LDV, TM)                                                                         \
+  {                                                                                                                 \
+    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)pl.smem_bytes));                                                         \
+    wr_tc_bwd_kernel<TPV, DQV, LDV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                     \
+  }
+#define TGFR_LAUNCH_BWD(TPV, DQV, TM)                     \
+  case TPV:                                               \
+    if (load) TGFR_LAUNCH_BWD1(TPV, DQV, true, TM)        \
+    else TGFR_LAUNCH_BWD1(TPV, DQV, false, TM)            \
     break;
   if (dctx) {
     CUtensorMap tm_dc;
@@ -1120,6 +1240,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     TGFR_LAUNCH_OK();
   }
 #undef TGFR_LAUNCH_BWD
+#undef TGFR_LAUNCH_BWD1
   return TGFR_OK;
 }
 
@@ -1127,6 +1248,13 @@ int wordregion_tc_set_trace(void* dev_buf) {
   long long* p = reinterpret_cast<long long*>(dev_buf);
   TGFR_CUDA_OK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return TGFR_OK;
+}
+
+// bytes of the forward -> backward records: one per unit (0 if the shape has no plan)
+size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D) {
+  TcPlan pl;
+  if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return 0;
+  return (size_t)Bc * pl.G * saved_unit_bytes(pl);
 }
 
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
@@ -1137,7 +1265,8 @@ size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
 
 int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* words, int64_t wsb,
                       int64_t wst, int64_t wsd, const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D, float g1,
-                      float g2, float g3, float eps, float* sim, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      float g2, float g3, float eps, float* sim, void* ws, size_t ws_bytes, void* saved, size_t saved_bytes,
+                      cudaStream_t st) {
   (void)eps;
   TcPlan pl;
   if (int rc = make_plan(Bc, Bq, T, R, D, &pl)) return rc;
@@ -1167,6 +1296,13 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
   p.off_q = pl.off_q; p.off_e = pl.off_e; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3;
+  const bool save = saved != nullptr;
+  p.sv_stride = saved_unit_bytes(pl);
+  if (save) {
+    TGFR_REQUIRE(saved_bytes >= (size_t)p.total_units * p.sv_stride, "wordregion(tc): saved buffer too small");
+    TGFR_REQUIRE((reinterpret_cast<uintptr_t>(saved) & 127) == 0, "wordregion(tc): saved buffer must be 128-byte aligned");
+  }
+  p.saved = reinterpret_cast<uint8_t*>(saved);
 
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));
@@ -1176,11 +1312,16 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     const int v = atoi(dg);
     if (v > 0 && v < grid) grid = v;
   }
-#define TGFR_LAUNCH_FWD(TPV)                                                                                    \
-  case TPV:                                                                                                    \
-    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+#define TGFR_LAUNCH_FWD1(TPV, SV)                                                                               \
+  {                                                                                                            \
+    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       (int)pl.smem_bytes));                                                    \
-    wr_tc_fwd_kernel<TPV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);                               \
+    wr_tc_fwd_kernel<TPV, SV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);                           \
+  }
+#define TGFR_LAUNCH_FWD(TPV)                  \
+  case TPV:                                   \
+    if (save) TGFR_LAUNCH_FWD1(TPV, true)     \
+    else TGFR_LAUNCH_FWD1(TPV, false)         \
     break;
   switch (pl.Tp) {
     TGFR_LAUNCH_FWD(8)
@@ -1192,6 +1333,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
       return TGFR_E_INVALID;
   }
 #undef TGFR_LAUNCH_FWD
+#undef TGFR_LAUNCH_FWD1
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }

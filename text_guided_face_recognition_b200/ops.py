@@ -85,10 +85,19 @@ class _WordRegionSim(torch.autograd.Function):
         lib = _lib.load()
         wsb = lib.tgfr_wordregion_workspace_bytes(Bc, Bq, T, R, D, precision)
         ws = _workspace(wsb, feats.device)
+        # forward -> backward image of the word softmax / attention (fp16): the backward then skips the score
+        # GEMM and every exponential.  TGFR_WORDREGION_SAVE=0 (or a buffer above the cap) selects recomputation.
+        saved, svb = None, 0
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _save_enabled():
+            svb = lib.tgfr_wordregion_saved_bytes(Bc, Bq, T, R, D, precision)
+            if 0 < svb <= _SAVE_CAP_BYTES:
+                saved = torch.empty(svb, dtype=torch.uint8, device=feats.device)
+            else:
+                svb = 0
         _call("tgfr_wordregion_fwd", feats.data_ptr(), *feats.stride(), words.data_ptr(), *words.stride(),
               ptr(cap_lens), Bc, Bq, T, R, D, g1, g2, g3, eps, sim.data_ptr(), ptr(attn), diag_off,
-              precision, ptr(ws), wsb, stream_ptr())
-        ctx.save_for_backward(feats, words, cap_lens)
+              precision, ptr(ws), wsb, ptr(saved), svb, stream_ptr())
+        ctx.save_for_backward(feats, words, cap_lens, saved)
         ctx.cfg = (g1, g2, g3, eps, precision)
         if attn is not None:
             ctx.mark_non_differentiable(attn)
@@ -96,7 +105,7 @@ class _WordRegionSim(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gsim, _gattn):
-        feats, words, cap_lens = ctx.saved_tensors
+        feats, words, cap_lens, saved = ctx.saved_tensors
         g1, g2, g3, eps, precision = ctx.cfg
         Bc, R, D = feats.shape
         Bq, T, _ = words.shape
@@ -109,8 +118,15 @@ class _WordRegionSim(torch.autograd.Function):
         ws = _workspace(wsb, feats.device)
         _call("tgfr_wordregion_bwd", feats.data_ptr(), *feats.stride(), words.data_ptr(), *words.stride(),
               ptr(cap_lens), Bc, Bq, T, R, D, g1, g2, g3, eps, gsim.data_ptr(), ptr(dctx), ptr(dwords),
-              precision, ptr(ws), wsb, stream_ptr())
+              precision, ptr(ws), wsb, ptr(saved), 0 if saved is None else saved.numel(), stream_ptr())
         return dctx, dwords, None, None, None, None, None, None, None, None
+
+
+_SAVE_CAP_BYTES = 24 << 30
+
+
+def _save_enabled() -> bool:
+    return os.environ.get("TGFR_WORDREGION_SAVE", "1").lower() not in ("0", "no", "off", "false")
 
 
 def tc_supported(T, R, D) -> bool:
