@@ -281,19 +281,40 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step(*sets[k % n_sets])
-    barrier()
+    # One CUDA graph per input set (single GPU): the eager Python / autograd launch path (~0.9 ms per step) is
+    # slower than the device work (~0.75 ms), so the step is captured once per rotating input set and replayed.
+    # Multi-GPU steps contain NCCL collectives and run eagerly.
+    use_graph = (world == 1) and not args.no_graph
+    runners = None
+
+    def build_runners():
+        from text_guided_face_recognition_b200.graphs import GraphedStep
+        out = []
+        for k in range(n_sets):
+            st_ = sets[k]
+            out.append(GraphedStep(lambda st_=st_: step(*st_)))
+        return out
+
+    def run_step(k):
+        return runners[k % n_sets]() if runners is not None else step(*sets[k % n_sets])
+
     ops.launch_counter.n = 0
+    step(*sets[0])
+    launches_per_step = ops.launch_counter.n                # kernels one step issues (captured or eager alike)
+    if use_graph:
+        runners = build_runners()
+    for k in range(args.warmup):
+        run_step(k)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         e0.record()
         for k in range(args.steps):
-            step(*sets[(args.warmup + k) % n_sets])
+            run_step(args.warmup + k)
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = ops.launch_counter.n
+    launches = launches_per_step * args.steps
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -329,7 +350,7 @@ def run_b200(args):
                 issue_copy(k + 1)
             slot = k % 2
             main_stream.wait_event(copied[slot])
-            total = step(*sets[slot])
+            total = run_step(slot)
             consumed[slot].record(main_stream)
             loss_host.copy_(total.detach().reshape(1), non_blocking=True)
             main_stream.synchronize()                          # the caller reads the loss every step
@@ -356,12 +377,16 @@ def run_b200(args):
     for st_ in sets:
         st_[1].requires_grad_(other == "both")
     n_other = max(3, min(args.steps, 50))
+    if use_graph:
+        runners = None
+        torch.cuda.synchronize()
+        runners = build_runners()
     for k in range(n_sets + 3):                               # every input set once: gradient buffers get allocated
-        step(*sets[k % n_sets])
+        run_step(k)
     barrier()
     e0.record()
     for k in range(n_other):
-        step(*sets[(3 + k) % n_sets])
+        run_step(3 + k)
     e1.record()
     barrier()
     other_ms = e0.elapsed_time(e1)
@@ -382,7 +407,8 @@ def run_b200(args):
                                f"captions per rank, T={T}, R={R}, D={D}",
                    "global_batch": Bg, "local_batch": B, "grads": args.grads, "parallelism": f"row-sharded x{world}",
                    "precision": "fp32-simt" if precision == _lib.PREC_FP32 else "tcgen05",
-                   "l2": f"rotating {n_sets} input sets ({n_sets * bytes_per_set >> 20} MiB > 126 MiB L2)"},
+                   "l2": f"rotating {n_sets} input sets ({n_sets * bytes_per_set >> 20} MiB > 126 MiB L2)",
+                   "launch": "one CUDA graph replay per step (graphs.GraphedStep)" if use_graph else "eager"},
         "clocks": clk.result, "e2e": e2e, "gpu_launches": launches,
         "other_grads": {"grads": other, "value": pairs / (other_ms * 1e-3), "unit": "pairs/s", "ms_per_step": other_ms,
                         "steps": n_other},
@@ -451,11 +477,15 @@ def run_b200(args):
         for _ in range(3):
             head_step()
         torch.cuda.synchronize()
+        head_run = head_step
+        if use_graph:
+            from text_guided_face_recognition_b200.graphs import GraphedStep
+            head_run = GraphedStep(head_step)
         hs = []
         for _ in range(max(3, min(args.steps, 10))):
             flush.zero_()
             e0.record()
-            head_step()
+            head_run()
             e1.record()
             torch.cuda.synchronize()
             hs.append(e0.elapsed_time(e1))
@@ -463,6 +493,8 @@ def run_b200(args):
         hflops = 6 * h["Din"] * h["C"] * h["B"]
         line["margin_head"] = {"metric": "arcface_focal_fwd_bwd_samples_per_sec", "value": h["B"] / (h_ms * 1e-3),
                                "unit": "samples/s", "ms_per_step": h_ms, "config": h,
+                               "precision": os.environ.get("TGFR_HEAD_PRECISION", "tc"),
+                               "launch": "CUDA graph replay" if use_graph else "eager",
                                "tflops": hflops / (h_ms * 1e-3) / 1e12,
                                "frac_of_tensor_peak": hflops / (h_ms * 1e-3) / 1e12 / pk["tf_burst"]}
 
@@ -495,6 +527,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--grads", default="ctx", choices=["ctx", "both"],
                     help="gradients of the word-region loss: ctx = face side only (the reference's training step), both")
     args = ap.parse_args()

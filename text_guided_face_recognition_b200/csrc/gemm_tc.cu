@@ -234,7 +234,14 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.kt_per_split = per; p.alpha = alpha; p.dscale = dscale; p.clamp = clamp;
   p.atomic = splits > 1; p.a_mn = a_mn; p.b_mn = b_mn;
   if (splits > 1) TGFR_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
-  TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  bool& attr_set = attr_done[dev & 63];
+  if (!attr_set) {
+    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    attr_set = true;
+  }
   const dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
   gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
   TGFR_LAUNCH_OK();

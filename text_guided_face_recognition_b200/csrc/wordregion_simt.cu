@@ -460,7 +460,15 @@ template <int TP, int MODE>
 int launch_fwd(const Params& p, cudaStream_t st) {
   const size_t bytes = smem_floats<TP>(p.R, p.D, false) * sizeof(float);
   auto k = wr_fwd_kernel<TP, MODE>;
-  TGFR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  {
+    static bool attr_done[64] = {};   // once per instantiation and device
+    int dev = 0;
+    TGFR_CUDA_OK(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+      TGFR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_done[dev & 63] = true;
+    }
+  }
   const dim3 grid(MODE == kLoss ? p.Bq : p.Bc, MODE == kLoss ? p.Bc : 1);
   k<<<grid, kThreads, bytes, st>>>(p);
   TGFR_LAUNCH_OK();
@@ -471,7 +479,15 @@ template <int TP, int MODE>
 int launch_bwd(const Params& p, cudaStream_t st) {
   const size_t bytes = smem_floats<TP>(p.R, p.D, true) * sizeof(float);
   auto k = wr_bwd_kernel<TP, MODE>;
-  TGFR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  {
+    static bool attr_done[64] = {};   // once per instantiation and device
+    int dev = 0;
+    TGFR_CUDA_OK(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+      TGFR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_done[dev & 63] = true;
+    }
+  }
   const dim3 grid(MODE == kLoss ? p.Bq : p.Bc, MODE == kLoss ? p.Bc : 1);
   k<<<grid, kThreads, bytes, st>>>(p);
   TGFR_LAUNCH_OK();

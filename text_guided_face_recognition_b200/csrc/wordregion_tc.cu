@@ -1195,8 +1195,13 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
 
 #define TGFR_LAUNCH_BWD1(TPV, DQV, LDV, TM)                                                                         \
   {                                                                                                                 \
-    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)pl.smem_bytes));                                                         \
+    static bool attr_done[64] = {};   /* once per instantiation and device, to the architectural maximum */         \
+    bool& attr_set = attr_done[dev & 63];                                                                           \
+    if (!attr_set) {                                                                                                \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        232448));                                                                   \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
     wr_tc_bwd_kernel<TPV, DQV, LDV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                     \
   }
 #define TGFR_LAUNCH_BWD(TPV, DQV, TM)                     \
@@ -1314,8 +1319,13 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   }
 #define TGFR_LAUNCH_FWD1(TPV, SV)                                                                               \
   {                                                                                                            \
-    TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                      (int)pl.smem_bytes));                                                    \
+    static bool attr_done[64] = {};                                                                            \
+    bool& attr_set = attr_done[dev & 63];                                                                      \
+    if (!attr_set) {                                                                                           \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        232448));                                                              \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
     wr_tc_fwd_kernel<TPV, SV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);                           \
   }
 #define TGFR_LAUNCH_FWD(TPV)                  \
