@@ -63,6 +63,27 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel, from the committed
+    `ncu --set full` summary of this round (profiles/r1_wr_tc_final_ncu_raw.txt, same shapes as this bench)."""
+    path = os.path.join(ROOT, "profiles", "r1_wr_tc_final_ncu_raw.txt")
+    try:
+        rd = wr = None
+        hit = False
+        for line in open(path):
+            if line.startswith("== "):
+                hit = kernel_substr in line
+            elif hit and line.startswith("dram__bytes_read.sum ="):
+                rd = float(line.split("=")[1])
+            elif hit and line.startswith("dram__bytes_write.sum ="):
+                wr = float(line.split("=")[1])
+        if rd is None or wr is None:
+            return None
+        return (rd + wr) * 1e6                                   # ncu prints MB
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """SM clock / throttle-reason sampler running during the timed region.
 
@@ -454,7 +475,11 @@ def run_b200(args):
         flops = (8 if args.grads == "both" else 6) * T * R * D * B * Bg
         achieved = flops / (k_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                            "frac": achieved / pk["tf_burst"], "traffic": None, "kernel": "wordregion_bwd",
+                            "frac": achieved / pk["tf_burst"],
+                            "traffic": ncu_traffic("wr_tc_bwd_kernel") if (world == 1 and args.grads == "ctx" and
+                                                                             precision == _lib.PREC_TC) else None,
+                            "traffic_source": "profiles/r1_wr_tc_final_ncu_raw.txt (ncu --set full, same shapes)",
+                            "kernel": "wordregion_bwd",
                             "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                             "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
                             "step_tflops": flops_per_pair(args.grads) * B * Bg / (ms * 1e-3) / 1e12,
