@@ -15,6 +15,7 @@ PyTorch implementation (oracle/ref_port.py) on the host cores instead.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -304,16 +305,18 @@ def run_b200(args):
 
     # One CUDA graph per input set (single GPU): the eager Python / autograd launch path (~0.9 ms per step) is
     # slower than the device work (~0.75 ms), so the step is captured once per rotating input set and replayed.
-    # Multi-GPU steps contain NCCL collectives and run eagerly.
-    use_graph = (world == 1) and not args.no_graph
+    # Multi-GPU steps contain NCCL collectives; NCCL launches are capturable, so they are graphed the same way.
+    # All graphs share one memory pool (they are replayed one at a time).
+    use_graph = not args.no_graph
     runners = None
 
     def build_runners():
         from text_guided_face_recognition_b200.graphs import GraphedStep
+        pool = torch.cuda.graph_pool_handle()                 # a fresh pool per build: it dies with its graphs
         out = []
         for k in range(n_sets):
             st_ = sets[k]
-            out.append(GraphedStep(lambda st_=st_: step(*st_)))
+            out.append(GraphedStep(lambda st_=st_: step(*st_), pool=pool))
         return out
 
     def run_step(k):
@@ -541,8 +544,16 @@ def run_b200(args):
                                               f"{t_used:.1f} s of oracle/ref_port.py on the host"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # release the captured graphs before the communicator goes away, then leave without the NCCL teardown
+        # (destroy_process_group() was seen to block when graphs holding captured collectives had existed)
+        runners = None
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -33,6 +33,7 @@ using namespace tc;
 constexpr int kThreadsTC = 320;
 constexpr int kEpiThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kSV = 256.f;   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
 
 enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull, kWuFull, kWuEmpty, kNumBars };
 
@@ -41,8 +42,11 @@ struct TcParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
-  uint8_t* saved;        // SAVE: per unit [E tile image: 2 * e_panel bytes][A1 fp16: nc x Rp x Tp], for the backward
-  uint32_t sv_stride;    // bytes per unit
+  // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
+  __half* sv_v;          // [total_units * nw_rows, D]   V_w = kSV * p_w * (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
+  uint8_t* sv_rec;       // [total_units][nc][Rp][A1 fp16 x Tp | E fp16 x Tp]   word softmax and exp(g1 (A1 - 1))
+  float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
+  uint32_t rec_stride;   // bytes of one unit's records
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
   float k1, k2, g3;
@@ -126,6 +130,8 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 128);   // [2][128]
   float* part_n = part_d + 256;                                        // [2][128]
   float* exs = part_n + 256;                                           // [128]
+  float* cosw = exs + 128;                                             // [128] SAVE: cos_w
+  float* inww = cosw + 128;                                            // [128] SAVE: 1 / |Wu_w|
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
@@ -144,10 +150,6 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tm_c);
     tma_prefetch_desc(&tm_q);
-  }
-  if constexpr (SAVE) {   // the E tile is copied out whole: its never-written padding columns must be defined
-    for (uint32_t k = tid; k < (2 * p.e_panel >> 4); k += kThreadsTC) reinterpret_cast<uint4*>(s_e)[k] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -198,10 +200,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
             const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
             umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
           }
-          if (t == 0) {
-            if constexpr (SAVE) tma_wait_group_read<0>();        // the previous unit's E tile has been copied out
-            umma_commit(&bars[kSFull0]);                         // the tile-0 epilogue group starts while tile 1 runs
-          }
+          if (t == 0) umma_commit(&bars[kSFull0]);                // the tile-0 epilogue group starts while tile 1 runs
         }
         umma_commit(&bars[kQEmpty]);
         umma_commit(&bars[kSFull1]);
@@ -217,12 +216,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
         }
         umma_commit(&bars[kWuFull]);
-        if constexpr (SAVE) {                                    // the E tile (as laid out for GEMM-2) -> saved record
-          bulk_store(p.saved + (int64_t)u * p.sv_stride, s_e, 2 * p.e_panel);
-          tma_commit_group();
-        }
       }
-      if constexpr (SAVE) tma_wait_group<0>();
     }
   } else {
     // ======================================= epilogue =======================================
@@ -244,16 +238,11 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         for (int c = 0; c < p.nc; ++c) {
           const int i = g * p.nc + c;
           if (i >= p.Bq) {
-            if constexpr (SAVE) {                               // missing captions: zero columns for the backward
+            if constexpr (SAVE) {                               // missing captions: zero records for the backward
               if (r < p.Rp) {
-                uint4* a1dst = reinterpret_cast<uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
-                               ((int64_t)c * p.Rp + r) * (TP / 8);
+                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + ((int64_t)c * p.Rp + r) * (TP / 4);
 #pragma unroll
-                for (int j = 0; j < TP / 8; ++j) {
-                  a1dst[j] = make_uint4(0, 0, 0, 0);
-                  const int w0 = c * TP + 8 * j;
-                  *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) = make_uint4(0, 0, 0, 0);
-                }
+                for (int j = 0; j < TP / 4; ++j) rdst[j] = make_uint4(0, 0, 0, 0);
               }
               continue;
             }
@@ -298,12 +287,13 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
               pe[t >> 1] = live_row ? pk : 0u;
             }
             if (r < p.Rp) {
-              // A1 [caption][row][Tp fp16]: a warp's 32 rows are contiguous in memory (coalesced); E leaves through
-              // the shared-memory tile below (one bulk copy per unit)
-              uint4* a1dst = reinterpret_cast<uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
-                             ((int64_t)c * p.Rp + r) * (TP / 8);
+              // [caption][row][A1 x Tp | E x Tp] fp16: a warp's 32 rows are contiguous in memory
+              uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + ((int64_t)c * p.Rp + r) * (TP / 4);
 #pragma unroll
-              for (int j = 0; j < TP / 8; ++j) a1dst[j] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+              for (int j = 0; j < TP / 8; ++j) {
+                rdst[j] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+                rdst[TP / 8 + j] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+              }
             }
           } else {
             const float kinv = p.k1 / sum;
@@ -374,22 +364,70 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       }
       dot = (dot + dot1) + (dot2 + dot3);
       n2 = (n2 + n21) + (n22 + n23);
-      tc_fence_before();
-      mbar_arrive(&bars[kWuEmpty]);
+      if constexpr (!SAVE) {
+        tc_fence_before();
+        mbar_arrive(&bars[kWuEmpty]);
+      }
       if (tid == 64) TGFR_TRACE(n, 5);
       part_d[tile * 128 + w] = dot;
       part_n[tile * 128 + w] = n2;
       epi_bar_sync();
       if (tile == 0) {
-        float ex = 0.f;
+        float ex = 0.f, cs = 0.f, inw = 0.f;
         if (valid) {
           const float dd = part_d[w] + part_d[128 + w], nn = part_n[w] + part_n[128 + w];
-          const float den = fmaxf(__ldg(p.qnorm + qrow) * sqrtf(nn), 1e-30f);
-          ex = fast_exp2(p.k2 * (dd / den));
+          const float nW = fmaxf(sqrtf(nn), 1e-30f);
+          cs = dd / (fmaxf(__ldg(p.qnorm + qrow), 1e-30f) * nW);
+          ex = fast_exp2(p.k2 * cs);
+          inw = 1.f / nW;
         }
         exs[w] = ex;
+        if constexpr (SAVE) {
+          cosw[w] = cs;
+          inww[w] = inw;
+          p.sv_inw[(int64_t)u * 128 + w] = inw;
+        }
       }
       epi_bar_sync();
+      if constexpr (SAVE) {
+        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 rows of the saved V tile.
+        // d sim[b,i] / d Wu_w = g2 g3 V_w / (kSV |Wu_w|): the backward needs no cosine / softmax work of its own.
+        float c1 = 0.f, c2 = 0.f;
+        if (valid) {
+          float ssum = 0.f;
+#pragma unroll
+          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
+          const float pw = kSV * exs[w] / ssum;
+          c1 = pw / fmaxf(__ldg(p.qnorm + qrow), 1e-30f);
+          c2 = pw * cosw[w] * inww[w];
+        }
+        // (the TMEM loads are warp-collective: only the stores are predicated on the word row)
+        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + ((int64_t)u * p.nw_rows + min(w, p.nw_rows - 1)) * p.D + tile * dhalf);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < nch) {
+            uint32_t v[32];
+            tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const __half2* qh = reinterpret_cast<const __half2*>(&qreg[4 * ch + cc]);
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 qf = __half22float2(qh[k]);
+                // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
+                o[k] = valid ? pack_half2(c1 * qf.x - c2 * __uint_as_float(v[8 * cc + 2 * k]),
+                                          c1 * qf.y - c2 * __uint_as_float(v[8 * cc + 2 * k + 1]))
+                             : 0u;
+              }
+              if (w < p.nw_rows) vdst[4 * ch + cc] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[kWuEmpty]);
+      }
       if (tile == 0 && w < p.nc) {
         const int ii = g * p.nc + w;
         if (ii < p.Bq) {
@@ -426,8 +464,6 @@ struct TcBwdParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   const float* gsim;     // [Bc, Bq]
-  const uint8_t* saved;  // LOAD: the forward's per-unit [E tile image][A1 fp16] records
-  uint32_t sv_stride;    // bytes per unit
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   uint32_t c_panel, q_panel, e_panel, off_q, off_x, off_misc;
   float k1, k2, g1, g23;   // g23 = gamma2 * gamma3
@@ -442,9 +478,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 // direct cosine gradient through Wu = E^T C) as fp16 into shared memory in the E layout, GEMM-4
 // dQ[w,d] = sum_r dS'[r,w] c_r[d] reuses GEMM-2's descriptors, and the drain subtracts the direct term in q_w and
 // reduce-adds into the padded [Bq*Tp, D] gradient (tm_dc is then the map of that buffer).
-// LOAD = true: the forward kernel saved the fp16 (A1 | E) image of every unit; GEMM-1 and epi-1 are replaced by
-// reading it back into TMEM / shared memory (no score recomputation, no exponentials).
-template <int TP, bool DQ, bool LOAD>
+// This kernel recomputes everything from C and Q (no forward records).  It serves d words and, when the forward kept
+// no records, d ctx; with records d ctx runs in wr_tc_bwd2_kernel below.
+template <int TP, bool DQ>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_dc, const TcBwdParams p) {
@@ -500,20 +536,15 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       int prev_b = -1, n = 0;
       for (int u = u0; u < u1; ++u, ++n) {
         const int b = u / p.G, g = u - b * p.G;
-        if constexpr (LOAD) {   // pull the next unit's saved record towards L2 while this unit runs
-          if (n == 0) bulk_prefetch_l2(p.saved + (int64_t)u * p.sv_stride, p.sv_stride);
-          if (u + 1 < u1) bulk_prefetch_l2(p.saved + (int64_t)(u + 1) * p.sv_stride, p.sv_stride);
-        }
         if (n > 0) mbar_wait(&bars[bDr3], (n - 1) & 1);   // previous unit fully drained: Q / X / C are free
         if (b != prev_b) {
           mbar_arrive_expect_tx(&bars[bCFull], kchunks * p.c_panel);
           for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[bCFull], kc * 64, 0, b);
           prev_b = b;
         }
-        mbar_arrive_expect_tx(&bars[bQFull], kchunks * p.q_panel + (LOAD ? 2 * p.e_panel : 0));
+        mbar_arrive_expect_tx(&bars[bQFull], kchunks * p.q_panel);
         for (int kc = 0; kc < kchunks; ++kc)
           tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[bQFull], kc * 64, g * p.nw_rows, 0);
-        if constexpr (LOAD) bulk_load(s_x, p.saved + (int64_t)u * p.sv_stride, 2 * p.e_panel, &bars[bQFull]);
       }
     }
   } else if (warp == 1) {
@@ -534,19 +565,17 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         TGFR_TRACE(n, 17);
         tc_fence_after();
         // GEMM-1: S_t = C_t . Q^T
-        if constexpr (!LOAD) {
-          for (int t = 0; t < p.n_tiles; ++t) {
-            for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
-              const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
-              const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
-              umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
-            }
-            if (t == 0) umma_commit(&bars[bSFull0]);
+        for (int t = 0; t < p.n_tiles; ++t) {
+          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
+            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
           }
-          umma_commit(&bars[bSFull1]);
+          if (t == 0) umma_commit(&bars[bSFull0]);
         }
-        // GEMM-2: Wu = E^T . C   (LOAD: the E tile arrived with the Q tile, straight from the saved record)
-        if constexpr (!LOAD) mbar_wait(&bars[bEFull], n & 1);
+        umma_commit(&bars[bSFull1]);
+        // GEMM-2: Wu = E^T . C
+        mbar_wait(&bars[bEFull], n & 1);
         TGFR_TRACE(n, 18);
         tc_fence_after();
         for (int j = 0; j < (p.Rp >> 4); ++j) {
@@ -642,45 +671,6 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
       const float sigma = (gmax > 0.f) ? exp2f(floorf(log2f(4096.f / (p.g23 * gmax)))) : 1.f;
       const float inv_sigma = 1.f / sigma;
 
-      if constexpr (LOAD) {
-        // ---------------- epi-1 (LOAD): saved A1 (global) and E (the shared-memory tile) -> TMEM ----------------
-        constexpr int NV = 5;                                      // captions whose A1 is fetched per batch
-        const uint4* a1src = reinterpret_cast<const uint4*>(p.saved + (int64_t)u * p.sv_stride + 2 * p.e_panel) +
-                             (int64_t)min(r, p.Rp - 1) * (TP / 8);
-        const int64_t cstride = (int64_t)p.Rp * (TP / 8);          // uint4 per caption
-        for (int c0 = 0; c0 < p.nc; c0 += NV) {
-          uint4 ld[NV][TP / 8];
-#pragma unroll
-          for (int cc = 0; cc < NV; ++cc)
-#pragma unroll
-            for (int j = 0; j < TP / 8; ++j) ld[cc][j] = __ldg(a1src + min(c0 + cc, p.nc - 1) * cstride + j);
-          if (c0 == 0) {
-            // every warp has finished draining the previous unit (TMEM holes, staging boxes over Q / X) ...
-            if (n > 0) mbar_wait(&bars[bDr3], (n - 1) & 1);
-            mbar_wait(&bars[bQFull], n & 1);                       // ... and this unit's E tile has landed
-            if (tid == 64) TGFR_TRACE(n, 2);
-            tc_fence_after();
-          }
-          if (warp_has_rows) {
-#pragma unroll
-            for (int cc = 0; cc < NV; ++cc) {
-              const int c = c0 + cc;
-              if (c < p.nc) {
-                const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
-#pragma unroll
-                for (int j = 0; j < TP / 8; ++j) {
-                  const int w0 = c * TP + 8 * j;
-                  const uint4 ev = *reinterpret_cast<const uint4*>(s_x + (w0 >> 6) * p.e_panel +
-                                                                   sw128_offset(min(r, p.Rp - 1), (w0 & 63) >> 3));
-                  tmem_st4(col + 4 * j, ld[cc][j].x, ld[cc][j].y, ld[cc][j].z, ld[cc][j].w);
-                  tmem_st4(col + TP / 2 + 4 * j, ev.x, ev.y, ev.z, ev.w);
-                }
-              }
-            }
-          }
-        }
-        if (warp_has_rows) tmem_st_wait();
-      } else {
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
       mbar_wait(&bars[tile == 0 ? bSFull0 : bSFull1], n & 1);
       if (tid == 64) TGFR_TRACE(n, 2);
@@ -739,7 +729,6 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         }
         tmem_st_wait();
       }
-      }  // !LOAD
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bars[bEFull]);
@@ -1049,6 +1038,326 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward (d ctx) from the forward's records: wr_tc_bwd2_kernel
+//
+// The forward (SAVE) leaves, per unit (face b, caption group g): A1 and E as fp16 rows, 1/|Wu_w|, and the tile
+//   V_w = kSV p_w (q^_w - cos_w w^_w),    d sim[b,i] / d Wu_w = g2 g3 V_w / (kSV |Wu_w|)   (w a word of caption i),
+// so the gradient of a pair is linear in G[b,i] = d loss / d sim[b,i] and needs no cosine / softmax work here:
+//   GEMM-3   dE~[r,w] = <c_r, V_w>                               M = 128 regions (one tile), N = 128 words, K = D
+//   epi-3    kappa_w = G[b,i] g2 g3 sigma_b / (kSV |Wu_w|);  Ek = E kappa;  dA1 = g1 Ek dE~;
+//            dS = A1 (dA1 - sum_t A1 dA1)  -> (dS | Ek) as fp16 A operands in TMEM
+//   GEMM-6/5 dC[r,:] += sum_w Ek[r,w] V_w + dS[r,w] q_w          A from TMEM, B = MN-major views of the V and Q tiles
+// A work item is (face b, region tile t, caption group g) with g innermost: the 128 x D fp32 block of d ctx of one
+// (b, t) stays in 256 TMEM columns while the CTA walks the caption groups and leaves once, by TMA reduce-add (a
+// (b, t) range may be split between two CTAs).  Per item the CTA streams the Q and V tiles (TMA) and the tile's
+// A1 | E rows (coalesced loads); there is no GEMM-1, GEMM-2, exponential or per-unit drain.
+// sigma_b is a per-face power of two that keeps the fp16 operands in the normal range.
+//
+// TMEM columns: [0,256) d ctx block, [256,384) dE~, [384,448) dS (fp16 pairs), [448,512) Ek (fp16 pairs).
+// ---------------------------------------------------------------------------------------------
+enum BarC { cCFull = 0, cVFull, cQFull, cDeFull, cOpsFull, cVFree, cAccDone, cDrained, cNum };
+
+struct TcBwd2Params {
+  const uint8_t* rec;    // [total_units][nc][Rp][A1 x Tp | E x Tp] fp16
+  const float* inw;      // [total_units][128]
+  const float* gsim;     // [Bc, Bq]
+  uint32_t rec_stride;   // bytes per unit
+  int Bc, Bq, R, Rp, D, nc, G, nw_rows, n_tiles, total_items;
+  uint32_t q_panel, off_q, off_v, off_misc;
+  float g1, g23;
+};
+
+template <int TP>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
+                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_dc,
+                  const TcBwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_c = smem;                         // C tile: D/64 panels of 128 rows x 128 B (K-major, GEMM-3's A)
+  uint8_t* s_q = smem + p.off_q;               // Q tile: D/64 panels of nw_rows x 128 B
+  uint8_t* s_v = smem + p.off_v;               // V tile: same shape; 1 KB of zeros follows it
+  uint8_t* misc = smem + p.off_misc;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+  float* kap = reinterpret_cast<float*>(misc + 256);           // [2][128] kappa_w, double buffered over items
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = (int)((int64_t)blockIdx.x * p.total_items / gridDim.x);
+  const int s1 = (int)((int64_t)(blockIdx.x + 1) * p.total_items / gridDim.x);
+  const int kchunks = p.D >> 6;
+  constexpr uint32_t kCPanel = 128 * 128;
+
+  if (tid == 0) {
+    mbar_init(&bars[cCFull], 1);
+    mbar_init(&bars[cVFull], 1);
+    mbar_init(&bars[cQFull], 1);
+    mbar_init(&bars[cDeFull], 1);
+    mbar_init(&bars[cOpsFull], kEpiThreads);
+    mbar_init(&bars[cVFree], 1);
+    mbar_init(&bars[cAccDone], 1);
+    mbar_init(&bars[cDrained], kEpiThreads);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_c);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_dc);
+  }
+  // operand tiles are read a few rows beyond what TMA writes (K / N padding of the MMA shapes): keep them finite
+  for (uint32_t k = tid; k < (p.off_misc >> 4); k += kThreadsTC) reinterpret_cast<uint4*>(smem)[k] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int prev_ft = -1, n = 0, m = -1;
+      for (int s = s0; s < s1; ++s, ++n) {
+        const int ft = s / p.G, g = s - ft * p.G;
+        const int b = ft / p.n_tiles, t = ft - b * p.n_tiles;
+        const int u = b * p.G + g;
+        {   // pull the tile's A1 | E rows of this item (first one) and the next towards L2
+          const int rows = min(p.Rp - t * 128, 128);
+          for (int k = (n == 0 ? 0 : 1); k < 2; ++k) {
+            const int sn = s + k;
+            if (sn >= s1) break;
+            const int ftn = sn / p.G, gn = sn - ftn * p.G, bn = ftn / p.n_tiles, tn = ftn - bn * p.n_tiles;
+            const int rows_n = (k == 0) ? rows : min(p.Rp - tn * 128, 128);
+            const uint8_t* base = p.rec + (int64_t)(bn * p.G + gn) * p.rec_stride;
+            for (int c = 0; c < p.nc; ++c)
+              bulk_prefetch_l2(base + ((int64_t)c * p.Rp + tn * 128) * (TP * 4), (uint32_t)rows_n * TP * 4);
+          }
+        }
+        if (n > 0) mbar_wait(&bars[cVFree], (n - 1) & 1);           // GEMM-3 and GEMM-6 of the previous item retired
+        if (ft != prev_ft) {
+          if (m >= 0) mbar_wait(&bars[cDrained], m & 1);            // drain boxes overlay the operand tiles
+          ++m;
+          mbar_arrive_expect_tx(&bars[cCFull], kchunks * kCPanel);
+          for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * kCPanel, &tm_c, &bars[cCFull], kc * 64, t * 128, b);
+          prev_ft = ft;
+        }
+        mbar_arrive_expect_tx(&bars[cVFull], kchunks * p.q_panel);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(s_v + kc * p.q_panel, &tm_v, &bars[cVFull], kc * 64, u * p.nw_rows, 0);
+        if (n > 0) mbar_wait(&bars[cAccDone], (n - 1) & 1);         // GEMM-5 of the previous item retired
+        mbar_arrive_expect_tx(&bars[cQFull], kchunks * p.q_panel);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[cQFull], kc * 64, g * p.nw_rows, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc3 = make_idesc_f16(128, 128, false, false);    // dE~
+      const uint32_t idesc5 = make_idesc_f16(128, p.D, false, true);     // d ctx block: A in TMEM, B MN-major
+      const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_v = smem_u32(s_v);
+      int prev_ft = -1, n = 0, m = -1;
+      for (int s = s0; s < s1; ++s, ++n) {
+        const int ft = s / p.G;
+        const bool first = ft != prev_ft;
+        if (first) {
+          ++m;
+          mbar_wait(&bars[cCFull], m & 1);
+          prev_ft = ft;
+        }
+        mbar_wait(&bars[cVFull], n & 1);
+        TGFR_TRACE(n, 17);
+        tc_fence_after();
+        for (int k16 = 0; k16 < (p.D >> 4); ++k16) {                     // GEMM-3
+          const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * kCPanel + (k16 & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(a_v + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+          umma_ss(tmem + 256, ad, bd, idesc3, k16 > 0);
+        }
+        umma_commit(&bars[cDeFull]);
+        mbar_wait(&bars[cOpsFull], n & 1);
+        TGFR_TRACE(n, 18);
+        tc_fence_after();
+        for (int k16 = 0; k16 < 8; ++k16) {                              // GEMM-6: Ek . V  (the first MMA of a (b, t) range overwrites)
+          const uint64_t bv = make_smem_desc(a_v + k16 * 2048, p.q_panel, 1024);
+          umma_ts(tmem, tmem + 448 + 8 * k16, bv, idesc5, !(first && k16 == 0));
+        }
+        umma_commit(&bars[cVFree]);
+        mbar_wait(&bars[cQFull], n & 1);
+        tc_fence_after();
+        for (int k16 = 0; k16 < 8; ++k16) {                              // GEMM-5: dS . Q
+          const uint64_t bq = make_smem_desc(a_q + k16 * 2048, p.q_panel, 1024);
+          umma_ts(tmem, tmem + 384 + 8 * k16, bq, idesc5, true);
+        }
+        umma_commit(&bars[cAccDone]);
+        TGFR_TRACE(n, 19);
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int h = (warp - 2) >> 2;               // warp group: which captions in epi-3, which half of D in the drain
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+    const int nc0 = (p.nc + 1) >> 1;
+    const int c_lo = h ? nc0 : 0, c_hi = h ? p.nc : nc0;
+    constexpr int NB = TP <= 24 ? 3 : 2;         // captions whose rows are fetched per batch (register budget)
+    if (h == 0) {                                // K padding (words nw_rows..127) of both operands: zero, once
+      for (int col = p.nw_rows >> 1; col < 64; col += 4) {
+        tmem_st4(tmem + t_lane + 384 + col, 0u, 0u, 0u, 0u);
+        tmem_st4(tmem + t_lane + 448 + col, 0u, 0u, 0u, 0u);
+      }
+      tmem_st_wait();
+    }
+    int prev_b = -1, n = 0;
+    float sigma = 1.f, inv_sigma = 1.f;
+    for (int s = s0; s < s1; ++s, ++n) {
+      const int ft = s / p.G, g = s - ft * p.G;
+      const int b = ft / p.n_tiles, t = ft - b * p.n_tiles;
+      const int u = b * p.G + g;
+      const bool last = (s + 1 == s1) || ((s + 1) / p.G != ft);
+      if (b != prev_b) {                         // per-face power-of-two scale from the largest |d loss / d sim[b, :]|
+        float gmax = 0.f;
+        for (int i = lane; i < p.Bq; i += 32) gmax = fmaxf(gmax, fabsf(__ldg(p.gsim + (int64_t)b * p.Bq + i)));
+        gmax = warp_max(gmax);
+        sigma = (gmax > 0.f) ? exp2f(floorf(log2f(4096.f / (p.g23 * gmax)))) : 1.f;
+        inv_sigma = 1.f / sigma;
+        prev_b = b;
+      }
+      float* const kp = kap + (n & 1) * 128;
+      if (h == 0) {
+        const int w = lrow, c = w / TP, i = g * p.nc + c;
+        float k = 0.f;
+        if (w < p.nw_rows && i < p.Bq)
+          k = __ldg(p.inw + (int64_t)u * 128 + w) * __ldg(p.gsim + (int64_t)b * p.Bq + i) * (p.g23 * sigma * (1.f / kSV));
+        kp[w] = k;
+      }
+      // this thread's A1 | E rows of its captions: issued before the waits so that the latency hides under GEMM-3
+      const int r = t * 128 + lrow;
+      const bool warp_has_rows = (t * 128 + quarter * 32) < p.Rp;
+      const uint4* rsrc = reinterpret_cast<const uint4*>(p.rec + (int64_t)u * p.rec_stride) + (int64_t)min(r, p.Rp - 1) * (TP / 4);
+      const int64_t cstride = (int64_t)p.Rp * (TP / 4);
+      epi_bar_sync();                            // kappa visible; the other buffer is free for the next item
+      bool waited = false;
+      for (int c0 = c_lo; c0 < c_hi; c0 += NB) {
+        uint4 rc[NB][TP / 4];
+        if (warp_has_rows) {
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+            for (int j = 0; j < TP / 4; ++j) rc[cc][j] = __ldg(rsrc + min(c0 + cc, c_hi - 1) * cstride + j);
+        }
+        if (!waited) {
+          mbar_wait(&bars[cDeFull], n & 1);      // GEMM-3 retired (and with it every MMA of the previous item)
+          if (tid == 64) TGFR_TRACE(n, 2);
+          tc_fence_after();
+          waited = true;
+        }
+        if (warp_has_rows) {
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc) {
+            const int c = c0 + cc;
+            if (c < c_hi) {
+              uint32_t vd[TP];
+#pragma unroll
+              for (int j = 0; j < TP / 8; ++j) tmem_ld8(tmem + t_lane + 256 + c * TP + 8 * j, vd + 8 * j);
+              tmem_ld_wait();
+              const uint32_t* ra = reinterpret_cast<const uint32_t*>(&rc[cc][0]);
+              float a1[TP], ek[TP], da[TP];
+              float innerp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int tt = 0; tt < TP; tt += 2) {
+                const float2 af = __half22float2(*reinterpret_cast<const __half2*>(&ra[tt >> 1]));
+                const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&ra[TP / 2 + (tt >> 1)]));
+                const float2 kk = *reinterpret_cast<const float2*>(kp + c * TP + tt);
+                a1[tt] = af.x;
+                a1[tt + 1] = af.y;
+                ek[tt] = ef.x * kk.x;
+                ek[tt + 1] = ef.y * kk.y;
+                da[tt] = p.g1 * ek[tt] * __uint_as_float(vd[tt]);
+                da[tt + 1] = p.g1 * ek[tt + 1] * __uint_as_float(vd[tt + 1]);
+                innerp[tt & 2] = fmaf(a1[tt], da[tt], innerp[tt & 2]);
+                innerp[(tt & 2) + 1] = fmaf(a1[tt + 1], da[tt + 1], innerp[(tt & 2) + 1]);
+              }
+              const float inner = (innerp[0] + innerp[1]) + (innerp[2] + innerp[3]);
+#pragma unroll
+              for (int j = 0; j < TP / 8; ++j) {
+                uint32_t ds[4], ee[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int t0 = 8 * j + 2 * k;
+                  ds[k] = pack_half2(a1[t0] * (da[t0] - inner), a1[t0 + 1] * (da[t0 + 1] - inner));
+                  ee[k] = pack_half2(ek[t0], ek[t0 + 1]);
+                }
+                tmem_st4(tmem + t_lane + 384 + ((c * TP) >> 1) + 4 * j, ds[0], ds[1], ds[2], ds[3]);
+                tmem_st4(tmem + t_lane + 448 + ((c * TP) >> 1) + 4 * j, ee[0], ee[1], ee[2], ee[3]);
+              }
+            }
+          }
+        }
+      }
+      if (!waited) {                             // a warp group without captions (nc = 1) still follows the barrier
+        mbar_wait(&bars[cDeFull], n & 1);
+        tc_fence_after();
+      }
+      if (warp_has_rows) tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[cOpsFull]);
+      if (tid == 64) TGFR_TRACE(n, 3);
+
+      if (last) {
+        // ---------------- drain: the (b, t) block / sigma -> per-warp 4 KB boxes -> TMA reduce-add into d ctx ----------------
+        mbar_wait(&bars[cAccDone], n & 1);
+        if (tid == 64) TGFR_TRACE(n, 8);
+        tc_fence_after();
+        const int row0 = t * 128 + quarter * 32;
+        const int dhalf = p.D >> 1;
+        if (row0 < p.R) {
+          uint8_t* const stage = smem + (warp - 2) * 8192;           // every operand tile is dead by now
+          int cur = 0;
+#pragma unroll 1
+          for (int ch = 0; ch < (dhalf >> 5); ++ch) {
+            const int col0 = h * dhalf + 32 * ch;
+            uint32_t v[32];
+            tmem_ld32(tmem + t_lane + col0, v);
+            tmem_ld_wait();
+            uint8_t* const buf = stage + cur * 4096;
+            if (lane == 0) tma_wait_group_read<1>();                 // the box written two stores ago has been read
+            __syncwarp();
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * c16 + 0]) * inv_sigma;
+              o.y = __uint_as_float(v[4 * c16 + 1]) * inv_sigma;
+              o.z = __uint_as_float(v[4 * c16 + 2]) * inv_sigma;
+              o.w = __uint_as_float(v[4 * c16 + 3]) * inv_sigma;
+              *reinterpret_cast<float4*>(buf + sw128_offset(lane, c16)) = o;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_3d(&tm_dc, buf, col0, row0, b);
+              tma_commit_group();
+            }
+            cur ^= 1;
+          }
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[cDrained]);
+        if (tid == 64) TGFR_TRACE(n, 9);
+      }
+    }
+    if (lane == 0) tma_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 struct TcPlan {
   int Tp, Rp, nc, G, nw_rows, n_tiles;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
@@ -1083,10 +1392,37 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   return TGFR_OK;
 }
 
-// per-unit record the forward leaves for the backward: the E tile exactly as GEMM-2 reads it (2 x e_panel bytes,
-// 128B-swizzled) followed by A1 as fp16 [nc][Rp][Tp]
-uint32_t saved_unit_bytes(const TcPlan& pl) {
-  return (uint32_t)align_up((size_t)2 * pl.e_panel + (size_t)pl.nc * pl.Rp * pl.Tp * 2, 128);
+// what the forward leaves for wr_tc_bwd2_kernel, in one caller-owned buffer:
+//   [V tiles: total_units * nw_rows rows x D fp16][records: total_units x (nc x Rp x 2 Tp fp16)][1/|Wu|: total_units x 128 fp32]
+struct SavedLayout {
+  size_t off_v, off_rec, off_inw, total;
+  uint32_t rec_stride;
+};
+SavedLayout saved_layout(const TcPlan& pl, int Bc, int D) {
+  SavedLayout L;
+  const size_t units = (size_t)Bc * pl.G;
+  L.rec_stride = (uint32_t)align_up((size_t)pl.nc * pl.Rp * pl.Tp * 4, 128);
+  L.off_v = 0;
+  L.off_rec = align_up(units * pl.nw_rows * D * 2, 1024);
+  L.off_inw = L.off_rec + align_up(units * L.rec_stride, 1024);
+  L.total = L.off_inw + units * 128 * 4;
+  return L;
+}
+
+// shared-memory plan of wr_tc_bwd2_kernel: one 128-row C tile, the Q and V tiles, 1 KB of zeros, misc
+struct TcBwd2Plan {
+  uint32_t q_panel, off_q, off_v, off_misc, smem_bytes;
+};
+int make_bwd2_plan(const TcPlan& fp, int D, TcBwd2Plan* pl) {
+  const int kch = D / 64;
+  pl->q_panel = fp.q_panel;
+  pl->off_q = kch * 128u * 128u;
+  pl->off_v = pl->off_q + kch * pl->q_panel;
+  pl->off_misc = pl->off_v + kch * pl->q_panel + 1024;
+  if (pl->off_misc < 65536) pl->off_misc = 65536;               // the drain boxes (8 warps x 8 KB) overlay the tiles
+  pl->smem_bytes = pl->off_misc + 2048 + 1024;                  // misc + alignment slack
+  TGFR_REQUIRE(pl->smem_bytes <= 232448, "wordregion(tc): backward shared memory plan needs %u bytes", pl->smem_bytes);
+  return TGFR_OK;
 }
 
 struct TcBwdPlan {
@@ -1177,50 +1513,84 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
   p.off_q = pl.off_q; p.off_x = pl.off_x; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g1 = g1; p.g23 = g2 * g3;
-  // the forward's saved (A1 | E) image is usable when both passes tile the captions identically
-  const uint32_t sv_stride = saved_unit_bytes(fp);
-  const bool load = saved != nullptr && pl.nc == fp.nc && pl.Rp == fp.Rp && pl.e_panel == fp.e_panel &&
-                    saved_bytes >= (size_t)p.total_units * sv_stride;
-  p.saved = load ? reinterpret_cast<const uint8_t*>(saved) : nullptr;
-  p.sv_stride = sv_stride;
 
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   TGFR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = p.total_units < sms ? p.total_units : sms;
-  if (const char* dg = getenv("TGFR_DEBUG_GRID")) {             // profiling aid: fewer CTAs -> no L2 contention
-    const int v = atoi(dg);
-    if (v > 0 && v < grid) grid = v;
-  }
+  int grid_dbg = 0;
+  if (const char* dg = getenv("TGFR_DEBUG_GRID")) grid_dbg = atoi(dg);   // profiling aid: fewer CTAs -> no L2 contention
+  if (grid_dbg > 0 && grid_dbg < grid) grid = grid_dbg;
 
-#define TGFR_LAUNCH_BWD1(TPV, DQV, LDV, TM)                                                                         \
-  {                                                                                                                 \
-    static bool attr_done[64] = {};   /* once per instantiation and device, to the architectural maximum */         \
-    bool& attr_set = attr_done[dev & 63];                                                                           \
-    if (!attr_set) {                                                                                                \
-      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        232448));                                                                   \
-      attr_set = true;                                                                                              \
-    }                                                                                                               \
-    wr_tc_bwd_kernel<TPV, DQV, LDV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                     \
-  }
-#define TGFR_LAUNCH_BWD(TPV, DQV, TM)                     \
-  case TPV:                                               \
-    if (load) TGFR_LAUNCH_BWD1(TPV, DQV, true, TM)        \
-    else TGFR_LAUNCH_BWD1(TPV, DQV, false, TM)            \
-    break;
+#define TGFR_LAUNCH_BWD(TPV, DQV, TM)                                                                             \
+  case TPV: {                                                                                                     \
+    static bool attr_done[64] = {};   /* once per instantiation and device, to the architectural maximum */       \
+    bool& attr_set = attr_done[dev & 63];                                                                         \
+    if (!attr_set) {                                                                                              \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd_kernel<TPV, DQV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                        232448));                                                                 \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    wr_tc_bwd_kernel<TPV, DQV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, TM, p);                        \
+  } break;
+#define TGFR_LAUNCH_BWD2(TPV)                                                                                     \
+  case TPV: {                                                                                                     \
+    static bool attr_done[64] = {};                                                                               \
+    bool& attr_set = attr_done[dev & 63];                                                                         \
+    if (!attr_set) {                                                                                              \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd2_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        232448));                                                                 \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    wr_tc_bwd2_kernel<TPV><<<grid2, kThreadsTC, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_v, tm_dc, p2);              \
+  } break;
   if (dctx) {
     CUtensorMap tm_dc;
     TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
     if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 32, 1)) return rc;
-    switch (pl.Tp) {
-      TGFR_LAUNCH_BWD(8, false, tm_dc)
-      TGFR_LAUNCH_BWD(16, false, tm_dc)
-      TGFR_LAUNCH_BWD(24, false, tm_dc)
-      TGFR_LAUNCH_BWD(32, false, tm_dc)
-      default:
-        set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
-        return TGFR_E_INVALID;
+    const SavedLayout L = saved_layout(fp, Bc, D);
+    if (saved != nullptr && saved_bytes >= L.total) {
+      // the forward left its records: (b, tile, caption group) items, d ctx accumulated in TMEM
+      TcBwd2Plan pl2;
+      if (int rc = make_bwd2_plan(fp, D, &pl2)) return rc;
+      const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+      CUtensorMap tm_c2, tm_q2, tm_v;
+      if (int rc = make_tmap_3d(&tm_c2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, 128, 1)) return rc;
+      if (int rc = make_tmap_3d(&tm_q2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * fp.Tp, 1, 64, fp.nw_rows, 1))
+        return rc;
+      if (int rc = make_tmap_3d(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, sv + L.off_v, D,
+                                (uint64_t)Bc * fp.G * fp.nw_rows, 1, 64, fp.nw_rows, 1))
+        return rc;
+      TcBwd2Params p2{};
+      p2.rec = sv + L.off_rec;
+      p2.inw = reinterpret_cast<const float*>(sv + L.off_inw);
+      p2.gsim = gsim;
+      p2.rec_stride = L.rec_stride;
+      p2.Bc = Bc; p2.Bq = Bq; p2.R = R; p2.Rp = fp.Rp; p2.D = D; p2.nc = fp.nc; p2.G = fp.G;
+      p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_items = Bc * fp.n_tiles * fp.G;
+      p2.q_panel = pl2.q_panel; p2.off_q = pl2.off_q; p2.off_v = pl2.off_v; p2.off_misc = pl2.off_misc;
+      p2.g1 = g1; p2.g23 = g2 * g3;
+      int grid2 = p2.total_items < sms ? p2.total_items : sms;
+      if (grid_dbg > 0 && grid_dbg < grid2) grid2 = grid_dbg;
+      switch (fp.Tp) {
+        TGFR_LAUNCH_BWD2(8)
+        TGFR_LAUNCH_BWD2(16)
+        TGFR_LAUNCH_BWD2(24)
+        TGFR_LAUNCH_BWD2(32)
+        default:
+          set_error("wordregion(tc): unsupported padded caption length %d", fp.Tp);
+          return TGFR_E_INVALID;
+      }
+    } else {
+      switch (pl.Tp) {
+        TGFR_LAUNCH_BWD(8, false, tm_dc)
+        TGFR_LAUNCH_BWD(16, false, tm_dc)
+        TGFR_LAUNCH_BWD(24, false, tm_dc)
+        TGFR_LAUNCH_BWD(32, false, tm_dc)
+        default:
+          set_error("wordregion(tc): unsupported padded caption length %d", pl.Tp);
+          return TGFR_E_INVALID;
+      }
     }
     TGFR_LAUNCH_OK();
   }
@@ -1245,7 +1615,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     TGFR_LAUNCH_OK();
   }
 #undef TGFR_LAUNCH_BWD
-#undef TGFR_LAUNCH_BWD1
+#undef TGFR_LAUNCH_BWD2
   return TGFR_OK;
 }
 
@@ -1259,7 +1629,7 @@ int wordregion_tc_set_trace(void* dev_buf) {
 size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D) {
   TcPlan pl;
   if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return 0;
-  return (size_t)Bc * pl.G * saved_unit_bytes(pl);
+  return saved_layout(pl, Bc, D).total;
 }
 
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
@@ -1302,12 +1672,16 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.off_q = pl.off_q; p.off_e = pl.off_e; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3;
   const bool save = saved != nullptr;
-  p.sv_stride = saved_unit_bytes(pl);
   if (save) {
-    TGFR_REQUIRE(saved_bytes >= (size_t)p.total_units * p.sv_stride, "wordregion(tc): saved buffer too small");
+    const SavedLayout L = saved_layout(pl, Bc, D);
+    TGFR_REQUIRE(saved_bytes >= L.total, "wordregion(tc): saved buffer too small (%zu < %zu)", saved_bytes, L.total);
     TGFR_REQUIRE((reinterpret_cast<uintptr_t>(saved) & 127) == 0, "wordregion(tc): saved buffer must be 128-byte aligned");
+    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
+    p.sv_v = reinterpret_cast<__half*>(sv + L.off_v);
+    p.sv_rec = sv + L.off_rec;
+    p.sv_inw = reinterpret_cast<float*>(sv + L.off_inw);
+    p.rec_stride = L.rec_stride;
   }
-  p.saved = reinterpret_cast<uint8_t*>(saved);
 
   int dev = 0, sms = 0;
   TGFR_CUDA_OK(cudaGetDevice(&dev));

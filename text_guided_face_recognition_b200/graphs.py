@@ -21,7 +21,9 @@ __all__ = ["GraphedStep"]
 
 
 class GraphedStep:
-    def __init__(self, fn, warmup: int = 3):
+    def __init__(self, fn, warmup: int = 3, pool=None):
+        """pool: a torch.cuda.graph_pool_handle() shared by graphs that are never replayed concurrently (their
+        private allocations -- e.g. the forward->backward attention records -- then reuse the same memory)."""
         self._fn = fn
         dev = torch.cuda.current_device()
         side = torch.cuda.Stream(device=dev)
@@ -32,7 +34,7 @@ class GraphedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self.out = fn()
 
     def __call__(self):
