@@ -25,6 +25,9 @@ def _lib():
     (0, 1, 2, 64, 128),      # A operand staged in TMEM by tcgen05.st (dS / E16 in the backward pass)
     (0, 1, 2, 256, 128),
     (0, 0, 2, 128, 256),
+    (0, 2, 0, 128, 256),     # B as planes [K/8][N][8] (one bulk copy), K-major without swizzle: dE~ = C x V^T
+    (0, 3, 2, 256, 128),     # the same storage read MN-major, A in TMEM: d ctx += Ek x V
+    (0, 3, 0, 256, 128),
 ])
 def test_umma_layouts(a_mn, b_mn, manual_a, N, K):
     L = _lib()
@@ -34,7 +37,12 @@ def test_umma_layouts(a_mn, b_mn, manual_a, N, K):
     B = torch.randn(N, K, generator=g).half()
     ref = A.float() @ B.float().t()
     a_dev = (A.t().contiguous() if a_mn else A.contiguous()).cuda()
-    b_dev = (B.t().contiguous() if b_mn else B.contiguous()).cuda()
+    if b_mn == 2:
+        b_dev = B.reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().cuda()
+    elif b_mn == 3:
+        b_dev = B.t().reshape(K, N // 8, 8).permute(1, 0, 2).contiguous().cuda()
+    else:
+        b_dev = (B.t().contiguous() if b_mn else B.contiguous()).cuda()
     out = torch.full((128, N), float("nan"), device="cuda")
     L.check(lib.tgfr_debug_umma(a_dev.data_ptr(), b_dev.data_ptr(), out.data_ptr(), N, K, a_mn, b_mn, manual_a,
                                 torch.cuda.current_stream().cuda_stream), "tgfr_debug_umma")

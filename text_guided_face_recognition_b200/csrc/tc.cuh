@@ -134,6 +134,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Shared-memory matrix descriptor without swizzle ("interleaved" canonical layout): the operand is a grid of
+// 8 x 16-byte core matrices, each stored as 128 contiguous bytes (8 rows of 8 halfs).
+//   K-major operand : a core matrix is 8 rows (M or N index) x 8 halfs of K; the next core matrix along K
+//                     is `lbo` bytes away, the next 8-row group `sbo` bytes away.
+//   MN-major operand: a core matrix is 8 rows (K index) x 8 halfs of M/N; the next 8-row group along K is
+//                     `lbo` bytes away, the next 8 halfs of M/N `sbo` bytes away.
+// A tile stored as planes [d / 8][row][8 halfs] is therefore BOTH a K-major operand over d (lbo = plane
+// stride, sbo = 128) and an MN-major operand over d with K = row (lbo = 128, sbo = plane stride).
+__device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+
 // Instruction descriptor for kind::f16 with fp16 operands and fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                              // D format: F32

@@ -11,12 +11,14 @@ using namespace tc;
 // D[128, N] = A[128, K] * B[N, K]^T on one CTA.  Operand layouts in GLOBAL memory (fp16):
 //   a_mn == 0: A_g[128][K] (K contiguous)      a_mn == 1: A_g[K][128] (M contiguous)
 //   b_mn == 0: B_g[N][K]                        b_mn == 1: B_g[K][N]
+//   b_mn == 2: B_g[K/8][N][8]  planes of 8-half K chunks, brought in by ONE bulk copy, read K-major without swizzle
+//   b_mn == 3: B_g[N/8][K][8]  planes of 8-half N chunks, one bulk copy, read MN-major without swizzle
 // manual_a (needs a_mn == 1, K <= 128): A is written to shared memory by the threads with the
 // hand-computed 128B swizzle instead of by TMA (the pattern the fused kernels use for E / dS).
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __half* __restrict__ a_g, float* __restrict__ out, int N, int K, int a_mn, int b_mn,
-                     int manual_a) {
+                     const __half* __restrict__ b_g, int manual_a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
   uint8_t* sa = base;                    // up to 128 x 256 halfs = 64 KB
@@ -66,16 +68,21 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (!a_mn) for (int kc = 0; kc < K / 64; ++kc) tma_load_3d(sa + kc * (128 * 128), &tmap_a, &bar_load, kc * 64, 0, 0);
       else       for (int p = 0; p < 2; ++p)         tma_load_3d(sa + p * (K * 128), &tmap_a, &bar_load, p * 64, 0, 0);
     }
-    if (!b_mn) for (int kc = 0; kc < K / 64; ++kc) tma_load_3d(sb + kc * (N * 128), &tmap_b, &bar_load, kc * 64, 0, 0);
+    if (b_mn >= 2) bulk_load(sb, b_g, b_bytes, &bar_load);
+    else if (!b_mn) for (int kc = 0; kc < K / 64; ++kc) tma_load_3d(sb + kc * (N * 128), &tmap_b, &bar_load, kc * 64, 0, 0);
     else       for (int p = 0; p < N / 64; ++p)     tma_load_3d(sb + p * (K * 128), &tmap_b, &bar_load, p * 64, 0, 0);
     mbar_wait(&bar_load, 0);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_f16(128, N, a_mn != 0, b_mn != 0);
+    const uint32_t idesc = make_idesc_f16(128, N, a_mn != 0, b_mn == 1 || b_mn == 3);
     for (int k16 = 0; k16 < K / 16; ++k16) {
       uint64_t ad, bd;
       if (!a_mn) ad = make_smem_desc(smem_u32(sa) + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
       else       ad = make_smem_desc(smem_u32(sa) + k16 * 2048, K * 128, 1024);
-      if (!b_mn) bd = make_smem_desc(smem_u32(sb) + (k16 >> 2) * (N * 128) + (k16 & 3) * 32, 16, 1024);
+      if (b_mn == 2) {
+        bd = make_smem_desc_ns(smem_u32(sb) + k16 * 2 * (N * 16), N * 16, 128);
+      } else if (b_mn == 3) {
+        bd = make_smem_desc_ns(smem_u32(sb) + k16 * 256, 128, K * 16);
+      } else if (!b_mn) bd = make_smem_desc(smem_u32(sb) + (k16 >> 2) * (N * 128) + (k16 & 3) * 32, 16, 1024);
       else       bd = make_smem_desc(smem_u32(sb) + k16 * 2048, K * 128, 1024);
       if (manual_a == 2) umma_ts(tmem, tmem + 256 + 8 * k16, bd, idesc, k16 > 0);
       else umma_ss(tmem, ad, bd, idesc, k16 > 0);
@@ -133,12 +140,12 @@ int debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn,
   CUtensorMap ta, tb;
   if (!a_mn) { if (int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, K, 128, 1, 64, 128, 1)) return rc; }
   else       { if (int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, 128, K, 1, 64, K, 1)) return rc; }
-  if (!b_mn) { if (int rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, K, N, 1, 64, N, 1)) return rc; }
-  else       { if (int rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, N, K, 1, 64, K, 1)) return rc; }
+  if (b_mn != 1) { if (int rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, K, N, 1, 64, N, 1)) return rc; }
+  else           { if (int rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, N, K, 1, 64, K, 1)) return rc; }
   const int smem = 65536 + 131072 + 1024;
   TGFR_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_selftest_kernel<<<1, 128, smem, st>>>(ta, tb, reinterpret_cast<const __half*>(a), out, N, K, a_mn, b_mn,
-                                             manual_a);
+                                             reinterpret_cast<const __half*>(b), manual_a);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }

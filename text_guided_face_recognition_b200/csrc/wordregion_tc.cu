@@ -43,8 +43,8 @@ struct TcParams {
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
   // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
-  __half* sv_v;          // [total_units * nw_rows, D]   V_w = kSV * p_w * (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
-  uint8_t* sv_rec;       // [total_units][nc][Rp][A1 fp16 x Tp | E fp16 x Tp]   word softmax and exp(g1 (A1 - 1))
+  __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
+  uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
   float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
   uint32_t rec_stride;   // bytes of one unit's records
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
@@ -240,9 +240,9 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           if (i >= p.Bq) {
             if constexpr (SAVE) {                               // missing captions: zero records for the backward
               if (r < p.Rp) {
-                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + ((int64_t)c * p.Rp + r) * (TP / 4);
+                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
 #pragma unroll
-                for (int j = 0; j < TP / 4; ++j) rdst[j] = make_uint4(0, 0, 0, 0);
+                for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
               }
               continue;
             }
@@ -287,12 +287,12 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
               pe[t >> 1] = live_row ? pk : 0u;
             }
             if (r < p.Rp) {
-              // [caption][row][A1 x Tp | E x Tp] fp16: a warp's 32 rows are contiguous in memory
-              uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + ((int64_t)c * p.Rp + r) * (TP / 4);
+              // [caption][16-byte chunk: A1 x Tp | E x Tp][row]: every store of a warp covers 512 contiguous bytes
+              uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
 #pragma unroll
               for (int j = 0; j < TP / 8; ++j) {
-                rdst[j] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
-                rdst[TP / 8 + j] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+                rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+                rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
               }
             }
           } else {
@@ -402,7 +402,10 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           c2 = pw * cosw[w] * inww[w];
         }
         // (the TMEM loads are warp-collective: only the stores are predicated on the word row)
-        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + ((int64_t)u * p.nw_rows + min(w, p.nw_rows - 1)) * p.D + tile * dhalf);
+        // planes [d / 8][word][8 halfs]: a warp's store covers 512 contiguous bytes, and the tile is both a K-major
+        // and an MN-major no-swizzle UMMA operand for the backward (tc.cuh make_smem_desc_ns)
+        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
+                      (int64_t)(tile * (dhalf >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           if (ch < nch) {
@@ -421,7 +424,7 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
                                           c1 * qf.y - c2 * __uint_as_float(v[8 * cc + 2 * k + 1]))
                              : 0u;
               }
-              if (w < p.nw_rows) vdst[4 * ch + cc] = make_uint4(o[0], o[1], o[2], o[3]);
+              if (w < p.nw_rows) vdst[(int64_t)(4 * ch + cc) * p.nw_rows] = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
@@ -1059,7 +1062,8 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 enum BarC { cCFull = 0, cVFull, cQFull, cDeFull, cOpsFull, cVFree, cAccDone, cDrained, cNum };
 
 struct TcBwd2Params {
-  const uint8_t* rec;    // [total_units][nc][Rp][A1 x Tp | E x Tp] fp16
+  const __half* v;       // [total_units][D/8][nw_rows][8] fp16 V tiles
+  const uint8_t* rec;    // [total_units][nc][Tp/4 chunks][Rp] x 16 bytes: A1 x Tp | E x Tp as fp16
   const float* inw;      // [total_units][128]
   const float* gsim;     // [Bc, Bq]
   uint32_t rec_stride;   // bytes per unit
@@ -1071,13 +1075,12 @@ struct TcBwd2Params {
 template <int TP>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
-                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_dc,
-                  const TcBwd2Params p) {
+                  const __grid_constant__ CUtensorMap tm_dc, const TcBwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_c = smem;                         // C tile: D/64 panels of 128 rows x 128 B (K-major, GEMM-3's A)
   uint8_t* s_q = smem + p.off_q;               // Q tile: D/64 panels of nw_rows x 128 B
-  uint8_t* s_v = smem + p.off_v;               // V tile: same shape; 1 KB of zeros follows it
+  uint8_t* s_v = smem + p.off_v;               // V tile: D/8 planes of nw_rows x 16 B (no swizzle); 1 KB of zeros follows
   uint8_t* misc = smem + p.off_misc;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
@@ -1101,7 +1104,6 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
     fence_barrier_init();
     tma_prefetch_desc(&tm_c);
     tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_dc);
   }
   // operand tiles are read a few rows beyond what TMA writes (K / N padding of the MMA shapes): keep them finite
@@ -1129,8 +1131,8 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             const int ftn = sn / p.G, gn = sn - ftn * p.G, bn = ftn / p.n_tiles, tn = ftn - bn * p.n_tiles;
             const int rows_n = (k == 0) ? rows : min(p.Rp - tn * 128, 128);
             const uint8_t* base = p.rec + (int64_t)(bn * p.G + gn) * p.rec_stride;
-            for (int c = 0; c < p.nc; ++c)
-              bulk_prefetch_l2(base + ((int64_t)c * p.Rp + tn * 128) * (TP * 4), (uint32_t)rows_n * TP * 4);
+            for (int cj = 0; cj < p.nc * (TP / 4); ++cj)
+              bulk_prefetch_l2(base + ((int64_t)cj * p.Rp + tn * 128) * 16, (uint32_t)rows_n * 16);
           }
         }
         if (n > 0) mbar_wait(&bars[cVFree], (n - 1) & 1);           // GEMM-3 and GEMM-6 of the previous item retired
@@ -1142,8 +1144,9 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           prev_ft = ft;
         }
         mbar_arrive_expect_tx(&bars[cVFull], kchunks * p.q_panel);
-        for (int kc = 0; kc < kchunks; ++kc)
-          tma_load_3d(s_v + kc * p.q_panel, &tm_v, &bars[cVFull], kc * 64, u * p.nw_rows, 0);
+        for (int kc = 0; kc < kchunks; ++kc)                        // the tile is one contiguous image: four bulk copies
+          bulk_load(s_v + kc * p.q_panel, p.v + (int64_t)u * p.nw_rows * p.D + (int64_t)kc * (p.q_panel >> 1), p.q_panel,
+                    &bars[cVFull]);
         if (n > 0) mbar_wait(&bars[cAccDone], (n - 1) & 1);         // GEMM-5 of the previous item retired
         mbar_arrive_expect_tx(&bars[cQFull], kchunks * p.q_panel);
         for (int kc = 0; kc < kchunks; ++kc)
@@ -1156,6 +1159,7 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
       const uint32_t idesc3 = make_idesc_f16(128, 128, false, false);    // dE~
       const uint32_t idesc5 = make_idesc_f16(128, p.D, false, true);     // d ctx block: A in TMEM, B MN-major
       const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_v = smem_u32(s_v);
+      const uint32_t v_plane = (uint32_t)p.nw_rows * 16u;                // bytes between consecutive 8-feature planes of V
       int prev_ft = -1, n = 0, m = -1;
       for (int s = s0; s < s1; ++s, ++n) {
         const int ft = s / p.G;
@@ -1170,7 +1174,7 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
         tc_fence_after();
         for (int k16 = 0; k16 < (p.D >> 4); ++k16) {                     // GEMM-3
           const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * kCPanel + (k16 & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(a_v + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_ns(a_v + k16 * 2 * v_plane, v_plane, 128);   // K-major over d
           umma_ss(tmem + 256, ad, bd, idesc3, k16 > 0);
         }
         umma_commit(&bars[cDeFull]);
@@ -1178,7 +1182,7 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
         TGFR_TRACE(n, 18);
         tc_fence_after();
         for (int k16 = 0; k16 < 8; ++k16) {                              // GEMM-6: Ek . V  (the first MMA of a (b, t) range overwrites)
-          const uint64_t bv = make_smem_desc(a_v + k16 * 2048, p.q_panel, 1024);
+          const uint64_t bv = make_smem_desc_ns(a_v + k16 * 256, 128, v_plane);           // MN-major over d, K = words
           umma_ts(tmem, tmem + 448 + 8 * k16, bv, idesc5, !(first && k16 == 0));
         }
         umma_commit(&bars[cVFree]);
@@ -1234,8 +1238,8 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
       // this thread's A1 | E rows of its captions: issued before the waits so that the latency hides under GEMM-3
       const int r = t * 128 + lrow;
       const bool warp_has_rows = (t * 128 + quarter * 32) < p.Rp;
-      const uint4* rsrc = reinterpret_cast<const uint4*>(p.rec + (int64_t)u * p.rec_stride) + (int64_t)min(r, p.Rp - 1) * (TP / 4);
-      const int64_t cstride = (int64_t)p.Rp * (TP / 4);
+      const uint4* rsrc = reinterpret_cast<const uint4*>(p.rec + (int64_t)u * p.rec_stride) + min(r, p.Rp - 1);
+      const int64_t cstride = (int64_t)p.Rp * (TP / 4);                  // uint4 per caption; chunk j is j * Rp further
       epi_bar_sync();                            // kappa visible; the other buffer is free for the next item
       bool waited = false;
       for (int c0 = c_lo; c0 < c_hi; c0 += NB) {
@@ -1244,7 +1248,7 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
 #pragma unroll
           for (int cc = 0; cc < NB; ++cc)
 #pragma unroll
-            for (int j = 0; j < TP / 4; ++j) rc[cc][j] = __ldg(rsrc + min(c0 + cc, c_hi - 1) * cstride + j);
+            for (int j = 0; j < TP / 4; ++j) rc[cc][j] = __ldg(rsrc + min(c0 + cc, c_hi - 1) * cstride + (int64_t)j * p.Rp);
         }
         if (!waited) {
           mbar_wait(&bars[cDeFull], n & 1);      // GEMM-3 retired (and with it every MMA of the previous item)
@@ -1393,7 +1397,8 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
 }
 
 // what the forward leaves for wr_tc_bwd2_kernel, in one caller-owned buffer:
-//   [V tiles: total_units * nw_rows rows x D fp16][records: total_units x (nc x Rp x 2 Tp fp16)][1/|Wu|: total_units x 128 fp32]
+//   [V tiles: total_units x (D/8 planes x nw_rows x 8 fp16)][records: total_units x (nc x Tp/4 chunks x Rp x 16 B)]
+//   [1/|Wu|: total_units x 128 fp32]
 struct SavedLayout {
   size_t off_v, off_rec, off_inw, total;
   uint32_t rec_stride;
@@ -1542,7 +1547,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
                                         232448));                                                                 \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    wr_tc_bwd2_kernel<TPV><<<grid2, kThreadsTC, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_v, tm_dc, p2);              \
+    wr_tc_bwd2_kernel<TPV><<<grid2, kThreadsTC, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_dc, p2);                    \
   } break;
   if (dctx) {
     CUtensorMap tm_dc;
@@ -1554,14 +1559,12 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
       TcBwd2Plan pl2;
       if (int rc = make_bwd2_plan(fp, D, &pl2)) return rc;
       const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
-      CUtensorMap tm_c2, tm_q2, tm_v;
+      CUtensorMap tm_c2, tm_q2;
       if (int rc = make_tmap_3d(&tm_c2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, 128, 1)) return rc;
       if (int rc = make_tmap_3d(&tm_q2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * fp.Tp, 1, 64, fp.nw_rows, 1))
         return rc;
-      if (int rc = make_tmap_3d(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, sv + L.off_v, D,
-                                (uint64_t)Bc * fp.G * fp.nw_rows, 1, 64, fp.nw_rows, 1))
-        return rc;
       TcBwd2Params p2{};
+      p2.v = reinterpret_cast<const __half*>(sv + L.off_v);
       p2.rec = sv + L.off_rec;
       p2.inw = reinterpret_cast<const float*>(sv + L.off_inw);
       p2.gsim = gsim;
