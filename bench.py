@@ -252,7 +252,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
-    from text_guided_face_recognition_b200 import _lib, ops
+    from text_guided_face_recognition_b200 import _lib, fcam, ops
     from text_guided_face_recognition_b200 import distributed as tdist
     from text_guided_face_recognition_b200.models import losses, metrics
 
@@ -288,12 +288,13 @@ def run_b200(args):
         for t in (c, w, a, b):
             t.grad = None
         c_ref = c.view(B, IH, IW, D).permute(0, 3, 1, 2)
+        # the sentence-loss chain (tiny kernels) runs on a side stream beside the word-region kernels (fcam.py)
         if world == 1:
-            l0, l1, _ = losses.words_loss(c_ref, w.transpose(1, 2), labels, None, None, B, margs)
-            s0, s1 = losses.sent_loss(a, b, labels, cid_dev, B, margs)
+            l0, l1, _, s0, s1 = fcam.fcam_losses(c_ref, w.transpose(1, 2), a, b, labels, None, cid_dev, B, margs)
         else:
-            l0, l1, _ = tdist.words_loss_sharded(c, w, None, *GAMMAS, precision=precision)
-            s0, s1 = tdist.sent_loss_sharded(a, b, cid_dev, GAMMAS[2])
+            (s0, s1), (l0, l1, _) = fcam.run_overlapped(
+                lambda: tdist.sent_loss_sharded(a, b, cid_dev, GAMMAS[2]),
+                lambda: tdist.words_loss_sharded(c, w, None, *GAMMAS, precision=precision), device=dev)
         total = l0 + l1 + s0 + s1
         total.backward()
         return total

@@ -374,3 +374,60 @@ def test_other_heads_run(api, hprec):
     assert torch.isfinite(x.grad).all()
     sp = api.metrics.SphereProduct(32, 20).cuda()
     assert tuple(sp(x, lab).shape) == (8, 20)
+
+
+def test_fcam_losses_overlapped_matches_sequential_calls():
+    """fcam.fcam_losses (sentence chain on a side stream) gives the same losses and gradients as the two
+    reference-shaped calls issued one after the other, eagerly and as a replayed CUDA graph."""
+    from text_guided_face_recognition_b200 import fcam
+    from text_guided_face_recognition_b200.graphs import GraphedStep
+    from text_guided_face_recognition_b200.models import losses
+    B, T, R, D = 16, 18, 196, 256
+    # BERT flavour: no caption lengths (the LSTM flavour reads them back on the host, as the reference does, and a
+    # host read cannot be captured); device-resident class ids: nothing to copy during capture
+    ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=3)
+    img, txt, cid = synth.sentence_inputs(B, D, seed=3, collisions=True)
+    cid = torch.from_numpy(cid).cuda()
+    args = make_args("BERT", T)
+    labels = torch.arange(B, device="cuda")
+    capt = None
+    leaves = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (ctx, words, img, txt)]
+
+    def views():
+        c, w, a, b = leaves
+        return c.view(B, 14, 14, D).permute(0, 3, 1, 2), w.transpose(1, 2), a, b
+
+    def sequential():
+        for t in leaves:
+            t.grad = None
+        c, w, a, b = views()
+        s0, s1 = losses.sent_loss(a, b, labels, cid, B, args)
+        w0, w1, _ = losses.words_loss(c, w, labels, capt, cid, B, args)
+        tot = w0 + w1 + s0 + s1
+        tot.backward()
+        return tot
+
+    def overlapped():
+        for t in leaves:
+            t.grad = None
+        c, w, a, b = views()
+        w0, w1, _, s0, s1 = fcam.fcam_losses(c, w, a, b, labels, capt, cid, B, args)
+        tot = w0 + w1 + s0 + s1
+        tot.backward()
+        return tot
+
+    ref = sequential().item()
+    ref_grads = [t.grad.clone() for t in leaves]
+    got = overlapped().item()
+    torch.cuda.synchronize()
+    assert got == ref
+    for g, t in zip(ref_grads, leaves):
+        # the tensor-core d ctx is accumulated with reduce-adds in a run-dependent order
+        assert torch.allclose(t.grad, g, rtol=1e-4, atol=1e-7)
+    step = GraphedStep(overlapped)
+    for _ in range(2):
+        out = step()
+    torch.cuda.synchronize()
+    assert abs(out.item() - ref) <= 1e-6 * abs(ref)
+    for g, t in zip(ref_grads, leaves):
+        assert torch.allclose(t.grad, g, rtol=1e-4, atol=1e-7)

@@ -200,22 +200,7 @@ __global__ void __launch_bounds__(kThreads, 2) wr_fwd_kernel(const Params p) {
   phase_a<TP>(p, s, cb, Ti);
 
   float wu[NJ][8], zs[NJ];
-  if (MODE == kAttention && p.wc == nullptr) {
-    // only the attention maps are wanted (the diagonal maps of the tensor-core path): Z[t] = sum_r E[r,t]
-    // is all that is needed from phase B, the context contraction is skipped
-    const int es = TP + 1;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int t = warp + 8 * j;
-      float z = 0.f;
-      for (int r = lane; r < p.R; r += 32) z += s.e[r * es + t];
-      zs[j] = warp_sum(z);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) wu[j][k] = 0.f;
-    }
-  } else {
-    word_gemm<TP>(wu, zs, s.e, cb, p.csr, p.csd, p.R, p.D);
-  }
+  word_gemm<TP>(wu, zs, s.e, cb, p.csr, p.csd, p.R, p.D);
 
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -456,6 +441,126 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_kernel(const Params p) {
   }
 }
 
+
+// Attention maps only (the B diagonal maps of the tensor-core path, or a func_attention caller that drops the
+// context): one CTA per pair, one WARP per region row, all rows in flight at once (the loss kernel's staged
+// thread-per-region contraction serialises eight load rounds, which is what a 128-CTA launch cannot hide).
+// Lane l holds c_r[l + 32 k]; the TP partial dot products of a row are reduced by one butterfly that leaves
+// word t's sum in lane t (31 shuffles instead of 5 TP), so the word softmax runs lane-parallel.
+template <int TP>
+__global__ void __launch_bounds__(kThreads, 1) attn_only_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int qs = p.D + 4, es = TP + 1;
+  float* sq = smem_raw;                    // [TP][qs] words of the caption (zero rows beyond its length)
+  float* se = sq + TP * qs;                // [R][es]  E = exp(g1 A1)
+  float* sz = se + p.R * es;               // [32]     Z[t] = sum_r E[r,t]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int Ti = p.T;
+  if (p.cap_lens) Ti = min(max(p.cap_lens[b], 1), p.T);
+  const float* cb = p.ctx + (int64_t)b * p.csb;
+  load_rows<TP>(sq, p.words + (int64_t)b * p.wsb, p.wst, p.wsd, Ti, p.D);
+  __syncthreads();
+
+  // four region rows per warp and step: every word feature read from shared memory feeds four dot products
+  // (shared-memory bandwidth, not arithmetic, bounds this kernel); the next step's rows load meanwhile
+  constexpr int kRB = 4;
+  float cn[kRB][8];
+#pragma unroll
+  for (int j = 0; j < kRB; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = lane + 32 * k, r = warp * kRB + j;
+      cn[j][k] = (d < p.D && r < p.R) ? __ldg(cb + r * p.csr + (int64_t)d * p.csd) : 0.f;
+    }
+  for (int r0 = warp * kRB; r0 < p.R; r0 += kWarps * kRB) {
+    float c[kRB][8];
+#pragma unroll
+    for (int j = 0; j < kRB; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = lane + 32 * k, rn = r0 + kWarps * kRB + j;
+        c[j][k] = cn[j][k];
+        cn[j][k] = (d < p.D && rn < p.R) ? __ldg(cb + rn * p.csr + (int64_t)d * p.csd) : 0.f;
+      }
+    float acc[kRB][TP];
+#pragma unroll
+    for (int t = 0; t < TP; ++t) {
+      float q[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = lane + 32 * k;
+        q[k] = (d < p.D) ? sq[t * qs + d] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kRB; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(c[j][k], q[k], a);
+        acc[j][t] = a;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRB; ++j) {
+      const int r = r0 + j;
+      if (r >= p.R) break;                   // warp-uniform
+      float v[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = (t < TP) ? acc[j][t] : 0.f;
+      // butterfly: after the step with distance s a lane keeps the half of its values whose word index has bit s
+      // equal to the lane's bit s; after the last step v[0] of lane l is the full sum of word l
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float send = up ? v[i] : v[i + s];
+          const float keep = up ? v[i + s] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      const bool valid = lane < Ti;
+      const float sc = v[0];
+      const float m = warp_max(valid ? sc : -INFINITY);
+      const float e = valid ? expf(sc - m) : 0.f;
+      const float inv = 1.f / warp_sum(e);
+      if (lane < TP) se[r * es + lane] = valid ? expf(p.g1 * (e * inv)) : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int t = warp; t < 32; t += kWarps) {
+    float z = 0.f;
+    if (t < Ti)
+      for (int r = lane; r < p.R; r += 32) z += se[r * es + t];
+    z = warp_sum(z);
+    if (lane == 0) sz[t] = (t < Ti) ? z : 1.f;
+  }
+  __syncthreads();
+  float* out = p.attn + (int64_t)b * p.T * p.R;
+  for (int idx = threadIdx.x; idx < p.T * p.R; idx += kThreads) {
+    const int t = idx / p.R, r = idx - t * p.R;
+    out[idx] = (t < Ti) ? se[r * es + t] / sz[t] : 0.f;
+  }
+}
+
+template <int TP>
+int launch_attn_only(const Params& p, cudaStream_t st) {
+  const size_t bytes = ((size_t)TP * (p.D + 4) + (size_t)p.R * (TP + 1) + 32) * sizeof(float);
+  auto k = attn_only_kernel<TP>;
+  {
+    static bool attr_done[64] = {};   // once per instantiation and device
+    int dev = 0;
+    TGFR_CUDA_OK(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+      TGFR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_done[dev & 63] = true;
+    }
+  }
+  k<<<p.Bc, kThreads, bytes, st>>>(p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
 template <int TP, int MODE>
 int launch_fwd(const Params& p, cudaStream_t st) {
   const size_t bytes = smem_floats<TP>(p.R, p.D, false) * sizeof(float);
@@ -561,6 +666,12 @@ int attention_fwd_simt(const float* ctx, int64_t csb, int64_t csr, int64_t csd, 
   p.wc = wc; p.attn = attn;
   if (int rc = check_shape(p)) return rc;
   TGFR_REQUIRE(wc != nullptr || attn != nullptr, "attention_fwd: no output requested");
+  if (wc == nullptr) {                      // attention maps only: the warp-per-region kernel
+    if (p.T <= 8) return launch_attn_only<8>(p, st);
+    if (p.T <= 16) return launch_attn_only<16>(p, st);
+    if (p.T <= 24) return launch_attn_only<24>(p, st);
+    return launch_attn_only<32>(p, st);
+  }
   return dispatch_fwd<kAttention>(p, st);
 }
 

@@ -32,10 +32,12 @@ using namespace tc;
 
 constexpr int kThreadsTC = 320;
 constexpr int kEpiThreads = 256;
+constexpr int kFwdThreads = 576;       // forward: 2 + 16 epilogue warps (four per TMEM lane quarter)
+constexpr int kFwdEpiThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kSV = 256.f;   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
 
-enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull, kWuFull, kWuEmpty, kNumBars };
+enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull0, kEFull1, kWuFull, kWuEmpty, kNumBars };
 
 struct TcParams {
   const __half* q16;     // [Bq*Tp, D]
@@ -74,6 +76,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void fwd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFwdEpiThreads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // prep: fp32 (any strides) -> fp16 canonical copies + exact fp32 word norms + caption lengths
@@ -118,7 +121,7 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int TP, bool SAVE>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,9 +130,9 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
   uint8_t* s_e = smem + p.off_e;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_misc + 64);
-  float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 128);   // [2][128]
-  float* part_n = part_d + 256;                                        // [2][128]
-  float* exs = part_n + 256;                                           // [128]
+  float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 128);   // [4][128]
+  float* part_n = part_d + 512;                                        // [4][128]
+  float* exs = part_n + 512;                                           // [128]
   float* cosw = exs + 128;                                             // [128] SAVE: cos_w
   float* inww = cosw + 128;                                            // [128] SAVE: 1 / |Wu_w|
 
@@ -144,9 +147,10 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
     mbar_init(&bars[kQEmpty], 1);
     mbar_init(&bars[kSFull0], 1);
     mbar_init(&bars[kSFull1], 1);
-    mbar_init(&bars[kEFull], kEpiThreads);
+    mbar_init(&bars[kEFull0], kFwdEpiThreads);
+    mbar_init(&bars[kEFull1], kFwdEpiThreads);
     mbar_init(&bars[kWuFull], 1);
-    mbar_init(&bars[kWuEmpty], kEpiThreads);
+    mbar_init(&bars[kWuEmpty], kFwdEpiThreads);
     fence_barrier_init();
     tma_prefetch_desc(&tm_c);
     tma_prefetch_desc(&tm_q);
@@ -204,180 +208,203 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
         }
         umma_commit(&bars[kQEmpty]);
         umma_commit(&bars[kSFull1]);
-        mbar_wait(&bars[kEFull], n & 1);
+        // GEMM-2 in two instalments: the K steps over tile 0's regions run while the epilogue still works on tile 1
+        mbar_wait(&bars[kEFull0], n & 1);
         TGFR_TRACE(n, 18);
-
         mbar_wait(&bars[kWuEmpty], (n & 1) ^ 1);
         TGFR_TRACE(n, 19);
         tc_fence_after();
-        for (int j = 0; j < (p.Rp >> 4); ++j) {
+        const int j0 = min(p.Rp >> 4, 8);
+        for (int j = 0; j < j0; ++j) {
           const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
           const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
           umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
+        }
+        mbar_wait(&bars[kEFull1], n & 1);
+        tc_fence_after();
+        for (int j = j0; j < (p.Rp >> 4); ++j) {
+          const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
+          const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
+          umma_ss(tmem + 256, ad, bd, idesc2, true);
         }
         umma_commit(&bars[kWuFull]);
       }
     }
   } else {
     // ======================================= epilogue =======================================
-    const int tile = (warp - 2) >> 2;            // region tile in epi-1, D half in epi-2
-    const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
+    // 16 warps: `quarter` = the TMEM lane quarter the warp may touch (warp % 4), `grp` = which of that quarter's four
+    // warps it is.  epi-1 deals the quarter's (region tile, caption) tasks round-robin to its four warps (four warps
+    // per scheduler hide the TMEM / MUFU latencies two could not); in epi-2 a warp owns its 32 word rows and a
+    // quarter of the features.
+    const int grp = (warp - 2) >> 2;
+    const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;        // lane row 0..127
     const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-    const int r = tile * 128 + lrow;
-    const bool warp_has_rows = tile < p.n_tiles && (tile * 128 + quarter * 32) < p.Rp;
-    const int dhalf = p.D >> 1;
+    const int tiles_q = (p.n_tiles == 2 && (128 + quarter * 32) < p.Rp) ? 2 : 1;   // region tiles with rows in this quarter
+    const int ntask = ((quarter * 32) < p.Rp) ? tiles_q * p.nc : 0;
+    const int dq = p.D >> 2;                     // features per warp in epi-2
+    const int nch = dq >> 4;                     // 16-column TMEM loads per pass
     int n = 0;
     for (int u = u0; u < u1; ++u, ++n) {
       const int b = u / p.G, g = u - b * p.G;
       // ---------------- epi-1: word softmax, E -> shared memory ----------------
-      mbar_wait(&bars[tile == 0 ? kSFull0 : kSFull1], n & 1);
-      if (tid == 64) TGFR_TRACE(n, 2);
-      tc_fence_after();
-      if (warp_has_rows) {
-        for (int c = 0; c < p.nc; ++c) {
-          const int i = g * p.nc + c;
-          if (i >= p.Bq) {
-            if constexpr (SAVE) {                               // missing captions: zero records for the backward
-              if (r < p.Rp) {
-                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-                for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
-              }
-              continue;
-            }
-            break;
-          }
-          const int len = __ldg(p.lens + i);
-          uint32_t v[TP];
-          const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
-#pragma unroll
-          for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
-          tmem_ld_wait();
-          float e[TP];
-          // four independent max / sum chains: with two warps per scheduler the dependent chain is the cost
-          float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
-#pragma unroll
-          for (int t = 0; t < TP; ++t) {
-            e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
-            mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
-          }
-          const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-          const float nmx = -mx * kLog2e;
-          float sump[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int t = 0; t < TP; ++t) {
-            e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
-            sump[t & 3] += e[t];
-          }
-          const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
-          const float nk1 = -p.k1;
-          uint32_t pe[TP / 2];
-          if constexpr (SAVE) {
-            // exactly what the backward's epi-1 would put in TMEM: A1 and E as fp16, zero on dead rows / words
-            // (padding words keep E = exp(-g1): the backward multiplies it by 1/|Wu_w| = 0; dead rows are zeroed)
-            const bool live_row = r < p.R;
-            const float inv = live_row ? 1.f / sum : 0.f;
-            uint32_t pa[TP / 2];
-#pragma unroll
-            for (int t = 0; t < TP; t += 2) {
-              const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
-              pa[t >> 1] = pack_half2(a0, a1);
-              const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
-              pe[t >> 1] = live_row ? pk : 0u;
-            }
+      bool seen0 = false, seen1 = false;
+      for (int k = grp; k < ntask; k += 4) {
+        const int tile = k >= p.nc ? 1 : 0;      // tile-0 tasks first: its scores arrive first
+        const int c = k - tile * p.nc;
+        if (tile == 1 && !seen1) {               // this thread's tile-0 rows of E are complete
+          fence_proxy_async();
+          mbar_arrive(&bars[kEFull0]);
+        }
+        if (tile == 0 && !seen0) {
+          mbar_wait(&bars[kSFull0], n & 1);
+          if (tid == 64) TGFR_TRACE(n, 2);
+          tc_fence_after();
+          seen0 = true;
+        }
+        if (tile == 1 && !seen1) {
+          mbar_wait(&bars[kSFull1], n & 1);
+          tc_fence_after();
+          seen1 = true;
+        }
+        const int r = tile * 128 + lrow;
+        const int i = g * p.nc + c;
+        if (i >= p.Bq) {
+          if constexpr (SAVE) {                                 // missing captions: zero records for the backward
             if (r < p.Rp) {
-              // [caption][16-byte chunk: A1 x Tp | E x Tp][row]: every store of a warp covers 512 contiguous bytes
               uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
 #pragma unroll
-              for (int j = 0; j < TP / 8; ++j) {
-                rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
-                rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-              }
+              for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
             }
-          } else {
-            const float kinv = p.k1 / sum;
+          }
+          continue;
+        }
+        const int len = __ldg(p.lens + i);
+        uint32_t v[TP];
+        const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
 #pragma unroll
-            for (int t = 0; t < TP; t += 2)
-              pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
+        for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
+        tmem_ld_wait();
+        float e[TP];
+        float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
+          mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
+        }
+        const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+        const float nmx = -mx * kLog2e;
+        float sump[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
+          sump[t & 3] += e[t];
+        }
+        const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
+        const float nk1 = -p.k1;
+        uint32_t pe[TP / 2];
+        if constexpr (SAVE) {
+          // A1 and E as the backward reads them: fp16, zero on dead rows
+          // (padding words keep E = exp(-g1): the backward multiplies it by 1/|Wu_w| = 0)
+          const bool live_row = r < p.R;
+          const float inv = live_row ? 1.f / sum : 0.f;
+          uint32_t pa[TP / 2];
+#pragma unroll
+          for (int t = 0; t < TP; t += 2) {
+            const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
+            pa[t >> 1] = pack_half2(a0, a1);
+            const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
+            pe[t >> 1] = live_row ? pk : 0u;
           }
           if (r < p.Rp) {
+            // [caption][16-byte chunk: A1 x Tp | E x Tp][row]: every store of a warp covers 512 contiguous bytes
+            uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
 #pragma unroll
             for (int j = 0; j < TP / 8; ++j) {
-              const int w0 = c * TP + 8 * j;
-              *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
-                  make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+              rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+              rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
             }
+          }
+        } else {
+          const float kinv = p.k1 / sum;
+#pragma unroll
+          for (int t = 0; t < TP; t += 2)
+            pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
+        }
+        if (r < p.Rp) {
+#pragma unroll
+          for (int j = 0; j < TP / 8; ++j) {
+            const int w0 = c * TP + 8 * j;
+            *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
+                make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
           }
         }
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bars[kEFull]);
+      if (!seen1) mbar_arrive(&bars[kEFull0]);
+      mbar_arrive(&bars[kEFull1]);
       if (tid == 64) TGFR_TRACE(n, 3);
 
-      // ---------------- epi-2: cosine, exp, log-sum ----------------
+      // ---------------- epi-2: cosine, exp, log-sum (and the V tile for the backward) ----------------
       const int w = lrow;
       const int c = w / TP, t = w - c * TP;
       const int i = g * p.nc + c;
       const bool valid = (w < p.nw_rows) && (i < p.Bq) && (t < __ldg(p.lens + min(i, p.Bq - 1)));
       const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
-      const int nch = dhalf >> 5;
-      // this thread's half of q_w is fetched before the wait so that its latency hides under GEMM-2
-      uint4 qreg[16];
+      // this thread's quarter of q_w is fetched before the wait so that its latency hides under GEMM-2
+      uint4 qreg[8];
       {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + tile * dhalf);
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + grp * dq);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) qreg[k] = (valid && k < 4 * nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < 8; ++k) qreg[k] = (valid && k < 2 * nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
       }
+      const float nq = valid ? fmaxf(__ldg(p.qnorm + qrow), 1e-30f) : 1.f;
       mbar_wait(&bars[kWuFull], n & 1);
       if (tid == 64) TGFR_TRACE(n, 4);
       tc_fence_after();
-      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f, dot2 = 0.f, dot3 = 0.f, n22 = 0.f, n23 = 0.f;
+      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
+      const uint32_t wu_col = tmem + t_lane + 256 + grp * dq;
+      uint32_t vb[2][16];                        // the next 16 columns load while the current ones are consumed
+      tmem_ld16(wu_col, vb[0]);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         if (ch < nch) {
-          uint32_t v[32];
-          tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
           tmem_ld_wait();
+          if (ch + 1 < nch) tmem_ld16(wu_col + 16 * (ch + 1), vb[(ch + 1) & 1]);
+          const uint32_t(&v)[16] = vb[ch & 1];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[4 * ch + cc]);
+          for (int cc = 0; cc < 2; ++cc) {
+            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[2 * ch + cc]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 qf = __half22float2(qh[k]);
               const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
-              if (k & 1) {
-                dot2 = fmaf(qf.x, w0, dot2);
-                dot3 = fmaf(qf.y, w1, dot3);
-                n22 = fmaf(w0, w0, n22);
-                n23 = fmaf(w1, w1, n23);
-              } else {
-                dot = fmaf(qf.x, w0, dot);
-                dot1 = fmaf(qf.y, w1, dot1);
-                n2 = fmaf(w0, w0, n2);
-                n21 = fmaf(w1, w1, n21);
-              }
+              dot = fmaf(qf.x, w0, dot);
+              dot1 = fmaf(qf.y, w1, dot1);
+              n2 = fmaf(w0, w0, n2);
+              n21 = fmaf(w1, w1, n21);
             }
           }
         }
       }
-      dot = (dot + dot1) + (dot2 + dot3);
-      n2 = (n2 + n21) + (n22 + n23);
+      dot += dot1;
+      n2 += n21;
       if constexpr (!SAVE) {
         tc_fence_before();
         mbar_arrive(&bars[kWuEmpty]);
       }
       if (tid == 64) TGFR_TRACE(n, 5);
-      part_d[tile * 128 + w] = dot;
-      part_n[tile * 128 + w] = n2;
-      epi_bar_sync();
-      if (tile == 0) {
+      part_d[grp * 128 + w] = dot;
+      part_n[grp * 128 + w] = n2;
+      fwd_bar_sync();
+      if (grp == 0) {
         float ex = 0.f, cs = 0.f, inw = 0.f;
         if (valid) {
-          const float dd = part_d[w] + part_d[128 + w], nn = part_n[w] + part_n[128 + w];
+          const float dd = (part_d[w] + part_d[128 + w]) + (part_d[256 + w] + part_d[384 + w]);
+          const float nn = (part_n[w] + part_n[128 + w]) + (part_n[256 + w] + part_n[384 + w]);
           const float nW = fmaxf(sqrtf(nn), 1e-30f);
-          cs = dd / (fmaxf(__ldg(p.qnorm + qrow), 1e-30f) * nW);
+          cs = dd / (nq * nW);
           ex = fast_exp2(p.k2 * cs);
           inw = 1.f / nW;
         }
@@ -388,7 +415,8 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
           p.sv_inw[(int64_t)u * 128 + w] = inw;
         }
       }
-      epi_bar_sync();
+      fwd_bar_sync();
+      if (tid == 64) TGFR_TRACE(n, 6);
       if constexpr (SAVE) {
         // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 rows of the saved V tile.
         // d sim[b,i] / d Wu_w = g2 g3 V_w / (kSV |Wu_w|): the backward needs no cosine / softmax work of its own.
@@ -398,23 +426,24 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 #pragma unroll
           for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
           const float pw = kSV * exs[w] / ssum;
-          c1 = pw / fmaxf(__ldg(p.qnorm + qrow), 1e-30f);
+          c1 = pw / nq;
           c2 = pw * cosw[w] * inww[w];
         }
-        // (the TMEM loads are warp-collective: only the stores are predicated on the word row)
         // planes [d / 8][word][8 halfs]: a warp's store covers 512 contiguous bytes, and the tile is both a K-major
-        // and an MN-major no-swizzle UMMA operand for the backward (tc.cuh make_smem_desc_ns)
+        // and an MN-major no-swizzle UMMA operand for the backward (tc.cuh make_smem_desc_ns).
+        // (the TMEM loads are warp-collective: only the stores are predicated on the word row)
         uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
-                      (int64_t)(tile * (dhalf >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
+                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
+        tmem_ld16(wu_col, vb[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           if (ch < nch) {
-            uint32_t v[32];
-            tmem_ld32(tmem + t_lane + 256 + tile * dhalf + 32 * ch, v);
             tmem_ld_wait();
+            if (ch + 1 < nch) tmem_ld16(wu_col + 16 * (ch + 1), vb[(ch + 1) & 1]);
+            const uint32_t(&v)[16] = vb[ch & 1];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const __half2* qh = reinterpret_cast<const __half2*>(&qreg[4 * ch + cc]);
+            for (int cc = 0; cc < 2; ++cc) {
+              const __half2* qh = reinterpret_cast<const __half2*>(&qreg[2 * ch + cc]);
               uint32_t o[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -424,14 +453,15 @@ wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
                                           c1 * qf.y - c2 * __uint_as_float(v[8 * cc + 2 * k + 1]))
                              : 0u;
               }
-              if (w < p.nw_rows) vdst[(int64_t)(4 * ch + cc) * p.nw_rows] = make_uint4(o[0], o[1], o[2], o[3]);
+              if (w < p.nw_rows) vdst[(int64_t)(2 * ch + cc) * p.nw_rows] = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
+        if (tid == 64) TGFR_TRACE(n, 7);
         tc_fence_before();
         mbar_arrive(&bars[kWuEmpty]);
       }
-      if (tile == 0 && w < p.nc) {
+      if (grp == 0 && w < p.nc) {
         const int ii = g * p.nc + w;
         if (ii < p.Bq) {
           float s = 0.f;
@@ -1051,10 +1081,12 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 //   epi-3    kappa_w = G[b,i] g2 g3 sigma_b / (kSV |Wu_w|);  Ek = E kappa;  dA1 = g1 Ek dE~;
 //            dS = A1 (dA1 - sum_t A1 dA1)  -> (dS | Ek) as fp16 A operands in TMEM
 //   GEMM-6/5 dC[r,:] += sum_w Ek[r,w] V_w + dS[r,w] q_w          A from TMEM, B = MN-major views of the V and Q tiles
-// A work item is (face b, region tile t, caption group g) with g innermost: the 128 x D fp32 block of d ctx of one
-// (b, t) stays in 256 TMEM columns while the CTA walks the caption groups and leaves once, by TMA reduce-add (a
-// (b, t) range may be split between two CTAs).  Per item the CTA streams the Q and V tiles (TMA) and the tile's
-// A1 | E rows (coalesced loads); there is no GEMM-1, GEMM-2, exponential or per-unit drain.
+// A work item is (face b, region tile t, caption group g): the 128 x D fp32 block of d ctx of one (b, t) stays in
+// 256 TMEM columns while the CTA walks the caption groups and leaves once, by TMA reduce-add (a face's groups may
+// be split between two CTAs).  CTAs 2k and 2k+1 walk the same (b, g) units, one region tile each, so that the
+// second reader of a V tile finds it in L2.  Per item the CTA streams the Q and V tiles (bulk copies, the next V
+// prefetched into L2 one item ahead) and the tile's A1 | E rows (coalesced loads); there is no GEMM-1, GEMM-2,
+// exponential or per-unit drain.
 // sigma_b is a per-face power of two that keeps the fp16 operands in the normal range.
 //
 // TMEM columns: [0,256) d ctx block, [256,384) dE~, [384,448) dS (fp16 pairs), [448,512) Ek (fp16 pairs).
@@ -1067,7 +1099,7 @@ struct TcBwd2Params {
   const float* inw;      // [total_units][128]
   const float* gsim;     // [Bc, Bq]
   uint32_t rec_stride;   // bytes per unit
-  int Bc, Bq, R, Rp, D, nc, G, nw_rows, n_tiles, total_items;
+  int Bc, Bq, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   uint32_t q_panel, off_q, off_v, off_misc;
   float g1, g23;
 };
@@ -1087,8 +1119,12 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
   float* kap = reinterpret_cast<float*>(misc + 256);           // [2][128] kappa_w, double buffered over items
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s0 = (int)((int64_t)blockIdx.x * p.total_items / gridDim.x);
-  const int s1 = (int)((int64_t)(blockIdx.x + 1) * p.total_items / gridDim.x);
+  // two region tiles: CTAs (2k, 2k+1) share a range of units and take one tile each (the grid is even)
+  const int t = (p.n_tiles == 2) ? (int)(blockIdx.x & 1) : 0;
+  const int share = (p.n_tiles == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nshare = (p.n_tiles == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int u0 = (int)((int64_t)share * p.total_units / nshare);
+  const int u1 = (int)((int64_t)(share + 1) * p.total_units / nshare);
   const int kchunks = p.D >> 6;
   constexpr uint32_t kCPanel = 128 * 128;
 
@@ -1118,30 +1154,26 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      int prev_ft = -1, n = 0, m = -1;
-      for (int s = s0; s < s1; ++s, ++n) {
-        const int ft = s / p.G, g = s - ft * p.G;
-        const int b = ft / p.n_tiles, t = ft - b * p.n_tiles;
-        const int u = b * p.G + g;
-        {   // pull the tile's A1 | E rows of this item (first one) and the next towards L2
-          const int rows = min(p.Rp - t * 128, 128);
-          for (int k = (n == 0 ? 0 : 1); k < 2; ++k) {
-            const int sn = s + k;
-            if (sn >= s1) break;
-            const int ftn = sn / p.G, gn = sn - ftn * p.G, bn = ftn / p.n_tiles, tn = ftn - bn * p.n_tiles;
-            const int rows_n = (k == 0) ? rows : min(p.Rp - tn * 128, 128);
-            const uint8_t* base = p.rec + (int64_t)(bn * p.G + gn) * p.rec_stride;
-            for (int cj = 0; cj < p.nc * (TP / 4); ++cj)
-              bulk_prefetch_l2(base + ((int64_t)cj * p.Rp + tn * 128) * 16, (uint32_t)rows_n * 16);
-          }
+      int prev_b = -1, n = 0, m = -1;
+      const uint32_t rec_rows = (uint32_t)min(p.Rp - t * 128, 128);
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G, g = u - b * p.G;
+        // towards L2, one item ahead: the tile's A1 | E rows and the V tile (HBM traffic spreads over the item)
+        for (int un = (n == 0 ? u : u + 1); un <= u + 1 && un < u1; ++un) {
+          const uint8_t* base = p.rec + (int64_t)un * p.rec_stride;
+          for (int cj = 0; cj < p.nc * (TP / 4); ++cj)
+            bulk_prefetch_l2(base + ((int64_t)cj * p.Rp + t * 128) * 16, rec_rows * 16);
+          if (un > u)
+            for (int kc = 0; kc < kchunks; ++kc)
+              bulk_prefetch_l2(p.v + (int64_t)un * p.nw_rows * p.D + (int64_t)kc * (p.q_panel >> 1), p.q_panel);
         }
         if (n > 0) mbar_wait(&bars[cVFree], (n - 1) & 1);           // GEMM-3 and GEMM-6 of the previous item retired
-        if (ft != prev_ft) {
+        if (b != prev_b) {
           if (m >= 0) mbar_wait(&bars[cDrained], m & 1);            // drain boxes overlay the operand tiles
           ++m;
           mbar_arrive_expect_tx(&bars[cCFull], kchunks * kCPanel);
           for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * kCPanel, &tm_c, &bars[cCFull], kc * 64, t * 128, b);
-          prev_ft = ft;
+          prev_b = b;
         }
         mbar_arrive_expect_tx(&bars[cVFull], kchunks * p.q_panel);
         for (int kc = 0; kc < kchunks; ++kc)                        // the tile is one contiguous image: four bulk copies
@@ -1160,14 +1192,14 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
       const uint32_t idesc5 = make_idesc_f16(128, p.D, false, true);     // d ctx block: A in TMEM, B MN-major
       const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_v = smem_u32(s_v);
       const uint32_t v_plane = (uint32_t)p.nw_rows * 16u;                // bytes between consecutive 8-feature planes of V
-      int prev_ft = -1, n = 0, m = -1;
-      for (int s = s0; s < s1; ++s, ++n) {
-        const int ft = s / p.G;
-        const bool first = ft != prev_ft;
+      int prev_b = -1, n = 0, m = -1;
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G;
+        const bool first = b != prev_b;
         if (first) {
           ++m;
           mbar_wait(&bars[cCFull], m & 1);
-          prev_ft = ft;
+          prev_b = b;
         }
         mbar_wait(&bars[cVFull], n & 1);
         TGFR_TRACE(n, 17);
@@ -1214,11 +1246,9 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
     }
     int prev_b = -1, n = 0;
     float sigma = 1.f, inv_sigma = 1.f;
-    for (int s = s0; s < s1; ++s, ++n) {
-      const int ft = s / p.G, g = s - ft * p.G;
-      const int b = ft / p.n_tiles, t = ft - b * p.n_tiles;
-      const int u = b * p.G + g;
-      const bool last = (s + 1 == s1) || ((s + 1) / p.G != ft);
+    for (int u = u0; u < u1; ++u, ++n) {
+      const int b = u / p.G, g = u - b * p.G;
+      const bool last = (u + 1 == u1) || ((u + 1) / p.G != b);
       if (b != prev_b) {                         // per-face power-of-two scale from the largest |d loss / d sim[b, :]|
         float gmax = 0.f;
         for (int i = lane; i < p.Bq; i += 32) gmax = fmaxf(gmax, fabsf(__ldg(p.gsim + (int64_t)b * p.Bq + i)));
@@ -1385,7 +1415,7 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   pl->off_q = kch * pl->c_panel;
   pl->off_e = pl->off_q + kch * pl->q_panel;
   pl->off_misc = pl->off_e + 2 * pl->e_panel;
-  pl->smem_bytes = pl->off_misc + 4096 + 1024;        // misc + alignment slack
+  pl->smem_bytes = pl->off_misc + 6144 + 1024;        // misc + alignment slack
   TGFR_REQUIRE(pl->smem_bytes <= 232448, "wordregion(tc): shared memory plan needs %u bytes", pl->smem_bytes);
   pl->ws_c16 = 0;
   pl->ws_q16 = align_up((size_t)Bc * R * D * 2, 256);
@@ -1398,19 +1428,24 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
 
 // what the forward leaves for wr_tc_bwd2_kernel, in one caller-owned buffer:
 //   [V tiles: total_units x (D/8 planes x nw_rows x 8 fp16)][records: total_units x (nc x Tp/4 chunks x Rp x 16 B)]
-//   [1/|Wu|: total_units x 128 fp32]
+//   [1/|Wu|: total_units x 128 fp32][the fp16 operand copies of ctx and words, word norms, caption lengths]
+// (the last group is what wr_tc_prep_kernel produces: the backward then skips its own conversion pass)
 struct SavedLayout {
-  size_t off_v, off_rec, off_inw, total;
+  size_t off_v, off_rec, off_inw, off_c16, off_q16, off_qnorm, off_lens, total;
   uint32_t rec_stride;
 };
-SavedLayout saved_layout(const TcPlan& pl, int Bc, int D) {
+SavedLayout saved_layout(const TcPlan& pl, int Bc, int Bq, int R, int D) {
   SavedLayout L;
   const size_t units = (size_t)Bc * pl.G;
   L.rec_stride = (uint32_t)align_up((size_t)pl.nc * pl.Rp * pl.Tp * 4, 128);
   L.off_v = 0;
   L.off_rec = align_up(units * pl.nw_rows * D * 2, 1024);
   L.off_inw = L.off_rec + align_up(units * L.rec_stride, 1024);
-  L.total = L.off_inw + units * 128 * 4;
+  L.off_c16 = L.off_inw + align_up(units * 128 * 4, 256);
+  L.off_q16 = L.off_c16 + align_up((size_t)Bc * R * D * 2, 256);
+  L.off_qnorm = L.off_q16 + align_up((size_t)Bq * pl.Tp * D * 2, 256);
+  L.off_lens = L.off_qnorm + align_up((size_t)Bq * pl.Tp * 4, 256);
+  L.total = L.off_lens + align_up((size_t)Bq * 4, 256);
   return L;
 }
 
@@ -1501,10 +1536,21 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   int* lens = reinterpret_cast<int*>(base + fp.ws_lens);
   float* dq_pad = reinterpret_cast<float*>(base + fp.ws_dq);
 
-  const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
-  wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc, Bq,
-                                                               T, pl.Tp, R, D, c16, q16, qnorm, lens);
-  TGFR_LAUNCH_OK();
+  const SavedLayout L = saved_layout(fp, Bc, Bq, R, D);
+  const bool have_saved = saved != nullptr && saved_bytes >= L.total;
+  if (have_saved) {
+    // the forward kept its fp16 operand copies next to the records: no second conversion pass
+    uint8_t* sv = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(saved));
+    c16 = reinterpret_cast<__half*>(sv + L.off_c16);
+    q16 = reinterpret_cast<__half*>(sv + L.off_q16);
+    qnorm = reinterpret_cast<float*>(sv + L.off_qnorm);
+    lens = reinterpret_cast<int*>(sv + L.off_lens);
+  } else {
+    const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
+    wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc,
+                                                                 Bq, T, pl.Tp, R, D, c16, q16, qnorm, lens);
+    TGFR_LAUNCH_OK();
+  }
 
   CUtensorMap tm_c, tm_q;
   if (int rc = make_tmap_3d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, pl.c_rows, 1)) return rc;
@@ -1553,8 +1599,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     CUtensorMap tm_dc;
     TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
     if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 32, 1)) return rc;
-    const SavedLayout L = saved_layout(fp, Bc, D);
-    if (saved != nullptr && saved_bytes >= L.total) {
+    if (have_saved) {
       // the forward left its records: (b, tile, caption group) items, d ctx accumulated in TMEM
       TcBwd2Plan pl2;
       if (int rc = make_bwd2_plan(fp, D, &pl2)) return rc;
@@ -1570,11 +1615,14 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
       p2.gsim = gsim;
       p2.rec_stride = L.rec_stride;
       p2.Bc = Bc; p2.Bq = Bq; p2.R = R; p2.Rp = fp.Rp; p2.D = D; p2.nc = fp.nc; p2.G = fp.G;
-      p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_items = Bc * fp.n_tiles * fp.G;
+      p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_units = Bc * fp.G;
       p2.q_panel = pl2.q_panel; p2.off_q = pl2.off_q; p2.off_v = pl2.off_v; p2.off_misc = pl2.off_misc;
       p2.g1 = g1; p2.g23 = g2 * g3;
-      int grid2 = p2.total_items < sms ? p2.total_items : sms;
-      if (grid_dbg > 0 && grid_dbg < grid2) grid2 = grid_dbg;
+      // one CTA per SM; with two region tiles CTAs (2k, 2k+1) share a unit range, one tile each
+      int shares = fp.n_tiles == 2 ? sms / 2 : sms;
+      if (grid_dbg > 0 && grid_dbg < shares) shares = grid_dbg;
+      if (shares > p2.total_units) shares = p2.total_units;
+      const int grid2 = shares * fp.n_tiles;
       switch (fp.Tp) {
         TGFR_LAUNCH_BWD2(8)
         TGFR_LAUNCH_BWD2(16)
@@ -1632,7 +1680,7 @@ int wordregion_tc_set_trace(void* dev_buf) {
 size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D) {
   TcPlan pl;
   if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return 0;
-  return saved_layout(pl, Bc, D).total;
+  return saved_layout(pl, Bc, Bq, R, D).total;
 }
 
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
@@ -1656,6 +1704,17 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   __half* q16 = reinterpret_cast<__half*>(base + pl.ws_q16);
   float* qnorm = reinterpret_cast<float*>(base + pl.ws_qnorm);
   int* lens = reinterpret_cast<int*>(base + pl.ws_lens);
+  const bool save = saved != nullptr;
+  const SavedLayout L = saved_layout(pl, Bc, Bq, R, D);
+  if (save) {
+    TGFR_REQUIRE(saved_bytes >= L.total, "wordregion(tc): saved buffer too small (%zu < %zu)", saved_bytes, L.total);
+    TGFR_REQUIRE((reinterpret_cast<uintptr_t>(saved) & 255) == 0, "wordregion(tc): saved buffer must be 256-byte aligned");
+    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);     // the operand copies live with the records: the backward reuses them
+    c16 = reinterpret_cast<__half*>(sv + L.off_c16);
+    q16 = reinterpret_cast<__half*>(sv + L.off_q16);
+    qnorm = reinterpret_cast<float*>(sv + L.off_qnorm);
+    lens = reinterpret_cast<int*>(sv + L.off_lens);
+  }
 
   const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
   wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc, Bq,
@@ -1674,11 +1733,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
   p.off_q = pl.off_q; p.off_e = pl.off_e; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3;
-  const bool save = saved != nullptr;
   if (save) {
-    const SavedLayout L = saved_layout(pl, Bc, D);
-    TGFR_REQUIRE(saved_bytes >= L.total, "wordregion(tc): saved buffer too small (%zu < %zu)", saved_bytes, L.total);
-    TGFR_REQUIRE((reinterpret_cast<uintptr_t>(saved) & 127) == 0, "wordregion(tc): saved buffer must be 128-byte aligned");
     uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
     p.sv_v = reinterpret_cast<__half*>(sv + L.off_v);
     p.sv_rec = sv + L.off_rec;
@@ -1703,7 +1758,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
                                         232448));                                                              \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    wr_tc_fwd_kernel<TPV, SV><<<grid, kThreadsTC, pl.smem_bytes, st>>>(tm_c, tm_q, p);                           \
+    wr_tc_fwd_kernel<TPV, SV><<<grid, kFwdThreads, pl.smem_bytes, st>>>(tm_c, tm_q, p);                           \
   }
 #define TGFR_LAUNCH_FWD(TPV)                  \
   case TPV:                                   \

@@ -12,9 +12,13 @@ trace = torch.zeros(16 * 32, dtype=torch.int64, device='cuda')
 def fwd(): return ops.wordregion_sim(f, w, None, 4., 5., 10., precision=_lib.PREC_TC, want_attn=False)[0]
 sim = fwd(); g = torch.randn_like(sim) / B
 sim.backward(g, retain_graph=True); torch.cuda.synchronize()
-names_e = {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 done', 6: 'dE ready', 7: 'epi3 done', 8: 'dC01 ready',
-           9: 'drain0 done', 10: 'drain1 done', 11: 'drain2 done', 12: 'drain3 done'}
-names_m = {17: 'Q ready', 18: 'E ready', 19: 'dW ready/WuEmpty', 20: 'dS ready', 21: 'dc01 issued', 22: 'dc2 issued', 23: 'dc3 issued'}
+names = {
+    'fwd': {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 pass1 done', 6: 'cos/exp done', 7: 'V pass done',
+            17: 'mma:Q ready', 18: 'mma:E ready', 19: 'mma:Wu free'},
+    # record-based backward (wr_tc_bwd2_kernel): one line per (face, tile, caption group) item
+    'bwd': {2: 'dE ready', 3: 'ops written', 8: 'acc done', 9: 'drained', 17: 'mma:V ready', 18: 'mma:ops ready',
+            19: 'mma:G5 issued'},
+}
 for which in ('fwd', 'bwd'):
     trace.zero_()
     _lib.check(lib.tgfr_debug_set_trace(trace.data_ptr()), 'trace')
@@ -27,5 +31,5 @@ for which in ('fwd', 'bwd'):
     print('====', which)
     for n in range(2, 8):
         evs = sorted((t[n, e] - base, e) for e in range(32) if t[n, e] > 0)
-        print('unit', n, ' '.join(f"{(names_e | names_m).get(e, e)}@{int(c)}" for c, e in evs))
+        print('unit', n, ' '.join(f"{names[which].get(e, e)}@{int(c)}" for c, e in evs))
     print('cycles per unit (epilogue thread):', np.diff(t[2:12, 3]))
