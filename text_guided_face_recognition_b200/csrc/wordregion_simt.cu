@@ -443,109 +443,121 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_kernel(const Params p) {
 
 
 // Attention maps only (the B diagonal maps of the tensor-core path, or a func_attention caller that drops the
-// context): one CTA per pair, one WARP per region row, all rows in flight at once (the loss kernel's staged
-// thread-per-region contraction serialises eight load rounds, which is what a 128-CTA launch cannot hide).
-// Lane l holds c_r[l + 32 k]; the TP partial dot products of a row are reduced by one butterfly that leaves
-// word t's sum in lane t (31 shuffles instead of 5 TP), so the word softmax runs lane-parallel.
+// context): phase A of the loss kernel with the region tile staged by cp.async, three buffers deep, so that the
+// eight 32-feature rounds overlap their loads with the FMAs instead of serialising load -> sync -> compute
+// (a 128-CTA launch has nothing else to hide that latency with).  The dot products run in the same order as
+// region_gemm, so the maps are bit-identical to the fp32 loss path's.
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int TP>
 __global__ void __launch_bounds__(kThreads, 1) attn_only_kernel(const Params p) {
   extern __shared__ __align__(16) float smem_raw[];
   const int qs = p.D + 4, es = TP + 1;
-  float* sq = smem_raw;                    // [TP][qs] words of the caption (zero rows beyond its length)
-  float* se = sq + TP * qs;                // [R][es]  E = exp(g1 A1)
-  float* sz = se + p.R * es;               // [32]     Z[t] = sum_r E[r,t]
+  float* sq = smem_raw;                              // [TP][qs] words of the caption (zero rows beyond its length)
+  float* cs0 = sq + TP * qs;                         // [3][kMaxR][kCStride] staged 32-feature chunks of the region tile
+  float* se = cs0 + 3 * kMaxR * kCStride;            // [R][es]  E = exp(g1 A1)
+  float* sz = se + p.R * es;                         // [32]     Z[t] = sum_r E[r,t]
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int Ti = p.T;
   if (p.cap_lens) Ti = min(max(p.cap_lens[b], 1), p.T);
   const float* cb = p.ctx + (int64_t)b * p.csb;
-  load_rows<TP>(sq, p.words + (int64_t)b * p.wsb, p.wst, p.wsd, Ti, p.D);
-  __syncthreads();
+  // 16-byte copies need contiguous, aligned feature rows; other layouts stage with plain loads
+  const bool vec = p.csd == 1 && (p.csr & 3) == 0 && (p.D & 31) == 0 && ((reinterpret_cast<uintptr_t>(cb) & 15) == 0);
+  const int nchunk = (p.D + kChunk - 1) / kChunk;
 
-  // four region rows per warp and step: every word feature read from shared memory feeds four dot products
-  // (shared-memory bandwidth, not arithmetic, bounds this kernel); the next step's rows load meanwhile
-  constexpr int kRB = 4;
-  float cn[kRB][8];
-#pragma unroll
-  for (int j = 0; j < kRB; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int d = lane + 32 * k, r = warp * kRB + j;
-      cn[j][k] = (d < p.D && r < p.R) ? __ldg(cb + r * p.csr + (int64_t)d * p.csd) : 0.f;
-    }
-  for (int r0 = warp * kRB; r0 < p.R; r0 += kWarps * kRB) {
-    float c[kRB][8];
-#pragma unroll
-    for (int j = 0; j < kRB; ++j)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int d = lane + 32 * k, rn = r0 + kWarps * kRB + j;
-        c[j][k] = cn[j][k];
-        cn[j][k] = (d < p.D && rn < p.R) ? __ldg(cb + rn * p.csr + (int64_t)d * p.csd) : 0.f;
+  auto stage = [&](int k) {
+    float* cs = cs0 + (k % 3) * (kMaxR * kCStride);
+    const int d0 = k * kChunk;
+    if (vec) {
+      for (int idx = threadIdx.x; idx < p.R * 8; idx += kThreads) {
+        const int rr = idx >> 3, q4 = idx & 7;
+        cp_async16(cs + rr * kCStride + 4 * q4, cb + (int64_t)rr * p.csr + d0 + 4 * q4);
       }
-    float acc[kRB][TP];
-#pragma unroll
-    for (int t = 0; t < TP; ++t) {
-      float q[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int d = lane + 32 * k;
-        q[k] = (d < p.D) ? sq[t * qs + d] : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < kRB; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a = fmaf(c[j][k], q[k], a);
-        acc[j][t] = a;
+    } else {
+      for (int idx = threadIdx.x; idx < p.R * kChunk; idx += kThreads) {
+        const int rr = idx >> 5, dd = idx & 31;
+        cs[rr * kCStride + dd] = (d0 + dd < p.D) ? __ldg(cb + rr * p.csr + (int64_t)(d0 + dd) * p.csd) : 0.f;
       }
     }
+    cp_async_commit();
+  };
+
+  stage(0);
+  if (nchunk > 1) stage(1);
+  load_rows<TP>(sq, p.words + (int64_t)b * p.wsb, p.wst, p.wsd, Ti, p.D);
+  const int r = threadIdx.x;
+  float acc[TP];
 #pragma unroll
-    for (int j = 0; j < kRB; ++j) {
-      const int r = r0 + j;
-      if (r >= p.R) break;                   // warp-uniform
-      float v[32];
+  for (int t = 0; t < TP; ++t) acc[t] = 0.f;
+  for (int k = 0; k < nchunk; ++k) {
+    if (k + 2 < nchunk) {
+      stage(k + 2);                 // two rounds ahead: that buffer's last readers passed the barrier closing round k-1
+      cp_async_wait<2>();
+    } else if (k + 1 < nchunk) {
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (r < p.R) {
+      const float* cs = cs0 + (k % 3) * (kMaxR * kCStride);
+      const int d0 = k * kChunk;
+      const int nq = min(kChunk, p.D - d0) >> 2;
+      for (int dq = 0; dq < nq; ++dq) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + r * kCStride + 4 * dq);
 #pragma unroll
-      for (int t = 0; t < 32; ++t) v[t] = (t < TP) ? acc[j][t] : 0.f;
-      // butterfly: after the step with distance s a lane keeps the half of its values whose word index has bit s
-      // equal to the lane's bit s; after the last step v[0] of lane l is the full sum of word l
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-          const float send = up ? v[i] : v[i + s];
-          const float keep = up ? v[i + s] : v[i];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        for (int t = 0; t < TP; ++t) {
+          const float4 v4 = *reinterpret_cast<const float4*>(sq + t * qs + d0 + 4 * dq);
+          acc[t] = fmaf(c4.x, v4.x, acc[t]);
+          acc[t] = fmaf(c4.y, v4.y, acc[t]);
+          acc[t] = fmaf(c4.z, v4.z, acc[t]);
+          acc[t] = fmaf(c4.w, v4.w, acc[t]);
         }
       }
-      const bool valid = lane < Ti;
-      const float sc = v[0];
-      const float m = warp_max(valid ? sc : -INFINITY);
-      const float e = valid ? expf(sc - m) : 0.f;
-      const float inv = 1.f / warp_sum(e);
-      if (lane < TP) se[r * es + lane] = valid ? expf(p.g1 * (e * inv)) : 0.f;
     }
+    __syncthreads();
+  }
+  if (r < p.R) {                    // word softmax and E, as phase_a
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < TP; ++t)
+      if (t < Ti) m = fmaxf(m, acc[t]);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < TP; ++t) {
+      acc[t] = (t < Ti) ? expf(acc[t] - m) : 0.f;
+      sum += acc[t];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int t = 0; t < TP; ++t) se[r * es + t] = (t < Ti) ? expf(p.g1 * (acc[t] * inv)) : 0.f;
   }
   __syncthreads();
   for (int t = warp; t < 32; t += kWarps) {
     float z = 0.f;
     if (t < Ti)
-      for (int r = lane; r < p.R; r += 32) z += se[r * es + t];
+      for (int rr = lane; rr < p.R; rr += 32) z += se[rr * es + t];
     z = warp_sum(z);
     if (lane == 0) sz[t] = (t < Ti) ? z : 1.f;
   }
   __syncthreads();
   float* out = p.attn + (int64_t)b * p.T * p.R;
   for (int idx = threadIdx.x; idx < p.T * p.R; idx += kThreads) {
-    const int t = idx / p.R, r = idx - t * p.R;
-    out[idx] = (t < Ti) ? se[r * es + t] / sz[t] : 0.f;
+    const int t = idx / p.R, rr = idx - t * p.R;
+    out[idx] = (t < Ti) ? se[rr * es + t] / sz[t] : 0.f;
   }
 }
 
 template <int TP>
 int launch_attn_only(const Params& p, cudaStream_t st) {
-  const size_t bytes = ((size_t)TP * (p.D + 4) + (size_t)p.R * (TP + 1) + 32) * sizeof(float);
+  const size_t bytes = ((size_t)TP * (p.D + 4) + 3 * (size_t)kMaxR * kCStride + (size_t)p.R * (TP + 1) + 32) * sizeof(float);
   auto k = attn_only_kernel<TP>;
   {
     static bool attr_done[64] = {};   // once per instantiation and device

@@ -28,3 +28,12 @@ for prec,name in precs:
         ms=e0.elapsed_time(e1)/10
         k = {'ctx': 6, 'words': 4, 'both': 8}[mode]
         print(name,f'bwd({mode}) ms',ms,f'TFLOP/s (alg {k}TRD)',k*T*R*D*B*B/ms/1e9)
+# diagonal attention maps: forward with and without them (the difference is the attention-only kernel)
+f = torch.from_numpy(ctx).cuda(); w = torch.from_numpy(words).cuda()
+for want in (False, True):
+    def fwd2(): return ops.wordregion_sim(f, w, None, 4., 5., 10., precision=_lib.PREC_TC, want_attn=want)[0]
+    for _ in range(3): fwd2()
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): fwd2()
+    e1.record(); torch.cuda.synchronize()
+    print('tc fwd (no records), want_attn =', want, 'ms', e0.elapsed_time(e1) / 20)
