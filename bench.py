@@ -548,6 +548,33 @@ def run_b200(args):
                                "tflops": hflops / (h_ms * 1e-3) / 1e12,
                                "frac_of_tensor_peak": hflops / (h_ms * 1e-3) / 1e12 / pk["tf_burst"]}
 
+        # the same head step through ArcMarginProduct.fused_loss (no [B, C] logits: an extension of the reference API)
+        def fused_step():
+            x.grad = None
+            head.weight.grad = None
+            head.fused_loss(x, labt, gamma=h["gamma"]).backward()
+        for _ in range(3):
+            fused_step()
+        torch.cuda.synchronize()
+        fused_run = fused_step
+        if use_graph:
+            from text_guided_face_recognition_b200.graphs import GraphedStep
+            fused_run = GraphedStep(fused_step)
+        hs = []
+        for _ in range(max(3, min(args.steps, 10))):
+            flush.zero_()
+            e0.record()
+            fused_run()
+            e1.record()
+            torch.cuda.synchronize()
+            hs.append(e0.elapsed_time(e1))
+        hf_ms = sum(hs) / len(hs)
+        line["margin_head"]["fused_loss"] = {"value": h["B"] / (hf_ms * 1e-3), "unit": "samples/s", "ms_per_step": hf_ms,
+                                             "tflops": hflops / (hf_ms * 1e-3) / 1e12,
+                                             "frac_of_tensor_peak": hflops / (hf_ms * 1e-3) / 1e12 / pk["tf_burst"],
+                                             "what": "ArcMarginProduct.fused_loss: margin + online softmax + softmax "
+                                                     "gradient in the tcgen05 GEMM epilogues, logits never written"}
+
         # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -564,6 +591,62 @@ def run_b200(args):
                                     "kind": "port",
                                     "sample": f"{n_pairs} pairs ({n_caps} of {B} captions x {B} faces per pass), "
                                               f"{t_used:.1f} s of oracle/ref_port.py on the host"}
+            # the same op-for-op port of the reference on THIS GPU (CUDA fp32, TF32 off): the like-for-like number
+            # SURVEY 8(d) asks for beside the CPU one (the reference itself does not travel to the GPU box)
+            from oracle import ref_port as P
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            gc_, gw_, ga_, gb_ = (torch.from_numpy(a_).to(dev) for a_ in (ctx, words, img, txt))
+            gc_.requires_grad_(True), ga_.requires_grad_(True), gb_.requires_grad_(True)
+            gw_.requires_grad_(args.grads == "both")
+
+            def ref_gpu_step():
+                for t_ in (gc_, gw_, ga_, gb_):
+                    t_.grad = None
+                l0_, l1_, _ = P.words_loss_port(gc_.view(B, IH, IW, D).permute(0, 3, 1, 2), gw_.transpose(1, 2), labels,
+                                                None, *GAMMAS)
+                s0_, s1_ = P.sent_loss_port(ga_, gb_, labels, cid, GAMMAS[2])
+                (l0_ + l1_ + s0_ + s1_).backward()
+            ref_gpu_step()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                ref_gpu_step()
+            e1.record()
+            torch.cuda.synchronize()
+            rg_ms = e0.elapsed_time(e1) / 3
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            line["reference_on_gpu"] = {"value": B * B / (rg_ms * 1e-3), "unit": "pairs/s", "ms_per_step": rg_ms,
+                                        "kind": "port", "dtype": "f32 (TF32 off)",
+                                        "what": "oracle/ref_port.py (the reference's PyTorch op sequence) on this B200, "
+                                                "full configs[1] step, eager"}
+            # margin head (configs[2]) on the host cores and on this GPU through the same port
+            hx = torch.from_numpy(xn).requires_grad_(True)
+            hw = torch.from_numpy(wn).requires_grad_(True)
+            hl = torch.from_numpy(lab)
+            P.arc_focal_port(hx, hw, hl, h["s"], h["m"], h["gamma"])[1].backward()
+            t0 = time.perf_counter()
+            n_h = 0
+            while time.perf_counter() - t0 < 3.0:
+                hx.grad = hw.grad = None
+                P.arc_focal_port(hx, hw, hl, h["s"], h["m"], h["gamma"])[1].backward()
+                n_h += 1
+            h_cpu = (time.perf_counter() - t0) / n_h
+            gx, gwt, gl = hx.detach().to(dev).requires_grad_(True), hw.detach().to(dev).requires_grad_(True), hl.to(dev)
+            for _ in range(3):
+                gx.grad = gwt.grad = None
+                P.arc_focal_port(gx, gwt, gl, h["s"], h["m"], h["gamma"])[1].backward()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                gx.grad = gwt.grad = None
+                P.arc_focal_port(gx, gwt, gl, h["s"], h["m"], h["gamma"])[1].backward()
+            e1.record()
+            torch.cuda.synchronize()
+            line["margin_head"]["cpu_baseline"] = {"value": h["B"] / h_cpu, "unit": "samples/s", "kind": "port",
+                                                   "cores": torch.get_num_threads(), "sample": f"{n_h} full steps"}
+            line["margin_head"]["reference_on_gpu"] = {"value": h["B"] / (e0.elapsed_time(e1) / 10 * 1e-3),
+                                                       "unit": "samples/s", "kind": "port", "dtype": "f32 (TF32 off)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # release the captured graphs before the communicator goes away, then leave without the NCCL teardown

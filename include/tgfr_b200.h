@@ -150,6 +150,27 @@ int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_
                         float* dx, float* dw, int precision, void* workspace, size_t workspace_bytes, void* stream);
 size_t tgfr_margin_workspace_bytes(int B, int C, int Din, int precision);
 
+/* Fused ArcFace + cross entropy (metrics.py:42-60 followed by nn.CrossEntropyLoss / FocalLoss, losses.py:313-325)
+ * on the tensor cores: the [B,C] logits are never written.  The forward leaves, for THIS class shard
+ * (columns class_off .. class_off + C - 1), the online-softmax statistics rowmax[B], rowsum[B] (sum of
+ * exp(logit - rowmax)), the target logit tgt[B] (0 when the label lives on another shard) and cos_t[B] (NaN then);
+ * the caller merges shards (all-reduce), and tgfr_focal_finish turns (rowmax, rowsum, tgt) into the loss, the
+ * per-row log-sum-exp `lse` and the focal factor.  The backward takes lse, the focal factor `coef` and the upstream
+ * gradient `gout` (device scalars, either may be NULL = 1) and returns dx [B,Din] (may be NULL) and dw (w's strides).
+ * `saved` (tgfr_arc_fused_saved_bytes) carries the fp16 normalised operands from the forward to the backward;
+ * workspace: tgfr_arc_fused_workspace_bytes; both 256-byte aligned. */
+size_t tgfr_arc_fused_workspace_bytes(int B, int C, int Din);
+size_t tgfr_arc_fused_saved_bytes(int B, int C, int Din);
+int tgfr_arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
+                       const int64_t* labels, int B, int C, int Din, int class_off, float s, float m, int easy_margin,
+                       float* xnorm, float* wnorm, float* rowmax, float* rowsum, float* tgt, float* cos_t,
+                       void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream);
+int tgfr_arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk,
+                       const int64_t* labels, const float* xnorm, const float* wnorm, const float* lse,
+                       const float* coef, const float* gout, int B, int C, int Din, int class_off, float s, float m,
+                       int easy_margin, float* dx, float* dw, void* workspace, size_t workspace_bytes,
+                       const void* saved, size_t saved_bytes, void* stream);
+
 /* MagFace: cos_m[b,c] from cos_s (= scale*cos) and per-row margins (magface.py:95-106). */
 int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale,
                         int easy_margin, float* cos_m_s, void* stream);

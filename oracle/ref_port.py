@@ -73,7 +73,7 @@ def sent_loss_port(cnn_code, rnn_code, labels, class_ids, g3, eps=1e-8):
     s = torch.bmm(a, b.transpose(1, 2)) / torch.bmm(na, nb.transpose(1, 2)).clamp(min=eps) * g3
     s = s.squeeze()
     if mask is not None:
-        s.data.masked_fill_(mask, -float("inf"))
+        s.data.masked_fill_(mask.to(s.device), -float("inf"))      # losses.py:29-30 (`masks.cuda()` under args.CUDA)
     return F.cross_entropy(s, labels), F.cross_entropy(s.t(), labels)
 
 

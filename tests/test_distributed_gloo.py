@@ -117,7 +117,29 @@ def _case_class_sharded_softmax(rank):
     assert abs(ce - want) < 1e-12 * abs(want)
 
 
+def _case_allreduce_gradients(rank):
+    """Bucketed all-reduce of replica gradients: mixed dtypes, a parameter without grad, several buckets."""
+    from text_guided_face_recognition_b200 import distributed as D
+    gen = torch.Generator().manual_seed(11)
+    shapes = [(256, 256), (256,), (17, 3), (640, 256), (5,)]
+    base = [torch.randn(*s_, generator=gen, dtype=torch.float64) for s_ in shapes]
+    params = []
+    for k, t in enumerate(base):
+        p = torch.nn.Parameter(torch.zeros_like(t, dtype=torch.float32 if k != 2 else torch.float64))
+        p.grad = (t * (rank + 1)).to(p.dtype)             # rank r contributes (r + 1) * base
+        params.append(p)
+    params.append(torch.nn.Parameter(torch.zeros(3)))     # no gradient: skipped
+    nb = D.allreduce_gradients(params, bucket_bytes=300_000)
+    assert nb >= 3                                        # two dtypes, and the fp32 gradients exceed one bucket
+    for p, t in zip(params, base):
+        assert torch.allclose(p.grad.double(), 3.0 * t, rtol=1e-6, atol=1e-6)
+    assert params[-1].grad is None
+    D.allreduce_gradients(params, average=True)
+    for p, t in zip(params, base):
+        assert torch.allclose(p.grad.double(), 3.0 * t, rtol=1e-6, atol=1e-6)   # mean of two equal tensors
+
+
 @pytest.mark.parametrize("case", ["_case_all_gather_rows", "_case_column_stats_and_pair_ce",
-                                  "_case_class_sharded_softmax"])
+                                  "_case_class_sharded_softmax", "_case_allreduce_gradients"])
 def test_gloo_world2(case, tmp_path):
     _run(case, tmp_path)

@@ -336,6 +336,46 @@ def test_arc_margin_config3_size_vs_oracle(api, hprec):
     assert rel(head.weight.grad.cpu().numpy(), dw) < hprec.grad
 
 
+@pytest.mark.parametrize("name", ["arc_small", "arc_small_easy"])
+def test_arc_fused_loss_small_vs_golden(api, golden_dir, name):
+    """ArcMarginProduct.fused_loss (no logits: margin / softmax statistics / softmax gradient in the GEMM epilogues)
+    against the reference's logits -> FocalLoss pair."""
+    g = load(golden_dir, name)
+    B, Din = g["x"].shape
+    C = g["weight"].shape[0]
+    head = api.metrics.ArcMarginProduct(Din, C, s=float(g["s"]), m=float(g["m"]), easy_margin=bool(g["easy"])).cuda()
+    with torch.no_grad():
+        head.weight.copy_(torch.from_numpy(g["weight"]))
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    label = torch.from_numpy(g["label"]).cuda()
+    loss = head.fused_loss(x, label, gamma=float(g["gamma"]))
+    assert abs(loss.item() - float(g["loss"])) < LOSS_RTOL * float(g["loss"])
+    loss.backward()
+    assert rel(x.grad.cpu().numpy(), g["dx"]) < GRAD_RTOL
+    assert rel(head.weight.grad.cpu().numpy(), g["dweight"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,Din,C,gamma,easy", [(512, 512, 10177, 2.0, False), (96, 256, 4500, 0.0, False),
+                                               (37, 72, 1003, 2.0, True)])
+def test_arc_fused_loss_vs_oracle(api, B, Din, C, gamma, easy):
+    """Config-3 size (and ragged sizes: rows / classes / features that do not fill the 128-wide tiles); gamma = 0 is
+    plain cross entropy; an upstream gradient other than 1 (the reference scales by lambda_id = 100)."""
+    xn, wn, label = synth.margin_inputs(B, Din, C, seed=100)
+    head = api.metrics.ArcMarginProduct(Din, C, s=30.0, m=0.5, easy_margin=easy).cuda()
+    with torch.no_grad():
+        head.weight.copy_(torch.from_numpy(wn))
+    x = torch.from_numpy(xn).cuda().requires_grad_(True)
+    lab = torch.from_numpy(label).cuda()
+    loss = head.fused_loss(x, lab, gamma=gamma)
+    ref = O.arc_margin(xn, wn, label, 30.0, 0.5, easy)
+    rl = O.focal_loss(ref, label, gamma)
+    assert abs(loss.item() - rl) < LOSS_RTOL * rl
+    (100.0 * loss).backward()
+    dx, dw = O.arc_margin_bwd(xn, wn, label, O.focal_loss_bwd(ref, label, gamma, 100.0), 30.0, 0.5, easy)
+    assert rel(x.grad.cpu().numpy(), dx) < GRAD_RTOL
+    assert rel(head.weight.grad.cpu().numpy(), dw) < GRAD_RTOL
+
+
 @pytest.mark.parametrize("name", ["mag_small_easy", "mag_small_hard"])
 def test_mag_head_vs_golden(api, golden_dir, name, hprec):
     g = load(golden_dir, name)

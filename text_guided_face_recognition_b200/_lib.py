@@ -42,6 +42,10 @@ SIGNATURES = {
     "tgfr_arc_margin_apply": (I, [P, L, P, I, I, I, F, F, I, P, P]),
     "tgfr_arc_margin_bwd": (I, [P, L, P, L, L, P, P, P, P, P, L, I, I, I, I, F, F, I, P, P, I, P, Z, P]),
     "tgfr_margin_workspace_bytes": (Z, [I, I, I, I]),
+    "tgfr_arc_fused_workspace_bytes": (Z, [I, I, I]),
+    "tgfr_arc_fused_saved_bytes": (Z, [I, I, I]),
+    "tgfr_arc_fused_fwd": (I, [P, L, P, L, L, P, I, I, I, I, F, F, I, P, P, P, P, P, P, P, Z, P, Z, P]),
+    "tgfr_arc_fused_bwd": (I, [P, L, P, L, L, P, P, P, P, P, P, I, I, I, I, F, F, I, P, P, P, Z, P, Z, P]),
     "tgfr_mag_margin_fwd": (I, [P, P, I, I, F, I, P, P]),
     "tgfr_mag_margin_bwd": (I, [P, P, P, P, I, I, F, I, P, P, P]),
     "tgfr_cos_logits_bwd": (I, [P, L, P, L, L, P, P, P, L, P, L, I, I, I, F, I, P, P, I, P, Z, P]),

@@ -54,6 +54,13 @@ size_t margin_workspace_bytes(int, int, int, int);
 int margin_bwd(const float*, int64_t, const float*, int64_t, int64_t, const float*, const float*, const int64_t*,
                const float*, const float*, int64_t, int, int, int, int, float, float, int, float*, float*, int, void*,
                size_t, cudaStream_t);
+size_t arc_fused_workspace_bytes(int, int, int);
+size_t arc_fused_saved_bytes(int, int, int);
+int arc_fused_fwd(const float*, int64_t, const float*, int64_t, int64_t, const int64_t*, int, int, int, int, float, float,
+                  int, float*, float*, float*, float*, float*, float*, void*, size_t, void*, size_t, cudaStream_t);
+int arc_fused_bwd(const float*, int64_t, const float*, int64_t, int64_t, const int64_t*, const float*, const float*,
+                  const float*, const float*, const float*, int, int, int, int, float, float, int, float*, float*, void*,
+                  size_t, const void*, size_t, cudaStream_t);
 int mag_margin_fwd(const float*, const float*, int, int, float, int, float*, cudaStream_t);
 int mag_margin_bwd(const float*, const float*, const float*, const float*, int, int, float, int, float*, float*,
                    cudaStream_t);
@@ -210,6 +217,25 @@ int tgfr_arc_margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_
 }
 size_t tgfr_margin_workspace_bytes(int B, int C, int Din, int precision) {
   return margin_workspace_bytes(B, C, Din, precision);
+}
+
+size_t tgfr_arc_fused_workspace_bytes(int B, int C, int Din) { return arc_fused_workspace_bytes(B, C, Din); }
+size_t tgfr_arc_fused_saved_bytes(int B, int C, int Din) { return arc_fused_saved_bytes(B, C, Din); }
+int tgfr_arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const int64_t* labels,
+                       int B, int C, int Din, int class_off, float s, float m, int easy_margin, float* xnorm,
+                       float* wnorm, float* rowmax, float* rowsum, float* tgt, float* cos_t, void* workspace,
+                       size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(x && w && labels && xnorm && wnorm && rowmax && rowsum && tgt && cos_t, "arc_fused_fwd: NULL tensor");
+  return arc_fused_fwd(x, x_sr, w, w_sc, w_sk, labels, B, C, Din, class_off, s, m, easy_margin, xnorm, wnorm, rowmax,
+                       rowsum, tgt, cos_t, workspace, workspace_bytes, saved, saved_bytes, ST(stream));
+}
+int tgfr_arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const int64_t* labels,
+                       const float* xnorm, const float* wnorm, const float* lse, const float* coef, const float* gout,
+                       int B, int C, int Din, int class_off, float s, float m, int easy_margin, float* dx, float* dw,
+                       void* workspace, size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(x && w && labels && xnorm && wnorm && lse, "arc_fused_bwd: NULL tensor");
+  return arc_fused_bwd(x, x_sr, w, w_sc, w_sk, labels, xnorm, wnorm, lse, coef, gout, B, C, Din, class_off, s, m,
+                       easy_margin, dx, dw, workspace, workspace_bytes, saved, saved_bytes, ST(stream));
 }
 
 int tgfr_mag_margin_fwd(const float* cos_s, const float* margin, int B, int C, float scale, int easy_margin,

@@ -569,6 +569,10 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
 int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, const float* norm, __half* out,
                        int ld_out, cudaStream_t st);
 int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st);
+int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
+                   int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
+                   float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
+                   __half* g16, int ld_g, cudaStream_t st);
 
 namespace {
 struct HeadWs {   // workspace layout of the head calls (fp32 part first, everything 256-byte aligned)
@@ -682,6 +686,100 @@ int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64
                                       dwh);
     TGFR_LAUNCH_OK();
   }
+  if (dx) {
+    normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dxh, Din, x, x_sr, 1, xnorm, 1e-12f, B, Din, dx, Din, 1);
+    TGFR_LAUNCH_OK();
+  }
+  normalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dwh, Din, w, w_sc, w_sk, wnorm, 1e-12f, C, Din, dw, w_sc, w_sk);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// fused ArcFace + cross entropy (tensor cores only): the [B, C] logits are never written.
+//   forward : norms, fp16 normalised operands (kept in `saved` for the backward), cos-theta GEMM whose epilogue
+//             applies the margin and reduces online-softmax partials; (rowmax, rowsum, tgt) describe THIS class
+//             shard -- the caller merges shards (all-reduce) and runs focal_finish for the loss and lse.
+//   backward: the same GEMM with the softmax-gradient epilogue -> g16, then the dX^ / dW^ GEMMs and the
+//             normalisation backward exactly as margin_bwd.
+// workspace: [part: 2 B ceil(C/128) fp32 | dxh | dwh | g16 | scale]; saved: [x16 | w16]
+// --------------------------------------------------------------------------------------------
+namespace {
+struct FusedWs {
+  size_t part, dxh, dwh, g16, scale, total, sv_x16, sv_w16, sv_total;
+  int Dp, Cp, nt;
+};
+FusedWs fused_ws(int B, int C, int Din) {
+  FusedWs f{};
+  f.Dp = (Din + 7) & ~7;
+  f.Cp = (C + 7) & ~7;
+  f.nt = ceil_div(C, 128);
+  size_t o = 0;
+  f.part = o; o += align_up(sizeof(float) * 2 * (size_t)B * f.nt, 256);
+  f.dxh = o; o += align_up(sizeof(float) * (size_t)B * Din, 256);
+  f.dwh = o; o += align_up(sizeof(float) * (size_t)C * Din, 256);
+  f.g16 = o; o += align_up(2 * (size_t)B * f.Cp, 256);
+  f.scale = o; o += 256;
+  f.total = o;
+  f.sv_x16 = 0;
+  f.sv_w16 = align_up(2 * (size_t)B * f.Dp, 256);
+  f.sv_total = f.sv_w16 + align_up(2 * (size_t)C * f.Dp, 256);
+  return f;
+}
+}  // namespace
+
+size_t arc_fused_workspace_bytes(int B, int C, int Din) { return fused_ws(B, C, Din).total; }
+size_t arc_fused_saved_bytes(int B, int C, int Din) { return fused_ws(B, C, Din).sv_total; }
+
+int arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const int64_t* labels, int B,
+                  int C, int Din, int class_off, float s, float m, int easy, float* xnorm, float* wnorm, float* rowmax,
+                  float* rowsum, float* tgt, float* cos_t, void* ws, size_t ws_bytes, void* saved, size_t saved_bytes,
+                  cudaStream_t st) {
+  TGFR_REQUIRE(B > 0 && C > 0 && Din > 0, "arc_fused_fwd: empty shape");
+  TGFR_REQUIRE(head_tc_supported(B, C, Din), "arc_fused_fwd: unsupported shape B=%d C=%d Din=%d", B, C, Din);
+  const FusedWs f = fused_ws(B, C, Din);
+  TGFR_REQUIRE(ws && ws_bytes >= f.total, "arc_fused_fwd: workspace too small (%zu < %zu)", ws_bytes, f.total);
+  TGFR_REQUIRE(saved && saved_bytes >= f.sv_total, "arc_fused_fwd: saved buffer too small (%zu < %zu)", saved_bytes, f.sv_total);
+  TGFR_REQUIRE(((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(saved)) & 255) == 0,
+               "arc_fused_fwd: workspace / saved must be 256-byte aligned");
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
+  __half* x16 = reinterpret_cast<__half*>(sv + f.sv_x16);
+  __half* w16 = reinterpret_cast<__half*>(sv + f.sv_w16);
+  if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
+  if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, f.Dp, st)) return rc;
+  if (int rc = head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, f.Dp, st)) return rc;
+  return gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 0,
+                        reinterpret_cast<float*>(base + f.part), rowmax, rowsum, tgt, cos_t, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, 0, st);
+}
+
+int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const int64_t* labels,
+                  const float* xnorm, const float* wnorm, const float* lse, const float* coef, const float* gout, int B,
+                  int C, int Din, int class_off, float s, float m, int easy, float* dx, float* dw, void* ws,
+                  size_t ws_bytes, const void* saved, size_t saved_bytes, cudaStream_t st) {
+  const FusedWs f = fused_ws(B, C, Din);
+  TGFR_REQUIRE(ws && ws_bytes >= f.total, "arc_fused_bwd: workspace too small (%zu < %zu)", ws_bytes, f.total);
+  TGFR_REQUIRE(saved && saved_bytes >= f.sv_total, "arc_fused_bwd: saved buffer too small");
+  TGFR_REQUIRE(dw != nullptr, "arc_fused_bwd: dw must not be NULL");
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+  const __half* x16 = reinterpret_cast<const __half*>(sv + f.sv_x16);
+  const __half* w16 = reinterpret_cast<const __half*>(sv + f.sv_w16);
+  float* dxh = reinterpret_cast<float*>(base + f.dxh);
+  float* dwh = reinterpret_cast<float*>(base + f.dwh);
+  __half* g16 = reinterpret_cast<__half*>(base + f.g16);
+  float* scale = reinterpret_cast<float*>(base + f.scale);
+  if (int rc = gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 1, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, lse, coef, gout, scale, g16, f.Cp, st))
+    return rc;
+  if (dx) {
+    const int tiles = ceil_div(B, 128) * ceil_div(Din, 128);
+    const int splits = tiles >= 148 ? 1 : ceil_div(296, tiles);
+    if (int rc = gemm_tc(g16, 0, f.Cp, w16, 1, f.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
+  }
+  if (int rc = gemm_tc(g16, 1, f.Cp, x16, 1, f.Dp, C, Din, B, s, scale, 0, dwh, Din, 1, st)) return rc;
   if (dx) {
     normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dxh, Din, x, x_sr, 1, xnorm, 1e-12f, B, Din, dx, Din, 1);
     TGFR_LAUNCH_OK();

@@ -7,6 +7,10 @@
 //   dW^    [C,Din] = g^T. x^           A = g  [B,C]   read MN-major,      B = x^ [B,Din] read MN-major
 // so no operand is ever transposed in memory: the UMMA shared-memory descriptors select the major-ness.
 //
+// The cos-theta GEMM also has two fused ArcFace epilogues that never write the [B, C] logits (kEpiCeStats,
+// kEpiCeGrad below): margin + online-softmax statistics in the forward, margin + softmax gradient as the fp16
+// operand of the two gradient GEMMs in the backward (metrics.py:45-57 + losses.py:321-325 in one pass each).
+//
 // One 128 x 128 output tile per CTA, 3-stage TMA pipeline over K in steps of 64 (32 KB per stage), two CTAs per SM
 // so that one CTA's epilogue overlaps the other's main loop.  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 // allocator, warps 2-5 epilogue (TMEM -> registers -> warp-private shared-memory transpose -> coalesced row stores,
@@ -26,6 +30,39 @@ constexpr uint32_t kTileBytes = kBM * kBK * 2;           // 16 KB per operand pe
 constexpr uint32_t kStageBytes = 2 * kTileBytes;
 constexpr uint32_t kGemmSmem = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment*/;
 
+enum Epi { kEpiStore = 0, kEpiCeStats = 1, kEpiCeGrad = 2 };
+
+// ArcFace margin on the label column (metrics.py:45-57): phi(c) and d phi / d c
+__device__ __forceinline__ float arc_phi_tc(float c, float cm, float sm, float th, float mm, int easy, float* dphi) {
+  const float one_m = 1.f - c * c;
+  const float sine = sqrtf(fminf(fmaxf(one_m, 0.f), 1.f));
+  const bool use = easy ? (c > 0.f) : (c > th);
+  if (dphi) {
+    const bool inside = one_m >= 0.f && one_m <= 1.f;
+    *dphi = use ? (cm + (inside ? c / sine : 0.f) * sm) : 1.f;
+  }
+  return use ? (c * cm - sine * sm) : (easy ? c : c - mm);
+}
+
+struct CeParams {            // fused ArcFace + cross-entropy epilogues (C = cos-theta tile, alpha = s)
+  const int64_t* labels;     // [M]
+  int class_off;             // global class index of column 0 (class-sharded heads)
+  float cm, sm, th, mm;      // cos m, sin m, cos(pi - m), sin(pi - m) m
+  int easy;
+  // kEpiCeStats: per (row, column tile) online-softmax partials, target logit and cos(theta_y) of the owner tile
+  float* pmax;               // [M, n_tiles]
+  float* psum;               // [M, n_tiles]
+  float* tgt;                // [M] pre-zeroed
+  float* cos_t;              // [M] pre-filled with NaN
+  // kEpiCeGrad: g16[b, c] = fp16(2^e k (softmax - onehot) (phi' on the label column)), k = coef gout / M
+  const float* lse;          // [M] global log-sum-exp of the rows
+  const float* coef;         // device scalar (focal factor) or NULL
+  const float* gout;         // device scalar (upstream gradient) or NULL
+  float* scale;              // scale[1] = 2^-e for the gradient GEMMs (written by block (0,0))
+  __half* g16;               // [M, ld_g]
+  int ld_g;
+};
+
 struct GemmTcParams {
   float* C;
   int64_t ldc;
@@ -36,8 +73,10 @@ struct GemmTcParams {
   int clamp;             // clamp the accumulator to [-1, 1] before scaling (magface.py:94)
   int atomic;            // accumulate with atomics (split-K; C pre-zeroed)
   int a_mn, b_mn;
+  CeParams ce;
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -120,6 +159,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
     const int row_base = m0 + q * 32;
     const float alpha = p.dscale ? p.alpha * __ldg(p.dscale + 1) : p.alpha;
+    if constexpr (EPI != kEpiStore) {
+      // a thread owns row (row_base + lane) of the tile: logits = s cos, phi on the label column
+      const int row = row_base + lane;
+      const bool row_ok = row < p.M;
+      const int64_t ycol = row_ok ? __ldg(p.ce.labels + row) - p.ce.class_off : -1;     // label column in this shard
+      float kscale = 0.f, lse = 0.f;
+      if constexpr (EPI == kEpiCeGrad) {
+        // power-of-two scale from the row-independent factor k: entries are k (p - onehot) phi', |.| <= k max(1, phi')
+        const float k = (p.ce.coef ? __ldg(p.ce.coef) : 1.f) * (p.ce.gout ? __ldg(p.ce.gout) : 1.f) / (float)p.M;
+        const float ak = fabsf(k);
+        const float sc = (ak > 0.f) ? exp2f(floorf(log2f(256.f / ak))) : 1.f;
+        kscale = k * sc;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) p.ce.scale[1] = 1.f / sc;
+        lse = row_ok ? __ldg(p.ce.lse + row) : 0.f;
+      }
+      float mx = -INFINITY, sum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < kBN / 32; ++ch) {
+        const int c0 = n0 + 32 * ch;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);      // warp-collective even past the last column
+        tmem_ld_wait();
+        float lg[32];
+        float dph = 1.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float c = __uint_as_float(v[j]);
+          float l = c * p.alpha;
+          if ((int64_t)(c0 + j) == ycol) {
+            l = p.alpha * arc_phi_tc(c, p.ce.cm, p.ce.sm, p.ce.th, p.ce.mm, p.ce.easy, &dph);
+            if constexpr (EPI == kEpiCeStats) {
+              p.ce.cos_t[row] = c;
+              p.ce.tgt[row] = l;
+            }
+          }
+          lg[j] = (c0 + j < p.N) ? l : -INFINITY;
+        }
+        if constexpr (EPI == kEpiCeStats) {
+          float cmx = lg[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cmx = fmaxf(cmx, lg[j]);
+          if (cmx > mx) {
+            sum *= expf(mx - cmx);          // exp(-inf) = 0 on the first chunk
+            mx = cmx;
+          }
+          if (mx > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += expf(lg[j] - mx);
+          }
+        } else {
+          // g16 rows through the warp-private transpose buffer: 64-byte row segments per store
+          __half* hstage = reinterpret_cast<__half*>(stage);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float g = 0.f;
+            if (row_ok && c0 + j < p.N) {
+              const bool on = (int64_t)(c0 + j) == ycol;
+              g = kscale * (expf(lg[j] - lse) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
+              g = fminf(fmaxf(g, -65504.f), 65504.f);
+            }
+            hstage[lane * 66 + j] = __float2half_rn(g);
+          }
+          __syncwarp();
+          const int col = c0 + lane;
+          if (col < p.ce.ld_g) {                                   // columns [N, ld_g) are the zero K padding
+            const int nrows = min(32, p.M - row_base);
+            for (int rr = 0; rr < nrows; ++rr)
+              p.ce.g16[(int64_t)(row_base + rr) * p.ce.ld_g + col] = hstage[rr * 66 + lane];
+          }
+          __syncwarp();
+        }
+      }
+      if constexpr (EPI == kEpiCeStats) {
+        if (row_ok) {
+          p.ce.pmax[(int64_t)row * gridDim.x + blockIdx.x] = mx;
+          p.ce.psum[(int64_t)row * gridDim.x + blockIdx.x] = sum;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int ch = 0; ch < kBN / 32; ++ch) {
       const int c0 = n0 + 32 * ch;
@@ -145,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
       __syncwarp();
+    }
     }
   }
   tc_fence_before();
@@ -209,6 +328,27 @@ __global__ void scale_to_f16_kernel(const float* __restrict__ g, int64_t ld, int
     dst[c] = __float2half_rn(c < cols ? __ldg(src + c) * sc : 0.f);
 }
 
+// merge the per-tile online-softmax partials of a row: (max, sum exp(. - max)) over nt column tiles
+__global__ void ce_merge_partials_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int rows, int nt,
+                                         float* __restrict__ rowmax, float* __restrict__ rowsum) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int k = lane; k < nt; k += 32) m = fmaxf(m, pmax[(int64_t)r * nt + k]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int k = lane; k < nt; k += 32) {
+    const float pm = pmax[(int64_t)r * nt + k];
+    if (pm > -INFINITY) s += psum[(int64_t)r * nt + k] * expf(pm - m);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    rowmax[r] = (m == -INFINITY) ? 0.f : m;
+    rowsum[r] = s;
+  }
+}
+
 }  // namespace
 
 // ---- host API (used by dense_simt.cu's head entry points when precision == TGFR_PREC_TC) ------------------------
@@ -239,12 +379,58 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
   TGFR_CUDA_OK(cudaGetDevice(&dev));
   bool& attr_set = attr_done[dev & 63];
   if (!attr_set) {
-    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     attr_set = true;
   }
   const dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
+  gemm_tc_kernel<kEpiStore><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
   TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// cos-theta GEMM (x16 [M, K] . w16 [N, K]^T, alpha = s) with a fused ArcFace cross-entropy epilogue.
+//   grad == 0: rowmax / rowsum [M] (of this class shard), tgt, cos_t (owner rows only; others 0 / NaN);
+//              part = 2 * M * ceil(N / 128) floats of scratch
+//   grad != 0: g16 [M, ld_g] and scale[1] from lse / coef / gout
+int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
+                   int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
+                   float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
+                   __half* g16, int ld_g, cudaStream_t st) {
+  CUtensorMap tm_a, tm_b;
+  if (int rc = operand_map(&tm_a, x16, 0, M, K, ldx)) return rc;
+  if (int rc = operand_map(&tm_b, w16, 0, N, K, ldw)) return rc;
+  const float pi = 3.14159265358979323846f;
+  const int nt = (N + kBN - 1) / kBN;
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K; p.kt_per_split = (K + kBK - 1) / kBK; p.alpha = s;
+  p.ce.labels = labels; p.ce.class_off = class_off;
+  p.ce.cm = cosf(m); p.ce.sm = sinf(m); p.ce.th = cosf(pi - m); p.ce.mm = sinf(pi - m) * m; p.ce.easy = easy;
+  p.ce.pmax = part; p.ce.psum = part ? part + (size_t)M * nt : nullptr; p.ce.tgt = tgt; p.ce.cos_t = cos_t;
+  p.ce.lse = lse; p.ce.coef = coef; p.ce.gout = gout; p.ce.scale = scale; p.ce.g16 = g16; p.ce.ld_g = ld_g;
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  const dim3 grid(nt, (M + kBM - 1) / kBM, 1);
+  if (!grad) {
+    static bool attr_done[64] = {};
+    if (!attr_done[dev & 63]) {
+      TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiCeStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+      attr_done[dev & 63] = true;
+    }
+    TGFR_CUDA_OK(cudaMemsetAsync(tgt, 0, sizeof(float) * M, st));
+    TGFR_CUDA_OK(cudaMemsetAsync(cos_t, 0xFF, sizeof(float) * M, st));          // NaN: label outside this shard
+    gemm_tc_kernel<kEpiCeStats><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
+    TGFR_LAUNCH_OK();
+    ce_merge_partials_kernel<<<(M + 7) / 8, 256, 0, st>>>(p.ce.pmax, p.ce.psum, M, nt, rowmax, rowsum);
+    TGFR_LAUNCH_OK();
+  } else {
+    static bool attr_done[64] = {};
+    if (!attr_done[dev & 63]) {
+      TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiCeGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+      attr_done[dev & 63] = true;
+    }
+    gemm_tc_kernel<kEpiCeGrad><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
+    TGFR_LAUNCH_OK();
+  }
   return TGFR_OK;
 }
 

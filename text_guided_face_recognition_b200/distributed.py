@@ -8,6 +8,9 @@ nn.DataParallel with the losses un-sharded on device 0); this replaces that.
                        One all-gather of the per-column (max, sum-exp) pairs closes the column-wise
                        cross entropy; the backward needs one reduce-scatter of d(words) and only when
                        the text side requires grad.
+  replica gradients  : the trainable heads (image_head: 692 864 fp32 parameters in the reference) are plain
+                       replicas; their gradients are summed with bucketed all-reduces (`allreduce_gradients`),
+                       which replaces nn.DataParallel's gather-to-device-0 reduce-add.
   margin head        : class-sharded partial FC.  Features/labels are all-gathered over the data
                        parallel batch, each rank holds W[c0:c1, :], the softmax statistics are
                        all-reduced (max, then sum-exp and target logit), dX is reduce-scattered.
@@ -26,7 +29,7 @@ from ._lib import ptr, stream_ptr
 
 __all__ = [
     "all_gather_rows", "merge_column_stats", "class_range", "words_loss_sharded", "sent_loss_sharded",
-    "ShardedArcMarginProduct", "sharded_focal_ce",
+    "ShardedArcMarginProduct", "sharded_focal_ce", "allreduce_gradients",
 ]
 
 
@@ -236,6 +239,16 @@ class _FocalCESharded(torch.autograd.Function):
         return gl, None, None, None, None
 
 
+def _merge_row_stats(rowmax, rowsum, tgt, group):
+    """Per-shard online-softmax statistics -> global ones: all-reduce(max), then all-reduce(sum) of the rescaled
+    sums and of the target logits (non-owners contribute 0)."""
+    gmax = rowmax.clone()
+    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    pack = torch.stack([rowsum * torch.exp(rowmax - gmax), tgt]).contiguous()
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    return gmax, pack[0].contiguous(), pack[1].contiguous()
+
+
 def sharded_focal_ce(logits_shard, target_all, gamma, class_off, group=None):
     """Focal loss of the batch-mean CE over class-sharded logits [B_global, C_local]."""
     target_all = target_all.view(-1).to(device=logits_shard.device, dtype=torch.int64).contiguous()
@@ -282,5 +295,53 @@ class ShardedArcMarginProduct(torch.nn.Module):
         return logits, lab_all
 
     def loss(self, input, label, gamma=2.0):
+        """Focal cross entropy of the sharded head.  On the tensor-core path the shard's logits are never written
+        (fused GEMM epilogues, ops.arc_fused_focal); TGFR_HEAD_PRECISION=fp32 materialises the [B, C_local] shard."""
+        if ops.head_precision(self.in_features) == _lib.PREC_TC:
+            x_all = all_gather_rows(input, self.group)
+            lab_all = all_gather_rows(label.view(-1).to(device=input.device, dtype=torch.int64), self.group)
+            return ops.arc_fused_focal(x_all, self.weight, lab_all, self.s, self.m, self.easy_margin, gamma, self.c0,
+                                       merge=lambda mx, sm, tg: _merge_row_stats(mx, sm, tg, self.group))
         logits, lab_all = self.forward(input, label)
         return sharded_focal_ce(logits, lab_all, gamma, self.c0, self.group)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradients of the replicated trainable modules (the reference wraps them in nn.DataParallel)
+# ---------------------------------------------------------------------------------------------
+def allreduce_gradients(params, group=None, bucket_bytes=16 << 20, average=False):
+    """Sum (or average) the .grad of replicated parameters over the group with a few large all-reduces.
+
+    Gradients are packed into flat buckets of at most `bucket_bytes` (per dtype), every bucket is reduced with
+    one asynchronous all-reduce -- over NVSwitch the cost is launch latency, not link count, so buckets are
+    sized to keep the launches few -- and unpacked in place once all of them have completed.
+    The sharded losses above already return gradients of the GLOBAL (batch-mean) loss, so the default is a
+    plain sum; `average=True` divides by the world size (per-rank mean losses).  Parameters without a
+    gradient are skipped.  Returns the number of buckets used."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    n, _ = _world(group)
+    buckets, cur, cur_bytes = [], [], 0
+    for g in sorted(grads, key=lambda t: str(t.dtype)):
+        nbytes = g.numel() * g.element_size()
+        if cur and (cur[0].dtype != g.dtype or cur_bytes + nbytes > bucket_bytes):
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(g)
+        cur_bytes += nbytes
+    buckets.append(cur)
+    flats, works = [], []
+    for b in buckets:
+        flat = torch.cat([g.reshape(-1) for g in b])
+        flats.append(flat)
+        works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for b, flat, w in zip(buckets, flats, works):
+        w.wait()
+        if average:
+            flat.div_(n)
+        off = 0
+        for g in b:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    return len(buckets)

@@ -43,6 +43,15 @@ class ArcMarginProduct(nn.Module):
             raise RuntimeError(f"ArcMarginProduct: expected input [B,{self.in_features}], got {tuple(input.shape)}")
         return ops.arc_logits(input, self.weight, label, self.s, self.m, self.easy_margin)
 
+    def fused_loss(self, input, label, gamma=0.0):
+        """FocalLoss(gamma)(self(input, label), label) -- the reference's `criterion(metric_fc(x, y), y)` pair
+        (src/train_encoders_bert.py:290-305) -- without materialising the [B, out_features] logits: margin, online
+        softmax and the softmax gradient run in the epilogues of the tensor-core cos-theta GEMM.  An extension of
+        the reference API (its forward must return dense logits); gamma=0 is plain nn.CrossEntropyLoss."""
+        if input.dim() != 2 or input.size(1) != self.in_features:
+            raise RuntimeError(f"ArcMarginProduct: expected input [B,{self.in_features}], got {tuple(input.shape)}")
+        return ops.arc_fused_focal(input, self.weight, label, self.s, self.m, self.easy_margin, gamma)
+
 
 class AddMarginProduct(nn.Module):
     r"""CosFace head, reference models/metrics.py:63-102: s*(cos(theta) - m) on the label column."""

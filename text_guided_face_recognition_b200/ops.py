@@ -14,7 +14,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
-    "mag_logits", "func_attention_canonical", "launch_counter",
+    "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal",
 ]
 
 
@@ -56,7 +56,7 @@ _KERNELS_PER_CALL = {
     "tgfr_cosine_scores_fwd": 3, "tgfr_cosine_scores_bwd": 4, "tgfr_pair_ce_stats": 1, "tgfr_pair_ce_finish": 1,
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
-    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1,
+    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5,
 }
 
 
@@ -283,6 +283,68 @@ def arc_logits(x, weight, label, s, m, easy_margin=False, class_off=0):
     label = label.view(-1).to(device=x.device, dtype=torch.int64).contiguous()
     return _ArcLogits.apply(_f32(x), _f32(weight).contiguous(), label, float(s), float(m), bool(easy_margin),
                             int(class_off))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused ArcFace logits + focal cross entropy: the [B, C] logits are never materialised
+# ---------------------------------------------------------------------------------------------
+class _ArcFusedFocal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, label, s, m, easy, gamma, class_off, merge):
+        # merge: None, or a callable (rowmax, rowsum, tgt) -> global (rowmax, rowsum, tgt) over class shards
+        _lib.ensure_device(x.device)
+        x = x.contiguous()
+        B, Din = x.shape
+        C = weight.shape[0]
+        dev = x.device
+        lib = _lib.load()
+        stats = torch.empty(7 * B + C, dtype=torch.float32, device=dev)
+        xn, rowmax, rowsum, tgt, cos_t, lse = (stats[k * B:(k + 1) * B] for k in range(6))
+        wn = stats[7 * B:]
+        wsb = lib.tgfr_arc_fused_workspace_bytes(B, C, Din)
+        svb = lib.tgfr_arc_fused_saved_bytes(B, C, Din)
+        ws = _workspace(wsb, dev)
+        saved = torch.empty(svb, dtype=torch.uint8, device=dev)
+        st = stream_ptr()
+        _call("tgfr_arc_fused_fwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0), weight.stride(1),
+              label.data_ptr(), B, C, Din, class_off, s, m, int(easy), xn.data_ptr(), wn.data_ptr(), rowmax.data_ptr(),
+              rowsum.data_ptr(), tgt.data_ptr(), cos_t.data_ptr(), ptr(ws), wsb, saved.data_ptr(), svb, st)
+        if merge is not None:
+            rowmax, rowsum, tgt = merge(rowmax, rowsum, tgt)
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        _call("tgfr_focal_finish", rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), B, gamma, out.data_ptr(),
+              lse.data_ptr(), stream_ptr())
+        ctx.save_for_backward(x, weight, label, stats, out, saved)
+        ctx.cfg = (s, m, easy, class_off)
+        return out[1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight, label, stats, out, saved = ctx.saved_tensors
+        s, m, easy, class_off = ctx.cfg
+        B, Din = x.shape
+        C = weight.shape[0]
+        xn, lse, wn = stats[:B], stats[5 * B:6 * B], stats[7 * B:]
+        gout = _f32(gout).reshape(1).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        lib = _lib.load()
+        wsb = lib.tgfr_arc_fused_workspace_bytes(B, C, Din)
+        ws = _workspace(wsb, x.device)
+        _call("tgfr_arc_fused_bwd", x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0), weight.stride(1),
+              label.data_ptr(), xn.data_ptr(), wn.data_ptr(), lse.data_ptr(), out[2:].data_ptr(), gout.data_ptr(),
+              B, C, Din, class_off, s, m, int(easy), ptr(dx), dw.data_ptr(), ptr(ws), wsb, saved.data_ptr(),
+              saved.numel(), stream_ptr())
+        return dx, dw, None, None, None, None, None, None, None
+
+
+def arc_fused_focal(x, weight, label, s, m, easy_margin=False, gamma=0.0, class_off=0, merge=None):
+    """FocalLoss(gamma)(ArcMarginProduct(x, label), label) (metrics.py:42-60 + losses.py:313-325) without the [B,C]
+    logits: margin, online-softmax statistics and the softmax gradient live in the epilogues of the tcgen05
+    cos-theta GEMM.  weight [C,Din]; class_off / merge serve the class-sharded head (distributed.py)."""
+    label = label.view(-1).to(device=x.device, dtype=torch.int64).contiguous()
+    return _ArcFusedFocal.apply(_f32(x), _f32(weight).contiguous(), label, float(s), float(m), bool(easy_margin),
+                                float(gamma), int(class_off), merge)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -86,19 +86,22 @@ def main():
     head.load_full_weight(torch.from_numpy(wn).to(dev))
     hx = torch.from_numpy(xn[sl]).to(dev).requires_grad_(True)
     hl = torch.from_numpy(lab[sl]).to(dev)
-    os.environ["TGFR_HEAD_PRECISION"] = "fp32"
-    loss = head.loss(hx, hl, gamma=2.0)
-    loss.backward()
     ref_logits = O.arc_margin(xn, wn, lab, 30.0, 0.5, False)
     ref_loss = O.focal_loss(ref_logits, lab, 2.0)
-    err = abs(loss.item() - ref_loss) / abs(ref_loss)
-    assert err < 1e-4, ("head loss", loss.item(), ref_loss)
-    report["head.loss"] = err
     dx_ref, dw_ref = O.arc_margin_bwd(xn, wn, lab, O.focal_loss_bwd(ref_logits, lab, 2.0), 30.0, 0.5, False)
-    e1 = rel(hx.grad.cpu().numpy(), dx_ref[sl])
-    e2 = rel(head.weight.grad.cpu().numpy(), dw_ref[head.c0:head.c1])
-    assert e1 < 1e-3 and e2 < 1e-3, ("head grads", e1, e2)
-    report["head.dx"], report["head.dw"] = e1, e2
+    # fp32: the [B, C_local] shard is materialised; tc: fused GEMM epilogues, no logits anywhere
+    for hp in ("fp32", "tc"):
+        os.environ["TGFR_HEAD_PRECISION"] = hp
+        hx.grad = None
+        head.weight.grad = None
+        loss = head.loss(hx, hl, gamma=2.0)
+        loss.backward()
+        err = abs(loss.item() - ref_loss) / abs(ref_loss)
+        assert err < 1e-4, ("head loss", hp, loss.item(), ref_loss)
+        e1 = rel(hx.grad.cpu().numpy(), dx_ref[sl])
+        e2 = rel(head.weight.grad.cpu().numpy(), dw_ref[head.c0:head.c1])
+        assert e1 < 1e-3 and e2 < 1e-3, ("head grads", hp, e1, e2)
+        report[f"head.{hp}.loss"], report[f"head.{hp}.dx"], report[f"head.{hp}.dw"] = err, e1, e2
 
     dist.barrier()
     if rank == 0:
