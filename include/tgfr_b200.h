@@ -204,6 +204,24 @@ int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, con
                      float* glogits, int64_t g_sr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * TextHeading (models/models.py:170-232): BERT tokens [B, L = bert_words_num - 1, E]
+ * (contiguous fp32) -> words [B, T = bert_words_num - 2, F] (unit rows, the layout tgfr_wordregion_* reads; the
+ * reference returns its transpose [B, F, T]) and sent [B, F].  w2 / w3 / w4: the Conv2d(1, F, (K, E)) weights
+ * [F, 1, K, E] as contiguous [F, K*E]; b2 / b3 / b4: their biases (NULL = none).  `saved`
+ * (tgfr_texthead_saved_bytes) carries the three ReLU outputs to the backward, which returns the weight / bias
+ * gradients for upstream gwords [B, T, F] and gsent [B, F] (either may be NULL); the tokens get no gradient
+ * (frozen BERT).  The last word is detached exactly as in the reference (models.py:206).  fp32 throughout.
+ * ------------------------------------------------------------------------------------------ */
+size_t tgfr_texthead_saved_bytes(int B, int L, int F);
+size_t tgfr_texthead_workspace_bytes(int B, int L, int F);
+int tgfr_texthead_fwd(const float* tokens, const float* w2, const float* w3, const float* w4,
+                      const float* b2, const float* b3, const float* b4, int B, int L, int E, int F,
+                      int bert_words_num, float* words, float* sent, void* saved, size_t saved_bytes, void* stream);
+int tgfr_texthead_bwd(const float* tokens, const float* gwords, const float* gsent, int B, int L, int E, int F,
+                      int bert_words_num, float* dw2, float* dw3, float* dw4, float* db2, float* db3, float* db4,
+                      void* workspace, size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-tests of the tcgen05 / TMA building blocks (used by tests/test_gpu_tc.py only).
  * tgfr_debug_umma: out[128,N] = A * B^T on one CTA with fp16 operands a (a_mn ? [K,128] : [128,K])
  * and b (b_mn ? [K,N] : [N,K]); manual_a stages A with the hand-written 128B swizzle.

@@ -55,3 +55,17 @@ def margin_inputs(B, Din, C, seed=100, mag=False):
         w = rs.uniform(-bound, bound, size=(C, Din)).astype(np.float32)
     label = rs.randint(0, C, size=B).astype(np.int64)
     return x, w, label
+
+
+def texthead_inputs(B, bert_words_num, F, E=768, seed=100):
+    """BERT-like token features [B, L, E] (L = bert_words_num - 1) and the three n-gram convolutions of
+    Bert_Word_Mapping: weights [F, K, E] and biases [F] for K = 2, 3, 4 (Conv2d default init range)."""
+    rs = np.random.RandomState(seed + 3)
+    L = bert_words_num - 1
+    tokens = rs.randn(B, L, E).astype(np.float32)
+    ws, bs = [], []
+    for K in (2, 3, 4):
+        bound = 1.0 / np.sqrt(K * E)
+        ws.append(rs.uniform(-bound, bound, size=(F, K, E)).astype(np.float32))
+        bs.append(rs.uniform(-bound, bound, size=(F,)).astype(np.float32))
+    return tokens, ws, bs

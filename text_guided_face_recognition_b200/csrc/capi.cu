@@ -69,6 +69,14 @@ int focal_finish(const float*, const float*, const float*, int, float, float*, f
 int ce_rows_bwd(const float*, int64_t, const int64_t*, const float*, const float*, const float*, int, int, int,
                 float*, int64_t, cudaStream_t);
 
+// texthead.cu
+size_t texthead_saved_bytes(int, int, int);
+size_t texthead_workspace_bytes(int, int, int);
+int texthead_fwd(const float*, const float* const*, const float* const*, int, int, int, int, int, float*, float*, void*,
+                 size_t, cudaStream_t);
+int texthead_bwd(const float*, const float*, const float*, int, int, int, int, int, float* const*, float* const*, void*,
+                 size_t, const void*, size_t, cudaStream_t);
+
 // tc_selftest.cu
 int debug_umma(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
 int debug_tma_reduce(float*, int, int, cudaStream_t);
@@ -279,4 +287,24 @@ int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream) {
   return debug_tma_reduce(out, rows, cols, ST(stream));
 }
 
+
+size_t tgfr_texthead_saved_bytes(int B, int L, int F) { return texthead_saved_bytes(B, L, F); }
+size_t tgfr_texthead_workspace_bytes(int B, int L, int F) { return texthead_workspace_bytes(B, L, F); }
+int tgfr_texthead_fwd(const float* tokens, const float* w2, const float* w3, const float* w4, const float* b2,
+                      const float* b3, const float* b4, int B, int L, int E, int F, int bert_words_num, float* words,
+                      float* sent, void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(tokens && w2 && w3 && w4 && words && sent, "texthead_fwd: NULL tensor");
+  const float* w[3] = {w2, w3, w4};
+  const float* b[3] = {b2, b3, b4};
+  return texthead_fwd(tokens, w, b, B, L, E, F, bert_words_num, words, sent, saved, saved_bytes, ST(stream));
+}
+int tgfr_texthead_bwd(const float* tokens, const float* gwords, const float* gsent, int B, int L, int E, int F,
+                      int bert_words_num, float* dw2, float* dw3, float* dw4, float* db2, float* db3, float* db4,
+                      void* workspace, size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(tokens && dw2 && dw3 && dw4 && db2 && db3 && db4, "texthead_bwd: NULL tensor");
+  float* dw[3] = {dw2, dw3, dw4};
+  float* db[3] = {db2, db3, db4};
+  return texthead_bwd(tokens, gwords, gsent, B, L, E, F, bert_words_num, dw, db, workspace, workspace_bytes, saved,
+                      saved_bytes, ST(stream));
+}
 }  // extern "C"

@@ -58,6 +58,7 @@ enum EpiMode {
   kEpiScale = 0,   // alpha * acc * inv(am[m]) * inv(bn[n])       (am/bn are norms, clamped at norm_eps)
   kEpiCosine = 1,  // alpha * acc / max(am[m]*bn[n], eps), -inf on class collisions
   kEpiClamp = 2,   // alpha * clamp(acc * inv(am[m]) * inv(bn[n]), -1, 1)
+  kEpiBiasRelu = 3,  // max(acc + bias[n], 0)   (bias may be NULL; relu optional: alpha < 0 switches it off)
 };
 
 struct Gemm {
@@ -75,12 +76,17 @@ struct Gemm {
   const int64_t* ids_m; // optional class ids for the -inf mask (kEpiCosine)
   const int64_t* ids_n;
   int diag_off;
+  const float* bias;    // kEpiBiasRelu: per-column bias
 };
 
 constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
 
 __device__ __forceinline__ float gemm_epilogue(const Gemm& g, float acc, int m, int n, float na, float nb) {
   float v;
+  if (g.mode == kEpiBiasRelu) {
+    v = acc + (g.bias ? __ldg(g.bias + n) : 0.f);
+    return g.alpha < 0.f ? v : fmaxf(v, 0.f);
+  }
   if (g.mode == kEpiCosine) {
     v = acc / fmaxf(na * nb, g.eps) * g.alpha;
     if (g.ids_m && g.ids_n && (m + g.diag_off) != n && __ldg(g.ids_m + m) == __ldg(g.ids_n + n)) v = -INFINITY;
@@ -560,6 +566,18 @@ int pair_ce_bwd(const float* scores, const float* rowlse, const float* collse, c
                                                                   inv_b, gscores);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
+}
+
+// plain strided fp32 product with an optional bias / ReLU epilogue (texthead.cu):
+// C[m,n] = act(sum_k A[m sAm + k sAk] B[k sBk + n sBn] + bias[n]); rows of A may overlap (sAm < K sAk)
+int sgemm_strided(const float* A, int64_t sAm, int64_t sAk, const float* Bm, int64_t sBk, int64_t sBn, float* C,
+                  int64_t sCm, int64_t sCn, int M, int N, int K, const float* bias, int relu, cudaStream_t st) {
+  Gemm g{};
+  g.A = A; g.sAm = sAm; g.sAk = sAk;
+  g.B = Bm; g.sBk = sBk; g.sBn = sBn;
+  g.C = C; g.sCm = sCm; g.sCn = sCn;
+  g.M = M; g.N = N; g.K = K; g.alpha = relu ? 1.f : -1.f; g.norm_eps = 1e-12f; g.mode = kEpiBiasRelu; g.bias = bias;
+  return launch_gemm(g, st);
 }
 
 // gemm_tc.cu

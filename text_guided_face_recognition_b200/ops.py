@@ -14,7 +14,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
-    "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal",
+    "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
 ]
 
 
@@ -56,7 +56,7 @@ _KERNELS_PER_CALL = {
     "tgfr_cosine_scores_fwd": 3, "tgfr_cosine_scores_bwd": 4, "tgfr_pair_ce_stats": 1, "tgfr_pair_ce_finish": 1,
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
-    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5,
+    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 4, "tgfr_texthead_bwd": 4,
 }
 
 
@@ -441,6 +441,62 @@ class _MagLogits(torch.autograd.Function):
 
 def mag_logits(x, weight, margin, scale, easy_margin=True):
     return _MagLogits.apply(_f32(x), _f32(weight).contiguous(), _f32(margin), float(scale), bool(easy_margin))
+
+
+# ---------------------------------------------------------------------------------------------
+# TextHeading: BERT tokens -> word / sentence features (n-gram convolutions, shifted max, L2 norm)
+# ---------------------------------------------------------------------------------------------
+class _TextHeading(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tokens, w2, w3, w4, b2, b3, b4, words_num):
+        _lib.ensure_device(tokens.device)
+        tokens = tokens.contiguous()
+        B, L, E = tokens.shape
+        F = w2.shape[0]
+        dev = tokens.device
+        lib = _lib.load()
+        words = torch.empty((B, words_num - 2, F), dtype=torch.float32, device=dev)
+        sent = torch.empty((B, F), dtype=torch.float32, device=dev)
+        svb = lib.tgfr_texthead_saved_bytes(B, L, F)
+        saved = torch.empty(svb, dtype=torch.uint8, device=dev)
+        ws_ = [w.contiguous() for w in (w2, w3, w4)]
+        _call("tgfr_texthead_fwd", tokens.data_ptr(), ws_[0].data_ptr(), ws_[1].data_ptr(), ws_[2].data_ptr(),
+              ptr(b2), ptr(b3), ptr(b4), B, L, E, F, words_num, words.data_ptr(), sent.data_ptr(), saved.data_ptr(), svb,
+              stream_ptr())
+        ctx.save_for_backward(tokens, saved)
+        ctx.cfg = (words_num, F, tuple(w.shape for w in (w2, w3, w4)), b2 is not None)
+        return words, sent
+
+    @staticmethod
+    def backward(ctx, gwords, gsent):
+        tokens, saved = ctx.saved_tensors
+        words_num, F, wshapes, has_bias = ctx.cfg
+        B, L, E = tokens.shape
+        dev = tokens.device
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("TextHeading: gradient w.r.t. the BERT tokens is not provided (the reference "
+                                      "trains the head on a frozen encoder)")
+        gwords = None if gwords is None else _f32(gwords).contiguous()
+        gsent = None if gsent is None else _f32(gsent).contiguous()
+        dws = [torch.empty(s_, dtype=torch.float32, device=dev) for s_ in wshapes]
+        dbs = [torch.empty(F, dtype=torch.float32, device=dev) for _ in range(3)]
+        lib = _lib.load()
+        wsb = lib.tgfr_texthead_workspace_bytes(B, L, F)
+        ws = _workspace(wsb, dev)
+        _call("tgfr_texthead_bwd", tokens.data_ptr(), ptr(gwords), ptr(gsent), B, L, E, F, words_num,
+              dws[0].data_ptr(), dws[1].data_ptr(), dws[2].data_ptr(), dbs[0].data_ptr(), dbs[1].data_ptr(),
+              dbs[2].data_ptr(), ptr(ws), wsb, saved.data_ptr(), saved.numel(), stream_ptr())
+        if not has_bias:
+            dbs = [None, None, None]
+        return (None, *dws, *dbs, None)
+
+
+def text_heading(tokens, weights, biases, bert_words_num):
+    """(words [B, T, F] unit rows, sent [B, F] unit rows) of models/models.py:170-232.
+    weights: the three Conv2d(1, F, (K, 768)) weights [F, 1, K, E]; biases: three [F] tensors (or Nones)."""
+    w2, w3, w4 = (_f32(w) for w in weights)
+    b2, b3, b4 = (None if b is None else _f32(b).contiguous() for b in biases)
+    return _TextHeading.apply(_f32(tokens), w2, w3, w4, b2, b3, b4, int(bert_words_num))
 
 
 # ---------------------------------------------------------------------------------------------
