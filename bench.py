@@ -575,6 +575,39 @@ def run_b200(args):
                                              "what": "ArcMarginProduct.fused_loss: margin + online softmax + softmax "
                                                      "gradient in the tcgen05 GEMM epilogues, logits never written"}
 
+        # ---- TextHeading (the BERT 768 -> 256 word / sentence projection of configs[1])
+        import types as _types
+        from text_guided_face_recognition_b200.models.text_heading import TextHeading
+        bwn = T + 2
+        tok_np, tw, tb = synth.texthead_inputs(B, bwn, D, seed=100)
+        th = TextHeading(_types.SimpleNamespace(aux_feat_dim_per_granularity=D, bert_words_num=bwn)).to(dev)
+        with torch.no_grad():
+            for conv, w_, b_ in zip(th.bwm.convs1, tw, tb):
+                conv.weight.copy_(torch.from_numpy(w_).unsqueeze(1))
+                conv.bias.copy_(torch.from_numpy(b_))
+        tok = torch.from_numpy(tok_np).to(dev)
+        gw_up, gs_up = torch.randn(B, D, T, device=dev), torch.randn(B, D, device=dev)
+
+        def th_step():
+            for conv in th.bwm.convs1:
+                conv.weight.grad = conv.bias.grad = None
+            wo, so = th(tok, None)
+            torch.autograd.backward([wo, so], [gw_up, gs_up])
+        for _ in range(3):
+            th_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            th_step()
+        e1.record()
+        torch.cuda.synchronize()
+        th_ms = e0.elapsed_time(e1) / 10
+        th_flops = 2 * 2 * B * (bwn - 1) * (2 + 3 + 4) * 768 * D       # three products forward, three backward
+        line["text_heading"] = {"metric": "text_heading_fwd_bwd_captions_per_sec", "value": B / (th_ms * 1e-3),
+                                "unit": "captions/s", "ms_per_step": th_ms, "dtype": "f32",
+                                "tflops": th_flops / (th_ms * 1e-3) / 1e12,
+                                "config": {"B": B, "bert_words_num": bwn, "E": 768, "F": D}}
+
         # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -643,6 +676,24 @@ def run_b200(args):
                 P.arc_focal_port(gx, gwt, gl, h["s"], h["m"], h["gamma"])[1].backward()
             e1.record()
             torch.cuda.synchronize()
+            # TextHeading through the port on this GPU (the reference's B x T Python loop of stack / amax calls)
+            tws = [torch.from_numpy(w_).unsqueeze(1).to(dev).requires_grad_(True) for w_ in tw]
+            tbs = [torch.from_numpy(b_).to(dev).requires_grad_(True) for b_ in tb]
+
+            def th_ref():
+                for t_ in tws + tbs:
+                    t_.grad = None
+                wo, so = P.text_heading_port(tok, tws, tbs, bwn)
+                torch.autograd.backward([wo, so], [gw_up, gs_up])
+            th_ref()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(2):
+                th_ref()
+            e1.record()
+            torch.cuda.synchronize()
+            line["text_heading"]["reference_on_gpu"] = {"value": B / (e0.elapsed_time(e1) / 2 * 1e-3), "unit": "captions/s",
+                                                        "ms_per_step": e0.elapsed_time(e1) / 2, "kind": "port"}
             line["margin_head"]["cpu_baseline"] = {"value": h["B"] / h_cpu, "unit": "samples/s", "kind": "port",
                                                    "cores": torch.get_num_threads(), "sample": f"{n_h} full steps"}
             line["margin_head"]["reference_on_gpu"] = {"value": h["B"] / (e0.elapsed_time(e1) / 10 * 1e-3),

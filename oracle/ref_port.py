@@ -92,3 +92,24 @@ def arc_focal_port(x, weight, label, s=30.0, m=0.5, gamma=2.0, easy_margin=False
     logp = F.cross_entropy(out, label)
     p = torch.exp(-logp)
     return out, ((1 - p) ** gamma * logp).mean()
+
+
+def text_heading_port(tokens, weights, biases, bert_words_num):
+    """models/models.py:170-232 op for op: three Conv2d + ReLU, the B x T Python loop of stack / amax calls of
+    get_each_word_feature (the reference's `torch.cuda.FloatTensor(...)` copy of the last word = detach + clone),
+    max_pool1d / mean / normalize.  weights: [F, 1, K, 768] x 3.  Returns (words [B, F, T], sent [B, F])."""
+    x = tokens.unsqueeze(1)
+    xs = [F.relu(F.conv2d(x, w, b)).squeeze(3) for w, b in zip(weights, biases)]
+    bs = xs[0].size(0)
+    a, b, c = (t.transpose(2, 1) for t in xs)
+    code = []
+    seq = bert_words_num - 1 - 3
+    for i in range(bs):
+        t = [torch.amax(torch.stack((a[i, j], b[i, j], c[i, j])), dim=0) for j in range(seq)]
+        t += [torch.amax(torch.stack((a[i, seq], b[i, seq])), dim=0)]
+        t += [a[i, seq + 1].detach().clone()]
+        code.append(torch.stack(t))
+    code = F.normalize(torch.stack(code), p=2, dim=2)
+    pooled = [F.max_pool1d(t, t.size(2)).squeeze(2) for t in xs]
+    sent = F.normalize(torch.stack(pooled).mean(dim=0), p=2, dim=1)
+    return code.transpose(1, 2), sent
