@@ -230,6 +230,9 @@ int tgfr_texthead_bwd(const float* tokens, const float* gwords, const float* gse
 int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,
                     void* stream);
 int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream);
+/* CTA pair (cta_group::2) probe: out[256,N] = A[256,K] * B[N,K]^T on a cluster of two CTAs (M = 256 MMAs issued by
+ * the leader, each CTA holding its 128 rows of A, half of B and its half of D in TMEM). */
+int tgfr_debug_umma_2cta(const void* a, const void* b, float* out, int N, int K, void* stream);
 /* Phase trace of the tensor-core word-region kernels: dev_buf = int64[16*32] (or NULL to switch
  * it off); CTA 0 stamps clock64() per pipeline phase of its first 16 units (tools/trace_wordregion.py). */
 int tgfr_debug_set_trace(void* dev_buf);

@@ -52,6 +52,24 @@ def test_umma_layouts(a_mn, b_mn, manual_a, N, K):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("N,K", [(128, 64), (128, 256), (256, 128), (64, 64)])
+def test_umma_cta_pair(N, K):
+    """cta_group::2: one M = 256 MMA spans a cluster of two CTAs (each: its 128 rows of A, half of B, its half of D)."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(77 + N + K)
+    A = torch.randn(256, K, generator=g).half()
+    B = torch.randn(N, K, generator=g).half()
+    ref = A.float() @ B.float().t()
+    a_dev, b_dev = A.cuda(), B.cuda()
+    out = torch.full((256, N), float("nan"), device="cuda")
+    L.check(lib.tgfr_debug_umma_2cta(a_dev.data_ptr(), b_dev.data_ptr(), out.data_ptr(), N, K,
+                                     torch.cuda.current_stream().cuda_stream), "tgfr_debug_umma_2cta")
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
 def test_tma_reduce_add():
     L = _lib()
     lib = L.load()

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tgfr_texthead_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, Z, P, Z, P]),
     "tgfr_debug_umma": (I, [P, P, P, I, I, I, I, I, P]),
     "tgfr_debug_tma_reduce": (I, [P, I, I, P]),
+    "tgfr_debug_umma_2cta": (I, [P, P, P, I, I, P]),
     "tgfr_debug_set_trace": (I, [P]),
 }
 

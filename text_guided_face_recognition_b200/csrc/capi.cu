@@ -80,6 +80,7 @@ int texthead_bwd(const float*, const float*, const float*, int, int, int, int, i
 // tc_selftest.cu
 int debug_umma(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
 int debug_tma_reduce(float*, int, int, cudaStream_t);
+int debug_umma_2cta(const void*, const void*, float*, int, int, cudaStream_t);
 
 }  // namespace tgfr
 
@@ -283,6 +284,10 @@ int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int 
   return debug_umma(a, b, out, N, K, a_mn, b_mn, manual_a, ST(stream));
 }
 int tgfr_debug_set_trace(void* dev_buf) { return wordregion_tc_set_trace(dev_buf); }
+int tgfr_debug_umma_2cta(const void* a, const void* b, float* out, int N, int K, void* stream) {
+  TGFR_REQUIRE(a && b && out, "debug_umma_2cta: NULL tensor");
+  return debug_umma_2cta(a, b, out, N, K, ST(stream));
+}
 int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream) {
   return debug_tma_reduce(out, rows, cols, ST(stream));
 }

@@ -105,6 +105,69 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// CTA pair (cta_group::2): D[256, N] = A[256, K] * B[N, K]^T on a cluster of two CTAs.  CTA r loads rows
+// [128 r, 128 r + 128) of A and rows [N/2 r, N/2 r + N/2) of B (both K-major, TMA, 128B swizzle); the leader issues
+// M = 256 MMAs; each CTA reads its 128 rows of D from its own TMEM.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_2cta_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          float* __restrict__ out, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = base;                    // 128 x K halfs (<= 64 KB)
+  uint8_t* sb = base + 65536;            // N/2 x K halfs (<= 64 KB)
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nh = N / 2;
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc_2cta(&tmem_base_s, 256);
+  tc_fence_before();
+  cluster_sync_all();                    // barriers initialised and TMEM allocated in both CTAs
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_load, (128u + (uint32_t)nh) * K * 2u);
+    for (int kc = 0; kc < K / 64; ++kc) {
+      tma_load_3d(sa + kc * (128 * 128), &tmap_a, &bar_load, kc * 64, (int)rank * 128, 0);
+      tma_load_3d(sb + kc * (nh * 128), &tmap_b, &bar_load, kc * 64, (int)rank * nh, 0);
+    }
+    mbar_wait(&bar_load, 0);
+  }
+  __syncthreads();
+  cluster_sync_all();                    // both CTAs' operands have landed
+  if (rank == 0 && tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(256, N, false, false);
+    for (int k16 = 0; k16 < K / 16; ++k16) {
+      const uint64_t ad = make_smem_desc(smem_u32(sa) + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+      const uint64_t bd = make_smem_desc(smem_u32(sb) + (k16 >> 2) * (nh * 128) + (k16 & 3) * 32, 16, 1024);
+      umma_ss_2cta(tmem, ad, bd, idesc, k16 > 0);
+    }
+    umma_commit_2cta(&bar_mma, 0b11);
+  }
+  __syncwarp();
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    float* o = out + (size_t)(rank * 128 + warp * 32 + lane) * N + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  cluster_sync_all();                    // both CTAs are done with TMEM before the pair's allocation goes away
+  if (warp == 0) tmem_dealloc_2cta(tmem, 256);
+}
+
 // out[r][c] += f(r, c) through a swizzled fp32 staging tile and cp.reduce.async.bulk.tensor
 __global__ void __launch_bounds__(128, 1)
 tma_reduce_selftest_kernel(const __grid_constant__ CUtensorMap tmap_out, int rows, int cols) {
@@ -146,6 +209,18 @@ int debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn,
   TGFR_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_selftest_kernel<<<1, 128, smem, st>>>(ta, tb, reinterpret_cast<const __half*>(a), out, N, K, a_mn, b_mn,
                                              reinterpret_cast<const __half*>(b), manual_a);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int debug_umma_2cta(const void* a, const void* b, float* out, int N, int K, cudaStream_t st) {
+  TGFR_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, "debug_umma_2cta: bad N/K");
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a, K, 256, 1, 64, 128, 1)) return rc;
+  if (int rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b, K, N, 1, 64, N / 2, 1)) return rc;
+  const int smem = 65536 + 65536 + 1024;
+  TGFR_CUDA_OK(cudaFuncSetAttribute(umma_2cta_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_2cta_selftest_kernel<<<2, 128, smem, st>>>(ta, tb, out, N, K);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
