@@ -608,6 +608,92 @@ def run_b200(args):
                                 "tflops": th_flops / (th_ms * 1e-3) / 1e12,
                                 "config": {"B": B, "bert_words_num": bwn, "E": 768, "F": D}}
 
+        # ---- verification scoring (configs[4] in its pair-list form, utils/modules.py:150-166):
+        # 6000 faces x 10 captions = 60 000 pairs of 640-d fused embeddings -> cosine -> ROC -> AUC / EER / TPR@FPR
+        import contextlib as _ctx
+        import io as _io
+        from text_guided_face_recognition_b200.utils import modules as scoring
+        NP, DF = 60000, 640
+        gen = torch.Generator(device="cpu").manual_seed(100)
+        pl_np = (torch.arange(NP) % 10 == 0).long()
+        ident = torch.randn(NP, DF, generator=gen)
+        o1 = (ident + 4.0 * torch.randn(NP, DF, generator=gen)).to(dev)
+        o2 = (torch.where(pl_np[:, None] == 1, ident, torch.randn(NP, DF, generator=gen))
+              + 4.0 * torch.randn(NP, DF, generator=gen)).to(dev)
+        pl = pl_np.to(dev)
+        del ident
+
+        def verif_step():
+            with _ctx.redirect_stdout(_io.StringIO()):
+                return scoring.score_pairs([(o1, o2, pl)])
+        for _ in range(3):
+            verif = verif_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            verif_step()
+        e1.record()
+        torch.cuda.synchronize()
+        v_ms = e0.elapsed_time(e1) / 10
+        cos_ms, roc_ms = [], []
+        sc = ops.pair_cosine(o1, o2)
+        for _ in range(10):
+            flush.zero_()
+            e0.record()
+            ops.pair_cosine(o1, o2)
+            e1.record()
+            torch.cuda.synchronize()
+            cos_ms.append(e0.elapsed_time(e1))
+            e0.record()
+            ops.roc_counts(sc, pl)
+            e1.record()
+            torch.cuda.synchronize()
+            roc_ms.append(e0.elapsed_time(e1))
+        cos_ms, roc_ms = float(np.median(cos_ms)), float(np.median(roc_ms))
+        NS = 1 << 24                                                             # sort throughput at a size that fills the GPU
+        big_s, big_l = torch.rand(NS, device=dev) * 2 - 1, (torch.rand(NS, device=dev) < 0.1).long()
+        ops.roc_counts(big_s, big_l)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ops.roc_counts(big_s, big_l)
+        e1.record()
+        torch.cuda.synchronize()
+        big_ms = e0.elapsed_time(e1) / 3
+        del big_s, big_l
+        cos_bytes = 2 * NP * DF * 4 + NP * 4
+        roc_bytes_per_key = 12 + 4 * (4 + 2 * 5) + 5 + 20                         # keys pass, 4 radix passes, curve, points
+        line["verification"] = {
+            "metric": "verification_pairs_per_sec", "value": NP / (v_ms * 1e-3), "unit": "pairs/s", "ms_per_step": v_ms,
+            "dtype": "f32 scores / u32 keys", "config": {"pairs": NP, "D": DF, "what": "pair cosine + exact ROC "
+                       "(sklearn roc_curve semantics) + AUC/EER/TPR@FPR, embeddings resident in HBM"},
+            "result": verif,
+            "roofline": {"bound": "hbm", "kernel": "cosine_rows_vec_kernel", "achieved": cos_bytes / (cos_ms * 1e-3) / 1e9,
+                         "peak": pk["hbm"], "unit": "GB/s", "frac": cos_bytes / (cos_ms * 1e-3) / 1e9 / pk["hbm"],
+                         "kernel_ms": cos_ms, "algorithmic_bytes_per_launch": cos_bytes, "traffic": None},
+            "roc": {"ms_60000": roc_ms, "ms_2p24": big_ms, "keys_per_sec_2p24": NS / (big_ms * 1e-3),
+                    "algorithmic_bytes_per_key": roc_bytes_per_key,
+                    "achieved_gbs_2p24": NS * roc_bytes_per_key / (big_ms * 1e-3) / 1e9,
+                    "frac_of_hbm_2p24": NS * roc_bytes_per_key / (big_ms * 1e-3) / 1e9 / pk["hbm"],
+                    "note": "whole tgfr_roc_curve call incl. workspace allocation and the count read-back"}}
+        if world == 1 and not args.no_cpu_baseline:
+            # the reference's own third-party calls on the host cores: torch CosineSimilarity + sklearn roc_curve / auc
+            from sklearn import metrics as _skm
+            torch.set_num_threads(os.cpu_count() or 1)
+            h1, h2, hl = o1.cpu(), o2.cpu(), pl_np.tolist()
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 3.0:
+                pred = torch.nn.CosineSimilarity(dim=1, eps=1e-6)(h1, h2).tolist()
+                f_, t_, _ = _skm.roc_curve(hl, pred)
+                _skm.auc(f_, t_)
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            line["verification"]["cpu_baseline"] = {"value": NP / dt, "unit": "pairs/s", "cores": torch.get_num_threads(),
+                                                    "kind": "reference", "sample": f"{reps} full passes of torch "
+                                                    "CosineSimilarity + sklearn roc_curve + auc over the 60 000 pairs"}
+        del o1, o2
+
         # ---- CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

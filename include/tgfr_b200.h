@@ -222,6 +222,26 @@ int tgfr_texthead_bwd(const float* tokens, const float* gwords, const float* gse
                       void* workspace, size_t workspace_bytes, const void* saved, size_t saved_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Verification / identification scoring (utils/modules.py:40-88,150-166).
+ * tgfr_pair_cosine: scores[i] = sum_k (x1[i,k] / max(|x1_i|, eps)) (x2[i,k] / max(|x2_i|, eps)), i.e.
+ *   nn.CosineSimilarity(dim=1, eps=1e-6)(out1, out2) of utils/modules.py:150-151; strides in elements.
+ * tgfr_roc_curve: the integer part of sklearn.metrics.roc_curve(y_true, y_score) (utils/modules.py:54; scikit-learn
+ *   1.9.0 _ranking.py roc_curve / confusion_matrix_at_thresholds): scores sorted descending, one point per distinct
+ *   score with tps = positives (label == 1) at or above it and fps = 1 + index - tps, then (drop_intermediate != 0)
+ *   only the end points and the points whose second difference of fps or tps is non-zero.  thresholds / fps / tps
+ *   need room for N entries; counts = int64[3] on the device: points written, 1 if a score was NaN, distinct scores.
+ *   The caller prepends the (inf, 0, 0) point and divides by the last entries (host side, float64, as sklearn does).
+ *   Bit-exact with scikit-learn for the same fp32 scores.  N < 2^31.
+ * tgfr_row_argmax: index[r] = first position of the maximum of scores[r, :] (np.argmax, utils/modules.py:84-85).
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_pair_cosine(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd,
+                     int64_t N, int D, float eps, float* scores, void* stream);
+size_t tgfr_roc_workspace_bytes(int64_t N);
+int tgfr_roc_curve(const float* scores, const int64_t* labels, int64_t N, int drop_intermediate, float* thresholds,
+                   int64_t* fps, int64_t* tps, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+int tgfr_row_argmax(const float* scores, int64_t sr, int rows, int cols, int64_t* index, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-tests of the tcgen05 / TMA building blocks (used by tests/test_gpu_tc.py only).
  * tgfr_debug_umma: out[128,N] = A * B^T on one CTA with fp16 operands a (a_mn ? [K,128] : [128,K])
  * and b (b_mn ? [K,N] : [N,K]); manual_a stages A with the hand-written 128B swizzle.

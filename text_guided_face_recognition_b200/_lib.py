@@ -56,6 +56,10 @@ SIGNATURES = {
     "tgfr_texthead_workspace_bytes": (Z, [I, I, I]),
     "tgfr_texthead_fwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, Z, P]),
     "tgfr_texthead_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, Z, P, Z, P]),
+    "tgfr_pair_cosine": (I, [P, L, L, P, L, L, L, I, F, P, P]),
+    "tgfr_roc_workspace_bytes": (Z, [L]),
+    "tgfr_roc_curve": (I, [P, P, L, I, P, P, P, P, P, Z, P]),
+    "tgfr_row_argmax": (I, [P, L, I, I, P, P]),
     "tgfr_debug_umma": (I, [P, P, P, I, I, I, I, I, P]),
     "tgfr_debug_tma_reduce": (I, [P, I, I, P]),
     "tgfr_debug_umma_2cta": (I, [P, P, P, I, I, P]),

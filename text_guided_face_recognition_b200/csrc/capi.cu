@@ -77,6 +77,12 @@ int texthead_fwd(const float*, const float* const*, const float* const*, int, in
 int texthead_bwd(const float*, const float*, const float*, int, int, int, int, int, float* const*, float* const*, void*,
                  size_t, const void*, size_t, cudaStream_t);
 
+// scoring.cu
+int pair_cosine(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float, float*, cudaStream_t);
+int row_argmax(const float*, int64_t, int, int, int64_t*, cudaStream_t);
+size_t roc_workspace_bytes(int64_t);
+int roc_curve(const float*, const int64_t*, int64_t, int, float*, int64_t*, int64_t*, int64_t*, void*, size_t, cudaStream_t);
+
 // tc_selftest.cu
 int debug_umma(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
 int debug_tma_reduce(float*, int, int, cudaStream_t);
@@ -277,6 +283,27 @@ int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt
 int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse, const float* coef,
                      const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, void* stream) {
   return ce_rows_bwd(logits, sr, labels, lse, coef, gout, B, C, class_off, glogits, g_sr, ST(stream));
+}
+
+int tgfr_pair_cosine(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd, int64_t N,
+                     int D, float eps, float* scores, void* stream) {
+  TGFR_REQUIRE(N >= 0 && D >= 1, "pair_cosine: bad shape N=%lld D=%d", (long long)N, D);
+  TGFR_REQUIRE(N == 0 || (x1 && x2 && scores), "pair_cosine: NULL tensor");
+  return pair_cosine(x1, x1_sr, x1_sd, x2, x2_sr, x2_sd, N, D, eps, scores, ST(stream));
+}
+int tgfr_row_argmax(const float* scores, int64_t sr, int rows, int cols, int64_t* index, void* stream) {
+  TGFR_REQUIRE(rows >= 0 && cols >= 1, "row_argmax: bad shape %d x %d", rows, cols);
+  TGFR_REQUIRE(rows == 0 || (scores && index), "row_argmax: NULL tensor");
+  return row_argmax(scores, sr, rows, cols, index, ST(stream));
+}
+size_t tgfr_roc_workspace_bytes(int64_t N) { return roc_workspace_bytes(N); }
+int tgfr_roc_curve(const float* scores, const int64_t* labels, int64_t N, int drop_intermediate, float* thresholds,
+                   int64_t* fps, int64_t* tps, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  TGFR_REQUIRE(N >= 0 && N < (int64_t(1) << 31), "roc_curve: N = %lld outside [0, 2^31)", (long long)N);
+  TGFR_REQUIRE(counts && workspace, "roc_curve: NULL counts / workspace");
+  TGFR_REQUIRE(N == 0 || (scores && labels && thresholds && fps && tps), "roc_curve: NULL tensor");
+  return roc_curve(scores, labels, N, drop_intermediate, thresholds, fps, tps, counts, workspace, workspace_bytes,
+                   ST(stream));
 }
 
 int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,

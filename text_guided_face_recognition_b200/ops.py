@@ -15,6 +15,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
     "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
+    "pair_cosine", "roc_counts", "row_argmax",
 ]
 
 
@@ -57,6 +58,7 @@ _KERNELS_PER_CALL = {
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
     "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 4, "tgfr_texthead_bwd": 4,
+    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1,
 }
 
 
@@ -577,3 +579,63 @@ class _CosLogits(torch.autograd.Function):
 def cos_logits(x, weight, s=1.0, clamp=False, w_class_dim=0):
     """s * normalize(x) @ normalize(weight)^T; weight is [C,Din] (w_class_dim=0) or [Din,C] (=1)."""
     return _CosLogits.apply(_f32(x), _f32(weight).contiguous(), float(s), bool(clamp), int(w_class_dim))
+
+
+# ---------------------------------------------------------------------------------------------
+# verification / identification scoring (utils/modules.py:40-88,150-166; no autograd: evaluation only)
+# ---------------------------------------------------------------------------------------------
+def pair_cosine(x1, x2, eps=1e-6):
+    """nn.CosineSimilarity(dim=1, eps)(x1, x2) of utils/modules.py:150-151 for [N, D] CUDA tensors -> [N] fp32."""
+    if x1.dim() != 2 or x1.shape != x2.shape:
+        raise RuntimeError(f"pair_cosine: expected two [N, D] tensors of one shape, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+    _lib.ensure_device(x1.device)
+    if x2.device != x1.device:
+        raise RuntimeError("pair_cosine: tensors on different devices")
+    x1, x2 = _f32(x1.detach()), _f32(x2.detach())
+    N, D = x1.shape
+    out = torch.empty(N, dtype=torch.float32, device=x1.device)
+    with torch.cuda.device(x1.device):
+        _call("tgfr_pair_cosine", ptr(x1), x1.stride(0), x1.stride(1), ptr(x2), x2.stride(0), x2.stride(1), N, D,
+              float(eps), ptr(out), stream_ptr())
+    return out
+
+
+def roc_counts(scores, labels, drop_intermediate=True):
+    """Integer part of sklearn.metrics.roc_curve(labels, scores) on the device: (thresholds fp32 [M], fps int64 [M],
+    tps int64 [M], distinct) for fp32 CUDA scores [N] and integer labels [N] (positive = 1), without the leading
+    (inf, 0, 0) point.  Raises ValueError on NaN scores (as scikit-learn's input validation does)."""
+    _lib.ensure_device(scores.device)
+    scores = _f32(scores.detach()).contiguous().view(-1)
+    labels = labels.detach().to(device=scores.device, dtype=torch.int64).contiguous().view(-1)
+    N = scores.numel()
+    if labels.numel() != N:
+        raise ValueError(f"roc_counts: {N} scores but {labels.numel()} labels")
+    dev = scores.device
+    thr = torch.empty(max(N, 1), dtype=torch.float32, device=dev)
+    fps = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    tps = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    counts = torch.empty(3, dtype=torch.int64, device=dev)
+    wsb = _lib.load().tgfr_roc_workspace_bytes(N)
+    ws = _workspace(wsb, dev)
+    with torch.cuda.device(dev):
+        _call("tgfr_roc_curve", ptr(scores), ptr(labels), N, 1 if drop_intermediate else 0, ptr(thr), ptr(fps), ptr(tps),
+              ptr(counts), ptr(ws), wsb, stream_ptr())
+    m, nan, distinct = (int(v) for v in counts.tolist())       # the one device -> host sync of the curve
+    if nan:
+        raise ValueError("Input y_score contains NaN.")
+    return thr[:m], fps[:m], tps[:m], distinct
+
+
+def row_argmax(scores):
+    """np.argmax(scores, axis=1) (first maximum; NaN counts as the maximum) for a [rows, cols] CUDA tensor -> int64 [rows]."""
+    if scores.dim() != 2:
+        raise RuntimeError(f"row_argmax: expected [rows, cols], got {tuple(scores.shape)}")
+    _lib.ensure_device(scores.device)
+    scores = _f32(scores.detach())
+    if scores.stride(1) != 1:
+        scores = scores.contiguous()
+    rows, cols = scores.shape
+    out = torch.empty(rows, dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _call("tgfr_row_argmax", ptr(scores), scores.stride(0), rows, cols, ptr(out), stream_ptr())
+    return out
