@@ -143,3 +143,27 @@ def _case_allreduce_gradients(rank):
                                   "_case_class_sharded_softmax", "_case_allreduce_gradients"])
 def test_gloo_world2(case, tmp_path):
     _run(case, tmp_path)
+
+
+# ------------------------------------------------------------------------------------------------
+def _case_gather_ragged(rank):
+    """Pair-sharded verification scoring: ranks hold different numbers of scores; the gather keeps rank order,
+    and the ROC of the gathered list equals the ROC of the unsplit list (oracle arithmetic on CPU)."""
+    from oracle import scoring_oracle as SO
+    from text_guided_face_recognition_b200 import distributed as D
+    rs = np.random.RandomState(3)
+    labels = (rs.rand(101) < 0.3).astype(np.int64)
+    scores = (np.round(rs.randn(101) * 4) / 8 + 0.3 * labels).astype(np.float32)
+    cut = [0, 37, 101]                                     # ragged shards
+    mine = slice(cut[rank], cut[rank + 1])
+    got_s = D.gather_ragged(torch.from_numpy(scores[mine]))
+    got_l = D.gather_ragged(torch.from_numpy(labels[mine]))
+    assert torch.equal(got_s, torch.from_numpy(scores)) and torch.equal(got_l, torch.from_numpy(labels))
+    a, b = SO.roc_counts(got_l.numpy(), got_s.numpy()), SO.roc_counts(labels, scores)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    empty = D.gather_ragged(torch.zeros(0 if rank == 0 else 2))
+    assert empty.numel() == 2
+
+
+def test_gather_ragged_world2(tmp_path):
+    _run("_case_gather_ragged", tmp_path)

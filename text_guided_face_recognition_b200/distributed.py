@@ -11,6 +11,8 @@ nn.DataParallel with the losses un-sharded on device 0); this replaces that.
   replica gradients  : the trainable heads (image_head: 692 864 fp32 parameters in the reference) are plain
                        replicas; their gradients are summed with bucketed all-reduces (`allreduce_gradients`),
                        which replaces nn.DataParallel's gather-to-device-0 reduce-add.
+  verification       : the pair list is split across ranks (no data-path collective: every pair is independent);
+                       the [N] scores and labels are gathered once (`gather_ragged`) for the ROC.
   margin head        : class-sharded partial FC.  Features/labels are all-gathered over the data
                        parallel batch, each rank holds W[c0:c1, :], the softmax statistics are
                        all-reduced (max, then sum-exp and target logit), dX is reduce-scattered.
@@ -29,7 +31,7 @@ from ._lib import ptr, stream_ptr
 
 __all__ = [
     "all_gather_rows", "merge_column_stats", "class_range", "words_loss_sharded", "sent_loss_sharded",
-    "ShardedArcMarginProduct", "sharded_focal_ce", "allreduce_gradients",
+    "ShardedArcMarginProduct", "sharded_focal_ce", "allreduce_gradients", "gather_ragged", "score_pairs_sharded",
 ]
 
 
@@ -345,3 +347,38 @@ def allreduce_gradients(params, group=None, bucket_bytes=16 << 20, average=False
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
     return len(buckets)
+
+
+# ---------------------------------------------------------------------------------------------
+# verification scoring: pair-sharded cosine, one gather of the scores for the ROC
+# ---------------------------------------------------------------------------------------------
+def gather_ragged(x, group=None):
+    """Concatenate every rank's 1-D tensor (lengths may differ) in rank order, on every rank."""
+    world, _ = _world(group)
+    x = x.contiguous().view(-1)
+    if world == 1:
+        return x
+    n = torch.tensor([x.numel()], dtype=torch.int64, device=x.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(v.item()) for v in sizes]
+    cap = max(max(sizes), 1)
+    padded = torch.zeros(cap, dtype=x.dtype, device=x.device)
+    padded[: x.numel()] = x
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
+def score_pairs_sharded(batches, args=None, group=None):
+    """utils/modules.py:150-166 with the pair list split across ranks: `batches` yields THIS rank's
+    (out1 [n, D], out2 [n, D], pair_label [n]); every rank returns the summary of the whole list."""
+    from .utils import modules
+    preds, labels = [], []
+    for out1, out2, pair_label in batches:
+        preds.append(modules.pair_scores(out1, out2))
+        labels.append(pair_label.to(device=out1.device, dtype=torch.int64).view(-1))
+    dev = preds[0].device if preds else torch.device("cuda", torch.cuda.current_device())
+    preds = torch.cat(preds) if preds else torch.zeros(0, device=dev)
+    labels = torch.cat(labels) if labels else torch.zeros(0, dtype=torch.int64, device=dev)
+    return modules.calculate_scores(gather_ragged(preds, group), gather_ragged(labels, group), args)

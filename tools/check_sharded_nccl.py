@@ -103,6 +103,28 @@ def main():
         assert e1 < 1e-3 and e2 < 1e-3, ("head grads", hp, e1, e2)
         report[f"head.{hp}.loss"], report[f"head.{hp}.dx"], report[f"head.{hp}.dw"] = err, e1, e2
 
+    # pair-sharded verification scoring: ragged shards of the pair list, one gather, the summary on every rank
+    import contextlib
+    import io
+    from oracle import scoring_oracle as SO
+    rs = np.random.RandomState(21)
+    NPAIR, DF = 5003, 640
+    plab = (np.arange(NPAIR) % 10 == 0).astype(np.int64)
+    ide = rs.randn(NPAIR, DF).astype(np.float32)
+    p1 = ide + 4.0 * rs.randn(NPAIR, DF).astype(np.float32)
+    p2 = np.where(plab[:, None] == 1, ide, rs.randn(NPAIR, DF).astype(np.float32)) + 4.0 * rs.randn(NPAIR, DF).astype(np.float32)
+    cuts = np.linspace(0, NPAIR, world + 1).astype(int)
+    cuts[1:-1] += 3                                         # uneven shards
+    mine = slice(cuts[rank], cuts[rank + 1])
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = tdist.score_pairs_sharded([(torch.from_numpy(p1[mine]).to(dev), torch.from_numpy(p2[mine]).to(dev),
+                                          torch.from_numpy(plab[mine]).to(dev))])
+    from text_guided_face_recognition_b200 import ops
+    all_scores = ops.pair_cosine(torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)).cpu().numpy()
+    want = SO.calculate_scores(all_scores, plab)
+    assert out["auc"] == want["auc"] and out["eer"] == want["eer"] and out["tpr_at_fpr"] == want["tpr_at_fpr"], (out, want)
+    report["verif.auc"] = out["auc"]
+
     dist.barrier()
     if rank == 0:
         print("sharded-nccl ok world=%d " % world + " ".join(f"{k}={v:.1e}" for k, v in report.items()), flush=True)
