@@ -41,6 +41,8 @@ __global__ void colnorm_kernel(const float* __restrict__ x, int64_t s_row, int r
   norm[c] = sqrtf(acc);
 }
 
+}  // namespace
+
 int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, float* norm, cudaStream_t st) {
   if (s_vec == 1 && s_elem != 1) {
     colnorm_kernel<<<ceil_div(nvec, 256), 256, 0, st>>>(x, s_elem, len, nvec, norm);
@@ -50,6 +52,8 @@ int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int le
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
+
+namespace {
 
 // --------------------------------------------------------------------------------------------
 // strided SGEMM:  C[m,n] = epilogue( sum_k A(m,k) * B(k,n) * bk[k] )
@@ -587,6 +591,8 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
 int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, const float* norm, __half* out,
                        int ld_out, cudaStream_t st);
 int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st);
+int head_prepare_operands(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C, int Din,
+                          float* xnorm, float* wnorm, __half* x16, __half* w16, int Dp, cudaStream_t st);
 int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
                    int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
                    float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
@@ -619,8 +625,10 @@ int cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, i
                    float s, int clamp_cos, float* out, int64_t out_sr, float* xnorm, float* wnorm, int precision,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
   TGFR_REQUIRE(B > 0 && C > 0 && Din > 0, "cos_logits: empty shape");
-  if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
-  if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  if (precision != TGFR_PREC_TC) {
+    if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
+    if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  }
   if (precision == TGFR_PREC_TC) {
     TGFR_REQUIRE(head_tc_supported(B, C, Din), "cos_logits(tc): unsupported shape B=%d C=%d Din=%d", B, C, Din);
     const HeadWs h = head_ws(B, C, Din, precision);
@@ -629,8 +637,7 @@ int cos_logits_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, i
     uint8_t* base = reinterpret_cast<uint8_t*>(ws);
     __half* x16 = reinterpret_cast<__half*>(base + h.x16);
     __half* w16 = reinterpret_cast<__half*>(base + h.w16);
-    if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, h.Dp, st)) return rc;
-    if (int rc = head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, h.Dp, st)) return rc;
+    if (int rc = head_prepare_operands(x, x_sr, w, w_sc, w_sk, B, C, Din, xnorm, wnorm, x16, w16, h.Dp, st)) return rc;
     return gemm_tc(x16, 0, h.Dp, w16, 0, h.Dp, B, C, h.Dp, s, nullptr, clamp_cos, out, out_sr, 1, st);
   }
   Gemm g{};
@@ -676,7 +683,7 @@ int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64
     if (int rc = head_scale_f16(g, g_sr, B, C, scale, g16, h.Cp, st)) return rc;     // g * 2^e as fp16, scale[1] = 2^-e
     if (dx) {   // dXhat[b,:] = s * sum_c g[b,c] w^_c : A = g16 K-major, B = w^ read MN-major, split over the classes
       const int tiles = ceil_div(B, 128) * ceil_div(Din, 128);
-      const int splits = tiles >= 148 ? 1 : ceil_div(296, tiles);
+      const int splits = tiles >= 148 ? 1 : 296 / tiles;      // every (tile, split) CTA co-resident at 2 per SM: no tail wave
       if (int rc = gemm_tc(g16, 0, h.Cp, w16, 1, h.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
     }
     // dWhat[c,:] = s * sum_b g[b,c] x^_b : A = g16 read MN-major, B = x^ read MN-major
@@ -764,10 +771,7 @@ int arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
   uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
   __half* x16 = reinterpret_cast<__half*>(sv + f.sv_x16);
   __half* w16 = reinterpret_cast<__half*>(sv + f.sv_w16);
-  if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
-  if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
-  if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, f.Dp, st)) return rc;
-  if (int rc = head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, f.Dp, st)) return rc;
+  if (int rc = head_prepare_operands(x, x_sr, w, w_sc, w_sk, B, C, Din, xnorm, wnorm, x16, w16, f.Dp, st)) return rc;
   return gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 0,
                         reinterpret_cast<float*>(base + f.part), rowmax, rowsum, tgt, cos_t, nullptr, nullptr, nullptr,
                         nullptr, nullptr, 0, st);
@@ -794,7 +798,7 @@ int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
     return rc;
   if (dx) {
     const int tiles = ceil_div(B, 128) * ceil_div(Din, 128);
-    const int splits = tiles >= 148 ? 1 : ceil_div(296, tiles);
+    const int splits = tiles >= 148 ? 1 : 296 / tiles;      // every (tile, split) CTA co-resident at 2 per SM: no tail wave
     if (int rc = gemm_tc(g16, 0, f.Cp, w16, 1, f.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
   }
   if (int rc = gemm_tc(g16, 1, f.Cp, x16, 1, f.Dp, C, Din, B, s, scale, 0, dwh, Din, 1, st)) return rc;

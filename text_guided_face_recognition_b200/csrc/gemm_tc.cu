@@ -11,8 +11,11 @@
 // kEpiCeGrad below): margin + online-softmax statistics in the forward, margin + softmax gradient as the fp16
 // operand of the two gradient GEMMs in the backward (metrics.py:45-57 + losses.py:321-325 in one pass each).
 //
-// One 128 x 128 output tile per CTA, 3-stage TMA pipeline over K in steps of 64 (32 KB per stage), two CTAs per SM
-// so that one CTA's epilogue overlaps the other's main loop.  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// One 128 x BN output tile per CTA, TMA pipeline over K in steps of 64, two or three CTAs per SM so that one CTA's
+// epilogue overlaps another's main loop.  A CTA lives ~10 us whatever it does (set-up, pipeline fill, epilogue), so a
+// partial second wave costs as much as the first: the host picks the tile width / residency that makes EVERY tile
+// co-resident (B = 512, C = 10177: 128-wide tiles are 320 CTAs for 296 slots; 160-wide tiles are 256; the MN-major
+// products, whose panels are 64 wide, run 128-wide tiles on 2 stages at three CTAs per SM = 444 slots).  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 // allocator, warps 2-5 epilogue (TMEM -> registers -> warp-private shared-memory transpose -> coalesced row stores,
 // which is what the unaligned row pitch of a [B, 10177] logits matrix needs).
 #include "common.cuh"
@@ -24,11 +27,12 @@ namespace {
 using namespace tc;
 
 constexpr int kGemmThreads = 192;
-constexpr int kStages = 3;
-constexpr int kBM = 128, kBN = 128, kBK = 64;
-constexpr uint32_t kTileBytes = kBM * kBK * 2;           // 16 KB per operand per stage
-constexpr uint32_t kStageBytes = 2 * kTileBytes;
-constexpr uint32_t kGemmSmem = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment*/;
+constexpr int kBM = 128, kBK = 64;
+constexpr uint32_t kTileBytes = kBM * kBK * 2;           // 16 KB of A per stage; B: BN x 128 bytes
+__host__ __device__ constexpr uint32_t gemm_stage_bytes(int bn) { return kTileBytes + (uint32_t)bn * kBK * 2; }
+__host__ __device__ constexpr uint32_t gemm_smem_bytes(int bn, int stages) {
+  return (uint32_t)stages * gemm_stage_bytes(bn) + 1024 /*barriers*/ + 1024 /*alignment*/;
+}
 
 enum Epi { kEpiStore = 0, kEpiCeStats = 1, kEpiCeGrad = 2 };
 
@@ -76,11 +80,14 @@ struct GemmTcParams {
   CeParams ce;
 };
 
-template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+template <int EPI, int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStages = STAGES, kBN = BN;
+  constexpr uint32_t kStageBytes = gemm_stage_bytes(BN);
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "tile width: whole 32-column epilogue chunks");
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* accum = empty + kStages;
@@ -103,7 +110,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  constexpr uint32_t kTmemCols = BN <= 128 ? 128 : 256;
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -270,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -301,6 +309,48 @@ __global__ void normalize_cols_f16_kernel(const float* __restrict__ x, int64_t s
   for (int r = ty; r < 32; r += 8) {
     const int v = v0 + r, k = k0 + tx;
     if (v < nvec && k < ld_out) out[(int64_t)v * ld_out + k] = __float2half_rn(tile[tx][r] / fmaxf(__ldg(norm + v), 1e-12f));
+  }
+}
+
+// norms + fp16 normalised operands of BOTH head operands in one launch (rows contiguous, len % 4 == 0, len <= 1024):
+// a warp per vector, the vector held in registers, so x and w are read once (the two-kernel form read them twice
+// and took four launches): norm[v] = |x_v|, out16[v, :] = x_v / max(|x_v|, 1e-12), zero padded to ld_out
+__global__ void __launch_bounds__(256) norm_f16_pair_kernel(const float* __restrict__ x, int64_t x_sr, int nx,
+                                                            const float* __restrict__ w, int64_t w_sr, int nw, int len,
+                                                            float* __restrict__ xnorm, float* __restrict__ wnorm,
+                                                            __half* __restrict__ x16, __half* __restrict__ w16, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int nv4 = len >> 2;
+  for (int v = blockIdx.x * 8 + (threadIdx.x >> 5); v < nx + nw; v += gridDim.x * 8) {
+    const bool is_x = v < nx;
+    const int r = is_x ? v : v - nx;
+    const float4* src = reinterpret_cast<const float4*>(is_x ? x + (int64_t)r * x_sr : w + (int64_t)r * w_sr);
+    float4 e[8];
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = k * 32 + lane;
+      e[k] = idx < nv4 ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc = fmaf(e[k].x, e[k].x, acc);
+      acc = fmaf(e[k].y, e[k].y, acc);
+      acc = fmaf(e[k].z, e[k].z, acc);
+      acc = fmaf(e[k].w, e[k].w, acc);
+    }
+    const float nrm = sqrtf(warp_sum(acc));
+    if (lane == 0) (is_x ? xnorm : wnorm)[r] = nrm;
+    const float inv = 1.f / fmaxf(nrm, 1e-12f);
+    __half* dst = (is_x ? x16 : w16) + (int64_t)r * ld_out;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = k * 32 + lane;
+      if (4 * idx < ld_out) {                                   // ld_out % 8 == 0 and len % 4 == 0: whole 8-byte groups
+        const __half2 lo = __floats2half2_rn(e[k].x * inv, e[k].y * inv), hi = __floats2half2_rn(e[k].z * inv, e[k].w * inv);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst + 4 * idx) = pk;
+      }
+    }
   }
 }
 
@@ -351,41 +401,77 @@ __global__ void ce_merge_partials_kernel(const float* __restrict__ pmax, const f
 
 }  // namespace
 
+int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, float* norm, cudaStream_t st);   // dense_simt.cu
+
 // ---- host API (used by dense_simt.cu's head entry points when precision == TGFR_PREC_TC) ------------------------
 bool head_tc_supported(int B, int C, int Din) { return B >= 1 && C >= 1 && Din >= 8; }
 
 // fp16 operand: `mn` = 0: memory [rows, K] (K contiguous, pitch ld);  1: memory [K, rows] (rows contiguous, pitch ld)
-static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld) {
+static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld, int box_rows = 128) {
   if (mn) return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, 1, 64, 64, 1, 128, (uint64_t)ld);
-  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, 128, 1, 128, (uint64_t)ld);
+  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, box_rows, 1, 128, (uint64_t)ld);
+}
+
+template <int EPI, int BN, int STAGES, int MINB>
+static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTcParams& p, cudaStream_t st) {
+  constexpr uint32_t smem = gemm_smem_bytes(BN, STAGES);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  gemm_tc_kernel<EPI, BN, STAGES, MINB><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+
+// tile plan: 0 = 128 wide, 3 stages, 2 CTAs / SM;  1 = 160 wide (K-major B only);  2 = 128 wide, 2 stages, 3 CTAs / SM
+// (plain-store epilogue only: its register count allows three residents).  TGFR_HEAD_TILE = 0 | 1 | 2 forces one.
+static int pick_tile_plan(int M, int N, int splits, int b_mn, int cover, bool allow3) {
+  const int sms = sm_count();
+  const int mt = (M + kBM - 1) / kBM;
+  const int t128 = ((N + 127) / 128) * mt * splits, t160 = ((N + 159) / 160) * mt * splits;
+  const bool ok160 = !b_mn && ((N + 159) / 160) * 160 >= cover;
+  if (const char* e = getenv("TGFR_HEAD_TILE")) {
+    const int v = atoi(e);
+    if (v == 1 && ok160) return 1;
+    if (v == 2 && allow3) return 2;
+    if (v == 0) return 0;
+  }
+  if (t128 <= 2 * sms) return 0;
+  if (ok160 && t160 <= 2 * sms) return 1;
+  if (allow3 && t128 <= 3 * sms) return 2;
+  return 0;
 }
 
 int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, int64_t ldb, int M, int N, int K,
             float alpha, const float* dscale, int clamp, float* C, int64_t ldc, int splits, cudaStream_t st) {
-  CUtensorMap tm_a, tm_b;
-  if (int rc = operand_map(&tm_a, A, a_mn, M, K, lda)) return rc;
-  if (int rc = operand_map(&tm_b, Bm, b_mn, N, K, ldb)) return rc;
   const int kt_total = (K + kBK - 1) / kBK;
   if (splits < 1) splits = 1;
   if (splits > kt_total) splits = kt_total;
   const int per = (kt_total + splits - 1) / splits;
   splits = (kt_total + per - 1) / per;                       // no empty split
+  const int plan = pick_tile_plan(M, N, splits, b_mn, 0, true);
+  const int bn = plan == 1 ? 160 : 128;
+  CUtensorMap tm_a, tm_b;
+  if (int rc = operand_map(&tm_a, A, a_mn, M, K, lda)) return rc;
+  if (int rc = operand_map(&tm_b, Bm, b_mn, N, K, ldb, bn)) return rc;
   GemmTcParams p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.kt_per_split = per; p.alpha = alpha; p.dscale = dscale; p.clamp = clamp;
   p.atomic = splits > 1; p.a_mn = a_mn; p.b_mn = b_mn;
   if (splits > 1) TGFR_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
-  static bool attr_done[64] = {};
-  int dev = 0;
-  TGFR_CUDA_OK(cudaGetDevice(&dev));
-  bool& attr_set = attr_done[dev & 63];
-  if (!attr_set) {
-    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    attr_set = true;
-  }
-  const dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  gemm_tc_kernel<kEpiStore><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
-  TGFR_LAUNCH_OK();
-  return TGFR_OK;
+  const dim3 grid((N + bn - 1) / bn, (M + kBM - 1) / kBM, splits);
+  if (plan == 1) return launch_gemm<kEpiStore, 160, 3, 2>(grid, tm_a, tm_b, p, st);
+  if (plan == 2) return launch_gemm<kEpiStore, 128, 2, 3>(grid, tm_a, tm_b, p, st);
+  return launch_gemm<kEpiStore, 128, 3, 2>(grid, tm_a, tm_b, p, st);
 }
 
 // cos-theta GEMM (x16 [M, K] . w16 [N, K]^T, alpha = s) with a fused ArcFace cross-entropy epilogue.
@@ -396,40 +482,32 @@ int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ld
                    int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
                    float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
                    __half* g16, int ld_g, cudaStream_t st) {
+  const int plan = pick_tile_plan(M, N, 1, 0, grad ? ld_g : 0, false);
+  const int bn = plan == 1 ? 160 : 128;
   CUtensorMap tm_a, tm_b;
   if (int rc = operand_map(&tm_a, x16, 0, M, K, ldx)) return rc;
-  if (int rc = operand_map(&tm_b, w16, 0, N, K, ldw)) return rc;
+  if (int rc = operand_map(&tm_b, w16, 0, N, K, ldw, bn)) return rc;
   const float pi = 3.14159265358979323846f;
-  const int nt = (N + kBN - 1) / kBN;
+  const int nt = (N + bn - 1) / bn;
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K; p.kt_per_split = (K + kBK - 1) / kBK; p.alpha = s;
   p.ce.labels = labels; p.ce.class_off = class_off;
   p.ce.cm = cosf(m); p.ce.sm = sinf(m); p.ce.th = cosf(pi - m); p.ce.mm = sinf(pi - m) * m; p.ce.easy = easy;
   p.ce.pmax = part; p.ce.psum = part ? part + (size_t)M * nt : nullptr; p.ce.tgt = tgt; p.ce.cos_t = cos_t;
   p.ce.lse = lse; p.ce.coef = coef; p.ce.gout = gout; p.ce.scale = scale; p.ce.g16 = g16; p.ce.ld_g = ld_g;
-  int dev = 0;
-  TGFR_CUDA_OK(cudaGetDevice(&dev));
   const dim3 grid(nt, (M + kBM - 1) / kBM, 1);
   if (!grad) {
-    static bool attr_done[64] = {};
-    if (!attr_done[dev & 63]) {
-      TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiCeStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-      attr_done[dev & 63] = true;
-    }
     TGFR_CUDA_OK(cudaMemsetAsync(tgt, 0, sizeof(float) * M, st));
     TGFR_CUDA_OK(cudaMemsetAsync(cos_t, 0xFF, sizeof(float) * M, st));          // NaN: label outside this shard
-    gemm_tc_kernel<kEpiCeStats><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
-    TGFR_LAUNCH_OK();
+    if (int rc = plan == 1 ? launch_gemm<kEpiCeStats, 160, 3, 2>(grid, tm_a, tm_b, p, st)
+                           : launch_gemm<kEpiCeStats, 128, 3, 2>(grid, tm_a, tm_b, p, st))
+      return rc;
     ce_merge_partials_kernel<<<(M + 7) / 8, 256, 0, st>>>(p.ce.pmax, p.ce.psum, M, nt, rowmax, rowsum);
     TGFR_LAUNCH_OK();
   } else {
-    static bool attr_done[64] = {};
-    if (!attr_done[dev & 63]) {
-      TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiCeGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-      attr_done[dev & 63] = true;
-    }
-    gemm_tc_kernel<kEpiCeGrad><<<grid, kGemmThreads, kGemmSmem, st>>>(tm_a, tm_b, p);
-    TGFR_LAUNCH_OK();
+    if (int rc = plan == 1 ? launch_gemm<kEpiCeGrad, 160, 3, 2>(grid, tm_a, tm_b, p, st)
+                           : launch_gemm<kEpiCeGrad, 128, 3, 2>(grid, tm_a, tm_b, p, st))
+      return rc;
   }
   return TGFR_OK;
 }
@@ -445,6 +523,24 @@ int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, 
   }
   TGFR_LAUNCH_OK();
   return TGFR_OK;
+}
+
+// norms and fp16 operands of x [B, Din] (row pitch x_sr) and w [C, Din] (strides w_sc, w_sk) for the cos-theta GEMM
+int head_prepare_operands(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C, int Din,
+                          float* xnorm, float* wnorm, __half* x16, __half* w16, int Dp, cudaStream_t st) {
+  const bool fused = w_sk == 1 && (Din & 3) == 0 && Din <= 1024 && (x_sr & 3) == 0 && (w_sc & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (Dp & 7) == 0;
+  if (fused) {
+    const int blocks = (B + C + 7) / 8;
+    norm_f16_pair_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, 256, 0, st>>>(x, x_sr, B, w, w_sc, C, Din, xnorm, wnorm, x16,
+                                                                             w16, Dp);
+    TGFR_LAUNCH_OK();
+    return TGFR_OK;
+  }
+  if (int rc = launch_norms(x, x_sr, 1, B, Din, xnorm, st)) return rc;
+  if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
+  if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, Dp, st)) return rc;
+  return head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, Dp, st);
 }
 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e
