@@ -591,6 +591,8 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
 int head_normalize_f16(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int len, const float* norm, __half* out,
                        int ld_out, cudaStream_t st);
 int head_scale_f16(const float* g, int64_t ld, int rows, int cols, float* scale, __half* out, int ld_out, cudaStream_t st);
+int head_normalize_bwd_pair(const float*, const float*, int64_t, const float*, float*, int, const float*, const float*, int64_t,
+                            int64_t, const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
 int head_prepare_operands(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, int B, int C, int Din,
                           float* xnorm, float* wnorm, __half* x16, __half* w16, int Dp, cudaStream_t st);
 int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
@@ -711,6 +713,8 @@ int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64
                                       dwh);
     TGFR_LAUNCH_OK();
   }
+  const int fused = head_normalize_bwd_pair(dxh, x, x_sr, xnorm, dx, B, dwh, w, w_sc, w_sk, wnorm, dw, w_sc, w_sk, C, Din, st);
+  if (fused <= 0) return fused;
   if (dx) {
     normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dxh, Din, x, x_sr, 1, xnorm, 1e-12f, B, Din, dx, Din, 1);
     TGFR_LAUNCH_OK();
@@ -802,6 +806,8 @@ int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
     if (int rc = gemm_tc(g16, 0, f.Cp, w16, 1, f.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
   }
   if (int rc = gemm_tc(g16, 1, f.Cp, x16, 1, f.Dp, C, Din, B, s, scale, 0, dwh, Din, 1, st)) return rc;
+  const int fused = head_normalize_bwd_pair(dxh, x, x_sr, xnorm, dx, B, dwh, w, w_sc, w_sk, wnorm, dw, w_sc, w_sk, C, Din, st);
+  if (fused <= 0) return fused;
   if (dx) {
     normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(dxh, Din, x, x_sr, 1, xnorm, 1e-12f, B, Din, dx, Din, 1);
     TGFR_LAUNCH_OK();

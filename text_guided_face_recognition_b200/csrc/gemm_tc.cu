@@ -217,26 +217,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int j = 0; j < 32; ++j) sum += expf(lg[j] - mx);
           }
         } else {
-          // g16 rows through the warp-private transpose buffer: 64-byte row segments per store
-          __half* hstage = reinterpret_cast<__half*>(stage);
+          // a thread owns 32 consecutive entries of ITS row: four 16-byte stores, no transpose (ld_g % 8 == 0)
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float g = 0.f;
-            if (row_ok && c0 + j < p.N) {
-              const bool on = (int64_t)(c0 + j) == ycol;
-              g = kscale * (expf(lg[j] - lse) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
-              g = fminf(fmaxf(g, -65504.f), 65504.f);
+          for (int j = 0; j < 32; j += 2) {
+            float g2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float g = 0.f;
+              if (c0 + j + u < p.N) {
+                const bool on = (int64_t)(c0 + j + u) == ycol;
+                g = kscale * (expf(lg[j + u] - lse) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
+                g = fminf(fmaxf(g, -65504.f), 65504.f);
+              }
+              g2[u] = g;
             }
-            hstage[lane * 66 + j] = __float2half_rn(g);
+            const __half2 h2 = __floats2half2_rn(g2[0], g2[1]);
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          __syncwarp();
-          const int col = c0 + lane;
-          if (col < p.ce.ld_g) {                                   // columns [N, ld_g) are the zero K padding
-            const int nrows = min(32, p.M - row_base);
-            for (int rr = 0; rr < nrows; ++rr)
-              p.ce.g16[(int64_t)(row_base + rr) * p.ce.ld_g + col] = hstage[rr * 66 + lane];
+          if (row_ok) {
+            __half* dst = p.ce.g16 + (int64_t)row * p.ce.ld_g + c0;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (c0 + 8 * q4 < p.ce.ld_g)                           // columns [N, ld_g) are the zero K padding
+                *reinterpret_cast<uint4*>(dst + 8 * q4) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
           }
-          __syncwarp();
         }
       }
       if constexpr (EPI == kEpiCeStats) {
@@ -246,6 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     } else {
+    const bool direct = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
 #pragma unroll 1
     for (int ch = 0; ch < kBN / 32; ++ch) {
       const int c0 = n0 + 32 * ch;
@@ -253,6 +259,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);
       tmem_ld_wait();
+      if (direct) {
+        // a thread owns 32 consecutive outputs of ITS row (128 contiguous bytes): 16-byte stores or vector reductions
+        const int row = row_base + lane;
+        if (row < p.M) {
+          float* dst = p.C + (int64_t)row * p.ldc + c0;
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float x = __uint_as_float(v[4 * g4 + u]);
+              if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
+              o[u] = x * alpha;
+            }
+            const int c = c0 + 4 * g4;
+            if (c + 3 < p.N) {
+              if (p.atomic) red_add_v4(dst + 4 * g4, o[0], o[1], o[2], o[3]);
+              else *reinterpret_cast<float4*>(dst + 4 * g4) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (c + u < p.N) {
+                  if (p.atomic) atomicAdd(dst + 4 * g4 + u, o[u]);
+                  else dst[4 * g4 + u] = o[u];
+                }
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(v[j]);
@@ -350,6 +386,49 @@ __global__ void __launch_bounds__(256) norm_f16_pair_kernel(const float* __restr
         pk.y = *reinterpret_cast<const uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(dst + 4 * idx) = pk;
       }
+    }
+  }
+}
+
+// d(normalize(v)) / dv projections of BOTH head operands in one launch: out = (g - <g, v^> v^) / |v| with
+// v^ = v / max(|v|, eps); rows contiguous, len % 4 == 0, len <= 1024: a warp per vector, everything in registers
+__global__ void __launch_bounds__(256) normalize_bwd_pair_kernel(const float* __restrict__ gx, const float* __restrict__ x,
+                                                                 int64_t x_sr, const float* __restrict__ xnorm,
+                                                                 float* __restrict__ dx, int nx, const float* __restrict__ gw,
+                                                                 const float* __restrict__ w, int64_t w_sr,
+                                                                 const float* __restrict__ wnorm, float* __restrict__ dw,
+                                                                 int64_t dw_sr, int nw, int len, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv4 = len >> 2;
+  for (int v = blockIdx.x * 8 + (threadIdx.x >> 5); v < nx + nw; v += gridDim.x * 8) {
+    const bool is_x = v < nx;
+    const int r = is_x ? v : v - nx;
+    const float4* gp = reinterpret_cast<const float4*>((is_x ? gx : gw) + (int64_t)r * len);
+    const float4* vp = reinterpret_cast<const float4*>(is_x ? x + (int64_t)r * x_sr : w + (int64_t)r * w_sr);
+    float4* op = reinterpret_cast<float4*>(is_x ? dx + (int64_t)r * len : dw + (int64_t)r * dw_sr);
+    const float inv = 1.f / fmaxf(__ldg((is_x ? xnorm : wnorm) + r), eps);
+    float4 g[8], vh[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < nv4) {
+        g[k] = __ldg(gp + idx);
+        const float4 t = __ldg(vp + idx);
+        vh[k] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+        dot = fmaf(g[k].x, vh[k].x, dot);
+        dot = fmaf(g[k].y, vh[k].y, dot);
+        dot = fmaf(g[k].z, vh[k].z, dot);
+        dot = fmaf(g[k].w, vh[k].w, dot);
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx < nv4)
+        op[idx] = make_float4((g[k].x - dot * vh[k].x) * inv, (g[k].y - dot * vh[k].y) * inv, (g[k].z - dot * vh[k].z) * inv,
+                              (g[k].w - dot * vh[k].w) * inv);
     }
   }
 }
@@ -541,6 +620,24 @@ int head_prepare_operands(const float* x, int64_t x_sr, const float* w, int64_t 
   if (int rc = launch_norms(w, w_sc, w_sk, C, Din, wnorm, st)) return rc;
   if (int rc = head_normalize_f16(x, x_sr, 1, B, Din, xnorm, x16, Dp, st)) return rc;
   return head_normalize_f16(w, w_sc, w_sk, C, Din, wnorm, w16, Dp, st);
+}
+
+// dx [B, Din] (contiguous) and dw (row pitch dw_sr) from the GEMM outputs gx [B, Din] / gw [C, Din]; gx / dx may be NULL.
+// Returns 1 if the shapes do not fit the fused kernel (the caller then runs normalize_bwd_kernel per operand).
+int head_normalize_bwd_pair(const float* gx, const float* x, int64_t x_sr, const float* xnorm, float* dx, int B, const float* gw,
+                            const float* w, int64_t w_sc, int64_t w_sk, const float* wnorm, float* dw, int64_t dw_sc,
+                            int64_t dw_sk, int C, int Din, cudaStream_t st) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(gw) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw) |
+                       (dx ? reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) : 0);
+  const bool ok = w_sk == 1 && dw_sk == 1 && (Din & 3) == 0 && Din <= 1024 && (x_sr & 3) == 0 && (w_sc & 3) == 0 &&
+                  (dw_sc & 3) == 0 && (al & 15) == 0;
+  if (!ok) return 1;
+  const int nx = dx ? B : 0;
+  const int blocks = (nx + C + 7) / 8;
+  normalize_bwd_pair_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, 256, 0, st>>>(gx, x, x_sr, xnorm, dx, nx, gw, w, w_sc, wnorm, dw,
+                                                                                dw_sc, C, Din, 1e-12f);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
 }
 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e

@@ -1,3 +1,3 @@
 cd /root/repo
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "arc or mag or head or focal or margin or cos_logits" 2>&1 | tail -6
-for t in 0 1 2 ""; do echo "TGFR_HEAD_TILE=$t"; if [ -n "$t" ]; then export TGFR_HEAD_TILE=$t; else unset TGFR_HEAD_TILE; fi; timeout 120 python tools/time_head.py 2>&1 | tail -2; done
+timeout 120 python tools/time_head.py 2>&1 | tail -2

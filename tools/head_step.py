@@ -11,8 +11,12 @@ x = torch.from_numpy(xn).cuda().requires_grad_(True)
 labt = torch.from_numpy(lab).cuda()
 crit = losses.FocalLoss(gamma=2.0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+fused = len(sys.argv) > 2 and sys.argv[2] == 'fused'
 for _ in range(n):
     x.grad = None; head.weight.grad = None
-    crit(head(x, labt), labt).backward()
+    if fused:
+        head.fused_loss(x, labt, gamma=2.0).backward()
+    else:
+        crit(head(x, labt), labt).backward()
 torch.cuda.synchronize()
 print('ok')
