@@ -604,7 +604,7 @@ def run_b200(args):
         th_ms = e0.elapsed_time(e1) / 10
         th_flops = 2 * 2 * B * (bwn - 1) * (2 + 3 + 4) * 768 * D       # three products forward, three backward
         line["text_heading"] = {"metric": "text_heading_fwd_bwd_captions_per_sec", "value": B / (th_ms * 1e-3),
-                                "unit": "captions/s", "ms_per_step": th_ms, "dtype": "f32",
+                                "unit": "captions/s", "ms_per_step": th_ms, "dtype": "f16 hi+lo split operands (3 accumulated tcgen05 terms, ~22 bits) / f32 accumulate",
                                 "tflops": th_flops / (th_ms * 1e-3) / 1e12,
                                 "config": {"B": B, "bert_words_num": bwn, "E": 768, "F": D}}
 

@@ -210,10 +210,12 @@ int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, con
  * [F, 1, K, E] as contiguous [F, K*E]; b2 / b3 / b4: their biases (NULL = none).  `saved`
  * (tgfr_texthead_saved_bytes) carries the three ReLU outputs to the backward, which returns the weight / bias
  * gradients for upstream gwords [B, T, F] and gsent [B, F] (either may be NULL); the tokens get no gradient
- * (frozen BERT).  The last word is detached exactly as in the reference (models.py:206).  fp32 throughout.
+ * (frozen BERT).  The last word is detached exactly as in the reference (models.py:206).  The six products run on
+ * tcgen05 as error-compensated fp16 hi/lo splits of the fp32 operands (three accumulated terms, ~22 significant bits,
+ * fp32 accumulation) when E % 8 == 0 and F % 8 == 0, else (or with TGFR_TEXTHEAD_PRECISION=fp32) on the fp32 SIMT GEMM.
  * ------------------------------------------------------------------------------------------ */
-size_t tgfr_texthead_saved_bytes(int B, int L, int F);
-size_t tgfr_texthead_workspace_bytes(int B, int L, int F);
+size_t tgfr_texthead_saved_bytes(int B, int L, int E, int F);
+size_t tgfr_texthead_workspace_bytes(int B, int L, int E, int F);
 int tgfr_texthead_fwd(const float* tokens, const float* w2, const float* w3, const float* w4,
                       const float* b2, const float* b3, const float* b4, int B, int L, int E, int F,
                       int bert_words_num, float* words, float* sent, void* saved, size_t saved_bytes, void* stream);

@@ -52,8 +52,8 @@ SIGNATURES = {
     "tgfr_ce_rows_stats": (I, [P, L, P, I, I, I, P, P, P, P]),
     "tgfr_focal_finish": (I, [P, P, P, I, F, P, P, P]),
     "tgfr_ce_rows_bwd": (I, [P, L, P, P, P, P, I, I, I, P, L, P]),
-    "tgfr_texthead_saved_bytes": (Z, [I, I, I]),
-    "tgfr_texthead_workspace_bytes": (Z, [I, I, I]),
+    "tgfr_texthead_saved_bytes": (Z, [I, I, I, I]),
+    "tgfr_texthead_workspace_bytes": (Z, [I, I, I, I]),
     "tgfr_texthead_fwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, Z, P]),
     "tgfr_texthead_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, Z, P, Z, P]),
     "tgfr_pair_cosine": (I, [P, L, L, P, L, L, L, I, F, P, P]),

@@ -70,8 +70,8 @@ int ce_rows_bwd(const float*, int64_t, const int64_t*, const float*, const float
                 float*, int64_t, cudaStream_t);
 
 // texthead.cu
-size_t texthead_saved_bytes(int, int, int);
-size_t texthead_workspace_bytes(int, int, int);
+size_t texthead_saved_bytes(int, int, int, int);
+size_t texthead_workspace_bytes(int, int, int, int);
 int texthead_fwd(const float*, const float* const*, const float* const*, int, int, int, int, int, float*, float*, void*,
                  size_t, cudaStream_t);
 int texthead_bwd(const float*, const float*, const float*, int, int, int, int, int, float* const*, float* const*, void*,
@@ -320,8 +320,8 @@ int tgfr_debug_tma_reduce(float* out, int rows, int cols, void* stream) {
 }
 
 
-size_t tgfr_texthead_saved_bytes(int B, int L, int F) { return texthead_saved_bytes(B, L, F); }
-size_t tgfr_texthead_workspace_bytes(int B, int L, int F) { return texthead_workspace_bytes(B, L, F); }
+size_t tgfr_texthead_saved_bytes(int B, int L, int E, int F) { return texthead_saved_bytes(B, L, E, F); }
+size_t tgfr_texthead_workspace_bytes(int B, int L, int E, int F) { return texthead_workspace_bytes(B, L, E, F); }
 int tgfr_texthead_fwd(const float* tokens, const float* w2, const float* w3, const float* w4, const float* b2,
                       const float* b3, const float* b4, int B, int L, int E, int F, int bert_words_num, float* words,
                       float* sent, void* saved, size_t saved_bytes, void* stream) {

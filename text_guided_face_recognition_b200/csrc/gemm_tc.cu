@@ -18,6 +18,8 @@
 // products, whose panels are 64 wide, run 128-wide tiles on 2 stages at three CTAs per SM = 444 slots).  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM
 // allocator, warps 2-5 epilogue (TMEM -> registers -> warp-private shared-memory transpose -> coalesced row stores,
 // which is what the unaligned row pitch of a [B, 10177] logits matrix needs).
+#include <string.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -78,11 +80,31 @@ struct GemmTcParams {
   int atomic;            // accumulate with atomics (split-K; C pre-zeroed)
   int a_mn, b_mn;
   CeParams ce;
+  // plain-store epilogue extras (TextHeading products): out = relu?(alpha acc + bias[col])
+  const float* bias;     // [N] or NULL
+  int relu;
+  const float* dscale2;  // second optional device scalar (alpha *= dscale2[1]): one power-of-two scale per operand
+  // error-compensated products: nterms = 3 accumulates A_hi B_hi + A_hi B_lo + A_lo B_hi (fp16 hi / lo splits of fp32
+  // operands, ~22 significant bits) in the one TMEM accumulator by walking K three times with different tensor maps
+  int nterms;            // 1 or 3
+  // batched = 1: blockIdx.z selects one of up to three independent products (own maps, shapes and outputs; no split-K)
+  int batched;
+  struct Z {
+    float* C;
+    const float* bias;
+    int64_t ldc;
+    int M, N, K;
+  } z[3];
+};
+
+struct GemmMaps {        // [product z][0 = hi (or the only operand), 1 = lo]
+  CUtensorMap a[3][2];
+  CUtensorMap b[3][2];
 };
 
 template <int EPI, int BN, int STAGES, int MINB>
 __global__ void __launch_bounds__(kGemmThreads, MINB)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kStages = STAGES, kBN = BN;
@@ -95,10 +117,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  const int kt_total = (p.K + kBK - 1) / kBK;
-  const int kt0 = blockIdx.z * p.kt_per_split;
-  const int kt1 = min(kt_total, kt0 + p.kt_per_split);
-  const int nkt = kt1 - kt0;                               // >= 1 by construction of the grid
+  const int zi = p.batched ? (int)blockIdx.z : 0;
+  const int Mz = p.batched ? p.z[zi].M : p.M, Nz = p.batched ? p.z[zi].N : p.N, Kz = p.batched ? p.z[zi].K : p.K;
+  float* const Cz = p.batched ? p.z[zi].C : p.C;
+  const int64_t ldcz = p.batched ? p.z[zi].ldc : p.ldc;
+  const float* const biasz = p.batched ? p.z[zi].bias : p.bias;
+  if (m0 >= Mz || n0 >= Nz) return;                        // batched products share one grid: tiles outside this one
+  const int kt_total = (Kz + kBK - 1) / kBK;
+  const int kt0 = p.batched ? 0 : blockIdx.z * p.kt_per_split;
+  const int kt1 = p.batched ? kt_total : min(kt_total, kt0 + p.kt_per_split);
+  const int nk1 = kt1 - kt0;                               // >= 1 by construction of the grid
+  const int nkt = nk1 * (p.nterms == 3 ? 3 : 1);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -107,8 +136,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     mbar_init(accum, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&maps.a[zi][0]);
+    tma_prefetch_desc(&maps.b[zi][0]);
   }
   constexpr uint32_t kTmemCols = BN <= 128 ? 128 : 256;
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -124,19 +153,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kTileBytes;
-        const int k0 = (kt0 + it) * kBK;
+        const int term = it / nk1;                           // 0: hi hi, 1: hi lo, 2: lo hi
+        const int k0 = (kt0 + it - term * nk1) * kBK;
+        const CUtensorMap* const ta = &maps.a[zi][term == 2 ? 1 : 0];
+        const CUtensorMap* const tb = &maps.b[zi][term == 1 ? 1 : 0];
         mbar_arrive_expect_tx(&full[s], kStageBytes);
         if (p.a_mn) {                                        // memory [K, M]: two panels of 64 M-elements x 64 K-rows
-          tma_load_3d(sa, &tm_a, &full[s], m0, k0, 0);
-          tma_load_3d(sa + 8192, &tm_a, &full[s], m0 + 64, k0, 0);
+          tma_load_3d(sa, ta, &full[s], m0, k0, 0);
+          tma_load_3d(sa + 8192, ta, &full[s], m0 + 64, k0, 0);
         } else {                                             // memory [M, K]: 128 rows x 64 K-elements
-          tma_load_3d(sa, &tm_a, &full[s], k0, m0, 0);
+          tma_load_3d(sa, ta, &full[s], k0, m0, 0);
         }
         if (p.b_mn) {
-          tma_load_3d(sb, &tm_b, &full[s], n0, k0, 0);
-          tma_load_3d(sb + 8192, &tm_b, &full[s], n0 + 64, k0, 0);
+          tma_load_3d(sb, tb, &full[s], n0, k0, 0);
+          tma_load_3d(sb + 8192, tb, &full[s], n0 + 64, k0, 0);
         } else {
-          tma_load_3d(sb, &tm_b, &full[s], k0, n0, 0);
+          tma_load_3d(sb, tb, &full[s], k0, n0, 0);
         }
       }
     }
@@ -166,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // the operand stages are dead now: warp-private 32 x 33 float transpose buffers live in stage 0
     float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
     const int row_base = m0 + q * 32;
-    const float alpha = p.dscale ? p.alpha * __ldg(p.dscale + 1) : p.alpha;
+    const float alpha = p.alpha * (p.dscale ? __ldg(p.dscale + 1) : 1.f) * (p.dscale2 ? __ldg(p.dscale2 + 1) : 1.f);
     if constexpr (EPI != kEpiStore) {
       // a thread owns row (row_base + lane) of the tile: logits = s cos, phi on the label column
       const int row = row_base + lane;
@@ -251,19 +283,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     } else {
-    const bool direct = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+    const bool direct = (ldcz & 3) == 0 && (reinterpret_cast<uintptr_t>(Cz) & 15) == 0;
 #pragma unroll 1
     for (int ch = 0; ch < kBN / 32; ++ch) {
       const int c0 = n0 + 32 * ch;
-      if (c0 >= p.N) break;
+      if (c0 >= Nz) break;
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);
       tmem_ld_wait();
       if (direct) {
         // a thread owns 32 consecutive outputs of ITS row (128 contiguous bytes): 16-byte stores or vector reductions
         const int row = row_base + lane;
-        if (row < p.M) {
-          float* dst = p.C + (int64_t)row * p.ldc + c0;
+        if (row < Mz) {
+          float* dst = Cz + (int64_t)row * ldcz + c0;
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4) {
             float o[4];
@@ -271,16 +303,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int u = 0; u < 4; ++u) {
               float x = __uint_as_float(v[4 * g4 + u]);
               if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
-              o[u] = x * alpha;
+              x *= alpha;
+              if (biasz && c0 + 4 * g4 + u < Nz) x += __ldg(biasz + c0 + 4 * g4 + u);
+              if (p.relu) x = fmaxf(x, 0.f);
+              o[u] = x;
             }
             const int c = c0 + 4 * g4;
-            if (c + 3 < p.N) {
+            if (c + 3 < Nz) {
               if (p.atomic) red_add_v4(dst + 4 * g4, o[0], o[1], o[2], o[3]);
               else *reinterpret_cast<float4*>(dst + 4 * g4) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (c + u < p.N) {
+                if (c + u < Nz) {
                   if (p.atomic) atomicAdd(dst + 4 * g4 + u, o[u]);
                   else dst[4 * g4 + u] = o[u];
                 }
@@ -293,14 +328,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(v[j]);
         if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
-        stage[lane * 33 + j] = x * alpha;
+        x *= alpha;
+        if (biasz && c0 + j < Nz) x += __ldg(biasz + c0 + j);
+        if (p.relu) x = fmaxf(x, 0.f);
+        stage[lane * 33 + j] = x;
       }
       __syncwarp();
       const int col = c0 + lane;
-      if (col < p.N) {
-        const int nrows = min(32, p.M - row_base);
+      if (col < Nz) {
+        const int nrows = min(32, Mz - row_base);
         for (int rr = 0; rr < nrows; ++rr) {
-          float* dst = p.C + (int64_t)(row_base + rr) * p.ldc + col;
+          float* dst = Cz + (int64_t)(row_base + rr) * ldcz + col;
           const float val = stage[rr * 33 + lane];
           if (p.atomic) atomicAdd(dst, val);
           else *dst = val;
@@ -457,6 +495,25 @@ __global__ void scale_to_f16_kernel(const float* __restrict__ g, int64_t ld, int
     dst[c] = __float2half_rn(c < cols ? __ldg(src + c) * sc : 0.f);
 }
 
+// x 2^e = hi + lo with fp16 hi, lo (about 22 significant bits): the operands of the error-compensated products.
+// 2^e puts the largest entry near 2^12, so lo (2^-11 of hi) stays in the fp16 normal range for entries down to
+// 2^-15 of the maximum; scale[0] = max|x| (maxabs_kernel), scale[1] = 2^-e
+__global__ void split_f16_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ scale,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, int ld_out) {
+  const float mx = scale[0];
+  const float sc = (mx > 0.f) ? exp2f(floorf(log2f(4096.f / mx))) : 1.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) scale[1] = 1.f / sc;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float* src = g + (int64_t)r * ld;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ld_out; c += gridDim.x * blockDim.x) {
+      const float x = c < cols ? __ldg(src + c) * sc : 0.f;
+      const __half h = __float2half_rn(x);
+      hi[(int64_t)r * ld_out + c] = h;
+      lo[(int64_t)r * ld_out + c] = __float2half_rn(x - __half2float(h));
+    }
+  }
+}
+
 // merge the per-tile online-softmax partials of a row: (max, sum exp(. - max)) over nt column tiles
 __global__ void ce_merge_partials_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int rows, int nt,
                                          float* __restrict__ rowmax, float* __restrict__ rowsum) {
@@ -486,13 +543,20 @@ int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int le
 bool head_tc_supported(int B, int C, int Din) { return B >= 1 && C >= 1 && Din >= 8; }
 
 // fp16 operand: `mn` = 0: memory [rows, K] (K contiguous, pitch ld);  1: memory [K, rows] (rows contiguous, pitch ld)
-static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld, int box_rows = 128) {
-  if (mn) return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, 1, 64, 64, 1, 128, (uint64_t)ld);
-  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, box_rows, 1, 128, (uint64_t)ld);
+static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld, int box_rows = 128,
+                       bool overlap = false) {
+  if (mn)
+    return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, 1, 64, 64, 1, 128, (uint64_t)ld,
+                        overlap);
+  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, box_rows, 1, 128,
+                      (uint64_t)ld, overlap);
 }
 
 template <int EPI, int BN, int STAGES, int MINB>
-static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTcParams& p, cudaStream_t st) {
+static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTcParams& p, cudaStream_t st);
+
+template <int EPI, int BN, int STAGES, int MINB>
+static int launch_gemm(dim3 grid, const GemmMaps& maps, const GemmTcParams& p, cudaStream_t st) {
   constexpr uint32_t smem = gemm_smem_bytes(BN, STAGES);
   static bool attr_done[64] = {};
   int dev = 0;
@@ -501,9 +565,18 @@ static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm
     TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev & 63] = true;
   }
-  gemm_tc_kernel<EPI, BN, STAGES, MINB><<<grid, kGemmThreads, smem, st>>>(tm_a, tm_b, p);
+  gemm_tc_kernel<EPI, BN, STAGES, MINB><<<grid, kGemmThreads, smem, st>>>(maps, p);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
+}
+
+template <int EPI, int BN, int STAGES, int MINB>
+static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTcParams& p, cudaStream_t st) {
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  maps.a[0][0] = tm_a;
+  maps.b[0][0] = tm_b;
+  return launch_gemm<EPI, BN, STAGES, MINB>(grid, maps, p, st);
 }
 
 static int sm_count() {
@@ -638,6 +711,54 @@ int head_normalize_bwd_pair(const float* gx, const float* x, int64_t x_sr, const
                                                                                 dw_sc, C, Din, 1e-12f);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
+}
+
+// max|x| over several fp32 blocks into scale[0] (scale[0..1] zeroed first), then their hi / lo splits with ONE scale
+int head_split_f16(int nblocks, const float* const* src, const int64_t* ld, const int* rows, const int* cols, float* scale,
+                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st) {
+  TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
+  for (int k = 0; k < nblocks; ++k) {
+    maxabs_kernel<<<rows[k] < 1184 ? rows[k] : 1184, 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale);
+    TGFR_LAUNCH_OK();
+  }
+  for (int k = 0; k < nblocks; ++k) {
+    split_f16_kernel<<<dim3((ld_out[k] + 1023) / 1024, rows[k] < 32768 ? rows[k] : 32768), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale, hi[k], lo[k],
+                                                                              ld_out[k]);
+    TGFR_LAUNCH_OK();
+  }
+  return TGFR_OK;
+}
+
+// up to three independent error-compensated products in one launch (blockIdx.z = product):
+//   C_z [M_z, N_z] = relu?( alpha dscale[1] dscale2[1] (A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T) + bias_z )
+// a_mn / b_mn as in gemm_tc; a_overlap / b_overlap: the operand's rows share memory (pitch < row length)
+struct Split3Product {
+  const __half *a_hi, *a_lo, *b_hi, *b_lo;
+  int64_t lda, ldb, ldc;
+  int M, N, K;
+  float* C;
+  const float* bias;
+};
+int gemm_tc_split3_batched(const Split3Product* prods, int n, int a_mn, int a_overlap, int b_mn, int b_overlap, float alpha,
+                           const float* dscale, const float* dscale2, int relu, cudaStream_t st) {
+  TGFR_REQUIRE(n >= 1 && n <= 3, "gemm_tc_split3_batched: 1..3 products");
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  GemmTcParams p{};
+  p.alpha = alpha; p.dscale = dscale; p.dscale2 = dscale2; p.relu = relu; p.a_mn = a_mn; p.b_mn = b_mn;
+  p.nterms = 3; p.batched = 1;
+  int mt = 0, nt = 0;
+  for (int z = 0; z < n; ++z) {
+    const Split3Product& q = prods[z];
+    if (int rc = operand_map(&maps.a[z][0], q.a_hi, a_mn, q.M, q.K, q.lda, 128, a_overlap != 0)) return rc;
+    if (int rc = operand_map(&maps.a[z][1], q.a_lo, a_mn, q.M, q.K, q.lda, 128, a_overlap != 0)) return rc;
+    if (int rc = operand_map(&maps.b[z][0], q.b_hi, b_mn, q.N, q.K, q.ldb, 128, b_overlap != 0)) return rc;
+    if (int rc = operand_map(&maps.b[z][1], q.b_lo, b_mn, q.N, q.K, q.ldb, 128, b_overlap != 0)) return rc;
+    p.z[z].C = q.C; p.z[z].bias = q.bias; p.z[z].ldc = q.ldc; p.z[z].M = q.M; p.z[z].N = q.N; p.z[z].K = q.K;
+    mt = mt > (q.M + kBM - 1) / kBM ? mt : (q.M + kBM - 1) / kBM;
+    nt = nt > (q.N + 127) / 128 ? nt : (q.N + 127) / 128;
+  }
+  return launch_gemm<kEpiStore, 128, 3, 2>(dim3(nt, mt, n), maps, p, st);
 }
 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e

@@ -324,6 +324,7 @@ PFN_tgfr_encodeTiled get_encode_tiled();
 // (box rows of up to 128 bytes) or 64 (box rows of up to 64 bytes); pitch_elems = row pitch of dimension 1 in
 // elements (0 = dense, d0).
 int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
-                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes = 128, uint64_t pitch_elems = 0);
+                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes = 128, uint64_t pitch_elems = 0,
+                 bool overlap = false);
 
 }  // namespace tgfr

@@ -19,12 +19,13 @@ PFN_tgfr_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
-                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes, uint64_t pitch_elems) {
+                 uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes, uint64_t pitch_elems, bool overlap) {
   PFN_tgfr_encodeTiled enc = get_encode_tiled();
   if (!enc) return TGFR_E_CUDA;
   TGFR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base address must be 16-byte aligned");
   const uint64_t pitch = pitch_elems ? pitch_elems : d0;
-  TGFR_REQUIRE(pitch >= d0 && (pitch * elem_bytes) % 16 == 0, "tensor map: row pitch must be a multiple of 16 bytes");
+  // overlap: rows may share memory (pitch < row length): the sliding n-gram windows of TextHeading
+  TGFR_REQUIRE((overlap || pitch >= d0) && (pitch * elem_bytes) % 16 == 0, "tensor map: row pitch must be a multiple of 16 bytes");
   TGFR_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64, "tensor map: swizzle must be 64 or 128 bytes");
   TGFR_REQUIRE(b0 * elem_bytes <= (uint32_t)swizzle_bytes && b1 <= 256 && b2 <= 256, "tensor map: box too large for the swizzle");
   cuuint64_t dims[3] = {d0, d1, d2};

@@ -18,14 +18,35 @@
 // Reference quirk kept: the last word is copied with `torch.cuda.FloatTensor(a[i, seq+1])` (models.py:206), which
 // detaches it -- it receives no gradient.
 //
-// This first version runs the products on the exact fp32 SIMT GEMM (dense_simt.cu): the max routing is a discrete
-// decision, and fp16-operand rounding would flip near ties.
+// Products.  The max routing is a discrete decision, so plain fp16-operand tensor-core products (2^-11 operand
+// rounding) are not good enough: they would flip near ties.  The tensor-core path therefore splits every fp32 operand
+// into fp16 hi + lo (x 2^e = hi + lo, about 22 significant bits) and accumulates the three terms hi hi + hi lo + lo hi
+// in one TMEM accumulator (gemm_tc.cu, nterms = 3) -- the accuracy of an fp32 SGEMM at 3x the tensor-core work, which is
+// still ~10x faster than the fp32 SIMT GEMM.  The sliding windows stay views: the TMA tensor map of Win_K has row pitch
+// E and row length K E (overlapping rows), K-major for the forward and MN-major for dW.  The three convolutions are one
+// launch each way (blockIdx.z).  Shapes with E % 8 or F % 8 != 0, or TGFR_TEXTHEAD_PRECISION=fp32, run the exact fp32
+// SIMT GEMM (dense_simt.cu).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tgfr {
 
 int sgemm_strided(const float* A, int64_t sAm, int64_t sAk, const float* Bm, int64_t sBk, int64_t sBn, float* C,
                   int64_t sCm, int64_t sCn, int M, int N, int K, const float* bias, int relu, cudaStream_t st);
+// gemm_tc.cu
+struct Split3Product {
+  const __half *a_hi, *a_lo, *b_hi, *b_lo;
+  int64_t lda, ldb, ldc;
+  int M, N, K;
+  float* C;
+  const float* bias;
+};
+int gemm_tc_split3_batched(const Split3Product* prods, int n, int a_mn, int a_overlap, int b_mn, int b_overlap, float alpha,
+                           const float* dscale, const float* dscale2, int relu, cudaStream_t st);
+int head_split_f16(int nblocks, const float* const* src, const int64_t* ld, const int* rows, const int* cols, float* scale,
+                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st);
 
 namespace {
 
@@ -165,9 +186,56 @@ __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T
 
 }  // namespace
 
-// saved: act_2 | act_3 | act_4, each [B L, F] fp32;  workspace (backward): G_2 | G_3 | G_4
-size_t texthead_saved_bytes(int B, int L, int F) { return sizeof(float) * kConvs * (size_t)B * L * F; }
-size_t texthead_workspace_bytes(int B, int L, int F) { return sizeof(float) * kConvs * (size_t)B * L * F; }
+// saved: act_2 | act_3 | act_4, each [B L, F] fp32; tensor-core path adds [scales: tokens, weights | tokens hi | lo | W hi | W lo]
+// workspace (backward): G_2 | G_3 | G_4 fp32; tensor-core path adds [scale | G hi | G lo]
+namespace {
+// TGFR_TEXTHEAD_PRECISION = mixed (default) | tc | fp32.
+//   mixed: the forward products, whose outputs feed the discrete max routing, on the exact fp32 SIMT GEMM; the dW
+//          products (nothing discrete downstream) on tcgen05 with hi / lo split operands
+//   tc   : both on tcgen05.  The activations are then good to ~3e-6 instead of ~5e-7 (the tensor core truncates when
+//          it aligns the fp32 accumulator), which at B = 128 flips the arg-max of about two near-tied
+//          (caption, word, feature) triples in 720 k against the fp64 oracle -- a legitimate sub-gradient choice, but a
+//          1e-3-sized change of dW, so it is opt-in
+//   fp32 : everything on the SIMT GEMM
+int texthead_mode(int E, int F) {      // 0 fp32, 1 mixed, 2 tc
+  if ((E & 7) != 0 || (F & 7) != 0) return 0;
+  const char* e = getenv("TGFR_TEXTHEAD_PRECISION");
+  if (e && (e[0] == 'f' || e[0] == 's' || e[0] == '0')) return 0;
+  if (e && e[0] == 't') return 2;
+  return 1;
+}
+bool use_tc(int E, int F) { return texthead_mode(E, F) != 0; }
+struct TextheadLayout {
+  size_t act, scales, tok_hi, tok_lo, w_hi, w_lo, saved_total;     // saved
+  size_t g, gscale, g_hi, g_lo, ws_total;                          // workspace
+};
+TextheadLayout texthead_layout(int B, int L, int E, int F) {
+  TextheadLayout t{};
+  const size_t acts = sizeof(float) * kConvs * (size_t)B * L * F;
+  size_t o = 0;
+  t.act = o; o += align_up(acts, 256);
+  if (use_tc(E, F)) {
+    t.scales = o; o += 256;
+    t.tok_hi = o; o += align_up(2 * (size_t)B * L * E, 256);
+    t.tok_lo = o; o += align_up(2 * (size_t)B * L * E, 256);
+    t.w_hi = o; o += align_up(2 * (size_t)F * 9 * E, 256);          // K = 2 + 3 + 4 rows of E per feature
+    t.w_lo = o; o += align_up(2 * (size_t)F * 9 * E, 256);
+  }
+  t.saved_total = o;
+  o = 0;
+  t.g = o; o += align_up(acts, 256);
+  if (use_tc(E, F)) {
+    t.gscale = o; o += 256;
+    t.g_hi = o; o += align_up(2 * (size_t)kConvs * B * L * F, 256);
+    t.g_lo = o; o += align_up(2 * (size_t)kConvs * B * L * F, 256);
+  }
+  t.ws_total = o;
+  return t;
+}
+}  // namespace
+
+size_t texthead_saved_bytes(int B, int L, int E, int F) { return texthead_layout(B, L, E, F).saved_total; }
+size_t texthead_workspace_bytes(int B, int L, int E, int F) { return texthead_layout(B, L, E, F).ws_total; }
 
 static int check(int B, int L, int E, int F, int words_num) {
   TGFR_REQUIRE(B > 0 && E > 0 && F > 0, "texthead: empty shape");
@@ -179,17 +247,62 @@ static int check(int B, int L, int E, int F, int words_num) {
 int texthead_fwd(const float* tokens, const float* const* w, const float* const* bias, int B, int L, int E, int F,
                  int words_num, float* words, float* sent, void* saved, size_t saved_bytes, cudaStream_t st) {
   if (int rc = check(B, L, E, F, words_num)) return rc;
-  TGFR_REQUIRE(saved && saved_bytes >= texthead_saved_bytes(B, L, F), "texthead_fwd: saved buffer too small");
+  const TextheadLayout lay = texthead_layout(B, L, E, F);
+  TGFR_REQUIRE(saved && saved_bytes >= lay.saved_total, "texthead_fwd: saved buffer too small");
   const int seq = words_num - 4, T = seq + 2;
-  float* act = reinterpret_cast<float*>(saved);
+  uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
+  float* act = reinterpret_cast<float*>(sv + lay.act);
+  const bool tc = use_tc(E, F);
+  TGFR_REQUIRE(!tc || (reinterpret_cast<uintptr_t>(saved) & 255) == 0, "texthead_fwd: saved must be 256-byte aligned");
   Acts acts{};
+  Split3Product prods[kConvs];
+  const bool tc_fwd = texthead_mode(E, F) == 2;
+  if (tc) {
+    // fp16 hi / lo splits: the tokens (kept in `saved` for the backward) and the three weight tensors (one scale)
+    float* scales = reinterpret_cast<float*>(sv + lay.scales);
+    __half* tok_hi = reinterpret_cast<__half*>(sv + lay.tok_hi);
+    __half* tok_lo = reinterpret_cast<__half*>(sv + lay.tok_lo);
+    {
+      const float* src[1] = {tokens};
+      const int64_t ld[1] = {E};
+      const int rows[1] = {B * L}, cols[1] = {E}, ldo[1] = {E};
+      __half* hi[1] = {tok_hi};
+      __half* lo[1] = {tok_lo};
+      if (int rc = head_split_f16(1, src, ld, rows, cols, scales, hi, lo, ldo, st)) return rc;
+    }
+    const float* src[kConvs];
+    int64_t ld[kConvs];
+    int rows[kConvs], cols[kConvs], ldo[kConvs];
+    __half* hi[kConvs];
+    __half* lo[kConvs];
+    size_t off = 0;
+    for (int k = 0; k < kConvs; ++k) {
+      const int K = k + 2;
+      src[k] = w[k]; ld[k] = (int64_t)K * E; rows[k] = F; cols[k] = K * E; ldo[k] = K * E;
+      hi[k] = reinterpret_cast<__half*>(sv + lay.w_hi) + off;
+      lo[k] = reinterpret_cast<__half*>(sv + lay.w_lo) + off;
+      off += (size_t)F * K * E;
+    }
+    if (tc_fwd)
+      if (int rc = head_split_f16(kConvs, src, ld, rows, cols, scales + 2, hi, lo, ldo, st)) return rc;
+    for (int k = 0; k < kConvs; ++k) {
+      const int K = k + 2;
+      prods[k] = Split3Product{tok_hi, tok_lo, hi[k], lo[k], E, (int64_t)K * E, F, B * L - K + 1, F, K * E,
+                               act + (size_t)k * B * L * F, bias[k]};
+    }
+  }
   for (int k = 0; k < kConvs; ++k) {
     const int K = k + 2, rows = B * L - K + 1;          // every token position that still has K tokens after it
     float* a = act + (size_t)k * B * L * F;
     acts.a[k] = a;
     // the last K - 1 rows are never produced: keep them defined
     TGFR_CUDA_OK(cudaMemsetAsync(a + (size_t)rows * F, 0, sizeof(float) * (size_t)(K - 1) * F, st));
-    if (int rc = sgemm_strided(tokens, E, 1, w[k], 1, (int64_t)K * E, a, F, 1, rows, F, K * E, bias[k], 1, st)) return rc;
+    if (!tc_fwd)
+      if (int rc = sgemm_strided(tokens, E, 1, w[k], 1, (int64_t)K * E, a, F, 1, rows, F, K * E, bias[k], 1, st)) return rc;
+  }
+  if (tc_fwd) {   // act_K = relu(Win_K W_K^T + b_K): A = the overlapping token windows (K-major), B = W_K (K-major)
+    const float* scales = reinterpret_cast<const float*>(sv + lay.scales);
+    if (int rc = gemm_tc_split3_batched(prods, kConvs, 0, 1, 0, 0, 1.f, scales, scales + 2, 1, st)) return rc;
   }
   const int threads = F >= 256 ? 256 : ((F + 31) & ~31);
   texthead_combine_fwd_kernel<<<B, threads, 0, st>>>(acts, L, F, T, seq, words, sent);
@@ -201,12 +314,18 @@ int texthead_bwd(const float* tokens, const float* gwords, const float* gsent, i
                  float* const* dw, float* const* db, void* ws, size_t ws_bytes, const void* saved, size_t saved_bytes,
                  cudaStream_t st) {
   if (int rc = check(B, L, E, F, words_num)) return rc;
-  TGFR_REQUIRE(saved && saved_bytes >= texthead_saved_bytes(B, L, F), "texthead_bwd: saved buffer too small");
-  TGFR_REQUIRE(ws && ws_bytes >= texthead_workspace_bytes(B, L, F), "texthead_bwd: workspace too small");
+  const TextheadLayout lay = texthead_layout(B, L, E, F);
+  TGFR_REQUIRE(saved && saved_bytes >= lay.saved_total, "texthead_bwd: saved buffer too small");
+  TGFR_REQUIRE(ws && ws_bytes >= lay.ws_total, "texthead_bwd: workspace too small");
   const int seq = words_num - 4, T = seq + 2;
-  const float* act = reinterpret_cast<const float*>(saved);
-  float* G = reinterpret_cast<float*>(ws);
-  TGFR_CUDA_OK(cudaMemsetAsync(G, 0, texthead_workspace_bytes(B, L, F), st));
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  const float* act = reinterpret_cast<const float*>(sv + lay.act);
+  float* G = reinterpret_cast<float*>(wsb + lay.g);
+  const bool tc = use_tc(E, F);
+  TGFR_REQUIRE(!tc || ((reinterpret_cast<uintptr_t>(saved) | reinterpret_cast<uintptr_t>(ws)) & 255) == 0,
+               "texthead_bwd: saved / workspace must be 256-byte aligned");
+  TGFR_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(float) * kConvs * (size_t)B * L * F, st));
   Acts acts{};
   Grads gr{};
   for (int k = 0; k < kConvs; ++k) {
@@ -218,6 +337,31 @@ int texthead_bwd(const float* tokens, const float* gwords, const float* gsent, i
   const int threads = F >= 256 ? 256 : ((F + 31) & ~31);
   texthead_combine_bwd_kernel<<<B, threads, 0, st>>>(acts, L, F, T, seq, gwords, gsent, gr);
   TGFR_LAUNCH_OK();
+  if (tc) {
+    // dW_K [F, K E] = G_K^T . Win_K: A = G_K read MN-major, B = the overlapping token windows read MN-major
+    float* gscale = reinterpret_cast<float*>(wsb + lay.gscale);
+    __half* g_hi = reinterpret_cast<__half*>(wsb + lay.g_hi);
+    __half* g_lo = reinterpret_cast<__half*>(wsb + lay.g_lo);
+    {
+      const float* src[1] = {G};
+      const int64_t ld[1] = {F};
+      const int rows[1] = {kConvs * B * L}, cols[1] = {F}, ldo[1] = {F};
+      __half* hi[1] = {g_hi};
+      __half* lo[1] = {g_lo};
+      if (int rc = head_split_f16(1, src, ld, rows, cols, gscale, hi, lo, ldo, st)) return rc;
+    }
+    const __half* tok_hi = reinterpret_cast<const __half*>(sv + lay.tok_hi);
+    const __half* tok_lo = reinterpret_cast<const __half*>(sv + lay.tok_lo);
+    const float* scales = reinterpret_cast<const float*>(sv + lay.scales);
+    Split3Product prods[kConvs];
+    for (int k = 0; k < kConvs; ++k) {
+      const int K = k + 2;
+      const size_t goff = (size_t)k * B * L * F;
+      prods[k] = Split3Product{g_hi + goff, g_lo + goff, tok_hi, tok_lo, F, E, (int64_t)K * E, F, K * E, B * L - K + 1,
+                               dw[k], nullptr};
+    }
+    return gemm_tc_split3_batched(prods, kConvs, 1, 0, 1, 1, 1.f, gscale, scales, 0, st);
+  }
   for (int k = 0; k < kConvs; ++k) {
     const int K = k + 2, rows = B * L - K + 1;
     // dW_K [F, K E] = G_K^T [F, rows] . Win_K [rows, K E]

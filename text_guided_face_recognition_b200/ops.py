@@ -459,7 +459,7 @@ class _TextHeading(torch.autograd.Function):
         lib = _lib.load()
         words = torch.empty((B, words_num - 2, F), dtype=torch.float32, device=dev)
         sent = torch.empty((B, F), dtype=torch.float32, device=dev)
-        svb = lib.tgfr_texthead_saved_bytes(B, L, F)
+        svb = lib.tgfr_texthead_saved_bytes(B, L, E, F)
         saved = torch.empty(svb, dtype=torch.uint8, device=dev)
         ws_ = [w.contiguous() for w in (w2, w3, w4)]
         _call("tgfr_texthead_fwd", tokens.data_ptr(), ws_[0].data_ptr(), ws_[1].data_ptr(), ws_[2].data_ptr(),
@@ -483,7 +483,7 @@ class _TextHeading(torch.autograd.Function):
         dws = [torch.empty(s_, dtype=torch.float32, device=dev) for s_ in wshapes]
         dbs = [torch.empty(F, dtype=torch.float32, device=dev) for _ in range(3)]
         lib = _lib.load()
-        wsb = lib.tgfr_texthead_workspace_bytes(B, L, F)
+        wsb = lib.tgfr_texthead_workspace_bytes(B, L, E, F)
         ws = _workspace(wsb, dev)
         _call("tgfr_texthead_bwd", tokens.data_ptr(), ptr(gwords), ptr(gsent), B, L, E, F, words_num,
               dws[0].data_ptr(), dws[1].data_ptr(), dws[2].data_ptr(), dbs[0].data_ptr(), dbs[1].data_ptr(),
