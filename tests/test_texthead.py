@@ -121,11 +121,12 @@ def test_gpu_texthead_config2_size_vs_oracle_and_feeds_words_loss():
 
 
 @pytest.mark.gpu
-def test_gpu_texthead_all_tensor_core_mode(monkeypatch):
-    """TGFR_TEXTHEAD_PRECISION=tc (opt-in): forward products on tcgen05 with hi / lo split operands.  Outputs within 1e-5;
-    the gradient equals the oracle's except where the arg-max of a near-tied triple flipped: nearly every (feature, token
-    column) of dW is within 1e-4, and the whole within 1e-2."""
-    monkeypatch.setenv("TGFR_TEXTHEAD_PRECISION", "tc")
+@pytest.mark.parametrize("mode", ["tc", "mixed", "fp32"])
+def test_gpu_texthead_modes_at_config2_size(monkeypatch, mode):
+    """Every arithmetic mode of the products (TGFR_TEXTHEAD_PRECISION) meets the same bar at B = 128: outputs within
+    1e-5, weight / bias gradients within 1e-4 of the fp64 oracle.  In the all-tensor-core mode this needs the exact
+    re-evaluation of the near-tied activations: without it about two arg-max decisions in 720 k flip (dW off by 3e-3)."""
+    monkeypatch.setenv("TGFR_TEXTHEAD_PRECISION", mode)
     B, wn, F = 128, 24, 256
     th, tokens, ws, bs = _head(B, wn, F, 7)
     words, sent = th(torch.from_numpy(tokens).cuda(), None)
@@ -137,8 +138,5 @@ def test_gpu_texthead_all_tensor_core_mode(monkeypatch):
     ((words.transpose(1, 2) * torch.from_numpy(gw).cuda()).sum() + (sent * torch.from_numpy(gs).cuda()).sum()).backward()
     dws, dbs = TO.backward(tokens, ws, bs, wn, gw, gs)
     for k, conv in enumerate(th.bwm.convs1):
-        got = conv.weight.grad.squeeze(1).cpu().numpy().astype(np.float64).reshape(F, -1)
-        ref = np.asarray(dws[k]).reshape(F, -1)
-        per_feature = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
-        assert (per_feature > 1e-4).sum() <= 4, per_feature.max()          # a flip touches one feature of two convolutions
-        assert rel(got, ref) < 1e-2
+        assert rel(conv.weight.grad.squeeze(1).cpu().numpy(), dws[k]) < 1e-4
+        assert rel(conv.bias.grad.cpu().numpy(), dbs[k]) < 1e-4

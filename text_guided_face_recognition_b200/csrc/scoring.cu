@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
   for (int k = threadIdx.x; k < kTile; k += kThreads) {
     const int64_t i = base + k;
     const uint32_t d = i < n ? ((__ldg(keys + i) >> shift) & 255u) : 256u;
-    const uint32_t mask = __match_any_sync(0xffffffffu, d);
-    if (lane == __ffs(mask) - 1) atomicAdd(&h[d], (uint32_t)__popc(mask));
+    // scores of one sign share their top digits: one add per warp then; mixed digits go to (mostly) distinct counters
+    if (__all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0))) {
+      if (lane == 0) atomicAdd(&h[d], 32u);
+    } else {
+      atomicAdd(&h[d], 1u);
+    }
   }
   __syncthreads();
   hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];     // [digit][tile]

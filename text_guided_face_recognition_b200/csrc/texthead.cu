@@ -102,6 +102,85 @@ __global__ void texthead_combine_fwd_kernel(const Acts acts, int L, int F, int T
   for (int f = threadIdx.x; f < F; f += blockDim.x) sent[(int64_t)b * F + f] *= inv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// all-tensor-core forward: exact re-evaluation of the near-tied activations
+//
+// The split-operand tensor-core products are good to ~3e-6 (the tensor core truncates when it aligns its fp32
+// accumulator), the fp32 SIMT GEMM to ~5e-7.  Outputs do not care, the arg-max routing of the backward does: two
+// activations closer than the error can swap.  So every activation that is within kTieTol of the maximum it competes
+// for (the per-word max over the convolutions, the per-convolution max over the positions) is listed and recomputed
+// as a float64 dot product -- correctly rounded, i.e. the routing then follows the exact values more closely than
+// the SIMT GEMM's does.  About one activation in 10^4 is listed.
+// ---------------------------------------------------------------------------------------------
+constexpr float kTieTol = 4e-5f;
+constexpr uint32_t kTieCap = 1u << 16;
+
+struct TieList {
+  uint32_t* count;      // [1] entries wanted (may exceed kTieCap: the rest keeps its tensor-core value)
+  uint2* items;         // [kTieCap] (row, feature | conv << 24)
+};
+__device__ __forceinline__ void tie_push(const TieList& tl, int k, int64_t row, int f) {
+  const uint32_t at = atomicAdd(tl.count, 1u);
+  if (at < kTieCap) tl.items[at] = make_uint2((uint32_t)row, (uint32_t)f | ((uint32_t)k << 24));
+}
+__global__ void texthead_mark_ties_kernel(const Acts acts, int L, int F, int T, int seq, const TieList tl) {
+  const int b = blockIdx.x;
+  const int64_t row0 = (int64_t)b * L;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int t = 0; t <= seq; ++t) {                       // word t: max over the convolutions that reach position t
+      const int nk = t < seq ? 3 : 2;
+      float v[kConvs], top = -INFINITY;
+      for (int k = 0; k < nk; ++k) {
+        v[k] = acts.a[k][(row0 + t) * F + f];
+        top = fmaxf(top, v[k]);
+      }
+      if (top <= 0.f) continue;                            // relu: nothing flows through a zero maximum
+      const float tol = kTieTol * fmaxf(1.f, top);
+      int close = 0;
+      for (int k = 0; k < nk; ++k) close += (top - v[k] < tol);
+      if (close > 1)
+        for (int k = 0; k < nk; ++k)
+          if (top - v[k] < tol) tie_push(tl, k, row0 + t, f);
+    }
+    for (int k = 0; k < kConvs; ++k) {                     // sentence: max over the positions of convolution k
+      float top = -INFINITY;
+      for (int j = 0; j < L - 1 - k; ++j) top = fmaxf(top, acts.a[k][(row0 + j) * F + f]);
+      if (top <= 0.f) continue;
+      const float tol = kTieTol * fmaxf(1.f, top);
+      int close = 0;
+      for (int j = 0; j < L - 1 - k; ++j) close += (top - acts.a[k][(row0 + j) * F + f] < tol);
+      if (close > 1)
+        for (int j = 0; j < L - 1 - k; ++j)
+          if (top - acts.a[k][(row0 + j) * F + f] < tol) tie_push(tl, k, row0 + j, f);
+    }
+  }
+}
+struct RefineArgs {
+  const float* w[kConvs];
+  const float* bias[kConvs];
+  float* act[kConvs];
+};
+// a warp per listed activation: relu(b_K[f] + <tokens[row .. row + K), W_K[f]>) in float64
+__global__ void texthead_refine_ties_kernel(const TieList tl, const float* __restrict__ tokens, const RefineArgs ra, int E,
+                                            int F) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = min(*tl.count, kTieCap);
+  for (uint32_t it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n; it += gridDim.x * (blockDim.x >> 5)) {
+    const uint2 e = tl.items[it];
+    const int k = (int)(e.y >> 24), f = (int)(e.y & 0xffffffu), len = (k + 2) * E;
+    const float* x = tokens + (int64_t)e.x * E;
+    const float* wk = ra.w[k] + (int64_t)f * len;
+    double acc = 0.0;
+    for (int j = lane; j < len; j += 32) acc = fma((double)__ldg(x + j), (double)__ldg(wk + j), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (ra.bias[k]) acc += (double)__ldg(ra.bias[k] + f);
+      ra.act[k][(int64_t)e.x * F + f] = fmaxf((float)acc, 0.f);
+    }
+  }
+}
+
 __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T, int seq,
                                             const float* __restrict__ gwords, const float* __restrict__ gsent,
                                             const Grads out) {
@@ -189,24 +268,23 @@ __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T
 // saved: act_2 | act_3 | act_4, each [B L, F] fp32; tensor-core path adds [scales: tokens, weights | tokens hi | lo | W hi | W lo]
 // workspace (backward): G_2 | G_3 | G_4 fp32; tensor-core path adds [scale | G hi | G lo]
 namespace {
-// TGFR_TEXTHEAD_PRECISION = mixed (default) | tc | fp32.
-//   mixed: the forward products, whose outputs feed the discrete max routing, on the exact fp32 SIMT GEMM; the dW
-//          products (nothing discrete downstream) on tcgen05 with hi / lo split operands
-//   tc   : both on tcgen05.  The activations are then good to ~3e-6 instead of ~5e-7 (the tensor core truncates when
-//          it aligns the fp32 accumulator), which at B = 128 flips the arg-max of about two near-tied
-//          (caption, word, feature) triples in 720 k against the fp64 oracle -- a legitimate sub-gradient choice, but a
-//          1e-3-sized change of dW, so it is opt-in
+// TGFR_TEXTHEAD_PRECISION = tc (default) | mixed | fp32.
+//   tc   : all six products on tcgen05 with hi / lo split operands.  The activations are good to ~3e-6 (the tensor
+//          core truncates when it aligns its fp32 accumulator; the SIMT GEMM reaches ~5e-7), which on its own flips the
+//          arg-max of about two near-tied (caption, word, feature) triples in 720 k at B = 128 -- a 1e-3-sized change
+//          of dW -- so the near-tied activations are re-evaluated exactly (texthead_refine_ties_kernel)
+//   mixed: forward products on the exact fp32 SIMT GEMM, dW products on tcgen05
 //   fp32 : everything on the SIMT GEMM
 int texthead_mode(int E, int F) {      // 0 fp32, 1 mixed, 2 tc
   if ((E & 7) != 0 || (F & 7) != 0) return 0;
   const char* e = getenv("TGFR_TEXTHEAD_PRECISION");
   if (e && (e[0] == 'f' || e[0] == 's' || e[0] == '0')) return 0;
-  if (e && e[0] == 't') return 2;
-  return 1;
+  if (e && e[0] == 'm') return 1;
+  return 2;
 }
 bool use_tc(int E, int F) { return texthead_mode(E, F) != 0; }
 struct TextheadLayout {
-  size_t act, scales, tok_hi, tok_lo, w_hi, w_lo, saved_total;     // saved
+  size_t act, scales, tok_hi, tok_lo, w_hi, w_lo, ties, saved_total;   // saved
   size_t g, gscale, g_hi, g_lo, ws_total;                          // workspace
 };
 TextheadLayout texthead_layout(int B, int L, int E, int F) {
@@ -220,6 +298,7 @@ TextheadLayout texthead_layout(int B, int L, int E, int F) {
     t.tok_lo = o; o += align_up(2 * (size_t)B * L * E, 256);
     t.w_hi = o; o += align_up(2 * (size_t)F * 9 * E, 256);          // K = 2 + 3 + 4 rows of E per feature
     t.w_lo = o; o += align_up(2 * (size_t)F * 9 * E, 256);
+    t.ties = o; o += 256 + sizeof(uint2) * (size_t)kTieCap;         // count | items (forward scratch)
   }
   t.saved_total = o;
   o = 0;
@@ -303,6 +382,20 @@ int texthead_fwd(const float* tokens, const float* const* w, const float* const*
   if (tc_fwd) {   // act_K = relu(Win_K W_K^T + b_K): A = the overlapping token windows (K-major), B = W_K (K-major)
     const float* scales = reinterpret_cast<const float*>(sv + lay.scales);
     if (int rc = gemm_tc_split3_batched(prods, kConvs, 0, 1, 0, 0, 1.f, scales, scales + 2, 1, st)) return rc;
+    // near-tied activations again, exactly (see texthead_mark_ties_kernel)
+    TieList tl{reinterpret_cast<uint32_t*>(sv + lay.ties), reinterpret_cast<uint2*>(sv + lay.ties + 256)};
+    TGFR_CUDA_OK(cudaMemsetAsync(tl.count, 0, sizeof(uint32_t), st));
+    const int mthreads = F >= 256 ? 256 : ((F + 31) & ~31);
+    texthead_mark_ties_kernel<<<B, mthreads, 0, st>>>(acts, L, F, T, seq, tl);
+    TGFR_LAUNCH_OK();
+    RefineArgs ra{};
+    for (int k = 0; k < kConvs; ++k) {
+      ra.w[k] = w[k];
+      ra.bias[k] = bias[k];
+      ra.act[k] = act + (size_t)k * B * L * F;
+    }
+    texthead_refine_ties_kernel<<<296, 256, 0, st>>>(tl, tokens, ra, E, F);
+    TGFR_LAUNCH_OK();
   }
   const int threads = F >= 256 ? 256 : ((F + 31) & ~31);
   texthead_combine_fwd_kernel<<<B, threads, 0, st>>>(acts, L, F, T, seq, words, sent);

@@ -50,5 +50,12 @@ for _ in range(passes):
     th = TextHeading(ns(aux_feat_dim_per_granularity=D, bert_words_num=T + 2)).cuda()
     wo, so = th(torch.from_numpy(tok).cuda(), None)
     (wo.sum() + so.sum()).backward()
+    # verification scoring at configs[4]'s pair count: cosine, exact ROC, identification argmax
+    from text_guided_face_recognition_b200 import ops
+    NP, DF = 60000, 640
+    o1, o2 = torch.randn(NP, DF, device="cuda"), torch.randn(NP, DF, device="cuda")
+    sc = ops.pair_cosine(o1, o2)
+    ops.roc_counts(sc, (torch.arange(NP, device="cuda") % 10 == 0).long())
+    ops.row_argmax(sc.view(6000, 10))
 torch.cuda.synchronize()
 print("profile_step ok")
