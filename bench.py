@@ -66,8 +66,8 @@ def peaks():
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel, from the committed
-    `ncu --set full` summary of this round (profiles/r1_wr_tc_v2_ncu_raw.txt, same shapes as this bench)."""
-    path = os.path.join(ROOT, "profiles", "r1_wr_tc_v2_ncu_raw.txt")
+    `ncu --set full` summary of this round (profiles/r1_final_ncu_raw.txt, same shapes as this bench)."""
+    path = os.path.join(ROOT, "profiles", "r1_final_ncu_raw.txt")
     try:
         rd = wr = None
         hit = False
@@ -502,7 +502,7 @@ def run_b200(args):
             v["frac"] = v["achieved"] / pk["tf_burst"]
         line["roofline"] = {"bound": "tensor", "achieved": kernels[dom]["achieved"], "peak": pk["tf_burst"],
                             "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
-                            "traffic_source": "profiles/r1_wr_tc_v2_ncu_raw.txt (ncu --set full, same shapes)",
+                            "traffic_source": "profiles/r1_final_ncu_raw.txt (ncu --set full, same shapes)",
                             "kernel": dom, "kernel_ms": kernels[dom]["kernel_ms"],
                             "algorithmic_flops_per_launch": kernels[dom]["algorithmic_flops_per_launch"],
                             "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
@@ -670,7 +670,8 @@ def run_b200(args):
             "result": verif,
             "roofline": {"bound": "hbm", "kernel": "cosine_rows_vec_kernel", "achieved": cos_bytes / (cos_ms * 1e-3) / 1e9,
                          "peak": pk["hbm"], "unit": "GB/s", "frac": cos_bytes / (cos_ms * 1e-3) / 1e9 / pk["hbm"],
-                         "kernel_ms": cos_ms, "algorithmic_bytes_per_launch": cos_bytes, "traffic": None},
+                         "kernel_ms": cos_ms, "algorithmic_bytes_per_launch": cos_bytes,
+                         "traffic": ncu_traffic("cosine_rows_vec_kernel")},
             "roc": {"ms_60000": roc_ms, "ms_2p24": big_ms, "keys_per_sec_2p24": NS / (big_ms * 1e-3),
                     "algorithmic_bytes_per_key": roc_bytes_per_key,
                     "achieved_gbs_2p24": NS * roc_bytes_per_key / (big_ms * 1e-3) / 1e9,
