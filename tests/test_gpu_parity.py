@@ -376,6 +376,43 @@ def test_arc_fused_loss_vs_oracle(api, B, Din, C, gamma, easy):
     assert rel(head.weight.grad.cpu().numpy(), dw) < GRAD_RTOL
 
 
+def test_arc_fused_class_shards_on_one_gpu():
+    """The class-sharded fused head (distributed.ShardedArcMarginProduct.loss) emulated on one GPU: two shards of
+    1003 classes, their (row max, sum-exp, target logit) merged by hand.  Labels 502..511 belong to shard 1 but lie
+    inside the zero padding of shard 0's last 128-wide tile: shard 0 must not see a label column there."""
+    from text_guided_face_recognition_b200 import ops
+    B, Din, C = 64, 256, 1003
+    xn, wn, label = synth.margin_inputs(B, Din, C, seed=7)
+    label[:4] = [505, 511, 502, 501]
+    cuts = [0, 502, C]
+    x = torch.from_numpy(xn).cuda()
+    lab = torch.from_numpy(label).cuda()
+    stats = []
+    for k in range(2):                                   # pass 1: every shard's own statistics
+        w = torch.from_numpy(wn[cuts[k]:cuts[k + 1]]).cuda()
+        ops.arc_fused_focal(x, w, lab, 30.0, 0.5, False, 2.0, cuts[k],
+                            merge=lambda mx, sm, tg: (stats.append((mx.clone(), sm.clone(), tg.clone())), (mx, sm, tg))[1])
+
+    def merged(mx, sm, tg, other):
+        omx, osm, otg = other
+        g = torch.maximum(mx, omx)
+        return g, (sm * torch.exp(mx - g) + osm * torch.exp(omx - g)).contiguous(), (tg + otg).contiguous()
+    ref = O.arc_margin(xn, wn, label, 30.0, 0.5, False)
+    rl = O.focal_loss(ref, label, 2.0)
+    dx_ref, dw_ref = O.arc_margin_bwd(xn, wn, label, O.focal_loss_bwd(ref, label, 2.0), 30.0, 0.5, False)
+    dx = torch.zeros_like(x)
+    for k in range(2):                                   # pass 2: the global loss and this shard's gradients
+        xk = x.clone().requires_grad_(True)
+        w = torch.from_numpy(wn[cuts[k]:cuts[k + 1]]).cuda().requires_grad_(True)
+        loss = ops.arc_fused_focal(xk, w, lab, 30.0, 0.5, False, 2.0, cuts[k],
+                                   merge=lambda mx, sm, tg, o=stats[1 - k]: merged(mx, sm, tg, o))
+        assert abs(loss.item() - rl) < LOSS_RTOL * rl, (k, loss.item(), rl)
+        loss.backward()
+        assert rel(w.grad.cpu().numpy(), dw_ref[cuts[k]:cuts[k + 1]]) < GRAD_RTOL
+        dx += xk.grad
+    assert rel(dx.cpu().numpy(), dx_ref) < GRAD_RTOL
+
+
 @pytest.mark.parametrize("name", ["mag_small_easy", "mag_small_hard"])
 def test_mag_head_vs_golden(api, golden_dir, name, hprec):
     g = load(golden_dir, name)

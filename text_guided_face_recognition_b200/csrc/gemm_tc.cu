@@ -227,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
         for (int j = 0; j < 32; ++j) {
           const float c = __uint_as_float(v[j]);
           float l = c * p.alpha;
-          if ((int64_t)(c0 + j) == ycol) {
+          if ((int64_t)(c0 + j) == ycol && c0 + j < p.N) {   // a label of the NEXT class shard can fall into this tile's padding
             l = p.alpha * arc_phi_tc(c, p.ce.cm, p.ce.sm, p.ce.th, p.ce.mm, p.ce.easy, &dph);
             if constexpr (EPI == kEpiCeStats) {
               p.ce.cos_t[row] = c;

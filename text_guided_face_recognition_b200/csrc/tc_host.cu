@@ -22,6 +22,13 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const
                  uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes, uint64_t pitch_elems, bool overlap) {
   PFN_tgfr_encodeTiled enc = get_encode_tiled();
   if (!enc) return TGFR_E_CUDA;
+  // The encoder is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT (201) on a thread that has not touched the
+  // runtime yet -- e.g. autograd's backward thread when a tensor-map-building backward is the first one of the process.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    TGFR_CUDA_OK(cudaFree(nullptr));        // binds the device's primary context to this thread
+    ctx_bound = true;
+  }
   TGFR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base address must be 16-byte aligned");
   const uint64_t pitch = pitch_elems ? pitch_elems : d0;
   // overlap: rows may share memory (pitch < row length): the sliding n-gram windows of TextHeading
