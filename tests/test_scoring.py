@@ -62,6 +62,20 @@ def test_oracle_rejects_nan_scores():
         SO.roc_counts([0, 1], [0.5, float("nan")])
 
 
+def test_host_side_of_the_mirror_is_sklearn_arithmetic():
+    """utils/modules.py mirror, host half (no GPU): get_tpr picks the reference's point, the trapezoid AUC on the flipped
+    (decreasing) fpr equals sklearn.metrics.auc bit for bit."""
+    from sklearn import metrics as skm
+    from text_guided_face_recognition_b200.utils import modules
+    for name in CASES:
+        g = load(name)
+        fprs, tprs = np.flipud(g["fpr"]), np.flipud(g["tpr"])
+        np.testing.assert_array_equal(np.array(modules.get_tpr(fprs, tprs)), g["get_tpr"])
+        assert modules._area(fprs, tprs) == skm.auc(fprs, tprs) == float(g["auc"])
+    with pytest.raises(ValueError):
+        modules._area(np.array([0.0, 1.0, 0.5]), np.array([0.0, 1.0, 1.0]))
+
+
 def test_product_refuses_cpu():
     from text_guided_face_recognition_b200 import _lib, ops
     with pytest.raises((_lib.TgfrError, RuntimeError)):
