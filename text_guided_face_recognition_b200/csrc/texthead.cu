@@ -61,13 +61,15 @@ struct Grads {
   float* db[kConvs];                   // [F] (pre-zeroed)
 };
 
-// one block per caption b, thread f owns feature f (strided when F > blockDim)
+// grid (T + 1, B): block (t, b) builds word t of caption b, block (T, b) its sentence feature; thread f owns
+// feature f (strided when F > blockDim)
 __global__ void texthead_combine_fwd_kernel(const Acts acts, int L, int F, int T, int seq, float* __restrict__ words,
                                             float* __restrict__ sent) {
   __shared__ float scratch[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int64_t row0 = (int64_t)b * L;
-  for (int t = 0; t < T; ++t) {
+  if ((int)blockIdx.x < T) {
+    const int t = blockIdx.x;
     float ss = 0.f;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
       float v = acts.a[0][(row0 + t) * F + f];
@@ -83,6 +85,7 @@ __global__ void texthead_combine_fwd_kernel(const Acts acts, int L, int F, int T
       if (t < seq) v = fmaxf(v, acts.a[2][(row0 + t) * F + f]);
       words[((int64_t)b * T + t) * F + f] = v * inv;
     }
+    return;
   }
   // sentence feature: max over the positions of each convolution, mean of the three
   float ss = 0.f;
@@ -123,11 +126,14 @@ __device__ __forceinline__ void tie_push(const TieList& tl, int k, int64_t row, 
   const uint32_t at = atomicAdd(tl.count, 1u);
   if (at < kTieCap) tl.items[at] = make_uint2((uint32_t)row, (uint32_t)f | ((uint32_t)k << 24));
 }
+// grid (seq + 2, B): block (t <= seq, b) checks word t, block (seq + 1, b) the sentence maxima
 __global__ void texthead_mark_ties_kernel(const Acts acts, int L, int F, int T, int seq, const TieList tl) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int64_t row0 = (int64_t)b * L;
+  const bool sentence = (int)blockIdx.x == seq + 1;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    for (int t = 0; t <= seq; ++t) {                       // word t: max over the convolutions that reach position t
+    if (!sentence) {                                       // word t: max over the convolutions that reach position t
+      const int t = blockIdx.x;
       const int nk = t < seq ? 3 : 2;
       float v[kConvs], top = -INFINITY;
       for (int k = 0; k < nk; ++k) {
@@ -141,6 +147,7 @@ __global__ void texthead_mark_ties_kernel(const Acts acts, int L, int F, int T, 
       if (close > 1)
         for (int k = 0; k < nk; ++k)
           if (top - v[k] < tol) tie_push(tl, k, row0 + t, f);
+      continue;
     }
     for (int k = 0; k < kConvs; ++k) {                     // sentence: max over the positions of convolution k
       float top = -INFINITY;
@@ -184,11 +191,15 @@ __global__ void texthead_refine_ties_kernel(const TieList tl, const float* __res
 __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T, int seq,
                                             const float* __restrict__ gwords, const float* __restrict__ gsent,
                                             const Grads out) {
+  // grid (T, B): block (t < T - 1, b) routes the gradient of word t, block (T - 1, b) the sentence feature's.  The two
+  // can meet in one element of G_K: both add atomically into the zeroed buffer (two addends: the sum does not depend
+  // on the order).  The last word is detached in the reference (models.py:206) and has no block.
   __shared__ float scratch[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int64_t row0 = (int64_t)b * L;
-  if (gwords) {
-    for (int t = 0; t < T - 1; ++t) {      // the last word is detached in the reference (models.py:206)
+  if ((int)blockIdx.x < T - 1) {
+    if (gwords) {
+      const int t = blockIdx.x;
       float ss = 0.f, gd = 0.f;
       for (int f = threadIdx.x; f < F; f += blockDim.x) {
         float v = acts.a[0][(row0 + t) * F + f];
@@ -214,9 +225,10 @@ __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T
         for (int k = 0; k < ncand; ++k) nt += (a[k] == v);
         const float share = dv / (float)nt;                       // torch.amax: ties share the gradient evenly
         for (int k = 0; k < ncand; ++k)
-          if (a[k] == v && a[k] > 0.f) out.g[k][(row0 + t) * F + f] += share;   // ReLU mask
+          if (a[k] == v && a[k] > 0.f) atomicAdd(&out.g[k][(row0 + t) * F + f], share);   // ReLU mask
       }
     }
+    return;
   }
   if (gsent) {
     float ss = 0.f, gd = 0.f;
@@ -250,17 +262,20 @@ __global__ void texthead_combine_bwd_kernel(const Acts acts, int L, int F, int T
       const float g = gsent[(int64_t)b * F + f];
       const float dout = nrm > kNormEps ? (g - gd * o / (nrm * nrm)) / nrm : g / kNormEps;
       for (int k = 0; k < kConvs; ++k)
-        if (m[k] > 0.f) out.g[k][(row0 + jm[k]) * F + f] += dout * (1.f / 3.f);
+        if (m[k] > 0.f) atomicAdd(&out.g[k][(row0 + jm[k]) * F + f], dout * (1.f / 3.f));
     }
   }
-  // bias gradients: this caption's column sums (thread f is the only writer of column f within the block)
-  __syncthreads();
-  for (int f = threadIdx.x; f < F; f += blockDim.x)
-    for (int k = 0; k < kConvs; ++k) {
-      float s = 0.f;
-      for (int j = 0; j < L - 1 - k; ++j) s += out.g[k][(row0 + j) * F + f];
-      if (s != 0.f) atomicAdd(out.db[k] + f, s);
-    }
+}
+
+// bias gradients: the column sums of G_K, caption by caption (grid (kConvs, B), after the routing kernel)
+__global__ void texthead_bias_grad_kernel(const Grads out, int L, int F) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const int64_t row0 = (int64_t)b * L;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < L - 1 - k; ++j) s += out.g[k][(row0 + j) * F + f];
+    if (s != 0.f) atomicAdd(out.db[k] + f, s);
+  }
 }
 
 }  // namespace
@@ -386,7 +401,7 @@ int texthead_fwd(const float* tokens, const float* const* w, const float* const*
     TieList tl{reinterpret_cast<uint32_t*>(sv + lay.ties), reinterpret_cast<uint2*>(sv + lay.ties + 256)};
     TGFR_CUDA_OK(cudaMemsetAsync(tl.count, 0, sizeof(uint32_t), st));
     const int mthreads = F >= 256 ? 256 : ((F + 31) & ~31);
-    texthead_mark_ties_kernel<<<B, mthreads, 0, st>>>(acts, L, F, T, seq, tl);
+    texthead_mark_ties_kernel<<<dim3(seq + 2, B), mthreads, 0, st>>>(acts, L, F, T, seq, tl);
     TGFR_LAUNCH_OK();
     RefineArgs ra{};
     for (int k = 0; k < kConvs; ++k) {
@@ -398,7 +413,7 @@ int texthead_fwd(const float* tokens, const float* const* w, const float* const*
     TGFR_LAUNCH_OK();
   }
   const int threads = F >= 256 ? 256 : ((F + 31) & ~31);
-  texthead_combine_fwd_kernel<<<B, threads, 0, st>>>(acts, L, F, T, seq, words, sent);
+  texthead_combine_fwd_kernel<<<dim3(T + 1, B), threads, 0, st>>>(acts, L, F, T, seq, words, sent);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
@@ -428,7 +443,9 @@ int texthead_bwd(const float* tokens, const float* gwords, const float* gsent, i
     TGFR_CUDA_OK(cudaMemsetAsync(db[k], 0, sizeof(float) * F, st));
   }
   const int threads = F >= 256 ? 256 : ((F + 31) & ~31);
-  texthead_combine_bwd_kernel<<<B, threads, 0, st>>>(acts, L, F, T, seq, gwords, gsent, gr);
+  texthead_combine_bwd_kernel<<<dim3(T, B), threads, 0, st>>>(acts, L, F, T, seq, gwords, gsent, gr);
+  TGFR_LAUNCH_OK();
+  texthead_bias_grad_kernel<<<dim3(kConvs, B), threads, 0, st>>>(gr, L, F);
   TGFR_LAUNCH_OK();
   if (tc) {
     // dW_K [F, K E] = G_K^T . Win_K: A = G_K read MN-major, B = the overlapping token windows read MN-major
