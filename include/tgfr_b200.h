@@ -244,6 +244,23 @@ int tgfr_roc_curve(const float* scores, const int64_t* labels, int64_t N, int dr
 int tgfr_row_argmax(const float* scores, int64_t sr, int rows, int cols, int64_t* index, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * FCFM fusion net `Working`, eval-mode forward (models/fusion_nets.py:217-258): the fused
+ * 640-d embedding [ Linear(maxpool(LayerNorm(SelfAttention(image, text)))) | LayerNorm(gl_img) | LayerNorm(sent) ]
+ * that tgfr_pair_cosine scores.  img logical [B,256,14,14], word logical [B,256,T] (1 <= T <= 64), both through
+ * element strides; gl_img / sent [B,256] (row stride, unit element stride); out [B,640].  params_host: HOST array of
+ * tgfr_fcfm_working_num_params() = 26 device pointers, the module's state_dict in this order: conv.weight, conv.bias,
+ * bn_img.{weight,bias,running_mean,running_var}, projection.{weight,bias}, bn_word.{weight,bias,running_mean,
+ * running_var}, sa.query_proj.{weight,bias}, sa.key_proj.{weight,bias}, sa.value_proj.{weight,bias}, ln.{weight,bias},
+ * linear.{weight,bias}, ln_gl_image.{weight,bias}, ln_sent.{weight,bias} (all contiguous fp32).  BatchNorm uses the
+ * running statistics (the evaluation path of utils/modules.py:141-147); training mode is not provided.
+ * ------------------------------------------------------------------------------------------ */
+int tgfr_fcfm_working_num_params(void);
+int tgfr_fcfm_working_fwd(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw, const float* word,
+                          int64_t word_sb, int64_t word_sd, int64_t word_st, const float* gl_img, int64_t gl_sr,
+                          const float* sent, int64_t sent_sr, const float* const* params_host, int n_params, int B, int T,
+                          float* out, int64_t out_sr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-tests of the tcgen05 / TMA building blocks (used by tests/test_gpu_tc.py only).
  * tgfr_debug_umma: out[128,N] = A * B^T on one CTA with fp16 operands a (a_mn ? [K,128] : [128,K])
  * and b (b_mn ? [K,N] : [N,K]); manual_a stages A with the hand-written 128B swizzle.

@@ -21,3 +21,63 @@ def test_working_oracle_matches_reference(name):
     # the two LayerNorm'd pass-through blocks are exactly normalised rows (before the affine terms)
     tail = (out[:, 128:384] - params["ln_gl_image.bias"]) / params["ln_gl_image.weight"]
     np.testing.assert_allclose(tail.mean(1), 0.0, atol=1e-9)
+
+
+def _module_from_fixture(g):
+    import torch
+    from text_guided_face_recognition_b200.models.fusion_nets import Working
+    net = Working(channel_dim=256)
+    state = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p:")}
+    missing = net.load_state_dict(state, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith("num_batches_tracked") for k in missing.missing_keys)
+    return net.cuda().eval()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["small", "bert22"])
+def test_gpu_working_forward_matches_reference(name):
+    """The one-kernel eval forward (csrc/fcfm.cu through the models/fusion_nets.py mirror) against the reference's own
+    output and the fp64 oracle; image features in both memory layouts (contiguous and IMIM's channels-last)."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, f"fusion_working_{name}.npz"))
+    net = _module_from_fixture(g)
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    ref64 = FO.working_forward(params, g["img"], g["word"], g["gl_img"], g["sent"])
+    img = torch.from_numpy(g["img"]).cuda()
+    word = torch.from_numpy(g["word"]).cuda()
+    gl, sent = torch.from_numpy(g["gl_img"]).cuda(), torch.from_numpy(g["sent"]).cuda()
+    for im in (img, img.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)):
+        for wd in (word, word.transpose(1, 2).contiguous().transpose(1, 2)):
+            out = net(im, wd, gl, sent).cpu().numpy()
+            assert out.shape == (img.shape[0], 640)
+            np.testing.assert_allclose(out, g["out"], atol=1e-4, rtol=0)       # the reference (CPU fp32)
+            np.testing.assert_allclose(out, ref64, atol=1e-4, rtol=0)          # the fp64 oracle
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(img, word, gl, sent)
+
+
+@pytest.mark.gpu
+def test_gpu_working_batch_independence_and_scoring():
+    """Size-independent property at a batch that fills the GPU: every sample's embedding equals the one computed alone;
+    the fused embeddings feed the pair-cosine kernel directly (configs[4]: fusion -> cosine)."""
+    import torch
+    from text_guided_face_recognition_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "fusion_working_bert22.npz"))
+    net = _module_from_fixture(g)
+    gen = torch.Generator().manual_seed(9)
+    B, T = 600, 30
+    img = torch.nn.functional.normalize(torch.randn(B, 14, 14, 256, generator=gen), dim=-1).permute(0, 3, 1, 2).cuda()
+    word = torch.nn.functional.normalize(torch.randn(B, T, 256, generator=gen), dim=2).transpose(1, 2).cuda()
+    gl = torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=1).cuda()
+    sent = torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=1).cuda()
+    out = net(img, word, gl, sent)
+    assert torch.isfinite(out).all()
+    for i in (0, 299, 599):
+        one = net(img[i:i + 1], word[i:i + 1], gl[i:i + 1], sent[i:i + 1])
+        assert torch.equal(one[0], out[i])
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    ref = FO.working_forward(params, img[:4].cpu().numpy(), word[:4].cpu().numpy(), gl[:4].cpu().numpy(), sent[:4].cpu().numpy())
+    np.testing.assert_allclose(out[:4].cpu().numpy(), ref, atol=1e-4, rtol=0)
+    scores = ops.pair_cosine(out[:300], out[300:])
+    assert scores.shape == (300,) and bool((scores.abs() <= 1 + 1e-5).all())

@@ -60,6 +60,8 @@ SIGNATURES = {
     "tgfr_roc_workspace_bytes": (Z, [L]),
     "tgfr_roc_curve": (I, [P, P, L, I, P, P, P, P, P, Z, P]),
     "tgfr_row_argmax": (I, [P, L, I, I, P, P]),
+    "tgfr_fcfm_working_num_params": (I, []),
+    "tgfr_fcfm_working_fwd": (I, [P, L, L, L, L, P, L, L, L, P, L, P, L, P, I, I, I, P, L, P]),
     "tgfr_debug_umma": (I, [P, P, P, I, I, I, I, I, P]),
     "tgfr_debug_tma_reduce": (I, [P, I, I, P]),
     "tgfr_debug_umma_2cta": (I, [P, P, P, I, I, P]),

@@ -15,7 +15,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
     "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
-    "pair_cosine", "roc_counts", "row_argmax",
+    "pair_cosine", "roc_counts", "row_argmax", "fcfm_working",
 ]
 
 
@@ -638,4 +638,44 @@ def row_argmax(scores):
     out = torch.empty(rows, dtype=torch.int64, device=scores.device)
     with torch.cuda.device(scores.device):
         _call("tgfr_row_argmax", ptr(scores), scores.stride(0), rows, cols, ptr(out), stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# FCFM fusion net `Working`, eval-mode forward (models/fusion_nets.py:217-258)
+# ---------------------------------------------------------------------------------------------
+FCFM_PARAM_ORDER = (
+    "conv.weight", "conv.bias", "bn_img.weight", "bn_img.bias", "bn_img.running_mean", "bn_img.running_var",
+    "projection.weight", "projection.bias", "bn_word.weight", "bn_word.bias", "bn_word.running_mean", "bn_word.running_var",
+    "sa.query_proj.weight", "sa.query_proj.bias", "sa.key_proj.weight", "sa.key_proj.bias", "sa.value_proj.weight",
+    "sa.value_proj.bias", "ln.weight", "ln.bias", "linear.weight", "linear.bias", "ln_gl_image.weight", "ln_gl_image.bias",
+    "ln_sent.weight", "ln_sent.bias",
+)
+
+
+def fcfm_working(img, word, gl_img, sent, state):
+    """Working.forward in eval mode: img [B,256,14,14] (any strides), word [B,256,T], gl_img / sent [B,256] -> [B,640].
+    `state` maps the reference module's state_dict names (FCFM_PARAM_ORDER) to CUDA tensors.  No autograd."""
+    import ctypes
+    _lib.ensure_device(img.device)
+    if img.dim() != 4 or tuple(img.shape[1:]) != (256, 14, 14):
+        raise RuntimeError(f"fcfm_working: expected img [B,256,14,14], got {tuple(img.shape)}")
+    B = img.shape[0]
+    if word.dim() != 3 or word.shape[0] != B or word.shape[1] != 256:
+        raise RuntimeError(f"fcfm_working: expected word [B,256,T], got {tuple(word.shape)}")
+    if tuple(gl_img.shape) != (B, 256) or tuple(sent.shape) != (B, 256):
+        raise RuntimeError(f"fcfm_working: expected gl_img / sent [B,256], got {tuple(gl_img.shape)} / {tuple(sent.shape)}")
+    img, word = _f32(img.detach()), _f32(word.detach())
+    gl_img, sent = _f32(gl_img.detach()), _f32(sent.detach())
+    if gl_img.stride(1) != 1:
+        gl_img = gl_img.contiguous()
+    if sent.stride(1) != 1:
+        sent = sent.contiguous()
+    params = [_f32(state[name].detach()).contiguous() for name in FCFM_PARAM_ORDER]
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    out = torch.empty((B, 640), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _call("tgfr_fcfm_working_fwd", ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), ptr(word),
+              word.stride(0), word.stride(1), word.stride(2), ptr(gl_img), gl_img.stride(0), ptr(sent), sent.stride(0),
+              ctypes.cast(arr, ctypes.c_void_p), len(params), B, word.shape[2], ptr(out), out.stride(0), stream_ptr())
     return out
