@@ -10,14 +10,14 @@
 // One CTA per sample, everything after the convolution lives in shared memory (a sample's intermediate state is
 // 36 x 36 floats per tensor), one launch instead of the reference's ~25.  fp32 throughout: the embeddings feed
 // verification decisions.  The convolution is the only real work (12 MFLOP per sample): input channels are staged in
-// chunks of 16 (image rows + the matching 36 x 16 x 9 weights), a thread keeps 18 output pixels of one output channel
-// in registers, so a weight load feeds 18 FMAs.
+// chunks of 16 (image rows + the matching 36 x 16 x 9 weights), a thread keeps 9 output pixels of two output channels
+// in registers, so an image value feeds two FMAs and a weight nine (11 shared-memory loads per 18 FMAs).
 #include "common.cuh"
 
 namespace tgfr {
 namespace {
 
-constexpr int kFT = 288;                 // 36 output channels x 8 pixel groups of 18
+constexpr int kFT = 288;                 // 18 output-channel pairs x 16 pixel groups of 9
 constexpr int kC = 36, kHW = 36, kCin = 256, kChunk = 16, kPix = 196, kConvPix = 144, kMaxT = 64;
 constexpr float kEps = 1e-5f;            // BatchNorm2d / LayerNorm default eps
 
@@ -66,16 +66,18 @@ __global__ void __launch_bounds__(kFT) fcfm_working_fwd_kernel(const float* __re
   const int b = blockIdx.x;
 
   // ---- 1. conv3x3 (valid) + ReLU                                                       fusion_nets.py:235
+  // thread = (pair of output channels, group of 9 output pixels): an image value feeds two FMAs, a weight nine
   {
-    const int oc = tid >> 3, sub = tid & 7;
-    int off[18];
-    float acc[18];
-    const float bias = __ldg(P.p[P_CONV_B] + oc);
+    const int oc0 = (tid >> 4) * 2, sub = tid & 15;
+    int off[9];
+    float acc0[9], acc1[9];
+    const float bias0 = __ldg(P.p[P_CONV_B] + oc0), bias1 = __ldg(P.p[P_CONV_B] + oc0 + 1);
 #pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      const int p = sub * 18 + i;
+    for (int i = 0; i < 9; ++i) {
+      const int p = sub * 9 + i;
       off[i] = (p / 12) * 14 + (p % 12);
-      acc[i] = bias;
+      acc0[i] = bias0;
+      acc1[i] = bias1;
     }
     const float* ib = img + (int64_t)b * isb;
     for (int c0 = 0; c0 < kCin; c0 += kChunk) {
@@ -98,19 +100,27 @@ __global__ void __launch_bounds__(kFT) fcfm_working_fwd_kernel(const float* __re
       }
       __syncthreads();
       for (int ci = 0; ci < kChunk; ++ci) {
-        const float* wrow = s_w + (oc * kChunk + ci) * 9;
+        const float* w0 = s_w + (oc0 * kChunk + ci) * 9;
+        const float* w1 = w0 + kChunk * 9;
         const float* xin = s_in + ci * kPix;
 #pragma unroll
         for (int kk = 0; kk < 9; ++kk) {
-          const float wv = wrow[kk];
+          const float wv0 = w0[kk], wv1 = w1[kk];
           const int d = (kk / 3) * 14 + (kk % 3);
 #pragma unroll
-          for (int i = 0; i < 18; ++i) acc[i] = fmaf(wv, xin[off[i] + d], acc[i]);
+          for (int i = 0; i < 9; ++i) {
+            const float x = xin[off[i] + d];
+            acc0[i] = fmaf(wv0, x, acc0[i]);
+            acc1[i] = fmaf(wv1, x, acc1[i]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 18; ++i) s_conv[oc * kConvPix + sub * 18 + i] = fmaxf(acc[i], 0.f);
+    for (int i = 0; i < 9; ++i) {
+      s_conv[oc0 * kConvPix + sub * 9 + i] = fmaxf(acc0[i], 0.f);
+      s_conv[(oc0 + 1) * kConvPix + sub * 9 + i] = fmaxf(acc1[i], 0.f);
+    }
   }
   __syncthreads();
   // ---- maxpool2 + BatchNorm (eval)                                                     :235-236
