@@ -81,3 +81,21 @@ def working_forward(p, img, word, gl_img, sent):
     g = _layernorm(gl_img, p["ln_gl_image.weight"], p["ln_gl_image.bias"])                         # :255
     s = _layernorm(sent, p["ln_sent.weight"], p["ln_sent.bias"])                                   # :256
     return np.concatenate((iw, g, s), axis=1)                                                      # :257
+
+
+def imim_forward(p, img):
+    """IMIM.forward (reference models/models.py:380-405), eval mode: the producer of the
+    word-region loss's region features.  img [B,256,14,14] -> [B,256,14,14] logical, unit L2 norm over the channel axis
+    at every position (memory order of the reference's result: channels-last, models.py:401-404)."""
+    p = {k: np.asarray(v, np.float64) for k, v in p.items()}
+    x = _bn_eval(np.asarray(img, np.float64), p, "bn_img")                                     # :394
+    x = self_attention(p, x, x)                                                                  # :395 (scale = 1)
+    x = _layernorm(x, p["ln.weight"], p["ln.bias"])                                              # :396
+    conv1 = lambda t, n: np.einsum("bchw,oc->bohw", t, p[f"{n}.weight"][:, :, 0, 0]) + p[f"{n}.bias"][None, :, None, None]
+    x = np.maximum(conv1(x, "conv1x1_1"), 0.0)                                                   # :398
+    x = np.maximum(conv1(x, "conv1x1_2"), 0.0)                                                   # :399
+    x = x.transpose(0, 2, 3, 1)                                                                  # :401
+    x = x @ p["project_local.projection.weight"].T + p["project_local.projection.bias"]         # ProjectionHead :112
+    x = x / np.maximum(np.sqrt((x * x).sum(-1, keepdims=True)), 1e-12)                           # :119, then again :403
+    x = x / np.maximum(np.sqrt((x * x).sum(-1, keepdims=True)), 1e-12)
+    return x.transpose(0, 3, 1, 2)                                                               # :404

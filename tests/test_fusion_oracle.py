@@ -81,3 +81,15 @@ def test_gpu_working_batch_independence_and_scoring():
     np.testing.assert_allclose(out[:4].cpu().numpy(), ref, atol=1e-4, rtol=0)
     scores = ops.pair_cosine(out[:300], out[300:])
     assert scores.shape == (300,) and bool((scores.abs() <= 1 + 1e-5).all())
+
+
+def test_imim_oracle_matches_reference():
+    """IMIM (reference models/models.py:380-405), eval mode: the oracle against the reference
+    module's output.  Checker only -- no kernel of this row exists yet.  Also pins the data contract of SURVEY 8(a) row
+    a0: unit-norm region vectors, channels-last memory."""
+    g = np.load(os.path.join(GOLDEN, "imim_small.npz"))
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    out = FO.imim_forward(params, g["img"])
+    np.testing.assert_allclose(out, g["out"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(np.sqrt((out * out).sum(1)), 1.0, atol=1e-12)
+    assert tuple(g["out_strides"]) == (50176, 1, 3584, 256)
