@@ -85,6 +85,27 @@ def ncu_traffic(kernel_substr):
         return None
 
 
+HEAD_STEP_KERNELS = ("norm_f16_pair", "gemm_tc_kernel", "normalize_bwd_pair", "maxabs", "scale_to_f16", "arc_fix",
+                     "ce_merge_partials", "focal_finish", "head_")
+
+
+def ncu_traffic_sum(kernel_substrs, fname="r2_head_step_ncu_raw.txt"):
+    """Sum of dram read + write bytes over every launch of one head step whose kernel name contains one of the
+    substrings, from the committed `ncu --set full` capture of tools/head_step.py (None when absent)."""
+    path = os.path.join(ROOT, "profiles", fname)
+    try:
+        total, hit, seen = 0.0, False, False
+        for line in open(path):
+            if line.startswith("== "):
+                hit = any(k in line for k in kernel_substrs)
+            elif hit and (line.startswith("dram__bytes_read.sum =") or line.startswith("dram__bytes_write.sum =")):
+                total += float(line.split("=")[1]) * 1e6
+                seen = True
+        return total if seen else None
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """SM clock / throttle-reason sampler running during the timed region.
 
@@ -248,6 +269,179 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# one-shot parity of the exact code path that is timed (oracle = checker only), printed as "parity" in the line
+# ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def parity_check(world, rank, dev, precision):
+    """Sharded (N > 1: NCCL all-gather / statistic merge / reduce-scatter) or single-GPU losses against the fp64
+    oracle on the gathered batch.  Word-region + sentence loss at the config-4 caption length (T = 30 -> Tp = 32),
+    R = 196, D = 256, 6 faces/captions per rank; the class-sharded fused ArcFace head at config 3 (512 x 10 177,
+    global B = 512, the class remainder 10 177 mod N included).  Rank 0 evaluates the oracle; gradients of every
+    rank are gathered to it.  Returns the dict on rank 0 (None elsewhere); never raises on a mismatch -- the
+    verdict is in "ok"."""
+    import torch.distributed as dist
+    from oracle import fcam_oracle as O
+    from text_guided_face_recognition_b200 import _lib, ops
+    from text_guided_face_recognition_b200 import distributed as tdist
+    from text_guided_face_recognition_b200.models import metrics
+    Bp, Tp_, Rp_, Dp_ = 6, 30, R, D
+    Bg = Bp * world
+    ctx, words, _ = synth.wordregion_inputs(Bg, Tp_, Rp_, Dp_, "BERT", seed=31)
+    img, txt, cid = synth.sentence_inputs(Bg, Dp_, seed=31, collisions=True)
+    sl = slice(rank * Bp, (rank + 1) * Bp)
+    c = torch.from_numpy(ctx[sl]).to(dev).requires_grad_(True)
+    w = torch.from_numpy(words[sl]).to(dev).requires_grad_(True)
+    a = torch.from_numpy(img[sl]).to(dev).requires_grad_(True)
+    b = torch.from_numpy(txt[sl]).to(dev).requires_grad_(True)
+    ids = torch.from_numpy(cid[sl]).to(dev)
+    if world > 1:
+        l0, l1, _ = tdist.words_loss_sharded(c, w, None, *GAMMAS, precision=precision)
+        s0, s1 = tdist.sent_loss_sharded(a, b, ids, GAMMAS[2])
+    else:
+        sim, _ = ops.wordregion_sim(c, w, None, *GAMMAS, 1e-8, precision, False, 0)
+        l0, l1 = ops.pair_ce(sim)
+        s0, s1 = ops.pair_ce(ops.cosine_scores(a, b, GAMMAS[2], True, 1e-8, ids, ids))
+    (l0 + l1 + s0 + s1).backward()
+
+    def gather(t):
+        if world == 1:
+            return t.detach().cpu().numpy()
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t.detach().contiguous())
+        return out.cpu().numpy()
+    g_c, g_w, g_a, g_b = gather(c.grad), gather(w.grad), gather(a.grad), gather(b.grad)
+
+    # class-sharded fused head, config 3
+    h = HEAD
+    xn, wn, lab = synth.margin_inputs(h["B"], h["Din"], h["C"], seed=100)
+    Bl = h["B"] // world
+    hs = slice(rank * Bl, (rank + 1) * Bl)
+    hx = torch.from_numpy(xn[hs]).to(dev).requires_grad_(True)
+    hl = torch.from_numpy(lab[hs]).to(dev)
+    if world > 1:
+        head = tdist.ShardedArcMarginProduct(h["Din"], h["C"], s=h["s"], m=h["m"]).to(dev)
+        head.load_full_weight(torch.from_numpy(wn).to(dev))
+        hloss = head.loss(hx, hl, gamma=h["gamma"])
+        c0, c1 = head.c0, head.c1
+    else:
+        head = metrics.ArcMarginProduct(h["Din"], h["C"], s=h["s"], m=h["m"]).to(dev)
+        with torch.no_grad():
+            head.weight.copy_(torch.from_numpy(wn))
+        hloss = head.fused_loss(hx, hl, gamma=h["gamma"])
+        c0, c1 = 0, h["C"]
+    hloss.backward()
+    g_hx = gather(hx.grad)
+    rows = -(-h["C"] // world)
+    pad = torch.zeros(rows, h["Din"], device=dev)
+    pad[:c1 - c0] = head.weight.grad
+    g_hw = gather(pad)
+    bounds = gather(torch.tensor([[c0, c1]], device=dev, dtype=torch.int64))
+    if rank != 0:
+        return None
+    ltol, gtol = (2e-5, 1e-4) if precision == _lib.PREC_FP32 else (1e-4, 1e-3)
+    r0, r1, _, _ = O.words_loss(ctx, words, None, None, *GAMMAS)
+    q0, q1, _ = O.sent_loss(img, txt, None, cid, GAMMAS[2])
+    dctx, dwords = O.words_loss_grads(ctx, words, None, None, *GAMMAS)
+    dimg, dtxt = O.sent_loss_grads(img, txt, None, cid, GAMMAS[2])
+    ref_logits = O.arc_margin(xn, wn, lab, h["s"], h["m"], False)
+    ref_hloss = O.focal_loss(ref_logits, lab, h["gamma"])
+    dx_ref, dw_ref = O.arc_margin_bwd(xn, wn, lab, O.focal_loss_bwd(ref_logits, lab, h["gamma"]), h["s"], h["m"], False)
+    dw_got = np.concatenate([g_hw[r * rows:r * rows + int(bounds[r, 1] - bounds[r, 0])] for r in range(world)])
+    loss_err = {"words_loss0": abs(l0.item() - r0) / abs(r0), "words_loss1": abs(l1.item() - r1) / abs(r1),
+                "sent_loss0": abs(s0.item() - q0) / abs(q0), "sent_loss1": abs(s1.item() - q1) / abs(q1),
+                "head_loss": abs(hloss.item() - ref_hloss) / abs(ref_hloss)}
+    grad_err = {"d_ctx": _rel(g_c, dctx), "d_words": _rel(g_w, dwords), "d_img": _rel(g_a, dimg), "d_txt": _rel(g_b, dtxt),
+                "head_dx": _rel(g_hx, dx_ref), "head_dw": _rel(dw_got, dw_ref)}
+    ok = all(v < ltol for v in loss_err.values()) and all(v < gtol for v in grad_err.values())
+    return {"ok": bool(ok), "world": world, "checker": "oracle/fcam_oracle.py (fp64) on the gathered batch, rank 0",
+            "workload": f"words_loss+sent_loss: {Bp} faces/captions per rank (global {Bg}), T={Tp_}, R={Rp_}, D={Dp_}, "
+                        f"class-id collisions; class-sharded fused ArcFace+focal head {h['B']} x {h['C']} x {h['Din']} "
+                        f"(classes per rank {[int(bounds[r, 1] - bounds[r, 0]) for r in range(world)]})",
+            "loss_rel_err": loss_err, "grad_rel_err": grad_err, "tol": {"loss": ltol, "grad": gtol}}
+
+
+def time_step(fn, flush, reps, use_graph, world=1, dev=None):
+    """ms per call of `fn` (CUDA-graph replay when use_graph), L2 flushed before every call, CUDA events on the launch
+    stream, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    run = fn
+    if use_graph:
+        from text_guided_face_recognition_b200.graphs import GraphedStep
+        run = GraphedStep(fn)
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, run
+
+
+def head_roofline(ms, pk, traffic=None):
+    """Tensor and HBM fractions of one fused margin-head step (6 Din C flops per sample; fp32 bytes:
+    W read twice + dW written once + X / dX)."""
+    h = HEAD
+    flops = 6 * h["Din"] * h["C"] * h["B"]
+    nbytes = 3 * 4 * h["C"] * h["Din"] + 2 * 4 * h["B"] * h["Din"]
+    tf, gbs = flops / (ms * 1e-3) / 1e12, nbytes / (ms * 1e-3) / 1e9
+    ft, fh = tf / pk["tf_burst"], gbs / pk["hbm"]
+    return {"bound": "tensor" if ft >= fh else "hbm", "achieved": tf if ft >= fh else gbs,
+            "peak": pk["tf_burst"] if ft >= fh else pk["hbm"], "unit": "TFLOP/s" if ft >= fh else "GB/s",
+            "frac": max(ft, fh), "traffic": traffic,
+            "tensor": {"achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ft,
+                       "algorithmic_flops_per_step": flops},
+            "hbm": {"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": fh, "algorithmic_bytes_per_step": nbytes},
+            "note": "the whole step (all launches of fwd+bwd), not one kernel: the head is latency/launch bound at "
+                    "this size, so both fractions are reported"}
+
+
+def sharded_head_leg(world, rank, dev, use_graph, flush, reps):
+    """BASELINE configs[2] on N ranks: global B = 512 samples (512 / N per rank, all-gathered), 10 177 classes split by
+    class (partial FC), fused margin + softmax statistics in the GEMM epilogues, ONE all-gather of the (max, sum-exp,
+    target) rows, dX reduce-scattered.  Strong scaling: the total work is fixed."""
+    from text_guided_face_recognition_b200 import distributed as tdist
+    h = HEAD
+    xn, wn, lab = synth.margin_inputs(h["B"], h["Din"], h["C"], seed=100)
+    Bl = h["B"] // world
+    hs = slice(rank * Bl, (rank + 1) * Bl)
+    head = tdist.ShardedArcMarginProduct(h["Din"], h["C"], s=h["s"], m=h["m"]).to(dev)
+    head.load_full_weight(torch.from_numpy(wn).to(dev))
+    x = torch.from_numpy(xn[hs]).to(dev).requires_grad_(True)
+    labt = torch.from_numpy(lab[hs]).to(dev)
+
+    def step():
+        x.grad = None
+        head.weight.grad = None
+        head.loss(x, labt, gamma=h["gamma"]).backward()
+    ms, _ = time_step(step, flush, reps, use_graph, world, dev)
+    return {"metric": "arcface_focal_fwd_bwd_samples_per_sec", "value": h["B"] / (ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": ms, "scaling": "strong", "n_gpus": world,
+            "config": dict(h, classes_per_rank=head.c1 - head.c0, samples_per_rank=Bl),
+            "collectives": "all-gather X [512,512] + labels, all-gather of [3,512] softmax statistics, "
+                           "reduce-scatter dX [512,512]",
+            "launch": "CUDA graph replay (NCCL captured)" if use_graph else "eager"}
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -283,6 +477,14 @@ def run_b200(args):
                           for j, a in enumerate((ctx, words, img, txt))))
     labels = torch.arange(B, device=dev)
     cid_dev = torch.arange(B, device=dev) + rank * B       # distinct classes: mask path runs, nothing masked
+
+    # one-shot parity of the path about to be timed (all ranks take part; the verdict goes into the JSON line)
+    try:
+        parity = parity_check(world, rank, dev, precision)
+    except Exception as e:                                 # a crash of the checker must not lose the measurement
+        parity = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
+    barrier_early = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+    barrier_early()
 
     def step(c, w, a, b):
         for t in (c, w, a, b):
@@ -423,6 +625,13 @@ def run_b200(args):
     for st_ in sets:
         st_[1].requires_grad_(args.grads == "both")
 
+    # ---- class-sharded margin head on all ranks (N > 1): the head's own curve beside the contrastive step
+    sharded_head = None
+    if world > 1:
+        flush_all = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
+        sharded_head = sharded_head_leg(world, rank, dev, use_graph, flush_all, max(3, min(args.steps, 20)))
+        del flush_all
+
     line = {
         "metric": "fcam_words+sent_loss_fwd_bwd_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -437,7 +646,10 @@ def run_b200(args):
         "clocks": clk.result, "e2e": e2e, "gpu_launches": launches,
         "other_grads": {"grads": other, "value": pairs / (other_ms * 1e-3), "unit": "pairs/s", "ms_per_step": other_ms,
                         "steps": n_other},
+        "parity": parity,
     }
+    if sharded_head is not None:
+        line["margin_head_sharded"] = sharded_head
 
     if rank == 0:
         # ---- dominant kernel: word-region backward, timed alone with CUDA events on the launch stream
@@ -510,6 +722,14 @@ def run_b200(args):
                             "step_tflops": flops_per_pair(args.grads) * B * Bg / (ms * 1e-3) / 1e12,
                             "step_frac_of_peak": flops_per_pair(args.grads) * B * Bg / (ms * 1e-3) / 1e12 / pk["tf_sus"]}
 
+    if rank == 0 and world > 1:
+        # N > 1: the margin head of this line IS the class-sharded one (all ranks timed it above); whole-job peaks
+        pk = peaks()
+        sharded_head["roofline"] = head_roofline(sharded_head["ms_per_step"],
+                                                 dict(pk, tf_burst=pk["tf_burst"] * world, hbm=pk["hbm"] * world))
+        line["margin_head"] = sharded_head
+        print(json.dumps(line), flush=True)
+    if rank == 0 and world == 1:
         # ---- margin head (BASELINE configs[2]) reported beside the headline metric
         h = HEAD
         xn, wn, lab = synth.margin_inputs(h["B"], h["Din"], h["C"], seed=100)
@@ -574,6 +794,39 @@ def run_b200(args):
                                              "frac_of_tensor_peak": hflops / (hf_ms * 1e-3) / 1e12 / pk["tf_burst"],
                                              "what": "ArcMarginProduct.fused_loss: margin + online softmax + softmax "
                                                      "gradient in the tcgen05 GEMM epilogues, logits never written"}
+        line["margin_head"]["roofline"] = head_roofline(hf_ms, pk, ncu_traffic_sum(HEAD_STEP_KERNELS))
+        line["margin_head"]["roofline"]["step"] = "fused_loss"
+
+        # ---- MagFace head at the same size: MagLinear(512, 10177, scale=64) + MagLoss (two dense [B,C] logit tensors
+        # are part of the reference API, models/magface.py:69-136), fwd + bwd of loss + 35 loss_g
+        from text_guided_face_recognition_b200.models import magface
+        mx_np, mw_np, mlab_np = synth.margin_inputs(h["B"], h["Din"], h["C"], seed=100, mag=True)
+        mhead = magface.MagLinear(h["Din"], h["C"], scale=64.0, easy_margin=True).to(dev)
+        with torch.no_grad():
+            mhead.weight.copy_(torch.from_numpy(mw_np))
+        mcrit = magface.MagLoss(10.0, 110.0, 0.45, 0.8, 64.0)
+        mx = torch.from_numpy(mx_np * 4.0).to(dev).requires_grad_(True)
+        mlab = torch.from_numpy(mlab_np).to(dev)
+
+        def mag_step():
+            mx.grad = None
+            mhead.weight.grad = None
+            lg, xnorm = mhead(mx, lambda v: (0.8 - 0.45) / (110.0 - 10.0) * (v - 10.0) + 0.45, 10.0, 110.0)
+            ml, mg, _ = mcrit(lg, mlab, xnorm)
+            (ml + 35.0 * mg).backward()
+        mag_ms, _ = time_step(mag_step, flush, max(3, min(args.steps, 10)), use_graph)
+        mag_bytes = 3 * 4 * h["C"] * h["Din"] + 2 * 4 * h["B"] * h["Din"] + 7 * 4 * h["B"] * h["C"]
+        line["mag_head"] = {"metric": "magface_fwd_bwd_samples_per_sec", "value": h["B"] / (mag_ms * 1e-3),
+                            "unit": "samples/s", "ms_per_step": mag_ms,
+                            "config": {"B": h["B"], "Din": h["Din"], "C": h["C"], "scale": 64.0, "l_a": 10, "u_a": 110,
+                                       "l_margin": 0.45, "u_margin": 0.8, "easy_margin": True},
+                            "tflops": hflops / (mag_ms * 1e-3) / 1e12,
+                            "roofline": {"bound": "hbm", "achieved": mag_bytes / (mag_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                                         "unit": "GB/s", "frac": mag_bytes / (mag_ms * 1e-3) / 1e9 / pk["hbm"],
+                                         "algorithmic_bytes_per_step": mag_bytes,
+                                         "note": "dense API: cos / cos_m / one_hot written (3), cos + cos_m read by the CE "
+                                                 "(2), two dense gradients written (2) = 7 x 4BC bytes on top of W / dW / X"}}
+        del mhead, mx
 
         # ---- TextHeading (the BERT 768 -> 256 word / sentence projection of configs[1])
         import types as _types
@@ -757,12 +1010,14 @@ def run_b200(args):
                 gx.grad = gwt.grad = None
                 P.arc_focal_port(gx, gwt, gl, h["s"], h["m"], h["gamma"])[1].backward()
             torch.cuda.synchronize()
-            e0.record()
+            eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eh0.record()
             for _ in range(10):
                 gx.grad = gwt.grad = None
                 P.arc_focal_port(gx, gwt, gl, h["s"], h["m"], h["gamma"])[1].backward()
-            e1.record()
+            eh1.record()
             torch.cuda.synchronize()
+            head_ref_gpu_ms = eh0.elapsed_time(eh1) / 10          # read out before any other event is re-recorded
             # TextHeading through the port on this GPU (the reference's B x T Python loop of stack / amax calls)
             tws = [torch.from_numpy(w_).unsqueeze(1).to(dev).requires_grad_(True) for w_ in tw]
             tbs = [torch.from_numpy(b_).to(dev).requires_grad_(True) for b_ in tb]
@@ -783,8 +1038,12 @@ def run_b200(args):
                                                         "ms_per_step": e0.elapsed_time(e1) / 2, "kind": "port"}
             line["margin_head"]["cpu_baseline"] = {"value": h["B"] / h_cpu, "unit": "samples/s", "kind": "port",
                                                    "cores": torch.get_num_threads(), "sample": f"{n_h} full steps"}
-            line["margin_head"]["reference_on_gpu"] = {"value": h["B"] / (e0.elapsed_time(e1) / 10 * 1e-3),
-                                                       "unit": "samples/s", "kind": "port", "dtype": "f32 (TF32 off)"}
+            line["margin_head"]["reference_on_gpu"] = {"value": h["B"] / (head_ref_gpu_ms * 1e-3), "unit": "samples/s",
+                                                       "ms_per_step": head_ref_gpu_ms, "kind": "port",
+                                                       "dtype": "f32 (TF32 off)",
+                                                       "what": "oracle/ref_port.py arc_focal_port (the reference's op "
+                                                               "sequence: normalize, linear, one_hot blend, CE) on this "
+                                                               "B200, eager, 10 steps"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # release the captured graphs before the communicator goes away, then leave without the NCCL teardown

@@ -202,6 +202,27 @@ int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt
 int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse,
                      const float* coef, const float* gout, int B, int C, int class_off,
                      float* glogits, int64_t g_sr, void* stream);
+/* cosine_similarity(x1, x2, dim=1, eps) of models/losses.py:12-16 for [N, D] rows (element strides sr / sd):
+ * out[n] = sum(x1 x2) / max(|x1| |x2|, eps); stats [N, 3] = (sum(x1 x2), |x1|, |x2|) is what the backward reads.
+ * dx1 / dx2 are contiguous [N, D] (either may be NULL). */
+int tgfr_cosine_rows_fwd(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr,
+                         int64_t x2_sd, int64_t N, int D, float eps, float* out, float* stats, void* stream);
+int tgfr_cosine_rows_bwd(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr,
+                         int64_t x2_sd, int64_t N, int D, float eps, const float* stats, const float* gout,
+                         float* dx1, float* dx2, void* stream);
+/* Cross-shard merge of online-softmax statistics after one all-gather: gathered [n][K][M] holds
+ * every shard's (max, sum exp(. - max)[, target logit]) rows (K = 2 or 3); out [K][M] = (global max, rescaled
+ * sum[, sum of the target logits -- non-owners hold 0]). */
+int tgfr_merge_softmax_stats(const float* gathered, int n, int K, int M, float* out, void* stream);
+/* MagLoss (models/magface.py:131-135): the blended logits output[b,c] = (c == label_b) ? cos_m[b,c] : cos_s[b,c]
+ * are never materialised -- the online-softmax row statistics read the two logit tensors (row stride sr) directly;
+ * one_hot [B,C] (the tensor the reference returns; NULL = skip) is written in the same pass.  Finish with
+ * tgfr_focal_finish(gamma = 0).  The backward writes both dense gradients: g_cos is zero on the label column,
+ * g_cosm is zero off it (contiguous [B,C]); gout is a DEVICE scalar (NULL = 1). */
+int tgfr_mag_ce_stats(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, int B, int C,
+                      float* rowmax, float* rowsum, float* tgt, float* one_hot, void* stream);
+int tgfr_mag_ce_bwd(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, const float* lse,
+                    const float* gout, int B, int C, float* g_cos, float* g_cosm, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * TextHeading (models/models.py:170-232): BERT tokens [B, L = bert_words_num - 1, E]

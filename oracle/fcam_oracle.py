@@ -101,6 +101,31 @@ def func_attention_bwd(query, context, gamma1, g_wc, g_attn):
 # --------------------------------------------------------------------------------------
 # word-region similarity matrix  (reference: models/losses.py:73-114, 122)
 # --------------------------------------------------------------------------------------
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """models/losses.py:12-16: sum(x1*x2, dim) / clamp(|x1|*|x2|, min=eps), squeezed."""
+    x1, x2 = np.asarray(x1, dtype=np.float64), np.asarray(x2, dtype=np.float64)
+    w12 = np.sum(x1 * x2, axis=dim)
+    w1 = np.sqrt(np.sum(x1 * x1, axis=dim))
+    w2 = np.sqrt(np.sum(x2 * x2, axis=dim))
+    return np.squeeze(w12 / np.maximum(w1 * w2, eps))
+
+
+def cosine_similarity_bwd(x1, x2, g, dim=1, eps=1e-8):
+    """(dx1, dx2) for an upstream gradient g of the un-squeezed result (the clamp passes no gradient below eps)."""
+    x1, x2 = np.asarray(x1, dtype=np.float64), np.asarray(x2, dtype=np.float64)
+    g = np.expand_dims(np.asarray(g, dtype=np.float64).reshape(np.sum(x1 * x2, axis=dim).shape), dim)
+    w12 = np.sum(x1 * x2, axis=dim, keepdims=True)
+    w1 = np.sqrt(np.sum(x1 * x1, axis=dim, keepdims=True))
+    w2 = np.sqrt(np.sum(x2 * x2, axis=dim, keepdims=True))
+    prod = w1 * w2
+    live = prod > eps
+    inv = 1.0 / np.maximum(prod, eps)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k1 = np.where(live & (w1 > 0), w12 * inv / (w1 * w1), 0.0)
+        k2 = np.where(live & (w2 > 0), w12 * inv / (w2 * w2), 0.0)
+    return g * (x2 * inv - k1 * x1), g * (x1 * inv - k2 * x2)
+
+
 def _lens(cap_lens, Bq, T):
     if cap_lens is None:
         return [T] * Bq
@@ -289,6 +314,11 @@ def global_loss(x, y, eps=1e-8, temp3=10.0):
     """loss0 + loss1, labels = arange   (losses.py:329-351)."""
     l0, l1, _ = sent_loss(x, y, None, None, temp3, eps)
     return l0 + l1
+
+
+def global_loss_grads(x, y, eps=1e-8, temp3=10.0):
+    """(dx, dy) of global_loss."""
+    return sent_loss_grads(x, y, None, None, temp3, 1.0, 1.0, eps)
 
 
 def clip_loss(text, image, logit_scale=1.0):

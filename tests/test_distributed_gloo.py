@@ -76,7 +76,13 @@ def _case_column_stats_and_pair_ce(rank):
     blk = scores[rank * Bl:(rank + 1) * Bl]      # this rank's row block [Bl, B]
     cmax = np.max(blk, axis=0)
     csum = np.sum(np.exp(blk - cmax), axis=0)
-    gmax, gsum = D.merge_column_stats(torch.from_numpy(cmax), torch.from_numpy(csum))
+    # the exchange is ONE all-gather of every rank's [2, B] statistics (distributed.gather_stats); the merge
+    # arithmetic is a CUDA kernel in the product (tgfr_merge_softmax_stats) and restated here in numpy
+    g = D.gather_stats([torch.from_numpy(cmax), torch.from_numpy(csum)]).numpy()          # [WORLD, 2, B]
+    assert g.shape == (WORLD, 2, B) and np.array_equal(g[rank, 0], cmax)
+    gm = g[:, 0].max(axis=0)
+    gmax = torch.from_numpy(gm)
+    gsum = torch.from_numpy((g[:, 1] * np.exp(g[:, 0] - gm)).sum(axis=0))
     full_max = np.max(scores, axis=0)
     full_sum = np.sum(np.exp(scores - full_max), axis=0)
     assert np.allclose(gmax.numpy(), full_max) and np.allclose(gsum.numpy(), full_sum, rtol=1e-12)
@@ -106,12 +112,11 @@ def _case_class_sharded_softmax(rank):
     rowmax = torch.from_numpy(shard.max(1))
     rowsum = torch.from_numpy(np.exp(shard - shard.max(1, keepdims=True)).sum(1))
     tgt = torch.tensor([shard[b, labels[b] - c0] if c0 <= labels[b] < c1 else 0.0 for b in range(B)])
-    # the exchange _FocalCESharded performs: all-reduce(max), then all-reduce(sum) of rescaled sums + targets
-    gmax = rowmax.clone()
-    dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
-    pack = torch.stack([rowsum * torch.exp(rowmax - gmax), tgt])
-    dist.all_reduce(pack)
-    ce = (gmax + torch.log(pack[0]) - pack[1]).mean().item()
+    # the exchange the class-sharded head performs: ONE all-gather of (max, sum-exp, target) per rank
+    g = D.gather_stats([rowmax, rowsum, tgt.double()])                                    # [WORLD, 3, B]
+    gmax = g[:, 0].max(dim=0).values
+    gsum = (g[:, 1] * torch.exp(g[:, 0] - gmax)).sum(dim=0)
+    ce = (gmax + torch.log(gsum) - g[:, 2].sum(dim=0)).mean().item()
     m = logits.max(1, keepdims=True)
     want = np.mean(m[:, 0] + np.log(np.exp(logits - m).sum(1)) - logits[np.arange(B), labels])
     assert abs(ce - want) < 1e-12 * abs(want)
@@ -128,15 +133,30 @@ def _case_allreduce_gradients(rank):
         p = torch.nn.Parameter(torch.zeros_like(t, dtype=torch.float32 if k != 2 else torch.float64))
         p.grad = (t * (rank + 1)).to(p.dtype)             # rank r contributes (r + 1) * base
         params.append(p)
-    params.append(torch.nn.Parameter(torch.zeros(3)))     # no gradient: skipped
+    # a parameter whose gradient exists on rank 1 only (an unused branch on rank 0): rank 0 contributes zeros and
+    # receives the sum -- the flat buffers have one layout on every rank (the old code packed
+    # `[p.grad for p in params if p.grad is not None]` per rank and hung / mis-added here)
+    lone = torch.nn.Parameter(torch.zeros(3))
+    if rank == 1:
+        lone.grad = torch.tensor([1.0, 2.0, 3.0])
+    params.insert(1, lone)
+    frozen = torch.nn.Parameter(torch.zeros(4), requires_grad=False)      # frozen: never touched
+    params.append(frozen)
     nb = D.allreduce_gradients(params, bucket_bytes=300_000)
     assert nb >= 3                                        # two dtypes, and the fp32 gradients exceed one bucket
-    for p, t in zip(params, base):
+    for p, t in zip([q for q in params if q is not lone and q is not frozen], base):
         assert torch.allclose(p.grad.double(), 3.0 * t, rtol=1e-6, atol=1e-6)
-    assert params[-1].grad is None
+    assert torch.equal(lone.grad, torch.tensor([1.0, 2.0, 3.0])) and frozen.grad is None
     D.allreduce_gradients(params, average=True)
-    for p, t in zip(params, base):
+    for p, t in zip([q for q in params if q is not lone and q is not frozen], base):
         assert torch.allclose(p.grad.double(), 3.0 * t, rtol=1e-6, atol=1e-6)   # mean of two equal tensors
+    # ranks that disagree on the parameter set raise instead of reducing mismatched buffers
+    extra = params + ([torch.nn.Parameter(torch.zeros(2))] if rank == 0 else [])
+    try:
+        D.allreduce_gradients(extra)
+        raise AssertionError("membership mismatch not detected")
+    except RuntimeError as e:
+        assert "disagree" in str(e)
 
 
 @pytest.mark.parametrize("case", ["_case_all_gather_rows", "_case_column_stats_and_pair_ce",

@@ -508,3 +508,76 @@ def test_fcam_losses_overlapped_matches_sequential_calls():
     assert abs(out.item() - ref) <= 1e-6 * abs(ref)
     for g, t in zip(ref_grads, leaves):
         assert torch.allclose(t.grad, g, rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: exported cosine_similarity, MagFace at BASELINE config 3 (rows a9 / a10)
+# ------------------------------------------------------------------------------------------------
+def test_cosine_similarity_vs_golden(api, golden_dir):
+    """models/losses.py:12-16 through tgfr_cosine_rows_fwd/bwd: zero rows, rows below the eps clamp, gradients."""
+    g = load(golden_dir, "cosine_small")
+    a = torch.from_numpy(g["x1"]).cuda().requires_grad_(True)
+    b = torch.from_numpy(g["x2"]).cuda().requires_grad_(True)
+    out = api.losses.cosine_similarity(a, b)
+    assert tuple(out.shape) == g["out"].shape
+    assert np.max(np.abs(out.detach().cpu().numpy() - g["out"])) < 1e-6
+    out.backward(torch.from_numpy(g["g"]).cuda())
+    assert rel(a.grad.cpu().numpy(), g["dx1"]) < FP32_GRAD_RTOL
+    assert rel(b.grad.cpu().numpy(), g["dx2"]) < FP32_GRAD_RTOL
+    # the call shape of words_loss (losses.py:99-104): [B*T, D] views of transposed tensors, dim=1 reduced
+    rs = np.random.RandomState(3)
+    w = rs.randn(6, 32, 5).astype(np.float32)
+    c = rs.randn(6, 32, 5).astype(np.float32)
+    wt = torch.from_numpy(w).cuda().transpose(1, 2).contiguous().view(30, 32)
+    ct = torch.from_numpy(c).cuda().transpose(1, 2).contiguous().view(30, 32)
+    got = api.losses.cosine_similarity(wt, ct).cpu().numpy()
+    ref = O.cosine_similarity(w.transpose(0, 2, 1).reshape(30, 32), c.transpose(0, 2, 1).reshape(30, 32))
+    assert np.max(np.abs(got - ref)) < 1e-6
+    # another reduced dimension and the trailing squeeze
+    x3 = torch.from_numpy(w).cuda()
+    got3 = api.losses.cosine_similarity(x3, torch.from_numpy(c).cuda(), dim=2)
+    assert np.max(np.abs(got3.cpu().numpy() - O.cosine_similarity(w, c, dim=2))) < 1e-6
+    one = api.losses.cosine_similarity(x3[:1, :, :1], torch.from_numpy(c).cuda()[:1, :, :1])
+    assert one.dim() == 0
+
+
+def test_mag_head_config3_vs_golden_and_oracle(api, golden_dir, hprec):
+    """MagLinear(512, 10177, scale=64) + MagLoss(10, 110, 0.45, 0.8), B = 512: the reference's own numbers
+    (tests/golden/mag_config3.npz) and the fp64 oracle for the full logits."""
+    g = load(golden_dir, "mag_config3")
+    B, Din, C = int(g["B"]), int(g["Din"]), int(g["C"])
+    l_a, u_a, l_m, u_m, scale = (float(g[k]) for k in ("l_a", "u_a", "l_margin", "u_margin", "scale"))
+    xn, wn, label = synth.margin_inputs(B, Din, C, seed=100, mag=True)
+    xn = xn * 4.0
+    head = api.magface.MagLinear(Din, C, scale=scale, easy_margin=True).cuda()
+    with torch.no_grad():
+        head.weight.copy_(torch.from_numpy(wn))
+    crit = api.magface.MagLoss(l_a, u_a, l_m, u_m, scale)
+    x = torch.from_numpy(xn).cuda().requires_grad_(True)
+    lab = torch.from_numpy(label).cuda()
+    logits, x_norm = head(x, lambda v: (u_m - l_m) / (u_a - l_a) * (v - l_a) + l_m, l_a, u_a)
+    (rc, rm), rxn = O.mag_linear(xn, wn, l_a, u_a, l_m, u_m, scale, True)
+    # |logit| <= scale = 64: the tc bound is scale * 2e-4 * sqrt-ish; fp32 SIMT is exact to round-off
+    tol = 4 * hprec.logit if hprec.tc else 2e-4
+    got_c, got_m = logits[0].detach().cpu().numpy(), logits[1].detach().cpu().numpy()
+    assert np.max(np.abs(got_c - rc)) < tol
+    # easy_margin switches at cos = 0 (magface.py:98): within the arithmetic's resolution of the threshold either
+    # branch is a correct rounding of the input, so cos_theta_m is compared away from it (everywhere in fp32 mode
+    # except the few elements closer to 0 than fp32 round-off)
+    clear = np.abs(rc) > (scale * 1e-3 if hprec.tc else scale * 1e-6)
+    assert clear.mean() > 0.97 and np.max(np.abs(got_m - rm)[clear]) < 2 * tol
+    assert np.max(np.abs(got_c[:8] - g["cos_head"])) < tol
+    assert argmax_matches(got_m, rm, 4 * tol if hprec.tc else 1e-3)
+    assert rel(x_norm.detach().cpu().numpy(), g["x_norm"]) < 1e-6
+    loss, loss_g, one_hot = crit(logits, lab, x_norm)
+    assert abs(loss.item() - float(g["loss"])) < hprec.loss * float(g["loss"])
+    assert abs(loss_g.item() - float(g["loss_g"])) < FP32_LOSS_RTOL * float(g["loss_g"])
+    oh = one_hot.cpu().numpy()
+    assert oh.sum() == float(g["one_hot_sum"]) and np.array_equal(oh.argmax(1), label) and oh.max() == 1.0
+    (loss + float(g["lam_g"]) * loss_g).backward()
+    assert rel(x.grad.cpu().numpy(), g["dx"]) < hprec.grad
+    dw = head.weight.grad.cpu().numpy()
+    assert rel(dw[:, :64], g["dweight_head"]) < hprec.grad
+    assert abs(np.linalg.norm(dw.astype(np.float64)) - float(g["dweight_norm"])) < hprec.grad * float(g["dweight_norm"])
+    _, dw_ref = O.mag_head_grads(xn, wn, label, l_a, u_a, l_m, u_m, scale, True, 1.0, float(g["lam_g"]))
+    assert rel(dw, dw_ref) < hprec.grad

@@ -199,3 +199,43 @@ def test_tc_backward_words_vs_oracle(B, T, R, D, flavour, ragged, bwd_mode):
         if both:
             errc = np.linalg.norm(feats.grad.cpu().numpy() - rc) / np.linalg.norm(rc)
             assert errc < TC_GRAD_RTOL, errc
+
+
+# ------------------------------------------------------------------------------------------------
+# gradient parity on the exact instances bench.py times: BASELINE config 2
+# (B=128, T=22 -> Tp=24, R=196, D=256; 148 persistent CTAs, CTA pairs, TMA reduce-add ordering) and the
+# config-4 caption length (T=30 -> Tp=32).  The fp64 oracle runs once per session (~2 min at B=128).
+# ------------------------------------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def _oracle_grads(B, T, R, D, seed):
+    key = (B, T, R, D, seed)
+    if key not in _ORACLE_CACHE:
+        ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=seed)
+        _ORACLE_CACHE[key] = (ctx, words) + tuple(O.words_loss_grads(ctx, words, None, None, 4.0, 5.0, 10.0))
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("B,T", [(128, 22), (32, 30), (48, 30)])
+@pytest.mark.parametrize("grads", ["ctx", "both"])
+def test_tc_grads_benchmarked_instances_vs_oracle(B, T, grads, bwd_mode):
+    from text_guided_face_recognition_b200 import _lib, ops
+    R, D = 196, 256
+    ctx, words, rc, rw = _oracle_grads(B, T, R, D, 100)
+    feats = torch.from_numpy(ctx).cuda().requires_grad_(True)
+    wd = torch.from_numpy(words).cuda().requires_grad_(grads == "both")
+    sim, _ = ops.wordregion_sim(feats, wd, None, 4.0, 5.0, 10.0, precision=_lib.PREC_TC, want_attn=False)
+    l0, l1 = ops.pair_ce(sim)
+    (l0 + l1).backward()
+    torch.cuda.synchronize()
+    got = feats.grad.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.linalg.norm(got - rc) / np.linalg.norm(rc)
+    assert err < TC_GRAD_RTOL, err
+    worst = max(np.linalg.norm(got[b] - rc[b]) / np.linalg.norm(rc[b]) for b in range(B))
+    assert worst < 2 * TC_GRAD_RTOL, worst
+    if grads == "both":
+        gw = wd.grad.cpu().numpy()
+        errw = np.linalg.norm(gw - rw) / np.linalg.norm(rw)
+        assert errw < TC_GRAD_RTOL, errw

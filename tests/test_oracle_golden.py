@@ -169,3 +169,64 @@ def test_ref_port_matches_golden(golden_dir):
     out, loss = P.arc_focal_port(x, torch.from_numpy(h["weight"]), torch.from_numpy(h["label"]), float(h["s"]),
                                  float(h["m"]), float(h["gamma"]), bool(h["easy"]))
     assert np.max(np.abs(out.numpy() - h["logits"])) < 1e-5 and abs(loss.item() - float(h["loss"])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 fixtures (tests/golden/make_golden_r2.py)
+# ------------------------------------------------------------------------------------------------
+def test_cosine_similarity(golden_dir):
+    g = load(golden_dir, "cosine_small")
+    out = O.cosine_similarity(g["x1"], g["x2"])
+    assert np.max(np.abs(out - g["out"])) < 1e-6
+    d1, d2 = O.cosine_similarity_bwd(g["x1"], g["x2"], g["g"])
+    assert rel(d1, g["dx1"]) < RTOL_GRAD and rel(d2, g["dx2"]) < RTOL_GRAD
+
+
+def test_mag_head_config3(golden_dir):
+    """MagLinear(512, 10177) + MagLoss, B = 512 (BASELINE configs[2]) as the reference computes it."""
+    g = load(golden_dir, "mag_config3")
+    B, Din, C = int(g["B"]), int(g["Din"]), int(g["C"])
+    x, w, label = synth.margin_inputs(B, Din, C, seed=100, mag=True)
+    x = x * 4.0
+    kw = dict(l_a=float(g["l_a"]), u_a=float(g["u_a"]), l_margin=float(g["l_margin"]),
+              u_margin=float(g["u_margin"]), scale=float(g["scale"]), easy_margin=True)
+    (cos, cos_m), xn = O.mag_linear(x, w, **kw)
+    assert np.max(np.abs(cos[:8] - g["cos_head"])) < 5e-5 and np.max(np.abs(cos_m[:8] - g["cos_m_head"])) < 5e-5
+    loss, loss_g, one_hot = O.mag_loss((cos, cos_m), label, xn, kw["u_a"])
+    assert abs(loss - float(g["loss"])) < RTOL_LOSS * abs(loss)
+    assert abs(loss_g - float(g["loss_g"])) < RTOL_LOSS * abs(loss_g)
+    assert one_hot.sum() == float(g["one_hot_sum"])
+    dx, dw = O.mag_head_grads(x, w, label, g_loss=1.0, g_lossg=float(g["lam_g"]), **kw)
+    assert rel(dx, g["dx"]) < RTOL_GRAD
+    assert rel(dw[:, :64], g["dweight_head"]) < RTOL_GRAD
+    assert abs(np.linalg.norm(dw) - float(g["dweight_norm"])) < 1e-5 * float(g["dweight_norm"])
+
+
+def test_train_block_composition(golden_dir):
+    """The reference's Train.train loss block (src/train_encoders_bert.py:267-323) equals the oracle's composition
+    words_loss + sent_loss + lambda_id (focal(arc(sent)) + focal(arc(img))) + lambda_clip global_loss."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_r2 import train_block_inputs
+    g = load(golden_dir, "train_block_bert")
+    B, T, D, C = int(g["B"]), int(g["T"]), int(g["D"]), int(g["C"])
+    ctx, words, img, txt, cid, w_img, w_txt = train_block_inputs(B, T, D, C)
+    w0, w1, _, _ = O.words_loss(ctx, words, None, None, 4.0, 5.0, 10.0)
+    s0, s1, _ = O.sent_loss(img, txt, None, cid, 10.0)
+    t_logits = O.arc_margin(txt, w_txt, cid, 35.0, 0.5, False)
+    i_logits = O.arc_margin(img, w_img, cid, 30.0, 0.5, False)
+    tid, iid = O.focal_loss(t_logits, cid, 2.0), O.focal_loss(i_logits, cid, 2.0)
+    cl = O.global_loss(img, txt)
+    total = w0 + w1 + s0 + s1 + 100 * (tid + iid) + 2.0 * cl
+    assert abs(total - float(g["total_loss"])) < 5e-6 * abs(total)
+    assert abs((w0 + w1) - float(g["w_total"])) < 5e-6 * (w0 + w1)
+    dctx, _ = O.words_loss_grads(ctx, words, None, None, 4.0, 5.0, 10.0)
+    got = g["d_words_features"].transpose(0, 2, 3, 1).reshape(B, 196, D)
+    assert rel(got, dctx) < RTOL_GRAD
+    dimg_s, _ = O.sent_loss_grads(img, txt, None, cid, 10.0)
+    dimg_i, dw_i = O.arc_margin_bwd(img, w_img, cid, O.focal_loss_bwd(i_logits, cid, 2.0, 100.0), 30.0, 0.5, False)
+    _, dw_t = O.arc_margin_bwd(txt, w_txt, cid, O.focal_loss_bwd(t_logits, cid, 2.0, 100.0), 35.0, 0.5, False)
+    assert rel(dw_i, g["d_image_cls"]) < RTOL_GRAD and rel(dw_t, g["d_text_cls"]) < RTOL_GRAD
+    dimg_c = O.global_loss_grads(img, txt)[0] if hasattr(O, "global_loss_grads") else None
+    if dimg_c is not None:
+        assert rel(dimg_s + dimg_i + 2.0 * dimg_c, g["d_img_features"]) < RTOL_GRAD

@@ -52,6 +52,11 @@ SIGNATURES = {
     "tgfr_ce_rows_stats": (I, [P, L, P, I, I, I, P, P, P, P]),
     "tgfr_focal_finish": (I, [P, P, P, I, F, P, P, P]),
     "tgfr_ce_rows_bwd": (I, [P, L, P, P, P, P, I, I, I, P, L, P]),
+    "tgfr_cosine_rows_fwd": (I, [P, L, L, P, L, L, L, I, F, P, P, P]),
+    "tgfr_cosine_rows_bwd": (I, [P, L, L, P, L, L, L, I, F, P, P, P, P, P]),
+    "tgfr_merge_softmax_stats": (I, [P, I, I, I, P, P]),
+    "tgfr_mag_ce_stats": (I, [P, P, L, P, I, I, P, P, P, P, P]),
+    "tgfr_mag_ce_bwd": (I, [P, P, L, P, P, P, I, I, P, P, P]),
     "tgfr_texthead_saved_bytes": (Z, [I, I, I, I]),
     "tgfr_texthead_workspace_bytes": (Z, [I, I, I, I]),
     "tgfr_texthead_fwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, Z, P]),
@@ -112,6 +117,11 @@ def ensure_device(device):
             f"tensor on {device}: text_guided_face_recognition_b200 runs on CUDA (sm_100a) only; "
             "there is no CPU fallback")
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream (stream_ptr); a tensor that lives elsewhere would be
+        # read through a foreign context.  nn.DataParallel's replica threads and torch.cuda.device(...) set this right.
+        raise TgfrError(f"tensor on cuda:{idx} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                        "wrap the call in `with torch.cuda.device(tensor.device)`")
     if idx in _checked_devices:
         return
     with torch.cuda.device(idx):

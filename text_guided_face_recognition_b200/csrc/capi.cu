@@ -68,6 +68,15 @@ int ce_rows_stats(const float*, int64_t, const int64_t*, int, int, int, float*, 
 int focal_finish(const float*, const float*, const float*, int, float, float*, float*, cudaStream_t);
 int ce_rows_bwd(const float*, int64_t, const int64_t*, const float*, const float*, const float*, int, int, int,
                 float*, int64_t, cudaStream_t);
+int cosine_rows_ref_fwd(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float, float*,
+                        float*, cudaStream_t);
+int cosine_rows_ref_bwd(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float,
+                        const float*, const float*, float*, float*, cudaStream_t);
+int merge_softmax_stats(const float*, int, int, int, float*, cudaStream_t);
+int mag_ce_stats(const float*, const float*, int64_t, const int64_t*, int, int, float*, float*, float*, float*,
+                 cudaStream_t);
+int mag_ce_bwd(const float*, const float*, int64_t, const int64_t*, const float*, const float*, int, int, float*,
+               float*, cudaStream_t);
 
 // texthead.cu
 size_t texthead_saved_bytes(int, int, int, int);
@@ -288,6 +297,27 @@ int tgfr_focal_finish(const float* rowmax, const float* rowsum, const float* tgt
 int tgfr_ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const float* lse, const float* coef,
                      const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, void* stream) {
   return ce_rows_bwd(logits, sr, labels, lse, coef, gout, B, C, class_off, glogits, g_sr, ST(stream));
+}
+int tgfr_cosine_rows_fwd(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd,
+                         int64_t N, int D, float eps, float* out, float* stats, void* stream) {
+  TGFR_REQUIRE(N >= 0 && D >= 1, "cosine_rows: bad shape N=%lld D=%d", (long long)N, D);
+  return cosine_rows_ref_fwd(x1, x1_sr, x1_sd, x2, x2_sr, x2_sd, N, D, eps, out, stats, ST(stream));
+}
+int tgfr_cosine_rows_bwd(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd,
+                         int64_t N, int D, float eps, const float* stats, const float* gout, float* dx1, float* dx2,
+                         void* stream) {
+  return cosine_rows_ref_bwd(x1, x1_sr, x1_sd, x2, x2_sr, x2_sd, N, D, eps, stats, gout, dx1, dx2, ST(stream));
+}
+int tgfr_merge_softmax_stats(const float* gathered, int n, int K, int M, float* out, void* stream) {
+  return merge_softmax_stats(gathered, n, K, M, out, ST(stream));
+}
+int tgfr_mag_ce_stats(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, int B, int C,
+                      float* rowmax, float* rowsum, float* tgt, float* one_hot, void* stream) {
+  return mag_ce_stats(cos_s, cos_m, sr, labels, B, C, rowmax, rowsum, tgt, one_hot, ST(stream));
+}
+int tgfr_mag_ce_bwd(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, const float* lse,
+                    const float* gout, int B, int C, float* g_cos, float* g_cosm, void* stream) {
+  return mag_ce_bwd(cos_s, cos_m, sr, labels, lse, gout, B, C, g_cos, g_cosm, ST(stream));
 }
 
 int tgfr_pair_cosine(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd, int64_t N,

@@ -381,6 +381,128 @@ __global__ void ce_rows_bwd_kernel(const float* __restrict__ lg, int64_t sr, con
 }
 
 // --------------------------------------------------------------------------------------------
+// cosine_similarity(x1, x2, dim=1, eps) of models/losses.py:12-16: sum(x1 x2) / max(|x1| |x2|, eps), one warp per row;
+// stats[row] = (w12, |x1|, |x2|) for the backward.  (The pair-scoring kernel of scoring.cu clamps each norm
+// separately, like nn.CosineSimilarity; this one clamps the product, like the reference's free function.)
+// --------------------------------------------------------------------------------------------
+__global__ void cosine_rows_ref_fwd_kernel(const float* __restrict__ x1, int64_t s1r, int64_t s1d,
+                                           const float* __restrict__ x2, int64_t s2r, int64_t s2d, int64_t n, int D,
+                                           float eps, float* __restrict__ out, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* a = x1 + row * s1r;
+  const float* b = x2 + row * s2r;
+  float w12 = 0.f, w1 = 0.f, w2 = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float u = a[(int64_t)d * s1d], v = b[(int64_t)d * s2d];
+    w12 = fmaf(u, v, w12);
+    w1 = fmaf(u, u, w1);
+    w2 = fmaf(v, v, w2);
+  }
+  w12 = warp_sum(w12);
+  w1 = sqrtf(warp_sum(w1));
+  w2 = sqrtf(warp_sum(w2));
+  if (lane == 0) {
+    out[row] = w12 / fmaxf(w1 * w2, eps);
+    stats[3 * row + 0] = w12;
+    stats[3 * row + 1] = w1;
+    stats[3 * row + 2] = w2;
+  }
+}
+
+__global__ void cosine_rows_ref_bwd_kernel(const float* __restrict__ x1, int64_t s1r, int64_t s1d,
+                                           const float* __restrict__ x2, int64_t s2r, int64_t s2d, int64_t n, int D,
+                                           float eps, const float* __restrict__ stats, const float* __restrict__ g,
+                                           float* __restrict__ d1, float* __restrict__ d2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float w12 = stats[3 * row], w1 = stats[3 * row + 1], w2 = stats[3 * row + 2], go = g[row];
+  const float prod = w1 * w2;
+  const bool live = prod > eps;                    // clamp(min=eps) passes no gradient to the norms below eps
+  const float inv = 1.f / fmaxf(prod, eps);
+  // d/dx1 = g (x2 inv - [live] w12 inv x1 / w1^2),  symmetric in x2
+  const float k1 = (live && w1 > 0.f) ? w12 * inv / (w1 * w1) : 0.f;
+  const float k2 = (live && w2 > 0.f) ? w12 * inv / (w2 * w2) : 0.f;
+  const float* a = x1 + row * s1r;
+  const float* b = x2 + row * s2r;
+  for (int d = lane; d < D; d += 32) {
+    const float u = a[(int64_t)d * s1d], v = b[(int64_t)d * s2d];
+    if (d1) d1[row * D + d] = go * (v * inv - k1 * u);
+    if (d2) d2[row * D + d] = go * (u * inv - k2 * v);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// merge of per-shard online-softmax statistics after ONE all-gather: in [n][K][M] with K = 2 (max, sum-exp) or
+// 3 (+ a value that is simply summed: the target logit, owned by one shard) -> out [K][M]
+// --------------------------------------------------------------------------------------------
+__global__ void merge_softmax_stats_kernel(const float* __restrict__ in, int n, int K, int M, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  float gmax = -INFINITY;
+  for (int r = 0; r < n; ++r) gmax = fmaxf(gmax, in[((int64_t)r * K) * M + j]);
+  float gsum = 0.f, gt = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float m = in[((int64_t)r * K) * M + j], sm = in[((int64_t)r * K + 1) * M + j];
+    gsum += (sm == 0.f) ? 0.f : sm * expf(m - gmax);
+    if (K > 2) gt += in[((int64_t)r * K + 2) * M + j];
+  }
+  out[j] = gmax;
+  out[M + j] = gsum;
+  if (K > 2) out[2 * M + j] = gt;
+}
+
+// --------------------------------------------------------------------------------------------
+// MagLoss blend + cross entropy (magface.py:131-135): output[b,c] = (c == label_b) ? cos_m[b,c] : cos[b,c]
+// is never materialised -- the row statistics read the two logit tensors directly and, as a by-product,
+// write the one_hot [B,C] tensor the reference returns.
+// --------------------------------------------------------------------------------------------
+__global__ void mag_ce_stats_kernel(const float* __restrict__ lc, const float* __restrict__ lm, int64_t sr,
+                                    const int64_t* __restrict__ labels, int C, float* __restrict__ rowmax,
+                                    float* __restrict__ rowsum, float* __restrict__ tgt, float* __restrict__ one_hot) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float* pc = lc + (int64_t)b * sr;
+  const float* pm = lm + (int64_t)b * sr;
+  const int64_t y = labels[b];
+  float m = -INFINITY, s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = (c == y) ? pm[c] : pc[c];
+    if (one_hot) one_hot[(int64_t)b * C + c] = (c == y) ? 1.f : 0.f;
+    if (v > m) { s = s * expf(m - v) + 1.f; m = v; }
+    else       { s += expf(v - m); }
+  }
+  const float bm = block_max(m, scratch);
+  const float bmm = (bm == -INFINITY) ? 0.f : bm;
+  s = (m == -INFINITY) ? 0.f : s * expf(m - bmm);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) {
+    rowmax[b] = bmm;
+    rowsum[b] = s;
+    tgt[b] = (y >= 0 && y < C) ? pm[y] : 0.f;
+  }
+}
+
+// g_cos[b,c] = k (p - 0) off the label column, 0 on it; g_cosm[b,c] = k (p - 1) on the label column, 0 elsewhere
+__global__ void mag_ce_bwd_kernel(const float* __restrict__ lc, const float* __restrict__ lm, int64_t sr,
+                                  const int64_t* __restrict__ labels, const float* __restrict__ lse,
+                                  const float* __restrict__ gout, int B, int C, float* __restrict__ g_cos,
+                                  float* __restrict__ g_cosm) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float k = (gout ? *gout : 1.f) / (float)B;
+  const bool on = (int64_t)c == labels[b];
+  const int64_t o = (int64_t)b * sr + c;
+  const float v = on ? lm[o] : lc[o];
+  const float g = k * (expf(v - lse[b]) - (on ? 1.f : 0.f));
+  g_cos[(int64_t)b * C + c] = on ? 0.f : g;
+  g_cosm[(int64_t)b * C + c] = on ? g : 0.f;
+}
+
+// --------------------------------------------------------------------------------------------
 // ArcFace margin on the label column (metrics.py:45-57) and its backward correction
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ float arc_phi(float c, float cm, float sm, float th, float mm, int easy, float* dphi) {
@@ -850,6 +972,45 @@ int ce_rows_bwd(const float* logits, int64_t sr, const int64_t* labels, const fl
                 const float* gout, int B, int C, int class_off, float* glogits, int64_t g_sr, cudaStream_t st) {
   ce_rows_bwd_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, st>>>(logits, sr, labels, lse, coef, gout, B, C, class_off,
                                                                 glogits, g_sr);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int mag_ce_stats(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, int B, int C, float* rowmax,
+                 float* rowsum, float* tgt, float* one_hot, cudaStream_t st) {
+  TGFR_REQUIRE(B > 0 && C > 0, "mag_ce_stats: empty shape");
+  mag_ce_stats_kernel<<<B, 256, 0, st>>>(cos_s, cos_m, sr, labels, C, rowmax, rowsum, tgt, one_hot);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int mag_ce_bwd(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, const float* lse,
+               const float* gout, int B, int C, float* g_cos, float* g_cosm, cudaStream_t st) {
+  mag_ce_bwd_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, st>>>(cos_s, cos_m, sr, labels, lse, gout, B, C, g_cos, g_cosm);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int cosine_rows_ref_fwd(const float* x1, int64_t s1r, int64_t s1d, const float* x2, int64_t s2r, int64_t s2d, int64_t n,
+                        int D, float eps, float* out, float* stats, cudaStream_t st) {
+  if (n == 0) return TGFR_OK;
+  cosine_rows_ref_fwd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x1, s1r, s1d, x2, s2r, s2d, n, D, eps, out, stats);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int cosine_rows_ref_bwd(const float* x1, int64_t s1r, int64_t s1d, const float* x2, int64_t s2r, int64_t s2d, int64_t n,
+                        int D, float eps, const float* stats, const float* g, float* d1, float* d2, cudaStream_t st) {
+  if (n == 0) return TGFR_OK;
+  cosine_rows_ref_bwd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x1, s1r, s1d, x2, s2r, s2d, n, D, eps, stats, g, d1,
+                                                                     d2);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+int merge_softmax_stats(const float* in, int n, int K, int M, float* out, cudaStream_t st) {
+  TGFR_REQUIRE(n >= 1 && (K == 2 || K == 3) && M >= 1, "merge_softmax_stats: bad shape n=%d K=%d M=%d", n, K, M);
+  merge_softmax_stats_kernel<<<ceil_div(M, 256), 256, 0, st>>>(in, n, K, M, out);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }

@@ -30,7 +30,7 @@ from . import _lib, ops
 from ._lib import ptr, stream_ptr
 
 __all__ = [
-    "all_gather_rows", "merge_column_stats", "class_range", "words_loss_sharded", "sent_loss_sharded",
+    "all_gather_rows", "gather_stats", "merge_column_stats", "class_range", "words_loss_sharded", "sent_loss_sharded",
     "ShardedArcMarginProduct", "sharded_focal_ce", "allreduce_gradients", "gather_ragged", "score_pairs_sharded",
 ]
 
@@ -75,18 +75,33 @@ def all_gather_rows(x, group=None):
         return _AllGatherRows.apply(x, group)
 
 
+def gather_stats(rows, group=None):
+    """The exchange of the statistic merge: every rank contributes K rows [M]; returns [n, K, M] (rank-major).
+    Device agnostic (unit-tested with gloo); the arithmetic of the merge is `_merge_stats`' CUDA kernel."""
+    n, _ = _world(group)
+    K, M = len(rows), rows[0].shape[0]
+    mine = torch.stack(rows).contiguous()                            # [K, M]
+    gathered = torch.empty((n * K, M), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    return gathered.view(n, K, M)
+
+
+def _merge_stats(rows, group):
+    """rows: list of K (2 or 3) [M] fp32 CUDA tensors (max, sum-exp[, summed value]) of this shard -> the K merged
+    [M] tensors.  ONE all-gather of [K, M] per rank, then one merge kernel -- not an all-reduce(max) followed by an
+    all-reduce(sum): over NVSwitch the exchange is launch-latency bound, so fewer collectives win."""
+    _lib.ensure_device(rows[0].device)
+    gathered = gather_stats([r.float() for r in rows], group)
+    n, K, M = gathered.shape
+    out = torch.empty((K, M), dtype=torch.float32, device=gathered.device)
+    ops._call("tgfr_merge_softmax_stats", gathered.data_ptr(), n, K, M, out.data_ptr(), stream_ptr())
+    return tuple(out[k] for k in range(K))
+
+
 def merge_column_stats(colmax, colsum, group=None):
     """Combine per-rank column (max, sum exp(s - max)) pairs of a row-sharded score matrix.
     Returns the global (max, sum) per column."""
-    n, _ = _world(group)
-    both = torch.stack([colmax, colsum]).contiguous()                # [2, By]
-    gathered = torch.empty((n * 2, both.shape[1]), dtype=both.dtype, device=both.device)   # concatenated along dim 0
-    dist.all_gather_into_tensor(gathered, both, group=group)
-    gathered = gathered.view(n, 2, both.shape[1])
-    maxes, sums = gathered[:, 0], gathered[:, 1]                     # [n, By]
-    gmax = maxes.max(dim=0).values
-    gsum = (sums * torch.exp(maxes - gmax)).sum(dim=0)
-    return gmax, gsum
+    return _merge_stats([colmax, colsum], group)
 
 
 def class_range(num_classes, world, rank):
@@ -216,11 +231,7 @@ class _FocalCESharded(torch.autograd.Function):
         rowmax, rowsum, tgt, lse = stats[:B], stats[B:2 * B], stats[2 * B:3 * B], stats[3 * B:]
         ops._call("tgfr_ce_rows_stats", logits.data_ptr(), logits.stride(0), target.data_ptr(), B, C, class_off,
                   rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), stream_ptr())
-        gmax = rowmax.clone()
-        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-        pack = torch.stack([rowsum * torch.exp(rowmax - gmax), tgt]).contiguous()
-        dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
-        gsum, gtgt = pack[0].contiguous(), pack[1].contiguous()
+        gmax, gsum, gtgt = _merge_row_stats(rowmax, rowsum, tgt, group)
         out = torch.empty(3, dtype=torch.float32, device=dev)
         ops._call("tgfr_focal_finish", gmax.data_ptr(), gsum.data_ptr(), gtgt.data_ptr(), B, gamma, out.data_ptr(),
                   lse.data_ptr(), stream_ptr())
@@ -242,13 +253,10 @@ class _FocalCESharded(torch.autograd.Function):
 
 
 def _merge_row_stats(rowmax, rowsum, tgt, group):
-    """Per-shard online-softmax statistics -> global ones: all-reduce(max), then all-reduce(sum) of the rescaled
-    sums and of the target logits (non-owners contribute 0)."""
-    gmax = rowmax.clone()
-    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-    pack = torch.stack([rowsum * torch.exp(rowmax - gmax), tgt]).contiguous()
-    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
-    return gmax, pack[0].contiguous(), pack[1].contiguous()
+    """Per-shard online-softmax statistics -> global ones (max, rescaled sum, target logit; non-owners hold 0):
+    one all-gather of [3, B] per rank + one merge kernel."""
+    gmax, gsum, gtgt = _merge_stats([rowmax, rowsum, tgt], group)
+    return gmax.contiguous(), gsum.contiguous(), gtgt.contiguous()
 
 
 def sharded_focal_ce(logits_shard, target_all, gamma, class_off, group=None):
@@ -311,31 +319,55 @@ class ShardedArcMarginProduct(torch.nn.Module):
 # ---------------------------------------------------------------------------------------------
 # gradients of the replicated trainable modules (the reference wraps them in nn.DataParallel)
 # ---------------------------------------------------------------------------------------------
-def allreduce_gradients(params, group=None, bucket_bytes=16 << 20, average=False):
+def _check_membership(plist, n, group):
+    fp = torch.tensor([float(len(plist)), float(sum(p.numel() for p in plist))], dtype=torch.float64,
+                      device=plist[0].device)
+    fp_sum = fp.clone()
+    dist.all_reduce(fp_sum, op=dist.ReduceOp.SUM, group=group)
+    fp_max = fp.clone()
+    dist.all_reduce(fp_max, op=dist.ReduceOp.MAX, group=group)
+    if not (torch.equal(fp_sum, fp * n) and torch.equal(fp_max, fp)):
+        raise RuntimeError("allreduce_gradients: the ranks disagree on the set of trainable parameters "
+                           f"(local: {int(fp[0])} tensors, {int(fp[1])} elements)")
+
+
+def allreduce_gradients(params, group=None, bucket_bytes=16 << 20, average=False, check=True):
     """Sum (or average) the .grad of replicated parameters over the group with a few large all-reduces.
 
+    Every parameter with requires_grad takes part, in the order given (identical on every rank for replicas); a
+    parameter whose .grad is None on this rank (an unused branch, a conditional head) contributes zeros and
+    receives the sum, so the flat buffers have the same size and layout everywhere whatever each rank's autograd
+    graph touched.  The first bucket carries a fingerprint (parameter count and total element count): ranks that
+    disagree raise instead of adding up mismatched gradients.
     Gradients are packed into flat buckets of at most `bucket_bytes` (per dtype), every bucket is reduced with
     one asynchronous all-reduce -- over NVSwitch the cost is launch latency, not link count, so buckets are
     sized to keep the launches few -- and unpacked in place once all of them have completed.
     The sharded losses above already return gradients of the GLOBAL (batch-mean) loss, so the default is a
-    plain sum; `average=True` divides by the world size (per-rank mean losses).  Parameters without a
-    gradient are skipped.  Returns the number of buckets used."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    plain sum; `average=True` divides by the world size (per-rank mean losses).  Returns the number of buckets."""
+    plist = [p for p in params if p.requires_grad]
+    if not plist:
         return 0
     n, _ = _world(group)
+    # same membership on every rank?  (count, elements) summed over the group must equal n x the local values.
+    # The comparison reads the result on the host, so it is skipped while a CUDA graph is being captured
+    # (run one eager step first) or with check=False.
+    capturing = plist[0].is_cuda and torch.cuda.is_current_stream_capturing()
+    if check and not capturing:
+        _check_membership(plist, n, group)
+    order = sorted(range(len(plist)), key=lambda i: (str(plist[i].dtype), i))
     buckets, cur, cur_bytes = [], [], 0
-    for g in sorted(grads, key=lambda t: str(t.dtype)):
-        nbytes = g.numel() * g.element_size()
-        if cur and (cur[0].dtype != g.dtype or cur_bytes + nbytes > bucket_bytes):
+    for i in order:
+        p = plist[i]
+        nbytes = p.numel() * p.element_size()
+        if cur and (cur[0].dtype != p.dtype or cur_bytes + nbytes > bucket_bytes):
             buckets.append(cur)
             cur, cur_bytes = [], 0
-        cur.append(g)
+        cur.append(p)
         cur_bytes += nbytes
     buckets.append(cur)
     flats, works = [], []
     for b in buckets:
-        flat = torch.cat([g.reshape(-1) for g in b])
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in b])
         flats.append(flat)
         works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
     for b, flat, w in zip(buckets, flats, works):
@@ -343,9 +375,13 @@ def allreduce_gradients(params, group=None, bucket_bytes=16 << 20, average=False
         if average:
             flat.div_(n)
         off = 0
-        for g in b:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        for p in b:
+            piece = flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = piece.clone()
+            else:
+                p.grad.copy_(piece)
+            off += p.numel()
     return len(buckets)
 
 

@@ -22,13 +22,17 @@ def _gammas(args):
 
 def _require_arange(labels, n, what):
     """The reference always passes labels = arange(batch) (prepare_labels); the fused B x B cross
-    entropy pairs row b with column b.  Checked once per labels tensor (one device sync)."""
-    key = (labels.data_ptr(), labels._version, n)
-    if _require_arange.seen.get("key") == key:
+    entropy pairs row b with column b.  Checked once per labels TENSOR OBJECT and version (one device sync the
+    first time; the object itself is remembered through a weak reference, so a different tensor that happens to
+    reuse a freed allocation is checked again)."""
+    import weakref
+    seen = _require_arange.seen
+    ref = seen.get("ref")
+    if ref is not None and ref() is labels and seen.get("ver") == (labels._version, n):
         return
     if labels.numel() != n or not bool((labels.view(-1).cpu() == torch.arange(n)).all()):
         raise NotImplementedError(f"{what}: only labels == arange(batch_size) is supported")
-    _require_arange.seen["key"] = key
+    seen["ref"], seen["ver"] = weakref.ref(labels), (labels._version, n)
 
 
 _require_arange.seen = {}
@@ -36,14 +40,18 @@ _require_arange.seen = {}
 
 # ################## Loss for matching text-image ###################
 def cosine_similarity(x1, x2, dim=1, eps=1e-8):
-    """Reference models/losses.py:12-16: sum(x1*x2) / max(|x1||x2|, eps), squeezed.
+    """Reference models/losses.py:12-16: sum(x1*x2, dim) / max(|x1||x2|, eps), squeezed.
 
-    Inside words_loss this computation is fused into the word-region kernel; the free function
-    is kept for API parity and evaluates the same formula with PyTorch ops."""
-    w12 = torch.sum(x1 * x2, dim)
-    w1 = torch.norm(x1, 2, dim)
-    w2 = torch.norm(x2, 2, dim)
-    return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
+    Inside words_loss this computation is fused into the word-region kernel; the free function runs the same
+    formula in libtgfr_b200.so (tgfr_cosine_rows_fwd/bwd, one warp per row, differentiable in both arguments):
+    the reduced dimension is moved last and every other dimension is flattened into rows."""
+    if x1.shape != x2.shape:
+        x1, x2 = torch.broadcast_tensors(x1, x2)
+    dim = dim % x1.dim()
+    a, b = x1.movedim(dim, -1), x2.movedim(dim, -1)
+    lead = a.shape[:-1]
+    out = ops.cosine_rows(a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1]), eps)
+    return out.reshape(lead).squeeze()
 
 
 def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, args, eps=1e-8):
@@ -193,7 +201,11 @@ class ClipLoss(nn.Module):
         return labels
 
     def get_logits(self, image_features, text_features, logit_scale):
-        logits_per_image = ops.cosine_scores(image_features, text_features, logit_scale, False)
+        if torch.is_tensor(logit_scale):
+            # a learnable temperature (CLIP's logit_scale.exp()) keeps its gradient: scale outside the kernel
+            logits_per_image = ops.cosine_scores(image_features, text_features, 1.0, False) * logit_scale
+        else:
+            logits_per_image = ops.cosine_scores(image_features, text_features, logit_scale, False)
         return logits_per_image, logits_per_image.t()
 
     def forward(self, text_features, image_features, args, logit_scale=1):

@@ -52,10 +52,7 @@ class MagLoss(torch.nn.Module):
     def forward(self, input, target, x_norm):
         loss_g = self.calc_loss_G(x_norm)
         cos_theta, cos_theta_m = input
-        idx = target.view(-1, 1)
-        one_hot = torch.zeros_like(cos_theta)
-        one_hot.scatter_(1, idx, 1.0)
-        # label column from cos_theta_m, every other column from cos_theta (magface.py:134)
-        output = cos_theta.scatter(1, idx, cos_theta_m.gather(1, idx))
-        loss = ops.focal_ce(output, target, 0.0)                           # mean CE, :135
+        # label column from cos_theta_m, every other column from cos_theta (magface.py:131-134), mean CE (:135):
+        # one pass over the two logit tensors in libtgfr_b200.so; one_hot is written by the same kernel
+        loss, one_hot = ops.mag_ce(cos_theta, cos_theta_m, target)
         return loss.mean(), loss_g, one_hot

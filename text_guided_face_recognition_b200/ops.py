@@ -14,7 +14,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
-    "mag_logits", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
+    "mag_logits", "mag_ce", "cosine_rows", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
     "pair_cosine", "roc_counts", "row_argmax", "fcfm_working",
 ]
 
@@ -57,7 +57,7 @@ _KERNELS_PER_CALL = {
     "tgfr_cosine_scores_fwd": 3, "tgfr_cosine_scores_bwd": 4, "tgfr_pair_ce_stats": 1, "tgfr_pair_ce_finish": 1,
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
-    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
+    "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_mag_ce_stats": 1, "tgfr_mag_ce_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
     "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1,
 }
 
@@ -443,6 +443,84 @@ class _MagLogits(torch.autograd.Function):
 
 def mag_logits(x, weight, margin, scale, easy_margin=True):
     return _MagLogits.apply(_f32(x), _f32(weight).contiguous(), _f32(margin), float(scale), bool(easy_margin))
+
+
+class _CosineRows(torch.autograd.Function):
+    """cosine_similarity(x1, x2, dim=1, eps) of models/losses.py:12-16 on [N, D] rows."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, eps):
+        _lib.ensure_device(x1.device)
+        N, D = x1.shape
+        out = torch.empty(N, dtype=torch.float32, device=x1.device)
+        stats = torch.empty((N, 3), dtype=torch.float32, device=x1.device)
+        _call("tgfr_cosine_rows_fwd", ptr(x1), x1.stride(0), x1.stride(1), ptr(x2), x2.stride(0), x2.stride(1), N, D, eps,
+              ptr(out), ptr(stats), stream_ptr())
+        ctx.save_for_backward(x1, x2, stats)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, stats = ctx.saved_tensors
+        N, D = x1.shape
+        g = _f32(g).contiguous()
+        d1 = torch.empty((N, D), dtype=torch.float32, device=x1.device) if ctx.needs_input_grad[0] else None
+        d2 = torch.empty((N, D), dtype=torch.float32, device=x1.device) if ctx.needs_input_grad[1] else None
+        _call("tgfr_cosine_rows_bwd", ptr(x1), x1.stride(0), x1.stride(1), ptr(x2), x2.stride(0), x2.stride(1), N, D,
+              ctx.eps, ptr(stats), ptr(g), ptr(d1), ptr(d2), stream_ptr())
+        return d1, d2, None
+
+
+def cosine_rows(x1, x2, eps=1e-8):
+    """sum(x1 x2, 1) / max(|x1| |x2|, eps) for two [N, D] CUDA tensors (any strides) -> [N], differentiable."""
+    if x1.dim() != 2 or x1.shape != x2.shape:
+        raise RuntimeError(f"cosine_rows: expected two [N, D] tensors of one shape, got {tuple(x1.shape)} / {tuple(x2.shape)}")
+    return _CosineRows.apply(_f32(x1), _f32(x2), float(eps))
+
+
+class _MagCE(torch.autograd.Function):
+    """MagLoss's blend + mean cross entropy (magface.py:131-135) without the blended [B,C] tensor."""
+
+    @staticmethod
+    def forward(ctx, cos_s, cos_m, target):
+        _lib.ensure_device(cos_s.device)
+        if cos_s.stride(1) != 1 or cos_m.stride() != cos_s.stride():
+            cos_s, cos_m = cos_s.contiguous(), cos_m.contiguous()
+        B, C = cos_s.shape
+        dev = cos_s.device
+        stats = torch.empty(4 * B, dtype=torch.float32, device=dev)
+        rowmax, rowsum, tgt, lse = stats[:B], stats[B:2 * B], stats[2 * B:3 * B], stats[3 * B:]
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        one_hot = torch.empty((B, C), dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        _call("tgfr_mag_ce_stats", cos_s.data_ptr(), cos_m.data_ptr(), cos_s.stride(0), target.data_ptr(), B, C,
+              rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), one_hot.data_ptr(), st)
+        _call("tgfr_focal_finish", rowmax.data_ptr(), rowsum.data_ptr(), tgt.data_ptr(), B, 0.0, out.data_ptr(),
+              lse.data_ptr(), st)
+        ctx.save_for_backward(cos_s, cos_m, target, stats)
+        ctx.mark_non_differentiable(one_hot)
+        return out[1].clone(), one_hot
+
+    @staticmethod
+    def backward(ctx, gout, _g_onehot):
+        cos_s, cos_m, target, stats = ctx.saved_tensors
+        B, C = cos_s.shape
+        lse = stats[3 * B:]
+        gout = _f32(gout).reshape(1).contiguous()
+        g_cos = torch.empty((B, C), dtype=torch.float32, device=cos_s.device)
+        g_cosm = torch.empty((B, C), dtype=torch.float32, device=cos_s.device)
+        _call("tgfr_mag_ce_bwd", cos_s.data_ptr(), cos_m.data_ptr(), cos_s.stride(0), target.data_ptr(), lse.data_ptr(),
+              gout.data_ptr(), B, C, g_cos.data_ptr(), g_cosm.data_ptr(), stream_ptr())
+        return g_cos, g_cosm, None
+
+
+def mag_ce(cos_s, cos_m, target):
+    """(mean CE of the MagLoss-blended logits, one_hot [B,C]) -- label column from cos_m, the rest from cos_s."""
+    if cos_s.dim() != 2 or cos_s.shape != cos_m.shape:
+        raise ValueError(f"mag_ce expects two [B,C] tensors, got {tuple(cos_s.shape)} / {tuple(cos_m.shape)}")
+    target = target.view(-1).to(device=cos_s.device, dtype=torch.int64).contiguous()
+    return _MagCE.apply(_f32(cos_s), _f32(cos_m), target)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -80,7 +80,8 @@ def _area(x, y):
     if np.any(dx < 0) and not np.all(dx <= 0):
         raise ValueError("x is neither increasing nor decreasing")
     direction = -1.0 if np.any(dx < 0) else 1.0
-    return float(direction * np.trapezoid(y, x))
+    trap = getattr(np, "trapezoid", None) or np.trapz          # NumPy >= 2.0 renamed trapz
+    return float(direction * trap(y, x))
 
 
 def calculate_scores(y_score, y_true, args=None):
