@@ -34,13 +34,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// A wait that never completes (a protocol bug) must not hang the GPU: after ~2^26 failed polls (tens of seconds)
+// the kernel traps and the host sees a launch failure.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+      ".reg .u32 spins;\n\t"
+      "mov.u32 spins, 0;\n\t"
       "WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
+      "add.u32 spins, spins, 1;\n\t"
+      "setp.gt.u32 p, spins, 0x4000000;\n\t"
+      "@p trap;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),

@@ -13,8 +13,9 @@ def fwd(): return ops.wordregion_sim(f, w, None, 4., 5., 10., precision=_lib.PRE
 sim = fwd(); g = torch.randn_like(sim) / B
 sim.backward(g, retain_graph=True); torch.cuda.synchronize()
 names = {
-    'fwd': {2: 'S ready', 3: 'epi1 done', 4: 'Wu ready', 5: 'epi2 pass1 done', 6: 'cos/exp done', 7: 'V pass done',
-            17: 'mma:Q ready', 18: 'mma:E ready', 19: 'mma:Wu free'},
+    # pipelined forward (wr_tc_fwd3_kernel): A = word-softmax warps, B = cosine / V warps
+    'fwd': {2: 'A:tile0 start', 3: 'A:tile0 done', 4: 'A:tile1 done', 5: 'B:Wu ready', 6: 'B:pass1 done', 7: 'B:V pass done',
+            17: 'mma:E0 ready', 18: 'mma:G2a+G1 issued', 19: 'mma:G2b issued'},
     # record-based backward (wr_tc_bwd2_kernel): one line per (face, tile, caption group) item
     'bwd': {2: 'dE ready', 3: 'ops written', 8: 'acc done', 9: 'drained', 17: 'mma:V ready', 18: 'mma:ops ready',
             19: 'mma:G5 issued'},
@@ -27,9 +28,10 @@ for which in ('fwd', 'bwd'):
     torch.cuda.synchronize()
     _lib.check(lib.tgfr_debug_set_trace(0), 'trace')
     t = trace.cpu().numpy().reshape(16, 32)
-    base = t[t > 0].min()
+    base = t[:, [2, 3, 17]][t[:, [2, 3, 17]] > 0].min()
     print('====', which)
     for n in range(2, 8):
-        evs = sorted((t[n, e] - base, e) for e in range(32) if t[n, e] > 0)
+        evs = sorted((t[n, e] - base, e) for e in range(32) if t[n, e] > 0 and not (8 <= e <= 12 or 24 <= e <= 26))
         print('unit', n, ' '.join(f"{names[which].get(e, e)}@{int(c)}" for c, e in evs))
-    print('cycles per unit (epilogue thread):', np.diff(t[2:12, 3]))
+    print('cycles per unit (epilogue thread):', np.diff(t[2:14, 3]))
+
