@@ -297,6 +297,38 @@ int tgfr_debug_umma_2cta(const void* a, const void* b, float* out, int N, int K,
  * it off); CTA 0 stamps clock64() per pipeline phase of its first 16 units (tools/trace_wordregion.py). */
 int tgfr_debug_set_trace(void* dev_buf);
 
+/* ------------------------------------------------------------------------------------------
+ * IMIM, the local branch of ImageHeading (models/models.py:380-405; SelfAttention models/fusion_nets.py:82-118;
+ * SURVEY.md 8(f) row f3): x [B,256,P = 14*14] (element strides x_sb / x_sc / x_sp) -> out [B, P, 256] contiguous =
+ * the reference's result in its memory order (logical [B,256,14,14], unit L2 norm over the channels at every
+ * position) -- the layout tgfr_wordregion_* reads.  params: 16 device pointers in the order
+ *   bn_img.weight, bn_img.bias, sa.query_proj.weight [256,256], .bias, sa.key_proj.weight, .bias, sa.value_proj.weight,
+ *   .bias, ln.weight [256*P], ln.bias, conv1x1_1.weight [128,256], .bias, conv1x1_2.weight [256,128], .bias,
+ *   project_local.projection.weight [256,256], .bias          (the reference's state_dict tensors, contiguous fp32).
+ * training != 0: BatchNorm uses the batch statistics and updates running_mean / running_var (momentum, unbiased
+ * variance; either may be NULL); else it normalises with them.  `saved` (tgfr_imim_saved_bytes) carries the
+ * activations to tgfr_imim_bwd, which takes gout [B,P,256] and the forward's `out`, and writes dparams (16 device
+ * pointers, same order and shapes) and, if not NULL, dx [B,256,P] contiguous. */
+size_t tgfr_imim_saved_bytes(int B, int P);
+size_t tgfr_imim_workspace_bytes(int B, int P);
+int tgfr_imim_num_params(void);
+int tgfr_imim_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sp, const void* const* params, int n_params,
+                  int B, int P, int training, float momentum, float eps, float* running_mean, float* running_var,
+                  float* out, void* saved, size_t saved_bytes, void* stream);
+int tgfr_imim_bwd(const float* gout, const float* out, const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sp,
+                  const void* const* params, int n_params, int B, int P, int training, const void* saved,
+                  size_t saved_bytes, void* const* dparams, float* dx, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ProjectionHead (models/models.py:96-119), the global branch of ImageHeading: out [M,N] = normalize(x W^T + b) for
+ * x [M,K] (row stride x_sr), weight [N,K], bias [N] (NULL = none); znorm [M] = |x W^T + b| for the backward, which
+ * writes dweight [N,K], dbias [N] and, if not NULL, dx [M,K]; dz_scratch is [M,N] floats. */
+int tgfr_proj_head_fwd(const float* x, int64_t x_sr, const float* weight, const float* bias, int M, int N, int K,
+                       float* out, float* znorm, void* stream);
+int tgfr_proj_head_bwd(const float* gout, const float* out, const float* znorm, const float* x, int64_t x_sr,
+                       const float* weight, int M, int N, int K, float* dz_scratch, float* dx, float* dweight,
+                       float* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

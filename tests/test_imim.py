@@ -1,0 +1,136 @@
+"""Image head: IMIM / ImageHeading / ProjectionHead through the mirror modules -> C ABI
+(csrc/imim.cu), against fixtures produced by the reference's own modules (tests/golden/make_golden_imim.py eval
+forward; make_golden_imim_r2.py training-mode forward + autograd at B = 3 and at the configs[1] batch B = 128) and the
+fp64 oracle (oracle/fusion_oracle.py::imim_forward, eval mode).  fp32 arithmetic: outputs within 2e-5, gradients within
+2e-4 relative (||delta|| / ||ref||)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_imim_r2 import imim_inputs  # noqa: E402  (seeded numpy inputs only; no reference access at import)
+
+OUT_TOL, GRAD_TOL = 2e-5, 2e-4
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def make_head(golden_dir, wg=None, bg=None):
+    from text_guided_face_recognition_b200.models.image_heading import ImageHeading
+    head = ImageHeading(types.SimpleNamespace(aux_feat_dim_per_granularity=256))
+    small = load(golden_dir, "imim_small")
+    sd = head.imim.state_dict()
+    missing = head.imim.load_state_dict({k: torch.from_numpy(small["p:" + k]) for k in sd if ("p:" + k) in small.files},
+                                        strict=False)
+    assert all(k.startswith("project_local.fc") or k.endswith("num_batches_tracked") for k in missing.missing_keys)
+    if wg is not None:
+        with torch.no_grad():
+            head.project_global.projection.weight.copy_(torch.from_numpy(wg))
+            head.project_global.projection.bias.copy_(torch.from_numpy(bg))
+    return head.cuda()
+
+
+def test_state_dict_names_match_the_reference(golden_dir):
+    """Every tensor of the reference IMIM's state_dict (names + shapes stored in imim_small.npz) exists in the mirror."""
+    from text_guided_face_recognition_b200.models.image_heading import IMIM
+    net = IMIM(types.SimpleNamespace(aux_feat_dim_per_granularity=256), channel_dim=256)
+    sd = net.state_dict()
+    small = load(golden_dir, "imim_small")
+    for k in small.files:
+        if k.startswith("p:"):
+            assert k[2:] in sd and tuple(sd[k[2:]].shape) == small[k].shape, k
+    assert "project_local.fc.weight" in sd and "bn_img.num_batches_tracked" in sd
+
+
+@pytest.mark.gpu
+def test_imim_eval_vs_reference_fixture_and_oracle(golden_dir):
+    from oracle import fusion_oracle as FO
+    g = load(golden_dir, "imim_small")
+    head = make_head(golden_dir).eval()
+    out = head.imim(torch.from_numpy(g["img"]).cuda())
+    assert tuple(out.shape) == g["out"].shape and tuple(out.stride()) == tuple(int(v) for v in g["out_strides"])
+    assert np.max(np.abs(out.detach().cpu().numpy() - g["out"])) < OUT_TOL
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    x, _, _, _, _, _ = imim_inputs(5, 3)
+    got = head.imim(torch.from_numpy(x).cuda()).detach().cpu().numpy()
+    ref = FO.imim_forward(params, x)
+    assert np.max(np.abs(got - ref)) < OUT_TOL
+    assert np.max(np.abs(np.linalg.norm(got, axis=1) - 1.0)) < 1e-5          # unit rows for the word-region kernels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_image_heading_train_vs_reference_fixture(golden_dir, layout):
+    g = load(golden_dir, "imim_train")
+    x, gout, xg, gg, wg, bg = imim_inputs(3, 7)
+    head = make_head(golden_dir, wg, bg).train()
+    xt = torch.from_numpy(x).cuda()
+    if layout == "channels_last":
+        xt = xt.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    xt.requires_grad_(True)
+    xgt = torch.from_numpy(xg).cuda().requires_grad_(True)
+    glob, loc = head(xgt, xt)
+    assert tuple(loc.stride()) == tuple(int(v) for v in g["out_strides"])
+    assert np.max(np.abs(loc.detach().cpu().numpy() - g["out"])) < OUT_TOL
+    assert np.max(np.abs(glob.detach().cpu().numpy() - g["glob"])) < OUT_TOL
+    torch.autograd.backward([loc, glob], [torch.from_numpy(gout).cuda(), torch.from_numpy(gg).cuda()])
+    assert rel(xt.grad.cpu().numpy(), g["dx"]) < GRAD_TOL
+    assert rel(xgt.grad.cpu().numpy(), g["dxg"]) < GRAD_TOL
+    assert rel(head.project_global.projection.weight.grad.cpu().numpy(), g["dwg"]) < GRAD_TOL
+    assert rel(head.project_global.projection.bias.grad.cpu().numpy(), g["dbg"]) < GRAD_TOL
+    for name, p in head.imim.named_parameters():
+        if name.startswith("project_local.fc"):
+            assert p.grad is None
+            continue
+        ref = g["g:" + name]
+        got = p.grad.cpu().numpy()
+        if np.linalg.norm(ref) < 1e-3:                 # sa.query_proj.bias: the softmax is invariant to it (exactly 0)
+            assert np.max(np.abs(got)) < 1e-3, name
+        else:
+            assert rel(got, ref) < GRAD_TOL, (name, rel(got, ref))
+    assert np.max(np.abs(head.imim.bn_img.running_mean.cpu().numpy() - g["running_mean"])) < 1e-5
+    assert rel(head.imim.bn_img.running_var.cpu().numpy(), g["running_var"]) < 1e-5
+    assert int(head.imim.bn_img.num_batches_tracked) == 1
+
+
+@pytest.mark.gpu
+def test_imim_config2_batch_vs_reference_fixture(golden_dir):
+    """B = 128 (the configs[1] batch the bench times): compact fixture of the reference's forward + autograd."""
+    g = load(golden_dir, "imim_config2")
+    x, gout, xg, gg, wg, bg = imim_inputs(128, 11)
+    head = make_head(golden_dir, wg, bg).train()
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    loc = head.imim(xt)
+    o = loc.detach().contiguous().cpu().numpy()
+    assert np.max(np.abs(o[:2] - g["out_head"])) < OUT_TOL
+    proj = o.transpose(0, 2, 3, 1).reshape(-1, 256) @ np.linspace(-1, 1, 256).astype(np.float32)
+    assert np.max(np.abs(proj - g["out_proj"])) < 1e-4
+    loc.backward(torch.from_numpy(gout).cuda())
+    dx = xt.grad.cpu().numpy()
+    assert rel(dx[:2], g["dx_head"]) < GRAD_TOL
+    assert abs(np.linalg.norm(dx.astype(np.float64)) - float(g["dx_norm"])) < GRAD_TOL * float(g["dx_norm"])
+    for name, p in head.imim.named_parameters():
+        if name.startswith("project_local.fc"):
+            continue
+        got = p.grad.cpu().numpy()
+        n_ref = float(g["n:" + name])
+        if n_ref < 1e-3:
+            assert np.linalg.norm(got) < 2e-2, name
+            continue
+        assert abs(np.linalg.norm(got.astype(np.float64)) - n_ref) < GRAD_TOL * n_ref, name
+        ref = g["g:" + name]
+        sl = got if got.size <= 512 else got.reshape(got.shape[0], -1)[:4]
+        assert rel(sl, ref) < 2 * GRAD_TOL, (name, rel(sl, ref))
+    assert rel(head.imim.bn_img.running_var.cpu().numpy(), g["running_var"]) < 1e-5

@@ -87,6 +87,18 @@ int texthead_fwd(const float*, const float* const*, const float* const*, int, in
 int texthead_bwd(const float*, const float*, const float*, int, int, int, int, int, float* const*, float* const*, void*,
                  size_t, const void*, size_t, cudaStream_t);
 
+// imim.cu
+size_t imim_saved_bytes(int, int);
+size_t imim_workspace_bytes(int, int);
+int imim_fwd(const float*, int64_t, int64_t, int64_t, const float* const*, int, int, int, float, float, float*, float*, float*,
+             void*, size_t, cudaStream_t);
+int imim_bwd(const float*, const float*, const float*, int64_t, int64_t, int64_t, const float* const*, int, int, int, const void*,
+             size_t, float* const*, float*, void*, size_t, cudaStream_t);
+
+int proj_head_fwd(const float*, int64_t, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int proj_head_bwd(const float*, const float*, const float*, const float*, int64_t, const float*, int, int, int, float*, float*,
+                  float*, float*, cudaStream_t);
+
 // scoring.cu
 int pair_cosine(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float, float*, cudaStream_t);
 int row_argmax(const float*, int64_t, int, int, int64_t*, cudaStream_t);
@@ -337,6 +349,39 @@ int tgfr_mag_ce_stats(const float* cos_s, const float* cos_m, int64_t sr, const 
 int tgfr_mag_ce_bwd(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, const float* lse,
                     const float* gout, int B, int C, float* g_cos, float* g_cosm, void* stream) {
   return mag_ce_bwd(cos_s, cos_m, sr, labels, lse, gout, B, C, g_cos, g_cosm, ST(stream));
+}
+
+size_t tgfr_imim_saved_bytes(int B, int P) { return imim_saved_bytes(B, P); }
+size_t tgfr_imim_workspace_bytes(int B, int P) { return imim_workspace_bytes(B, P); }
+int tgfr_imim_num_params(void) { return 16; }
+int tgfr_imim_fwd(const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sp, const void* const* params, int n_params, int B,
+                  int P, int training, float momentum, float eps, float* running_mean, float* running_var, float* out,
+                  void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(x && params && out, "imim_fwd: NULL tensor");
+  TGFR_REQUIRE(n_params == 16, "imim_fwd: expected 16 parameter tensors, got %d", n_params);
+  TGFR_REQUIRE(training || (running_mean && running_var), "imim_fwd: evaluation mode needs the running statistics");
+  return imim_fwd(x, x_sb, x_sc, x_sp, reinterpret_cast<const float* const*>(params), B, P, training, momentum, eps,
+                  running_mean, running_var, out, saved, saved_bytes, ST(stream));
+}
+int tgfr_imim_bwd(const float* gout, const float* out, const float* x, int64_t x_sb, int64_t x_sc, int64_t x_sp,
+                  const void* const* params, int n_params, int B, int P, int training, const void* saved, size_t saved_bytes,
+                  void* const* dparams, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  TGFR_REQUIRE(gout && out && x && params && dparams, "imim_bwd: NULL tensor");
+  TGFR_REQUIRE(n_params == 16, "imim_bwd: expected 16 parameter tensors, got %d", n_params);
+  return imim_bwd(gout, out, x, x_sb, x_sc, x_sp, reinterpret_cast<const float* const*>(params), B, P, training, saved,
+                  saved_bytes, reinterpret_cast<float* const*>(dparams), dx, workspace, workspace_bytes, ST(stream));
+}
+
+int tgfr_proj_head_fwd(const float* x, int64_t x_sr, const float* weight, const float* bias, int M, int N, int K, float* out,
+                       float* znorm, void* stream) {
+  TGFR_REQUIRE(x && weight && out && znorm, "proj_head_fwd: NULL tensor");
+  return proj_head_fwd(x, x_sr, weight, bias, M, N, K, out, znorm, ST(stream));
+}
+int tgfr_proj_head_bwd(const float* gout, const float* out, const float* znorm, const float* x, int64_t x_sr,
+                       const float* weight, int M, int N, int K, float* dz_scratch, float* dx, float* dweight, float* dbias,
+                       void* stream) {
+  TGFR_REQUIRE(gout && out && znorm && x && weight && dz_scratch && dweight && dbias, "proj_head_bwd: NULL tensor");
+  return proj_head_bwd(gout, out, znorm, x, x_sr, weight, M, N, K, dz_scratch, dx, dweight, dbias, ST(stream));
 }
 
 int tgfr_pair_cosine(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd, int64_t N,

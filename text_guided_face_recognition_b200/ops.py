@@ -15,7 +15,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
     "mag_logits", "mag_ce", "cosine_rows", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
-    "pair_cosine", "roc_counts", "row_argmax", "fcfm_working",
+    "pair_cosine", "roc_counts", "row_argmax", "fcfm_working", "imim", "proj_head",
 ]
 
 
@@ -58,7 +58,8 @@ _KERNELS_PER_CALL = {
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
     "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_mag_ce_stats": 1, "tgfr_mag_ce_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
-    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1,
+    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 12, "tgfr_imim_bwd": 34,
+    "tgfr_proj_head_fwd": 2, "tgfr_proj_head_bwd": 5,
 }
 
 
@@ -757,3 +758,105 @@ def fcfm_working(img, word, gl_img, sent, state):
               word.stride(0), word.stride(1), word.stride(2), ptr(gl_img), gl_img.stride(0), ptr(sent), sent.stride(0),
               ctypes.cast(arr, ctypes.c_void_p), len(params), B, word.shape[2], ptr(out), out.stride(0), stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# ImageHeading (models/models.py:328-338, 380-405): IMIM local branch and the global ProjectionHead
+# ---------------------------------------------------------------------------------------------
+IMIM_PARAM_ORDER = (
+    "bn_img.weight", "bn_img.bias", "sa.query_proj.weight", "sa.query_proj.bias", "sa.key_proj.weight", "sa.key_proj.bias",
+    "sa.value_proj.weight", "sa.value_proj.bias", "ln.weight", "ln.bias", "conv1x1_1.weight", "conv1x1_1.bias",
+    "conv1x1_2.weight", "conv1x1_2.bias", "project_local.projection.weight", "project_local.projection.bias",
+)
+
+
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[ptr(t) for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class _Imim(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, running_mean, running_var, training, momentum, eps, *params):
+        _lib.ensure_device(x.device)
+        B, C, H, Wd = x.shape
+        P = H * Wd
+        dev = x.device
+        lib = _lib.load()
+        prm = [_f32(p_.detach()).contiguous() for p_ in params]
+        out = torch.empty((B, P, C), dtype=torch.float32, device=dev)
+        svb = lib.tgfr_imim_saved_bytes(B, P)
+        saved = torch.empty(svb, dtype=torch.uint8, device=dev)
+        xs = x if x.stride(2) == Wd * x.stride(3) else x.contiguous()     # the (h, w) axes must merge into one position axis
+        sb, sc, sp = xs.stride(0), xs.stride(1), xs.stride(3)
+        arr, parr = _ptr_array(prm)
+        _call("tgfr_imim_fwd", ptr(xs), sb, sc, sp, parr, len(prm), B, P, int(training), float(momentum), float(eps),
+              ptr(running_mean), ptr(running_var), ptr(out), ptr(saved), svb, stream_ptr())
+        ctx.save_for_backward(xs, out, saved, *prm)
+        ctx.cfg = (B, C, H, Wd, sb, sc, sp, bool(training))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xs, out, saved, *prm = ctx.saved_tensors
+        B, C, H, Wd, sb, sc, sp, training = ctx.cfg
+        P = H * Wd
+        dev = out.device
+        lib = _lib.load()
+        gout = _f32(gout).contiguous()
+        dprm = [torch.empty_like(p_) for p_ in prm]
+        dx = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        wsb = lib.tgfr_imim_workspace_bytes(B, P)
+        ws = _workspace(wsb, dev)
+        arr, parr = _ptr_array(prm)
+        darr, dparr = _ptr_array(dprm)
+        _call("tgfr_imim_bwd", ptr(gout), ptr(out), ptr(xs), sb, sc, sp, parr, len(prm), B, P, int(training), ptr(saved),
+              saved.numel(), dparr, ptr(dx), ptr(ws), wsb, stream_ptr())
+        return (dx, None, None, None, None, None, *dprm)
+
+
+def imim(x, params, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    """IMIM.forward: x [B,256,14,14] -> [B, 196, 256] unit rows (the reference's result in ITS memory order);
+    params: the 16 tensors of IMIM_PARAM_ORDER.  Differentiable w.r.t. x and the parameters."""
+    if x.dim() != 4 or x.shape[1] != 256:
+        raise RuntimeError(f"imim: expected x [B,256,H,W], got {tuple(x.shape)}")
+    return _Imim.apply(_f32(x), running_mean, running_var, bool(training), float(momentum), float(eps), *params)
+
+
+class _ProjHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _lib.ensure_device(x.device)
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        weight = weight.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        znorm = torch.empty(M, dtype=torch.float32, device=x.device)
+        _call("tgfr_proj_head_fwd", ptr(x), x.stride(0), ptr(weight), ptr(bias), M, N, K, ptr(out), ptr(znorm), stream_ptr())
+        ctx.save_for_backward(x, weight, out, znorm)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out, znorm = ctx.saved_tensors
+        M, K = x.shape
+        N = weight.shape[0]
+        g = _f32(g).contiguous()
+        dz = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        dx = torch.empty((M, K), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight)
+        db = torch.empty(N, dtype=torch.float32, device=x.device)
+        _call("tgfr_proj_head_bwd", ptr(g), ptr(out), ptr(znorm), ptr(x), x.stride(0), ptr(weight), M, N, K, ptr(dz), ptr(dx),
+              ptr(dw), ptr(db), stream_ptr())
+        return dx, dw, (db if ctx.has_bias else None)
+
+
+def proj_head(x, weight, bias):
+    """normalize(x @ weight.T + bias, dim=-1) (ProjectionHead.forward, models/models.py:111-119) for x [..., K]."""
+    lead = x.shape[:-1]
+    out = _ProjHead.apply(_f32(x).reshape(-1, x.shape[-1]), _f32(weight), None if bias is None else _f32(bias).contiguous())
+    return out.reshape(*lead, weight.shape[0])
