@@ -441,6 +441,47 @@ def sharded_head_leg(world, rank, dev, use_graph, flush, reps):
             "launch": "CUDA graph replay (NCCL captured)" if use_graph else "eager"}
 
 
+def config4_leg(world, rank, dev, use_graph, flush, reps):
+    """BASELINE configs[3] ("Full FCAM train step ... global B = 1024 over 8 x B200"): fcam.FcamTrainStep -- TextHeading
+    (no_grad), ImageHeading (IMIM + ProjectionHead, trainable), words / sent / global losses row-sharded with the captions
+    all-gathered, two class-sharded ArcFace + focal heads over 10 177 identities, backward, all-reduce of the image
+    head's gradients.  128 faces + captions per rank, 32 BERT tokens -> T = 30 words.  The frozen encoders (IResNet-50,
+    BERT) are out of scope: their outputs are the step's (synthetic) inputs."""
+    import types as _t
+    from text_guided_face_recognition_b200.fcam import FcamTrainStep
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_imim_r2 import imim_inputs
+    Bl, bwn, C = 128, 32, HEAD["C"]
+    ns = _t.SimpleNamespace
+    a4 = ns(aux_feat_dim_per_granularity=256, bert_words_num=bwn, en_type="BERT",
+            TRAIN=ns(SMOOTH=ns(GAMMA1=GAMMAS[0], GAMMA2=GAMMAS[1], GAMMA3=GAMMAS[2])))
+    step = FcamTrainStep(a4, C, dev)
+    x, _, xg, _, _, _ = imim_inputs(Bl, 100 + rank)
+    tok, _, _ = synth.texthead_inputs(Bl, bwn, 256, seed=100 + rank)
+    gfeat, lfeat = torch.from_numpy(xg).to(dev), torch.from_numpy(x).to(dev)
+    tokens = torch.from_numpy(tok).to(dev)
+    cid = (torch.arange(Bl, device=dev) + rank * Bl) % C
+
+    def run():
+        step.zero_grad()
+        return step(gfeat, lfeat, tokens, cid)
+    ms, _ = time_step(run, flush, reps, use_graph, world, dev)
+    Bg = Bl * world
+    T4 = bwn - 2
+    wr_flops = 10 * T4 * R * D * Bg * Bg                       # word-region loss, face-side gradient (SURVEY 8(d))
+    imim_flops = 3 * 2 * 83.9e6 * Bg                           # IMIM fwd + bwd: 83.9 M MACs per sample forward
+    head_flops = 2 * 6 * 256 * C * Bg
+    return {"metric": "fcam_full_step_pairs_per_sec", "value": Bg * Bg / (ms * 1e-3), "unit": "pairs/s",
+            "samples_per_sec": Bg / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world, "scaling": "weak",
+            "config": {"workload": "configs[3]: TextHeading (no_grad) + ImageHeading + words/sent/global losses + two "
+                                   "ArcFace+focal heads + backward + image-head gradient all-reduce; frozen IResNet-50 / "
+                                   "BERT excluded (their outputs are the inputs)",
+                       "global_batch": Bg, "local_batch": Bl, "T": T4, "R": R, "D": D, "classes": C,
+                       "launch": "one CUDA graph replay per step" if use_graph else "eager"},
+            "algorithmic_tflops": (wr_flops + imim_flops + head_flops) / (ms * 1e-3) / 1e12,
+            "flops_breakdown": {"wordregion": wr_flops, "imim": imim_flops, "heads": head_flops}}
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -625,12 +666,17 @@ def run_b200(args):
     for st_ in sets:
         st_[1].requires_grad_(args.grads == "both")
 
-    # ---- class-sharded margin head on all ranks (N > 1): the head's own curve beside the contrastive step
+    # ---- class-sharded margin head on all ranks (N > 1): the head's own curve beside the contrastive step;
+    # ---- the assembled configs[3] step on every rank
     sharded_head = None
+    flush_all = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
     if world > 1:
-        flush_all = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device=dev)
         sharded_head = sharded_head_leg(world, rank, dev, use_graph, flush_all, max(3, min(args.steps, 20)))
-        del flush_all
+    try:
+        config4 = config4_leg(world, rank, dev, use_graph, flush_all, max(3, min(args.steps, 10)))
+    except Exception as e:                                  # never lose the headline line to a side leg
+        config4 = {"error": f"{type(e).__name__}: {e}"[:300]}
+    del flush_all
 
     line = {
         "metric": "fcam_words+sent_loss_fwd_bwd_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -647,6 +693,7 @@ def run_b200(args):
         "other_grads": {"grads": other, "value": pairs / (other_ms * 1e-3), "unit": "pairs/s", "ms_per_step": other_ms,
                         "steps": n_other},
         "parity": parity,
+        "full_step": config4,
     }
     if sharded_head is not None:
         line["margin_head_sharded"] = sharded_head
@@ -827,6 +874,34 @@ def run_b200(args):
                                          "note": "dense API: cos / cos_m / one_hot written (3), cos + cos_m read by the CE "
                                                  "(2), two dense gradients written (2) = 7 x 4BC bytes on top of W / dW / X"}}
         del mhead, mx
+
+        # ---- image head local branch (IMIM) at the configs[1] batch: fwd + bwd, training mode
+        import types as _types2
+        from text_guided_face_recognition_b200.models.image_heading import ImageHeading
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden_imim_r2 import imim_inputs
+        ih = ImageHeading(_types2.SimpleNamespace(aux_feat_dim_per_granularity=D)).to(dev).train()
+        ix_np, ig_np, _, _, _, _ = imim_inputs(B, 100)
+        ix, ig = torch.from_numpy(ix_np).to(dev), torch.from_numpy(ig_np).to(dev)
+
+        def imim_step():
+            for p_ in ih.imim.parameters():
+                p_.grad = None
+            ih.imim(ix).backward(ig)
+        im_ms, _ = time_step(imim_step, flush, max(3, min(args.steps, 10)), use_graph)
+        im_flops = 3 * 2 * 83.9e6 * B
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                      # FMA lanes x 2 x max SM clock: fp32 SIMT ceiling
+        line["image_head"] = {"metric": "imim_fwd_bwd_samples_per_sec", "value": B / (im_ms * 1e-3), "unit": "samples/s",
+                              "ms_per_step": im_ms, "dtype": "f32",
+                              "config": {"B": B, "positions": R, "channels": D, "mode": "training (batch statistics)"},
+                              "roofline": {"bound": "fp32-simt", "achieved": im_flops / (im_ms * 1e-3) / 1e12,
+                                           "peak": fp32_peak, "unit": "TFLOP/s", "frac": im_flops / (im_ms * 1e-3) / 1e12 / fp32_peak,
+                                           "peak_source": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz (no measured fp32 peak in "
+                                                          "MEASURED_PEAKS.json)",
+                                           "algorithmic_flops_per_step": im_flops,
+                                           "note": "fp32 register-blocked GEMMs (not tensor cores): the contractions are "
+                                                   "83.9 M MACs per sample forward, x3 with the backward"}}
+        del ih, ix, ig
 
         # ---- TextHeading (the BERT 768 -> 256 word / sentence projection of configs[1])
         import types as _types

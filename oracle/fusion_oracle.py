@@ -83,12 +83,22 @@ def working_forward(p, img, word, gl_img, sent):
     return np.concatenate((iw, g, s), axis=1)                                                      # :257
 
 
-def imim_forward(p, img):
-    """IMIM.forward (reference models/models.py:380-405), eval mode: the producer of the
+def _bn_train(x, p, name, eps=1e-5):
+    """BatchNorm2d in training mode: batch statistics over (B, H, W), biased variance (what normalises)."""
+    g, b = p[f"{name}.weight"], p[f"{name}.bias"]
+    m = x.mean(axis=(0, 2, 3), keepdims=True)
+    v = x.var(axis=(0, 2, 3), keepdims=True)
+    return (x - m) / np.sqrt(v + eps) * g[None, :, None, None] + b[None, :, None, None]
+
+
+def imim_forward(p, img, training=False):
+    """IMIM.forward (reference models/models.py:380-405), eval mode (running statistics) or
+    training mode (batch statistics; pinned by tests/golden/imim_train.npz): the producer of the
     word-region loss's region features.  img [B,256,14,14] -> [B,256,14,14] logical, unit L2 norm over the channel axis
     at every position (memory order of the reference's result: channels-last, models.py:401-404)."""
     p = {k: np.asarray(v, np.float64) for k, v in p.items()}
-    x = _bn_eval(np.asarray(img, np.float64), p, "bn_img")                                     # :394
+    x = np.asarray(img, np.float64)
+    x = _bn_train(x, p, "bn_img") if training else _bn_eval(x, p, "bn_img")                     # :394
     x = self_attention(p, x, x)                                                                  # :395 (scale = 1)
     x = _layernorm(x, p["ln.weight"], p["ln.bias"])                                              # :396
     conv1 = lambda t, n: np.einsum("bchw,oc->bohw", t, p[f"{n}.weight"][:, :, 0, 0]) + p[f"{n}.bias"][None, :, None, None]

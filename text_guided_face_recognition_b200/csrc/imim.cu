@@ -24,7 +24,7 @@ constexpr float kLnEps = 1e-5f;
 // ------------------------------------------------------------------------------------------------------------
 // fp32 GEMM, row-major:  C[b] (+)= alpha * op(A[b]) * op(B[b]) (+ bias) (relu)
 //   mode 0 (NT): A [M,K] lda, B [N,K] ldb          mode 1 (NN): A [M,K], B [K,N]          mode 2 (TN): A [K,M], B [K,N]
-// 64 x 64 tile, 16-deep K slices, 256 threads, 4 x 4 outputs per thread; blockIdx.z = batch * splits + split.
+// blockIdx.z = batch * splits + split.
 // ------------------------------------------------------------------------------------------------------------
 struct SgemmP {
   const float *A, *B;
@@ -35,11 +35,13 @@ struct SgemmP {
   float alpha;
 };
 
+// 128 x 128 tile, 8-deep K slices (double-buffered in shared memory, global loads of slice k+1 in flight while slice k
+// is multiplied), 256 threads, 8 x 8 outputs per thread as 2 x 2 blocks of 4 x 4 (conflict-free float4 reads).
 template <int MODE>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
   const int bz = blockIdx.z / p.splits, sp = blockIdx.z - bz * p.splits;
   const float* A = p.A + (int64_t)bz * p.sa;
   const float* Bm = p.B + (int64_t)bz * p.sb;
@@ -48,63 +50,82 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
   const int kper = ((p.K + p.splits - 1) / p.splits + BK - 1) / BK * BK;
   const int k_begin = sp * kper, k_end = min(p.K, k_begin + kper);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
+  // staging: every thread moves 4 elements of A and 4 of B per slice
+  //   k-contiguous operand ([rows, K]):  row = tid >> 1, k = (tid & 1) * 4 .. +3
+  //   row-contiguous operand ([K, rows]): k = tid >> 5, rows (tid & 31) * 4 .. +3
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    if (MODE == 2) {
+      const int kk = tid >> 5, mm = (tid & 31) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = (gk < k_end && m0 + mm + j < p.M) ? A[(int64_t)gk * p.lda + m0 + mm + j] : 0.f;
+    } else {
+      const int mm = tid >> 1, kk = (tid & 1) * 4, gm = m0 + mm;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = (gm < p.M && k0 + kk + j < k_end) ? A[(int64_t)gm * p.lda + k0 + kk + j] : 0.f;
+    }
+    if (MODE == 0) {
+      const int nn = tid >> 1, kk = (tid & 1) * 4, gn = n0 + nn;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = (gn < p.N && k0 + kk + j < k_end) ? Bm[(int64_t)gn * p.ldb + k0 + kk + j] : 0.f;
+    } else {
+      const int kk = tid >> 5, nn = (tid & 31) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = (gk < k_end && n0 + nn + j < p.N) ? Bm[(int64_t)gk * p.ldb + n0 + nn + j] : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+    if (MODE == 2) {
+      const int kk = tid >> 5, mm = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&As[buf][kk][mm]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    } else {
+      const int mm = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[buf][kk + j][mm] = ra[j];
+    }
+    if (MODE == 0) {
+      const int nn = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[buf][kk + j][nn] = rb[j];
+    } else {
+      const int kk = tid >> 5, nn = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kk][nn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
+  };
+  float acc[8][8] = {};
+  int buf = 0;
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-    // stage A -> As[k][m], B -> Bs[k][n]
-    if (MODE == 2) {                     // A [K,M]: rows k, m contiguous
-      const int kk = tid >> 4, mm = (tid & 15) * 4;
-      const int gk = k0 + kk;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gm = m0 + mm + j;
-        As[kk][mm + j] = (gk < k_end && gm < p.M) ? A[(int64_t)gk * p.lda + gm] : 0.f;
-      }
-    } else {                             // A [M,K]: rows m, k contiguous
-      const int mm = tid >> 2, kk = (tid & 3) * 4;
-      const int gm = m0 + mm;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gk = k0 + kk + j;
-        As[kk + j][mm] = (gm < p.M && gk < k_end) ? A[(int64_t)gm * p.lda + gk] : 0.f;
-      }
-    }
-    if (MODE == 0) {                     // B [N,K]
-      const int nn = tid >> 2, kk = (tid & 3) * 4;
-      const int gn = n0 + nn;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gk = k0 + kk + j;
-        Bs[kk + j][nn] = (gn < p.N && gk < k_end) ? Bm[(int64_t)gn * p.ldb + gk] : 0.f;
-      }
-    } else {                             // B [K,N]
-      const int kk = tid >> 4, nn = (tid & 15) * 4;
-      const int gk = k0 + kk;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gn = n0 + nn + j;
-        Bs[kk][nn + j] = (gk < k_end && gn < p.N) ? Bm[(int64_t)gk * p.ldb + gn] : 0.f;
-      }
-    }
-    __syncthreads();
+    const bool more = k0 + BK < k_end;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (gm >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
       if (gn >= p.N) continue;
       float v = p.alpha * acc[i][j];
       if (p.bias && sp == 0) v += p.bias[gn];
@@ -121,7 +142,7 @@ int sgemm(int mode, const float* A, int64_t lda, int64_t sa, const float* B, int
     TGFR_REQUIRE(batch == 1 && ldc == N, "sgemm: split-K needs one dense output");
     TGFR_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
   }
-  const dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch * p.splits);
+  const dim3 grid(ceil_div(N, 128), ceil_div(M, 128), batch * p.splits);
   if (mode == 0) sgemm_kernel<0><<<grid, 256, 0, st>>>(p);
   else if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, st>>>(p);
   else sgemm_kernel<2><<<grid, 256, 0, st>>>(p);
