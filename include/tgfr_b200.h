@@ -329,6 +329,31 @@ int tgfr_proj_head_bwd(const float* gout, const float* out, const float* znorm, 
                        const float* weight, int M, int N, int K, float* dz_scratch, float* dx, float* dweight,
                        float* dbias, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * FCFM fusion net `Working`, TRAINING-mode forward + backward (models/fusion_nets.py:217-258 under autograd, as the
+ * fusion training step src/fusion_bert.py:205-233 runs it).  tgfr_fcfm_working_fwd above is the
+ * evaluation forward.  img [B,256,14,14] (element strides), word [B,256,T] (strides word_sb / word_sc, T contiguous),
+ * gl_img / sent [B,256] (row strides) -> out [B,640] (row stride out_sr).  params: 22 device pointers in the order
+ *   conv.weight [36,2304], conv.bias, bn_img.weight, bn_img.bias, projection.weight [36,256], projection.bias,
+ *   bn_word.weight, bn_word.bias, sa.query_proj.weight [36,36], .bias, sa.key_proj.weight, .bias, sa.value_proj.weight,
+ *   .bias, ln.weight [36*36], ln.bias, linear.weight [128,324], linear.bias, ln_gl_image.weight [256], .bias,
+ *   ln_sent.weight [256], .bias;
+ * running_stats: {bn_img.running_mean, bn_img.running_var, bn_word.running_mean, bn_word.running_var} (entries may be
+ * NULL when training; updated with `momentum` then).  The backward writes dparams (22 pointers, same order / shapes) and,
+ * where not NULL, dimg [B,256,14,14], dword [B,256,T], dgl_img / dsent [B,256] (all contiguous). */
+size_t tgfr_fcfm_train_saved_bytes(int B, int T);
+size_t tgfr_fcfm_train_workspace_bytes(int B, int T);
+int tgfr_fcfm_train_fwd(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw,
+                        const float* word, int64_t word_sb, int64_t word_sc, const float* gl_img, int64_t gl_sr,
+                        const float* sent, int64_t sent_sr, const void* const* params, int n_params, int B, int T,
+                        int training, float momentum, float eps, void* const* running_stats, float* out,
+                        int64_t out_sr, void* saved, size_t saved_bytes, void* stream);
+int tgfr_fcfm_train_bwd(const float* gout, int64_t gout_sr, const float* word, int64_t word_sb, int64_t word_sc,
+                        const float* gl_img, int64_t gl_sr, const float* sent, int64_t sent_sr,
+                        const void* const* params, int n_params, int B, int T, int training, const void* saved,
+                        size_t saved_bytes, void* const* dparams, float* dimg, float* dword, float* dgl_img,
+                        float* dsent, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 """FCFM fusion net `Working` (reference models/fusion_nets.py:217-258): the numpy oracle against
-fixtures generated from the reference module in eval mode (tests/golden/make_golden_fusion.py).  CPU only -- the CUDA
-kernel of this row is not built yet; this pins the checker it will be built against."""
+fixtures generated from the reference module in eval mode (tests/golden/make_golden_fusion.py); the one-launch eval
+kernel (csrc/fcfm.cu) and the training-mode forward + backward (csrc/fcfm_train.cu) against the reference's outputs and
+autograd gradients (tests/golden/make_golden_fusion_r2.py)."""
 import os
 
 import numpy as np
@@ -48,13 +49,55 @@ def test_gpu_working_forward_matches_reference(name):
     gl, sent = torch.from_numpy(g["gl_img"]).cuda(), torch.from_numpy(g["sent"]).cuda()
     for im in (img, img.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)):
         for wd in (word, word.transpose(1, 2).contiguous().transpose(1, 2)):
-            out = net(im, wd, gl, sent).cpu().numpy()
+            with torch.no_grad():                                              # verification path: the one-launch kernel
+                out = net(im, wd, gl, sent).cpu().numpy()
             assert out.shape == (img.shape[0], 640)
             np.testing.assert_allclose(out, g["out"], atol=1e-4, rtol=0)       # the reference (CPU fp32)
             np.testing.assert_allclose(out, ref64, atol=1e-4, rtol=0)          # the fp64 oracle
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(img, word, gl, sent)
+            out_ag = net(im, wd, gl, sent)                                     # eval mode under autograd: batch-wide kernels
+            assert out_ag.requires_grad
+            np.testing.assert_allclose(out_ag.detach().cpu().numpy(), g["out"], atol=1e-4, rtol=0)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["contiguous", "channels_last"])
+def test_gpu_working_training_matches_reference_autograd(layout):
+    """Training mode (BatchNorm batch statistics): output, the gradients of all 26 parameters and of the four inputs, and
+    the updated running statistics against the reference module under autograd (fusion_working_train.npz)."""
+    import sys
+    import torch
+    sys.path.insert(0, GOLDEN)
+    from make_golden_fusion_r2 import fusion_inputs
+    base = np.load(os.path.join(GOLDEN, "fusion_working_bert22.npz"))
+    g = np.load(os.path.join(GOLDEN, "fusion_working_train.npz"))
+    net = _module_from_fixture(base).train()
+    img, word, gl, sent, gout = fusion_inputs(5, 22, 9)
+    it = torch.from_numpy(img).cuda()
+    if layout == "channels_last":
+        it = it.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    leaves = [it.requires_grad_(True)] + [torch.from_numpy(a).cuda().requires_grad_(True) for a in (word, gl, sent)]
+    out = net(*leaves)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=0)
+    out.backward(torch.from_numpy(gout).cuda())
+    for t, name in zip(leaves, ("dimg", "dword", "dgl", "dsent")):
+        assert _rel(t.grad.cpu().numpy(), g[name]) < 3e-4, (name, _rel(t.grad.cpu().numpy(), g[name]))
+    for name, p in net.named_parameters():
+        ref = g["g:" + name]
+        got = p.grad.cpu().numpy()
+        if np.linalg.norm(ref) < 1e-4:                    # sa.query_proj.bias: the softmax is invariant to it
+            assert np.max(np.abs(got)) < 1e-4, name
+        else:
+            assert _rel(got, ref) < 3e-4, (name, _rel(got, ref))
+    sd = net.state_dict()
+    for k in g.files:
+        if k.startswith("s:"):
+            assert _rel(sd[k[2:]].cpu().numpy(), g[k]) < 1e-5, k
+    assert int(sd["bn_img.num_batches_tracked"]) == 1
 
 
 @pytest.mark.gpu
@@ -71,11 +114,12 @@ def test_gpu_working_batch_independence_and_scoring():
     word = torch.nn.functional.normalize(torch.randn(B, T, 256, generator=gen), dim=2).transpose(1, 2).cuda()
     gl = torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=1).cuda()
     sent = torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=1).cuda()
-    out = net(img, word, gl, sent)
-    assert torch.isfinite(out).all()
-    for i in (0, 299, 599):
-        one = net(img[i:i + 1], word[i:i + 1], gl[i:i + 1], sent[i:i + 1])
-        assert torch.equal(one[0], out[i])
+    with torch.no_grad():                          # the verification path runs under no_grad (utils/modules.py:129)
+        out = net(img, word, gl, sent)
+        assert torch.isfinite(out).all()
+        for i in (0, 299, 599):
+            one = net(img[i:i + 1], word[i:i + 1], gl[i:i + 1], sent[i:i + 1])
+            assert torch.equal(one[0], out[i])
     params = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
     ref = FO.working_forward(params, img[:4].cpu().numpy(), word[:4].cpu().numpy(), gl[:4].cpu().numpy(), sent[:4].cpu().numpy())
     np.testing.assert_allclose(out[:4].cpu().numpy(), ref, atol=1e-4, rtol=0)

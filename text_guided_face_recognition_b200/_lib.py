@@ -74,6 +74,10 @@ SIGNATURES = {
     "tgfr_imim_bwd": (I, [P, P, P, L, L, L, P, I, I, I, I, P, Z, P, P, P, Z, P]),
     "tgfr_proj_head_fwd": (I, [P, L, P, P, I, I, I, P, P, P]),
     "tgfr_proj_head_bwd": (I, [P, P, P, P, L, P, I, I, I, P, P, P, P, P]),
+    "tgfr_fcfm_train_saved_bytes": (Z, [I, I]),
+    "tgfr_fcfm_train_workspace_bytes": (Z, [I, I]),
+    "tgfr_fcfm_train_fwd": (I, [P, L, L, L, L, P, L, L, P, L, P, L, P, I, I, I, I, F, F, P, P, L, P, Z, P]),
+    "tgfr_fcfm_train_bwd": (I, [P, L, P, L, L, P, L, P, L, P, I, I, I, I, P, Z, P, P, P, P, P, P, Z, P]),
     "tgfr_debug_umma": (I, [P, P, P, I, I, I, I, I, P]),
     "tgfr_debug_tma_reduce": (I, [P, I, I, P]),
     "tgfr_debug_umma_2cta": (I, [P, P, P, I, I, P]),

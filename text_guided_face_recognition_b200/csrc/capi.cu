@@ -99,6 +99,16 @@ int proj_head_fwd(const float*, int64_t, const float*, const float*, int, int, i
 int proj_head_bwd(const float*, const float*, const float*, const float*, int64_t, const float*, int, int, int, float*, float*,
                   float*, float*, cudaStream_t);
 
+// fcfm_train.cu
+size_t fcfm_train_saved_bytes(int, int);
+size_t fcfm_train_workspace_bytes(int, int);
+int fcfm_train_fwd(const float*, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, const float*, int64_t,
+                   const float*, int64_t, const float* const*, int, int, int, float, float, float* const*, float*, int64_t, void*,
+                   size_t, cudaStream_t);
+int fcfm_train_bwd(const float*, int64_t, const float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t,
+                   const float* const*, int, int, int, const void*, size_t, float* const*, float*, float*, float*, float*, void*,
+                   size_t, cudaStream_t);
+
 // scoring.cu
 int pair_cosine(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float, float*, cudaStream_t);
 int row_argmax(const float*, int64_t, int, int, int64_t*, cudaStream_t);
@@ -382,6 +392,32 @@ int tgfr_proj_head_bwd(const float* gout, const float* out, const float* znorm, 
                        void* stream) {
   TGFR_REQUIRE(gout && out && znorm && x && weight && dz_scratch && dweight && dbias, "proj_head_bwd: NULL tensor");
   return proj_head_bwd(gout, out, znorm, x, x_sr, weight, M, N, K, dz_scratch, dx, dweight, dbias, ST(stream));
+}
+
+size_t tgfr_fcfm_train_saved_bytes(int B, int T) { return fcfm_train_saved_bytes(B, T); }
+size_t tgfr_fcfm_train_workspace_bytes(int B, int T) { return fcfm_train_workspace_bytes(B, T); }
+int tgfr_fcfm_train_fwd(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw, const float* word,
+                        int64_t word_sb, int64_t word_sc, const float* gl_img, int64_t gl_sr, const float* sent, int64_t sent_sr,
+                        const void* const* params, int n_params, int B, int T, int training, float momentum, float eps,
+                        void* const* running_stats, float* out, int64_t out_sr, void* saved, size_t saved_bytes, void* stream) {
+  TGFR_REQUIRE(img && word && gl_img && sent && params && out && running_stats, "fcfm_train_fwd: NULL tensor");
+  TGFR_REQUIRE(n_params == 22, "fcfm_train_fwd: expected 22 parameter tensors, got %d", n_params);
+  TGFR_REQUIRE(B >= 1 && T >= 1, "fcfm_train_fwd: empty shape");
+  return fcfm_train_fwd(img, img_sb, img_sc, img_sh, img_sw, word, word_sb, word_sc, gl_img, gl_sr, sent, sent_sr,
+                        reinterpret_cast<const float* const*>(params), B, T, training, momentum, eps,
+                        reinterpret_cast<float* const*>(running_stats), out, out_sr, saved, saved_bytes, ST(stream));
+}
+int tgfr_fcfm_train_bwd(const float* gout, int64_t gout_sr, const float* word, int64_t word_sb, int64_t word_sc,
+                        const float* gl_img, int64_t gl_sr, const float* sent, int64_t sent_sr, const void* const* params,
+                        int n_params, int B, int T, int training, const void* saved, size_t saved_bytes, void* const* dparams,
+                        float* dimg, float* dword, float* dgl_img, float* dsent, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  TGFR_REQUIRE(gout && word && gl_img && sent && params && dparams, "fcfm_train_bwd: NULL tensor");
+  TGFR_REQUIRE(n_params == 22, "fcfm_train_bwd: expected 22 parameter tensors, got %d", n_params);
+  return fcfm_train_bwd(gout, gout_sr, word, word_sb, word_sc, gl_img, gl_sr, sent, sent_sr,
+                        reinterpret_cast<const float* const*>(params), B, T, training, saved, saved_bytes,
+                        reinterpret_cast<float* const*>(dparams), dimg, dword, dgl_img, dsent, workspace, workspace_bytes,
+                        ST(stream));
 }
 
 int tgfr_pair_cosine(const float* x1, int64_t x1_sr, int64_t x1_sd, const float* x2, int64_t x2_sr, int64_t x2_sd, int64_t N,

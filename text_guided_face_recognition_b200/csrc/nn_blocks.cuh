@@ -1,0 +1,417 @@
+// Dense building blocks shared by the trainable heads (csrc/imim.cu, csrc/fcfm_train.cu): a register-blocked fp32 GEMM
+// (NT / NN / TN, strided batch, split-K), BatchNorm over channels of position-major or channel-major data, row softmax,
+// LayerNorm over a whole sample, row L2 normalisation, ReLU masks and column sums -- each with its backward.
+// Everything lives in an anonymous namespace: every translation unit that includes this header gets its own copy.
+#pragma once
+#include "common.cuh"
+
+namespace tgfr {
+namespace {
+
+constexpr float kLnEps = 1e-5f;
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 GEMM, row-major:  C[b] (+)= alpha * op(A[b]) * op(B[b]) (+ bias) (relu)
+//   mode 0 (NT): A [M,K] lda, B [N,K] ldb          mode 1 (NN): A [M,K], B [K,N]          mode 2 (TN): A [K,M], B [K,N]
+// blockIdx.z = batch * splits + split.
+// ------------------------------------------------------------------------------------------------------------
+struct SgemmP {
+  const float *A, *B;
+  float* C;
+  const float* bias;
+  int64_t lda, ldb, ldc, sa, sb, sc;   // leading dimensions and batch strides (elements)
+  int M, N, K, splits, relu, atomic, accumulate;
+  float alpha;
+};
+
+// 128 x 128 tile, 8-deep K slices (double-buffered in shared memory, global loads of slice k+1 in flight while slice k
+// is multiplied), 256 threads, 8 x 8 outputs per thread as 2 x 2 blocks of 4 x 4 (conflict-free float4 reads).
+template <int MODE>
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int bz = blockIdx.z / p.splits, sp = blockIdx.z - bz * p.splits;
+  const float* A = p.A + (int64_t)bz * p.sa;
+  const float* Bm = p.B + (int64_t)bz * p.sb;
+  float* C = p.C + (int64_t)bz * p.sc;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kper = ((p.K + p.splits - 1) / p.splits + BK - 1) / BK * BK;
+  const int k_begin = sp * kper, k_end = min(p.K, k_begin + kper);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // staging: every thread moves 4 elements of A and 4 of B per slice
+  //   k-contiguous operand ([rows, K]):  row = tid >> 1, k = (tid & 1) * 4 .. +3
+  //   row-contiguous operand ([K, rows]): k = tid >> 5, rows (tid & 31) * 4 .. +3
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+    if (MODE == 2) {
+      const int kk = tid >> 5, mm = (tid & 31) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = (gk < k_end && m0 + mm + j < p.M) ? A[(int64_t)gk * p.lda + m0 + mm + j] : 0.f;
+    } else {
+      const int mm = tid >> 1, kk = (tid & 1) * 4, gm = m0 + mm;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = (gm < p.M && k0 + kk + j < k_end) ? A[(int64_t)gm * p.lda + k0 + kk + j] : 0.f;
+    }
+    if (MODE == 0) {
+      const int nn = tid >> 1, kk = (tid & 1) * 4, gn = n0 + nn;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = (gn < p.N && k0 + kk + j < k_end) ? Bm[(int64_t)gn * p.ldb + k0 + kk + j] : 0.f;
+    } else {
+      const int kk = tid >> 5, nn = (tid & 31) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = (gk < k_end && n0 + nn + j < p.N) ? Bm[(int64_t)gk * p.ldb + n0 + nn + j] : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+    if (MODE == 2) {
+      const int kk = tid >> 5, mm = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&As[buf][kk][mm]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    } else {
+      const int mm = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[buf][kk + j][mm] = ra[j];
+    }
+    if (MODE == 0) {
+      const int nn = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[buf][kk + j][nn] = rb[j];
+    } else {
+      const int kk = tid >> 5, nn = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kk][nn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
+  };
+  float acc[8][8] = {};
+  int buf = 0;
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (gn >= p.N) continue;
+      float v = p.alpha * acc[i][j];
+      if (p.bias && sp == 0) v += p.bias[gn];
+      if (p.atomic) atomicAdd(&C[(int64_t)gm * p.ldc + gn], v);
+      else if (p.accumulate) C[(int64_t)gm * p.ldc + gn] += v;
+      else C[(int64_t)gm * p.ldc + gn] = p.relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
+// splits > 1: split-K with atomics into a zeroed C.  sc == 0 with batch > 1: every batch adds (atomically) into ONE C.
+// accumulate: C += result (plain read-modify-write; not combinable with the atomic modes).
+int sgemm(int mode, const float* A, int64_t lda, int64_t sa, const float* B, int64_t ldb, int64_t sb, float* C, int64_t ldc,
+          int64_t sc, int M, int N, int K, int batch, float alpha, const float* bias, int relu, int splits, cudaStream_t st,
+          int accumulate = 0) {
+  if (M <= 0 || N <= 0 || batch <= 0) return TGFR_OK;
+  const bool batch_sum = batch > 1 && sc == 0;
+  SgemmP p{A, B, C, bias, lda, ldb, ldc, sa, sb, sc, M, N, K, splits < 1 ? 1 : splits, relu, (splits > 1 || batch_sum) ? 1 : 0,
+           accumulate, alpha};
+  if (p.atomic) {
+    TGFR_REQUIRE((batch == 1 || batch_sum) && !accumulate && !relu, "sgemm: atomic mode needs one output, no relu");
+    TGFR_REQUIRE(!bias || batch == 1, "sgemm: bias with a batch-summed output");
+    TGFR_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+  }
+  const dim3 grid(ceil_div(N, 128), ceil_div(M, 128), batch * p.splits);
+  if (mode == 0) sgemm_kernel<0><<<grid, 256, 0, st>>>(p);
+  else if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, st>>>(p);
+  else sgemm_kernel<2><<<grid, 256, 0, st>>>(p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BatchNorm2d over x [B, C, P] (element strides): per-channel statistics, apply + transpose to [B*P, C], backward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sp, int B, int P, float eps,
+                                float momentum, int training, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                float* __restrict__ mean, float* __restrict__ invstd) {
+  __shared__ float scratch[32];
+  const int c = blockIdx.x;
+  if (!training) {
+    if (threadIdx.x == 0) {
+      mean[c] = run_mean[c];
+      invstd[c] = rsqrtf(run_var[c] + eps);
+    }
+    return;
+  }
+  const int n = B * P;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += x[(k / P) * sb + c * sc + (k % P) * sp];
+  const float mu = block_sum(s, scratch) / (float)n;
+  float v = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float d = x[(k / P) * sb + c * sc + (k % P) * sp] - mu;
+    v = fmaf(d, d, v);
+  }
+  const float var = block_sum(v, scratch) / (float)n;          // biased variance normalises (as torch does)
+  if (threadIdx.x == 0) {
+    mean[c] = mu;
+    invstd[c] = rsqrtf(var + eps);
+    if (run_mean) {                                            // running statistics: unbiased variance, momentum update
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)n / (float)max(n - 1, 1));
+    }
+  }
+}
+
+// xn[(b*P + p), c] = (x[b,c,p] - mean[c]) invstd[c] gamma[c] + beta[c]; a 32 x 32 tile transposed through shared memory
+__global__ void bn_apply_t_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sp, int C, int P,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, pp = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && pp < P) ? x[b * sb + c * sc + pp * sp] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int pp = p0 + j, c = c0 + threadIdx.x;
+    if (pp < P && c < C) xn[((int64_t)b * P + pp) * C + c] = (tile[threadIdx.x][j] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+  }
+}
+
+// per-channel sums for the BatchNorm backward: s1[c] = sum dxn, s2[c] = sum dxn * xhat  (xhat recomputed from x)
+__global__ void bn_bwd_sums_kernel(const float* __restrict__ dxn, const float* __restrict__ x, int64_t sb, int64_t sc,
+                                   int64_t sp, int B, int C, int P, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float scratch[32];
+  const int c = blockIdx.x, n = B * P;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float g = dxn[(int64_t)k * C + c];
+    const float xh = (x[(k / P) * sb + c * sc + (k % P) * sp] - mean[c]) * invstd[c];
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+  }
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  if (threadIdx.x == 0) {
+    dbeta[c] = s1;
+    dgamma[c] = s2;
+  }
+}
+
+// dx[b,c,p] (element strides dsb / dsc / dsp) = gamma invstd (dxn - [training] (s1 + xhat s2) / n)
+__global__ void bn_bwd_dx_kernel(const float* __restrict__ dxn, const float* __restrict__ x, int64_t sb, int64_t sc,
+                                 int64_t sp, int B, int C, int P, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                 const float* __restrict__ dgamma, const float* __restrict__ dbeta, int training,
+                                 float* __restrict__ dx, int64_t dsb, int64_t dsc, int64_t dsp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int pp = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (pp < P && c < C) ? dxn[((int64_t)b * P + pp) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (float)(B * P);
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, pp = p0 + threadIdx.x;
+    if (c < C && pp < P) {
+      float g = tile[threadIdx.x][j];
+      if (training) {
+        const float xh = (x[b * sb + c * sc + pp * sp] - mean[c]) * invstd[c];
+        g -= (dbeta[c] + xh * dgamma[c]) * inv_n;
+      }
+      dx[b * dsb + c * dsc + pp * dsp] = g * gamma[c] * invstd[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// softmax over the last axis of [rows, n] in place, and its backward dS = scale * P (dP - sum_j P dP)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* p = s + (int64_t)row * n;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, p[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float e = expf(p[j] - m);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < n; j += 32) p[j] *= inv;
+}
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ prob, float* __restrict__ dp, int rows, int n, float scale) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = prob + (int64_t)row * n;
+  float* d = dp + (int64_t)row * n;
+  float inner = 0.f;
+  for (int j = lane; j < n; j += 32) inner = fmaf(p[j], d[j], inner);
+  inner = warp_sum(inner);
+  for (int j = lane; j < n; j += 32) d[j] = scale * p[j] * (d[j] - inner);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm([C, 14, 14]) per sample on position-major data o [B, P, C]; affine weight / bias indexed [c * P + p]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void ln_fwd_kernel(const float* __restrict__ o, int64_t o_stride, int P, int C, const float* __restrict__ w,
+                              const float* __restrict__ bia, float* __restrict__ y, int64_t y_stride, float* __restrict__ mu_out,
+                              float* __restrict__ rstd_out) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x, n = P * C;
+  const float* src = o + (int64_t)b * o_stride;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += src[k];
+  const float mu = block_sum(s, scratch) / (float)n;
+  float v = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float d = src[k] - mu;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(block_sum(v, scratch) / (float)n + kLnEps);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    y[(int64_t)b * y_stride + k] = (src[k] - mu) * rstd * w[c * P + pp] + bia[c * P + pp];
+  }
+  if (threadIdx.x == 0) {
+    mu_out[b] = mu;
+    rstd_out[b] = rstd;
+  }
+}
+// dO = rstd (dh - mean(dh) - yhat mean(dh yhat)), dh = dY w   (dx may alias dy)
+__global__ void ln_bwd_dx_kernel(const float* dy, int64_t dy_stride, const float* __restrict__ o, int64_t o_stride, int P,
+                                 int C, const float* __restrict__ w, const float* __restrict__ mu_in,
+                                 const float* __restrict__ rstd_in, float* dx, int64_t dx_stride) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x, n = P * C;
+  const float mu = mu_in[b], rstd = rstd_in[b];
+  const float* g = dy + (int64_t)b * dy_stride;
+  const float* src = o + (int64_t)b * o_stride;
+  float* out = dx + (int64_t)b * dx_stride;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    const float dh = g[k] * w[c * P + pp];
+    s1 += dh;
+    s2 = fmaf(dh, (src[k] - mu) * rstd, s2);
+  }
+  s1 = block_sum(s1, scratch) / (float)n;
+  s2 = block_sum(s2, scratch) / (float)n;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    const float dh = g[k] * w[c * P + pp];
+    out[k] = rstd * (dh - s1 - (src[k] - mu) * rstd * s2);
+  }
+}
+// d ln.weight[c*P+p] = sum_b dY yhat, d ln.bias = sum_b dY  (one thread per (p, c); must run BEFORE an in-place ln_bwd_dx_kernel)
+__global__ void ln_bwd_params_kernel(const float* __restrict__ dy, int64_t dy_stride, const float* __restrict__ o,
+                                     int64_t o_stride, int B, int P, int C, const float* __restrict__ mu,
+                                     const float* __restrict__ rstd, float* __restrict__ dw, float* __restrict__ db) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, n = P * C;
+  if (k >= n) return;
+  const int pp = k / C, c = k - pp * C;
+  float a = 0.f, s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float g = dy[(int64_t)b * dy_stride + k];
+    a = fmaf(g, (o[(int64_t)b * o_stride + k] - mu[b]) * rstd[b], a);
+    s += g;
+  }
+  dw[c * P + pp] = a;
+  db[c * P + pp] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// row-wise helpers on [M, C]: L2 normalisation (applied twice, models.py:119 + :403) and its backward; ReLU mask;
+// column sums (bias gradients)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void l2norm2_rows_kernel(const float* __restrict__ z, int M, int C, float* __restrict__ out,
+                                    float* __restrict__ znorm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* p = z + (int64_t)row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(p[c], p[c], s);
+  const float n1 = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+  float s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = p[c] / n1;
+    s2 = fmaf(v, v, s2);
+  }
+  const float n2 = fmaxf(sqrtf(warp_sum(s2)), 1e-12f);
+  for (int c = lane; c < C; c += 32) out[(int64_t)row * C + c] = (p[c] / n1) / n2;
+  if (lane == 0) znorm[row] = n1 * n2;
+}
+__global__ void l2norm_rows_kernel(const float* __restrict__ z, int M, int C, float* __restrict__ out,
+                                   float* __restrict__ znorm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* p = z + (int64_t)row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(p[c], p[c], s);
+  const float n1 = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+  for (int c = lane; c < C; c += 32) out[(int64_t)row * C + c] = p[c] / n1;
+  if (lane == 0) znorm[row] = n1;
+}
+// dZ = (g - (g . o) o) / |Z|   (o = the unit output rows)
+__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ o,
+                                       const float* __restrict__ znorm, int M, int C, float* __restrict__ dz) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* gp = g + (int64_t)row * C;
+  const float* op = o + (int64_t)row * C;
+  float d = 0.f;
+  for (int c = lane; c < C; c += 32) d = fmaf(gp[c], op[c], d);
+  d = warp_sum(d);
+  const float inv = 1.f / znorm[row];
+  for (int c = lane; c < C; c += 32) dz[(int64_t)row * C + c] = (gp[c] - d * op[c]) * inv;
+}
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t n) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    if (!(act[k] > 0.f)) g[k] = 0.f;
+}
+// out[c] = sum_m g[m, ld*.. + c]: blocks of 256 rows, atomics into a zeroed vector
+__global__ void colsum_kernel(const float* __restrict__ g, int64_t ld, int M, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int m0 = blockIdx.y * 256, m1 = min(M, m0 + 256);
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += g[(int64_t)m * ld + c];
+  atomicAdd(&out[c], s);
+}
+
+int colsum(const float* g, int64_t ld, int M, int C, float* out, cudaStream_t st) {
+  TGFR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  colsum_kernel<<<dim3(ceil_div(C, 128), ceil_div(M, 256)), 128, 0, st>>>(g, ld, M, C, out);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
+}  // namespace
+}  // namespace tgfr

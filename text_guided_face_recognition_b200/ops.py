@@ -15,7 +15,7 @@ from ._lib import PREC_FP32, PREC_TC, check, ptr, stream_ptr
 __all__ = [
     "default_precision", "tc_supported", "wordregion_sim", "pair_ce", "cosine_scores", "arc_logits", "focal_ce",
     "mag_logits", "mag_ce", "cosine_rows", "func_attention_canonical", "launch_counter", "arc_fused_focal", "text_heading",
-    "pair_cosine", "roc_counts", "row_argmax", "fcfm_working", "imim", "proj_head",
+    "pair_cosine", "roc_counts", "row_argmax", "fcfm_working", "fcfm_working_train", "imim", "proj_head",
 ]
 
 
@@ -59,7 +59,7 @@ _KERNELS_PER_CALL = {
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
     "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_mag_ce_stats": 1, "tgfr_mag_ce_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
     "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 12, "tgfr_imim_bwd": 34,
-    "tgfr_proj_head_fwd": 2, "tgfr_proj_head_bwd": 5,
+    "tgfr_proj_head_fwd": 2, "tgfr_proj_head_bwd": 5, "tgfr_fcfm_train_fwd": 21, "tgfr_fcfm_train_bwd": 45,
 }
 
 
@@ -860,3 +860,78 @@ def proj_head(x, weight, bias):
     lead = x.shape[:-1]
     out = _ProjHead.apply(_f32(x).reshape(-1, x.shape[-1]), _f32(weight), None if bias is None else _f32(bias).contiguous())
     return out.reshape(*lead, weight.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# FCFM fusion net `Working`, training-mode forward + backward (models/fusion_nets.py:217-258 under autograd)
+# ---------------------------------------------------------------------------------------------
+FCFM_TRAIN_PARAM_ORDER = (
+    "conv.weight", "conv.bias", "bn_img.weight", "bn_img.bias", "projection.weight", "projection.bias", "bn_word.weight",
+    "bn_word.bias", "sa.query_proj.weight", "sa.query_proj.bias", "sa.key_proj.weight", "sa.key_proj.bias",
+    "sa.value_proj.weight", "sa.value_proj.bias", "ln.weight", "ln.bias", "linear.weight", "linear.bias",
+    "ln_gl_image.weight", "ln_gl_image.bias", "ln_sent.weight", "ln_sent.bias",
+)
+
+
+class _FcfmTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, word, gl_img, sent, run_stats, training, momentum, eps, *params):
+        _lib.ensure_device(img.device)
+        B, T = img.shape[0], word.shape[2]
+        dev = img.device
+        lib = _lib.load()
+        if word.stride(2) != 1:
+            word = word.contiguous()
+        gl_img = gl_img if gl_img.stride(1) == 1 else gl_img.contiguous()
+        sent = sent if sent.stride(1) == 1 else sent.contiguous()
+        prm = [_f32(p_.detach()).contiguous() for p_ in params]
+        out = torch.empty((B, 640), dtype=torch.float32, device=dev)
+        svb = lib.tgfr_fcfm_train_saved_bytes(B, T)
+        saved = torch.empty(svb, dtype=torch.uint8, device=dev)
+        arr, parr = _ptr_array(prm)
+        rarr, rparr = _ptr_array(list(run_stats))
+        _call("tgfr_fcfm_train_fwd", ptr(img), *img.stride(), ptr(word), word.stride(0), word.stride(1), ptr(gl_img),
+              gl_img.stride(0), ptr(sent), sent.stride(0), parr, len(prm), B, T, int(training), float(momentum), float(eps),
+              rparr, ptr(out), out.stride(0), ptr(saved), svb, stream_ptr())
+        ctx.save_for_backward(word, gl_img, sent, saved, *prm)
+        ctx.cfg = (B, T, bool(training))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        word, gl_img, sent, saved, *prm = ctx.saved_tensors
+        B, T, training = ctx.cfg
+        dev = word.device
+        lib = _lib.load()
+        gout = _f32(gout)
+        if gout.stride(1) != 1:
+            gout = gout.contiguous()
+        need = ctx.needs_input_grad
+        dimg = torch.empty((B, 256, 14, 14), dtype=torch.float32, device=dev) if need[0] else None
+        dword = torch.empty((B, 256, T), dtype=torch.float32, device=dev) if need[1] else None
+        dgl = torch.empty((B, 256), dtype=torch.float32, device=dev) if need[2] else None
+        dsent = torch.empty((B, 256), dtype=torch.float32, device=dev) if need[3] else None
+        dprm = [torch.empty_like(p_) for p_ in prm]
+        wsb = lib.tgfr_fcfm_train_workspace_bytes(B, T)
+        ws = _workspace(wsb, dev)
+        arr, parr = _ptr_array(prm)
+        darr, dparr = _ptr_array(dprm)
+        _call("tgfr_fcfm_train_bwd", ptr(gout), gout.stride(0), ptr(word), word.stride(0), word.stride(1), ptr(gl_img),
+              gl_img.stride(0), ptr(sent), sent.stride(0), parr, len(prm), B, T, int(training), ptr(saved), saved.numel(), dparr,
+              ptr(dimg), ptr(dword), ptr(dgl), ptr(dsent), ptr(ws), wsb, stream_ptr())
+        return (dimg, dword, dgl, dsent, None, None, None, None, *dprm)
+
+
+def fcfm_working_train(img, word, gl_img, sent, params, run_stats, training=True, momentum=0.1, eps=1e-5):
+    """Working.forward under autograd: img [B,256,14,14], word [B,256,T], gl_img / sent [B,256] -> [B,640];
+    params: the 22 tensors of FCFM_TRAIN_PARAM_ORDER (4-D / 3-D weights flattened to 2-D / 1-D);
+    run_stats: (bn_img.running_mean, bn_img.running_var, bn_word.running_mean, bn_word.running_var), updated in place."""
+    if img.dim() != 4 or tuple(img.shape[1:]) != (256, 14, 14):
+        raise RuntimeError(f"fcfm_working_train: expected img [B,256,14,14], got {tuple(img.shape)}")
+    B = img.shape[0]
+    if word.dim() != 3 or word.shape[0] != B or word.shape[1] != 256:
+        raise RuntimeError(f"fcfm_working_train: expected word [B,256,T], got {tuple(word.shape)}")
+    if tuple(gl_img.shape) != (B, 256) or tuple(sent.shape) != (B, 256):
+        raise RuntimeError("fcfm_working_train: expected gl_img / sent [B,256]")
+    return _FcfmTrain.apply(_f32(img), _f32(word), _f32(gl_img), _f32(sent), tuple(run_stats), bool(training),
+                            float(momentum), float(eps), *params)
