@@ -903,6 +903,54 @@ def run_b200(args):
                                                    "83.9 M MACs per sample forward, x3 with the backward"}}
         del ih, ix, ig
 
+        # ---- configs[4]: FCFM fusion (eval kernel) + verification scoring in ONE timed call: 6 000 faces x 10 captions
+        # = 60 000 pairs; a pair fuses (face_a, caption_a) and (face_b, caption_b) -> two 640-d embeddings -> cosine ->
+        # exact ROC / AUC / EER / TPR@FPR (utils/modules.py:129-166).  Faces and caption features are resident in HBM.
+        import contextlib as _ctx
+        import io as _io
+        from text_guided_face_recognition_b200.models.fusion_nets import Working
+        from text_guided_face_recognition_b200.utils import modules as scoring
+        fus = Working(channel_dim=256).to(dev).eval()
+        NF, NCAP, TF = 6000, 10, 22
+        gen5 = torch.Generator(device="cpu").manual_seed(5)
+        faces_l = torch.nn.functional.normalize(torch.randn(NF, 14, 14, D, generator=gen5), dim=-1).to(dev).permute(0, 3, 1, 2)
+        faces_g = torch.nn.functional.normalize(torch.randn(NF, D, generator=gen5), dim=1).to(dev)
+        caps_w = [torch.nn.functional.normalize(torch.randn(NF, TF, D, generator=gen5), dim=2).to(dev).transpose(1, 2)
+                  for _ in range(2)]
+        caps_s = [torch.nn.functional.normalize(torch.randn(NF, D, generator=gen5), dim=1).to(dev) for _ in range(2)]
+        plab5 = (torch.arange(NF * NCAP) % 10 == 0).long().to(dev)
+        perm = torch.roll(torch.arange(NF), 1).to(dev)
+
+        def fusion_verif():
+            with torch.no_grad():
+                o1, o2 = [], []
+                for cset in range(NCAP):
+                    o1.append(fus(faces_l, caps_w[cset & 1], faces_g, caps_s[cset & 1]))
+                    o2.append(fus(faces_l, caps_w[(cset + 1) & 1], faces_g, caps_s[(cset + 1) & 1])[perm])
+                with _ctx.redirect_stdout(_io.StringIO()):
+                    return scoring.score_pairs([(torch.cat(o1), torch.cat(o2), plab5)])
+        fusion_verif()
+        torch.cuda.synchronize()
+        e0.record()
+        fusion_verif()
+        e1.record()
+        torch.cuda.synchronize()
+        fv_ms = e0.elapsed_time(e1)
+        conv_flops = 2 * 2 * NF * NCAP * 144 * 36 * 2304              # the 3x3 convolution of both fusions of every pair
+        line["fusion_verification"] = {
+            "metric": "fusion_verification_pairs_per_sec", "value": NF * NCAP / (fv_ms * 1e-3), "unit": "pairs/s",
+            "ms_per_call": fv_ms, "dtype": "f32",
+            "config": {"workload": "configs[4]: 6000 faces x 10 captions = 60000 pairs; 2 x Working (eval kernel) per pair "
+                                   "-> pair cosine -> exact ROC / AUC / EER / TPR@FPR, one call", "pairs": NF * NCAP,
+                       "fusion_samples": 2 * NF * NCAP, "T": TF},
+            "fusion_samples_per_sec": 2 * NF * NCAP / (fv_ms * 1e-3),
+            "roofline": {"bound": "fp32-simt", "achieved": conv_flops / (fv_ms * 1e-3) / 1e12, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": conv_flops / (fv_ms * 1e-3) / 1e12 / fp32_peak,
+                         "algorithmic_flops_per_call": conv_flops,
+                         "note": "dominant kernel = the fused Working forward (3x3 convolution 256->36 on 14x14: 11.9 M MACs "
+                                 "per sample, fp32 SIMT)"}}
+        del fus, faces_l, faces_g, caps_w, caps_s
+
         # ---- TextHeading (the BERT 768 -> 256 word / sentence projection of configs[1])
         import types as _types
         from text_guided_face_recognition_b200.models.text_heading import TextHeading

@@ -137,3 +137,46 @@ def test_imim_oracle_matches_reference():
     np.testing.assert_allclose(out, g["out"], atol=2e-5, rtol=0)
     np.testing.assert_allclose(np.sqrt((out * out).sum(1)), 1.0, atol=1e-12)
     assert tuple(g["out_strides"]) == (50176, 1, 3584, 256)
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_training_step_runs_on_the_mirror():
+    """The fusion training step of the reference (src/fusion_bert.py:205-233): image_head -> Working -> metric_fc
+    (ArcMarginProduct(640, C)) -> FocalLoss(2) -> backward, on the mirror modules; every trainable parameter of the three
+    modules and both text inputs (`.requires_grad_()` leaves there) receive a finite gradient, and a second step after an
+    SGD update lowers the loss (the gradients point downhill)."""
+    import types
+    import torch
+    from text_guided_face_recognition_b200.models import losses, metrics
+    from text_guided_face_recognition_b200.models.fusion_nets import Working
+    from text_guided_face_recognition_b200.models.image_heading import ImageHeading
+    torch.manual_seed(3)
+    B, T, C = 16, 22, 40
+    head = ImageHeading(types.SimpleNamespace(aux_feat_dim_per_granularity=256)).cuda().train()
+    fusion = Working(channel_dim=256).cuda().train()
+    metric_fc = metrics.ArcMarginProduct(640, C, s=30, m=0.5, easy_margin=False).cuda()
+    criterion = losses.FocalLoss(gamma=2)
+    gen = torch.Generator().manual_seed(3)
+    imgs_g = torch.randn(B, 512, generator=gen).cuda()
+    imgs_l = torch.randn(B, 256, 14, 14, generator=gen).cuda()
+    words_emb = torch.nn.functional.normalize(torch.randn(B, T, 256, generator=gen), dim=2).transpose(1, 2).cuda().requires_grad_()
+    sent_emb = torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=1).cuda().requires_grad_()
+    label = torch.randint(0, C, (B,), generator=gen).cuda()
+    params = list(head.parameters()) + list(fusion.parameters()) + list(metric_fc.parameters())
+    opt = torch.optim.SGD([p for p in params], lr=0.05)
+    vals = []
+    for _ in range(3):
+        img_feats, local_feats = head(imgs_g, imgs_l)
+        output = fusion(local_feats, words_emb, img_feats, sent_emb)           # get_fusion_output, fusion_bert.py:190-203
+        output = metric_fc(output, label)
+        opt.zero_grad()
+        loss = criterion(output, label)
+        loss.backward()
+        vals.append(loss.item())
+        for n, p in list(head.named_parameters()) + list(fusion.named_parameters()) + list(metric_fc.named_parameters()):
+            if n.startswith("imim.project_local.fc") or n.startswith("project_global.fc"):
+                continue
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        assert torch.isfinite(words_emb.grad).all() and torch.isfinite(sent_emb.grad).all()
+        opt.step()
+    assert vals[-1] < vals[0], vals
