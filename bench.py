@@ -66,8 +66,8 @@ def peaks():
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel, from the committed
-    `ncu --set full` summary of this round (profiles/r1_final_ncu_raw.txt, same shapes as this bench)."""
-    path = os.path.join(ROOT, "profiles", "r1_final_ncu_raw.txt")
+    `ncu --set full` summary of this round (profiles/r2_final_ncu_raw.txt, same shapes as this bench)."""
+    path = os.path.join(ROOT, "profiles", "r2_final_ncu_raw.txt")
     try:
         rd = wr = None
         hit = False
@@ -85,8 +85,7 @@ def ncu_traffic(kernel_substr):
         return None
 
 
-HEAD_STEP_KERNELS = ("norm_f16_pair", "gemm_tc_kernel", "normalize_bwd_pair", "maxabs", "scale_to_f16", "arc_fix",
-                     "ce_merge_partials", "focal_finish", "head_")
+HEAD_STEP_KERNELS = ("norm_f16_pair", "gemm_tc_kernel", "normalize_bwd", "ce_merge_partials", "focal_finish")
 
 
 def ncu_traffic_sum(kernel_substrs, fname="r2_head_step_ncu_raw.txt"):
@@ -751,7 +750,7 @@ def run_b200(args):
         kernels = {
             "wordregion_fwd": {"kernel_ms": f_ms, "algorithmic_flops_per_launch": f_flops,
                                "achieved": f_flops / (f_ms * 1e-3) / 1e12,
-                               "traffic": ncu_traffic("wr_tc_fwd_kernel") if tc_mode else None},
+                               "traffic": ncu_traffic("wr_tc_fwd3_kernel") if tc_mode else None},
             "wordregion_bwd": {"kernel_ms": b_ms, "algorithmic_flops_per_launch": b_flops,
                                "achieved": b_flops / (b_ms * 1e-3) / 1e12,
                                "traffic": ncu_traffic("wr_tc_bwd2_kernel") if tc_mode else None},
@@ -761,7 +760,7 @@ def run_b200(args):
             v["frac"] = v["achieved"] / pk["tf_burst"]
         line["roofline"] = {"bound": "tensor", "achieved": kernels[dom]["achieved"], "peak": pk["tf_burst"],
                             "unit": "TFLOP/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
-                            "traffic_source": "profiles/r1_final_ncu_raw.txt (ncu --set full, same shapes)",
+                            "traffic_source": "profiles/r2_final_ncu_raw.txt (ncu --set full, same shapes)",
                             "kernel": dom, "kernel_ms": kernels[dom]["kernel_ms"],
                             "algorithmic_flops_per_launch": kernels[dom]["algorithmic_flops_per_launch"],
                             "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",

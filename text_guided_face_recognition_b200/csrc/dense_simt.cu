@@ -4,6 +4,8 @@
 // SGEMM with fused normalisation scales; everything else is bandwidth-bound glue around it.
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tgfr {
@@ -903,6 +905,33 @@ int arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
                         nullptr, nullptr, 0, st);
 }
 
+// per-device side stream + fork / join events of the head backward (TGFR_HEAD_OVERLAP=0 disables the overlap)
+static int head_side_stream(cudaStream_t st, cudaStream_t* side, cudaEvent_t* join) {
+  static cudaStream_t streams[64] = {};
+  static cudaEvent_t forks[64] = {}, joins[64] = {};
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TGFR_HEAD_OVERLAP");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  *side = st;
+  *join = nullptr;
+  if (!enabled) return TGFR_OK;
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  dev &= 63;
+  if (!streams[dev]) {
+    TGFR_CUDA_OK(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    TGFR_CUDA_OK(cudaEventCreateWithFlags(&forks[dev], cudaEventDisableTiming));
+    TGFR_CUDA_OK(cudaEventCreateWithFlags(&joins[dev], cudaEventDisableTiming));
+  }
+  TGFR_CUDA_OK(cudaEventRecord(forks[dev], st));
+  TGFR_CUDA_OK(cudaStreamWaitEvent(streams[dev], forks[dev], 0));
+  *side = streams[dev];
+  *join = joins[dev];
+  return TGFR_OK;
+}
+
 int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64_t w_sk, const int64_t* labels,
                   const float* xnorm, const float* wnorm, const float* lse, const float* coef, const float* gout, int B,
                   int C, int Din, int class_off, float s, float m, int easy, float* dx, float* dw, void* ws,
@@ -922,12 +951,19 @@ int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
   if (int rc = gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 1, nullptr, nullptr,
                               nullptr, nullptr, nullptr, lse, coef, gout, scale, g16, f.Cp, st))
     return rc;
+  // dX^ = g w^ and dW^ = g^T x^ are independent given g16 and each is latency bound at this size (tensor pipe < 20 %):
+  // the first runs on a per-device side stream beside the second (fork / join by events; capturable into a graph)
+  cudaStream_t side = st;
+  cudaEvent_t ev_join = nullptr;
   if (dx) {
+    if (int rc = head_side_stream(st, &side, &ev_join)) return rc;
     const int tiles = ceil_div(B, 128) * ceil_div(Din, 128);
-    const int splits = tiles >= 148 ? 1 : 296 / tiles;      // every (tile, split) CTA co-resident at 2 per SM: no tail wave
-    if (int rc = gemm_tc(g16, 0, f.Cp, w16, 1, f.Dp, B, Din, C, s, scale, 0, dxh, Din, splits, st)) return rc;
+    const int splits = tiles >= 148 ? 1 : 148 / tiles;      // half the slots: the dW^ product runs beside it
+    if (int rc = gemm_tc(g16, 0, f.Cp, w16, 1, f.Dp, B, Din, C, s, scale, 0, dxh, Din, splits < 1 ? 1 : splits, side)) return rc;
+    if (side != st) TGFR_CUDA_OK(cudaEventRecord(ev_join, side));
   }
   if (int rc = gemm_tc(g16, 1, f.Cp, x16, 1, f.Dp, C, Din, B, s, scale, 0, dwh, Din, 1, st)) return rc;
+  if (dx && side != st) TGFR_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
   const int fused = head_normalize_bwd_pair(dxh, x, x_sr, xnorm, dx, B, dwh, w, w_sc, w_sk, wnorm, dw, w_sc, w_sk, C, Din, st);
   if (fused <= 0) return fused;
   if (dx) {

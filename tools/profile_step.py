@@ -57,5 +57,25 @@ for _ in range(passes):
     sc = ops.pair_cosine(o1, o2)
     ops.roc_counts(sc, (torch.arange(NP, device="cuda") % 10 == 0).long())
     ops.row_argmax(sc.view(6000, 10))
+    # round 2: MagFace head at configs[2] size, the exported cosine_similarity, the image head (IMIM + global projection) and
+    # the FCFM fusion net in training mode (fwd + bwd each)
+    from text_guided_face_recognition_b200.models import magface
+    from text_guided_face_recognition_b200.models.fusion_nets import Working
+    from text_guided_face_recognition_b200.models.image_heading import ImageHeading
+    mxn, mwn, mlab = synth.margin_inputs(hB, Din, C, seed=100, mag=True)
+    mhead = magface.MagLinear(Din, C, scale=64.0, easy_margin=True).cuda()
+    with torch.no_grad():
+        mhead.weight.copy_(torch.from_numpy(mwn))
+    mx = torch.from_numpy(mxn * 4.0).cuda().requires_grad_(True)
+    lg, xnorm = mhead(mx, lambda v: 0.0035 * (v - 10.0) + 0.45, 10.0, 110.0)
+    ml, mg, _ = magface.MagLoss(10.0, 110.0, 0.45, 0.8, 64.0)(lg, torch.from_numpy(mlab).cuda(), xnorm)
+    (ml + 35.0 * mg).backward()
+    losses.cosine_similarity(x, x.detach().roll(1, 0)).sum().backward()
+    ih = ImageHeading(ns(aux_feat_dim_per_granularity=D)).cuda().train()
+    gi, li = ih(torch.randn(B, 512, device="cuda"), torch.randn(B, 256, 14, 14, device="cuda"))
+    (gi.sum() + (li * li.detach().roll(1, 0)).sum()).backward()
+    fus = Working(channel_dim=256).cuda().train()
+    fo = fus(li.detach(), w.transpose(1, 2), gi.detach(), b.detach())
+    fo.square().sum().backward()
 torch.cuda.synchronize()
 print("profile_step ok")
