@@ -134,10 +134,11 @@ def test_tc_forward_vs_oracle(B, T, R, D, flavour, ragged):
 TC_GRAD_RTOL = 1e-3      # contract for the TF32-class path; emulation of the fp16-operand pipeline gives ~4e-4
 
 
-@pytest.fixture(params=["save", "recompute"])
+@pytest.fixture(params=["save", "wu", "recompute"])
 def bwd_mode(request, monkeypatch):
-    """The backward either reads the forward's saved fp16 attention image or recomputes it on chip."""
-    monkeypatch.setenv("TGFR_WORDREGION_SAVE", "1" if request.param == "save" else "0")
+    """What the forward leaves for the backward: its fp16 word-softmax / attention records (default), only the Wu
+    tiles (TGFR_WORDREGION_SAVE=wu: the backward recomputes the scores), or nothing (full recomputation)."""
+    monkeypatch.setenv("TGFR_WORDREGION_SAVE", {"save": "1", "wu": "wu", "recompute": "0"}[request.param])
     return request.param
 
 

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math" if False else "-DTGFR_NO_FAST_MATH",   # accuracy first: no fast-math
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + (["-DTGFR_DEBUG_SPIN"] if os.environ.get("TGFR_DEBUG_SPIN") else [])
 
 
 def _nvcc():

@@ -29,6 +29,7 @@ int attention_bwd_simt(const float*, int64_t, int64_t, int64_t, const float*, in
 // wordregion_tc.cu
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D);
 size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D);
+int wordregion_tc_saved_mode(int Bc, int Bq, int T, int R, int D, const void* saved, size_t saved_bytes);
 bool wordregion_tc_recompute_ok(int Bq, int T, int R, int D);
 int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                       const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t, void*,
@@ -193,8 +194,7 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
       // The recompute kernel (text-side gradient; face-side gradient without forward records) has no shared-memory
       // plan for this shape (T = 30 with R = 196, D = 256).  The face-side gradient from the forward's records -- the
       // reference's live path -- still runs on the tensor cores; the rest runs the exact fp32 CUDA kernels.
-      const size_t need = wordregion_tc_saved_bytes(Bc, Bq, T, R, D);
-      const bool have_saved = saved != nullptr && need > 0 && saved_bytes >= need;
+      const bool have_saved = wordregion_tc_saved_mode(Bc, Bq, T, R, D, saved, saved_bytes) != 0;
       float* dctx_simt = (dctx && !have_saved) ? dctx : nullptr;
       if (dctx_simt || dwords) {
         if (int rc = wordregion_bwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,

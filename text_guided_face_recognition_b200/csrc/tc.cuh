@@ -36,6 +36,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // A wait that never completes (a protocol bug) must not hang the GPU: after ~2^26 failed polls (tens of seconds)
 // the kernel traps and the host sees a launch failure.
+#ifdef TGFR_DEBUG_SPIN
+// debugging aid: a wait that does not complete reports itself (block, thread, barrier offset, parity) and returns
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 2)
+    printf("mbar timeout: block %d warp %d bar@%u parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), addr & 0xffffu, parity);
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -54,6 +75,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+
+#endif
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -21,6 +21,7 @@
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
 // warps 2-9 = epilogue (4 warps per 128-lane region tile; the two groups split D in epi-2).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -32,10 +33,7 @@ using namespace tc;
 
 constexpr int kThreadsTC = 320;
 constexpr int kEpiThreads = 256;
-constexpr int kFwdThreads = 576;       // forward: 2 + 16 epilogue warps (four per TMEM lane quarter)
-constexpr int kFwdEpiThreads = 512;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kSV = 256.f;   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
 
 enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull0, kEFull1, kWuFull, kWuEmpty, kNumBars };
 
@@ -44,15 +42,14 @@ struct TcParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
-  // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
-  __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
-  uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
-  float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
-  uint32_t rec_stride;   // bytes of one unit's records
+  // SAVE: what the record-free backward (wr_tc_bwd3_kernel) needs beside its own recomputation of S, per unit u = b * G + g:
+  __half* sv_wu;         // [total_units][D/8][nw_rows][8]  Wu_w as fp16 planes (the un-normalised context of word w)
+  float* sv_ab;          // [total_units][2][128]  alpha_w = g2 g3 p_w / (|q_w| |Wu_w|), beta_w = g2 g3 p_w cos_w / |Wu_w|^2:
+                         //   d sim[b,i] / d Wu_w = alpha_w q_w - beta_w Wu_w   (0 for padding words and missing captions)
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   int uniform_len;       // > 0: every caption has this many words (no cap_lens given); else read `lens`
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
-  float k1, k2, g3;
+  float k1, k2, g3, g23;
 };
 
 // optional phase trace (tgfr_debug_set_trace): clock64 stamps of CTA 0's first units
@@ -77,7 +74,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ void fwd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFwdEpiThreads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // prep: fp32 (any strides) -> fp16 canonical copies + exact fp32 word norms + caption lengths
@@ -115,368 +111,6 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
     }
     acc = warp_sum(acc);
     if (lane == 0) qnorm[wrow] = sqrtf(acc);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
-template <int TP, bool SAVE>
-__global__ void __launch_bounds__(kFwdThreads, 1)
-wr_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_c = smem;
-  uint8_t* s_q = smem + p.off_q;
-  uint8_t* s_e = smem + p.off_e;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_misc);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_misc + 64);
-  float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 128);   // [4][128]
-  float* part_n = part_d + 512;                                        // [4][128]
-  float* exs = part_n + 512;                                           // [128]
-  float* cosw = exs + 128;                                             // [128] SAVE: cos_w
-  float* inww = cosw + 128;                                            // [128] SAVE: 1 / |Wu_w|
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
-  const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.total_units / gridDim.x);
-  const int kchunks = p.D >> 6;
-
-  if (tid == 0) {
-    mbar_init(&bars[kCFull], 1);
-    mbar_init(&bars[kQFull], 1);
-    mbar_init(&bars[kQEmpty], 1);
-    mbar_init(&bars[kSFull0], 1);
-    mbar_init(&bars[kSFull1], 1);
-    mbar_init(&bars[kEFull0], kFwdEpiThreads);
-    mbar_init(&bars[kEFull1], kFwdEpiThreads);
-    mbar_init(&bars[kWuFull], 1);
-    mbar_init(&bars[kWuEmpty], kFwdEpiThreads);
-    fence_barrier_init();
-    tma_prefetch_desc(&tm_c);
-    tma_prefetch_desc(&tm_q);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int prev_b = -1, n = 0;
-      for (int u = u0; u < u1; ++u, ++n) {
-        const int b = u / p.G, g = u - b * p.G;
-        // GEMM-1(n-1) has retired => GEMM-2(n-2) has too, so kWuFull is at most one phase behind
-        // the parity tested below (waiting on it before this point could alias two phases).
-        mbar_wait(&bars[kQEmpty], (n & 1) ^ 1);
-        if (b != prev_b) {
-          if (n > 0) mbar_wait(&bars[kWuFull], (n - 1) & 1);      // every MMA reading the old C_b has retired
-          mbar_arrive_expect_tx(&bars[kCFull], kchunks * p.c_panel);
-          for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[kCFull], kc * 64, 0, b);
-          prev_b = b;
-        }
-        mbar_arrive_expect_tx(&bars[kQFull], kchunks * p.q_panel);
-        for (int kc = 0; kc < kchunks; ++kc)
-          tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[kQFull], kc * 64, g * p.nw_rows, 0);
-      }
-    }
-  } else if (warp == 1) {
-    // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);
-      const uint32_t idesc2 = make_idesc_f16(128, p.D, true, true);
-      const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_e = smem_u32(s_e);
-      int prev_b = -1, n = 0, m = -1;
-      for (int u = u0; u < u1; ++u, ++n) {
-        const int b = u / p.G;
-        if (b != prev_b) {
-          ++m;
-          mbar_wait(&bars[kCFull], m & 1);
-          prev_b = b;
-        }
-        mbar_wait(&bars[kQFull], n & 1);
-        TGFR_TRACE(n, 17);
-        tc_fence_after();
-        for (int t = 0; t < p.n_tiles; ++t) {
-          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
-            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
-            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
-          }
-          if (t == 0) umma_commit(&bars[kSFull0]);                // the tile-0 epilogue group starts while tile 1 runs
-        }
-        umma_commit(&bars[kQEmpty]);
-        umma_commit(&bars[kSFull1]);
-        // GEMM-2 in two instalments: the K steps over tile 0's regions run while the epilogue still works on tile 1
-        mbar_wait(&bars[kEFull0], n & 1);
-        TGFR_TRACE(n, 18);
-        mbar_wait(&bars[kWuEmpty], (n & 1) ^ 1);
-        TGFR_TRACE(n, 19);
-        tc_fence_after();
-        const int j0 = min(p.Rp >> 4, 8);
-        for (int j = 0; j < j0; ++j) {
-          const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
-          const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
-          umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
-        }
-        mbar_wait(&bars[kEFull1], n & 1);
-        tc_fence_after();
-        for (int j = j0; j < (p.Rp >> 4); ++j) {
-          const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
-          const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
-          umma_ss(tmem + 256, ad, bd, idesc2, true);
-        }
-        umma_commit(&bars[kWuFull]);
-      }
-    }
-  } else {
-    // ======================================= epilogue =======================================
-    // 16 warps: `quarter` = the TMEM lane quarter the warp may touch (warp % 4), `grp` = which of that quarter's four
-    // warps it is.  epi-1 deals the quarter's (region tile, caption) tasks round-robin to its four warps (four warps
-    // per scheduler hide the TMEM / MUFU latencies two could not); in epi-2 a warp owns its 32 word rows and a
-    // quarter of the features.
-    const int grp = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;        // lane row 0..127
-    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-    const int tiles_q = (p.n_tiles == 2 && (128 + quarter * 32) < p.Rp) ? 2 : 1;   // region tiles with rows in this quarter
-    const int ntask = ((quarter * 32) < p.Rp) ? tiles_q * p.nc : 0;
-    const int dq = p.D >> 2;                     // features per warp in epi-2
-    const int nch = dq >> 4;                     // 16-column TMEM loads per pass
-    int n = 0;
-    for (int u = u0; u < u1; ++u, ++n) {
-      const int b = u / p.G, g = u - b * p.G;
-      // ---------------- epi-1: word softmax, E -> shared memory ----------------
-      bool seen0 = false, seen1 = false;
-      for (int k = grp; k < ntask; k += 4) {
-        const int tile = k >= p.nc ? 1 : 0;      // tile-0 tasks first: its scores arrive first
-        const int c = k - tile * p.nc;
-        if (tile == 1 && !seen1) {               // this thread's tile-0 rows of E are complete
-          fence_proxy_async();
-          mbar_arrive(&bars[kEFull0]);
-        }
-        if (tile == 0 && !seen0) {
-          mbar_wait(&bars[kSFull0], n & 1);
-          if (tid == 64) TGFR_TRACE(n, 2);
-          tc_fence_after();
-          seen0 = true;
-        }
-        if (tile == 1 && !seen1) {
-          mbar_wait(&bars[kSFull1], n & 1);
-          tc_fence_after();
-          seen1 = true;
-        }
-        const int r = tile * 128 + lrow;
-        const int i = g * p.nc + c;
-        if (i >= p.Bq) {
-          if constexpr (SAVE) {                                 // missing captions: zero records for the backward
-            if (r < p.Rp) {
-              uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-              for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
-            }
-          }
-          continue;
-        }
-        const int len = __ldg(p.lens + i);
-        uint32_t v[TP];
-        const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
-#pragma unroll
-        for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
-        tmem_ld_wait();
-        float e[TP];
-        float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
-#pragma unroll
-        for (int t = 0; t < TP; ++t) {
-          e[t] = (t < len) ? __uint_as_float(v[t]) : -INFINITY;
-          mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
-        }
-        const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-        const float nmx = -mx * kLog2e;
-        float sump[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int t = 0; t < TP; ++t) {
-          e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
-          sump[t & 3] += e[t];
-        }
-        const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
-        const float nk1 = -p.k1;
-        uint32_t pe[TP / 2];
-        if constexpr (SAVE) {
-          // A1 and E as the backward reads them: fp16, zero on dead rows
-          // (padding words keep E = exp(-g1): the backward multiplies it by 1/|Wu_w| = 0)
-          const bool live_row = r < p.R;
-          const float inv = live_row ? 1.f / sum : 0.f;
-          uint32_t pa[TP / 2];
-#pragma unroll
-          for (int t = 0; t < TP; t += 2) {
-            const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
-            pa[t >> 1] = pack_half2(a0, a1);
-            const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
-            pe[t >> 1] = live_row ? pk : 0u;
-          }
-          if (r < p.Rp) {
-            // [caption][16-byte chunk: A1 x Tp | E x Tp][row]: every store of a warp covers 512 contiguous bytes
-            uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-            for (int j = 0; j < TP / 8; ++j) {
-              rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
-              rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-            }
-          }
-        } else {
-          const float kinv = p.k1 / sum;
-#pragma unroll
-          for (int t = 0; t < TP; t += 2)
-            pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
-        }
-        if (r < p.Rp) {
-#pragma unroll
-          for (int j = 0; j < TP / 8; ++j) {
-            const int w0 = c * TP + 8 * j;
-            *reinterpret_cast<uint4*>(s_e + (w0 >> 6) * p.e_panel + sw128_offset(r, (w0 & 63) >> 3)) =
-                make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-          }
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      if (!seen1) mbar_arrive(&bars[kEFull0]);
-      mbar_arrive(&bars[kEFull1]);
-      if (tid == 64) TGFR_TRACE(n, 3);
-
-      // ---------------- epi-2: cosine, exp, log-sum (and the V tile for the backward) ----------------
-      const int w = lrow;
-      const int c = w / TP, t = w - c * TP;
-      const int i = g * p.nc + c;
-      const bool valid = (w < p.nw_rows) && (i < p.Bq) && (t < __ldg(p.lens + min(i, p.Bq - 1)));
-      const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
-      // this thread's quarter of q_w is fetched before the wait so that its latency hides under GEMM-2
-      uint4 qreg[8];
-      {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + grp * dq);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) qreg[k] = (valid && k < 2 * nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
-      }
-      const float nq = valid ? fmaxf(__ldg(p.qnorm + qrow), 1e-30f) : 1.f;
-      mbar_wait(&bars[kWuFull], n & 1);
-      if (tid == 64) TGFR_TRACE(n, 4);
-      tc_fence_after();
-      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
-      const uint32_t wu_col = tmem + t_lane + 256 + grp * dq;
-      uint32_t vb[2][16];                        // the next 16 columns load while the current ones are consumed
-      tmem_ld16(wu_col, vb[0]);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < nch) {
-          tmem_ld_wait();
-          if (ch + 1 < nch) tmem_ld16(wu_col + 16 * (ch + 1), vb[(ch + 1) & 1]);
-          const uint32_t(&v)[16] = vb[ch & 1];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[2 * ch + cc]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 qf = __half22float2(qh[k]);
-              const float w0 = __uint_as_float(v[8 * cc + 2 * k]), w1 = __uint_as_float(v[8 * cc + 2 * k + 1]);
-              dot = fmaf(qf.x, w0, dot);
-              dot1 = fmaf(qf.y, w1, dot1);
-              n2 = fmaf(w0, w0, n2);
-              n21 = fmaf(w1, w1, n21);
-            }
-          }
-        }
-      }
-      dot += dot1;
-      n2 += n21;
-      if constexpr (!SAVE) {
-        tc_fence_before();
-        mbar_arrive(&bars[kWuEmpty]);
-      }
-      if (tid == 64) TGFR_TRACE(n, 5);
-      part_d[grp * 128 + w] = dot;
-      part_n[grp * 128 + w] = n2;
-      fwd_bar_sync();
-      if (grp == 0) {
-        float ex = 0.f, cs = 0.f, inw = 0.f;
-        if (valid) {
-          const float dd = (part_d[w] + part_d[128 + w]) + (part_d[256 + w] + part_d[384 + w]);
-          const float nn = (part_n[w] + part_n[128 + w]) + (part_n[256 + w] + part_n[384 + w]);
-          const float nW = fmaxf(sqrtf(nn), 1e-30f);
-          cs = dd / (nq * nW);
-          ex = fast_exp2(p.k2 * cs);
-          inw = 1.f / nW;
-        }
-        exs[w] = ex;
-        if constexpr (SAVE) {
-          cosw[w] = cs;
-          inww[w] = inw;
-          p.sv_inw[(int64_t)u * 128 + w] = inw;
-        }
-      }
-      fwd_bar_sync();
-      if (tid == 64) TGFR_TRACE(n, 6);
-      if constexpr (SAVE) {
-        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 rows of the saved V tile.
-        // d sim[b,i] / d Wu_w = g2 g3 V_w / (kSV |Wu_w|): the backward needs no cosine / softmax work of its own.
-        float c1 = 0.f, c2 = 0.f;
-        if (valid) {
-          float ssum = 0.f;
-#pragma unroll
-          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
-          const float pw = kSV * exs[w] / ssum;
-          c1 = pw / nq;
-          c2 = pw * cosw[w] * inww[w];
-        }
-        // planes [d / 8][word][8 halfs]: a warp's store covers 512 contiguous bytes, and the tile is both a K-major
-        // and an MN-major no-swizzle UMMA operand for the backward (tc.cuh make_smem_desc_ns).
-        // (the TMEM loads are warp-collective: only the stores are predicated on the word row)
-        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
-                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
-        tmem_ld16(wu_col, vb[0]);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nch) {
-            tmem_ld_wait();
-            if (ch + 1 < nch) tmem_ld16(wu_col + 16 * (ch + 1), vb[(ch + 1) & 1]);
-            const uint32_t(&v)[16] = vb[ch & 1];
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const __half2* qh = reinterpret_cast<const __half2*>(&qreg[2 * ch + cc]);
-              uint32_t o[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 qf = __half22float2(qh[k]);
-                // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
-                o[k] = valid ? pack_half2(c1 * qf.x - c2 * __uint_as_float(v[8 * cc + 2 * k]),
-                                          c1 * qf.y - c2 * __uint_as_float(v[8 * cc + 2 * k + 1]))
-                             : 0u;
-              }
-              if (w < p.nw_rows) vdst[(int64_t)(2 * ch + cc) * p.nw_rows] = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-        }
-        if (tid == 64) TGFR_TRACE(n, 7);
-        tc_fence_before();
-        mbar_arrive(&bars[kWuEmpty]);
-      }
-      if (grp == 0 && w < p.nc) {
-        const int ii = g * p.nc + w;
-        if (ii < p.Bq) {
-          float s = 0.f;
-          for (int tt = 0; tt < TP; ++tt) s += exs[w * TP + tt];
-          p.sim[(int64_t)b * p.Bq + ii] = p.g3 * logf(s);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -708,16 +342,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           uint8_t* const e_row = s_e + (uint32_t)r * 128u;
           for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
             const int i = g * p.nc + c;
-            if (i >= p.Bq) {
-              if constexpr (SAVE) {                               // missing captions: zero records for the backward
-                if (r < p.Rp) {
-                  uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-                  for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
-                }
-              }
-              continue;
-            }
+            if (i >= p.Bq) continue;                              // missing captions: their E columns are never read back
             const int len = p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i);
             uint32_t v[TP];
             const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
@@ -750,39 +375,20 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
             const float nk1 = -p.k1;
             uint32_t pe[TP / 2];
-            uint32_t pa[SAVE ? TP / 2 : 1];
-            if constexpr (SAVE) {
-              const bool live_row = r < p.R;
-              const float inv = live_row ? 1.f / sum : 0.f;
-#pragma unroll
-              for (int t = 0; t < TP; t += 2) {
-                const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
-                pa[t >> 1] = pack_half2(a0, a1);
-                const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
-                pe[t >> 1] = live_row ? pk : 0u;
-              }
-            } else {
+            {
+              // rows beyond R (K padding of GEMM-2) multiply zero rows of C: their E values only have to be finite
               const float kinv = p.k1 / sum;
 #pragma unroll
               for (int t = 0; t < TP; t += 2)
                 pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
             }
             if (r < p.Rp) {
-              // E first: GEMM-2 waits for it; the records (global stores, LSU bound) follow
               const uint32_t w0 = (uint32_t)(c * TP);
 #pragma unroll
               for (int j = 0; j < TP / 8; ++j) {
                 const uint32_t ww = w0 + 8u * j;
                 *reinterpret_cast<uint4*>(e_row + (ww >> 6) * p.e_panel + ((((ww & 63u) >> 3) ^ rx) << 4)) =
                     make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-              }
-              if constexpr (SAVE) {
-                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-                for (int j = 0; j < TP / 8; ++j) {
-                  rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
-                  rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-                }
               }
             }
           }
@@ -824,6 +430,13 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
       tc_fence_after();
       float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
       uint32_t vb[2][8];                          // the next 8 columns load while the current ones are consumed
+      // SAVE: Wu_w leaves for the backward as fp16 planes [d / 8][word][8 halfs] in this same pass (a warp's store covers
+      // 512 contiguous bytes; the tile is both a K-major and an MN-major no-swizzle UMMA operand, tc.cuh)
+      uint4* wdst = nullptr;
+      if constexpr (SAVE)
+        wdst = reinterpret_cast<uint4*>(p.sv_wu + (int64_t)u * p.nw_rows * p.D) + (int64_t)(grp * (dq >> 3)) * p.nw_rows +
+               min(w, p.nw_rows - 1);
+      const int64_t wstep = p.nw_rows;
       tmem_ld8(wu_col, vb[0]);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
@@ -832,6 +445,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
           const uint32_t(&v)[8] = vb[ch & 1];
           const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
+          uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float2 qf = __half22float2(qh[k]);
@@ -840,15 +454,16 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             dot1 = fmaf(qf.y, w1, dot1);
             n2 = fmaf(w0, w0, n2);
             n21 = fmaf(w1, w1, n21);
+            if constexpr (SAVE) o[k] = valid ? pack_half2(w0, w1) : 0u;   // padding words / missing captions: exact zeros
           }
+          if constexpr (SAVE)
+            if (w < p.nw_rows) wdst[ch * wstep] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       dot += dot1;
       n2 += n21;
-      if constexpr (!SAVE) {
-        tc_fence_before();
-        mbar_arrive(&bars[f3WuEmpty]);
-      }
+      tc_fence_before();
+      mbar_arrive(&bars[f3WuEmpty]);               // Wu is read once: the next unit's GEMM-2 may overwrite it
       if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 6);
       part_d[grp * 128 + w] = dot;
       part_n[grp * 128 + w] = n2;
@@ -871,46 +486,24 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
         if constexpr (SAVE) {
           cosw[w] = cs;
           inww[w] = inw;
-          p.sv_inw[(int64_t)u * 128 + w] = inw;
         }
       }
       f3b_bar_sync();
       if constexpr (SAVE) {
-        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 planes of the saved V tile
-        float c1 = 0.f, c2 = 0.f;
-        if (valid) {
-          float ssum = 0.f;
+        if (grp == 1) {
+          // d sim[b,i] / d Wu_w = alpha_w q_w - beta_w Wu_w with p_w = softmax over the caption's words of g2 cos
+          float al = 0.f, be = 0.f;
+          if (valid) {
+            float ssum = 0.f;
 #pragma unroll
-          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
-          const float pw = kSV * exs[w] / ssum;
-          c1 = pw / nq;
-          c2 = pw * cosw[w] * inww[w];
-        }
-        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
-                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
-        const int64_t vstep = p.nw_rows;
-        tmem_ld8(wu_col, vb[0]);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          if (ch < nch) {
-            tmem_ld_wait();
-            if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
-            const uint32_t(&v)[8] = vb[ch & 1];
-            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
-            uint32_t o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 qf = __half22float2(qh[k]);
-              // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
-              o[k] = valid ? pack_half2(fmaf(-c2, __uint_as_float(v[2 * k]), c1 * qf.x),
-                                        fmaf(-c2, __uint_as_float(v[2 * k + 1]), c1 * qf.y))
-                           : 0u;
-            }
-            if (w < p.nw_rows) vdst[ch * vstep] = make_uint4(o[0], o[1], o[2], o[3]);
+            for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
+            const float pw = p.g23 * exs[w] / ssum;
+            al = pw * inww[w] / nq;
+            be = pw * cosw[w] * inww[w] * inww[w];
           }
+          p.sv_ab[(int64_t)u * 256 + w] = al;
+          p.sv_ab[(int64_t)u * 256 + 128 + w] = be;
         }
-        tc_fence_before();
-        mbar_arrive(&bars[f3WuEmpty]);
         if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 7);
       }
       if (grp == 0 && w < p.nc) {
@@ -964,7 +557,7 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 // dQ[w,d] = sum_r dS'[r,w] c_r[d] reuses GEMM-2's descriptors, and the drain subtracts the direct term in q_w and
 // reduce-adds into the padded [Bq*Tp, D] gradient (tm_dc is then the map of that buffer).
 // This kernel recomputes everything from C and Q (no forward records).  It serves d words and, when the forward kept
-// no records, d ctx; with records d ctx runs in wr_tc_bwd2_kernel below.
+// nothing, d ctx; with the forward's Wu tiles d ctx runs in wr_tc_bwd3_kernel below.
 template <int TP, bool DQ>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
@@ -1524,6 +1117,800 @@ wr_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward (d ctx) without attention records: wr_tc_bwd3_kernel
+//
+// The forward (SAVE) leaves, per unit (face b, caption group g), only the un-normalised word contexts Wu_w as fp16 planes
+// and two scalars per word with   d sim[b,i] / d Wu_w = alpha_w q_w - beta_w Wu_w   (w a word of caption i).  Nothing of
+// size B x B x T x R is ever written: the word softmax A1 and E = exp(g1 (A1 - 1)) are recomputed here from one extra
+// score product, and the gradient of a pair stays linear in G[b,i] = d loss / d sim[b,i]:
+//   GEMM-1'  S[r,w]  = <c_r, q_w>                               M = 128 regions (one tile), N = 128 words, K = D
+//   GEMM-3'  X[r,w]  = <c_r, Wu_w>                              same shape, B = the Wu planes (K-major, no swizzle)
+//   epi      A1 = softmax over the caption's words of S, E = exp(g1 (A1 - 1))        (2 exponentials per element)
+//            ga_w = G sigma alpha_w, gb_w = G sigma beta_w;   dE = ga S - gb X;   dA1 = g1 E dE;
+//            dS = A1 (dA1 - sum_t A1 dA1);   A_Q = dS + ga E,   A_W = -gb E   -> fp16 A operands, IN PLACE over the
+//            caption's own S / X columns (a thread only overwrites columns it has read itself)
+//   GEMM-5'/6'  dC[r,:] += sum_w A_Q[r,w] q_w + A_W[r,w] Wu_w   A from TMEM, B = MN-major views of the Q and Wu tiles;
+//            a caption's Tp words take ceil(Tp / 16) K steps (the tail of the last step is zero in A)
+// A work item is (face b, region tile t, caption group g): the 128 x D fp32 block of d ctx of one (b, t) stays in
+// 256 TMEM columns while the CTA walks the caption groups and leaves once, by TMA reduce-add.  CTAs 2k and 2k+1 walk the
+// same (b, g) units, one region tile each, so that the second reader of a Wu tile finds it in L2.
+// sigma_b is a per-face power of two that keeps the fp16 operands in the normal range.
+//
+// TMEM columns: [0,256) d ctx block, [256,384) S -> A_Q, [384,512) X -> A_W.
+// ---------------------------------------------------------------------------------------------
+enum BarC { cCFull = 0, cVFull, cQFull, cSxFull, cOpsFull, cVFree, cAccDone, cDrained, cNum };
+constexpr int kB3NE = 3;                                   // epilogue warps per TMEM lane quarter
+constexpr int kB3EpiThreads = 128 * kB3NE;
+constexpr int kB3Threads = 64 + kB3EpiThreads;
+__device__ __forceinline__ void b3_bar_sync() { asm volatile("bar.sync 3, %0;" ::"n"(kB3EpiThreads) : "memory"); }
+
+struct TcBwd3Params {
+  const __half* wu;      // [total_units][D/8][nw_rows][8] fp16 Wu planes
+  const float* ab;       // [total_units][2][128]  alpha_w, beta_w
+  const float* gsim;     // [Bc, Bq]
+  const int* lens;       // [Bq]
+  int Bc, Bq, R, Rp, D, nc, G, nw_rows, n_tiles, total_units, uniform_len;
+  uint32_t q_panel, off_q, off_v, off_misc;
+  float k1, g1;          // k1 = g1 log2(e)
+};
+
+template <int TP>
+__global__ void __launch_bounds__(kB3Threads, 1)
+wr_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q,
+                  const __grid_constant__ CUtensorMap tm_dc, const TcBwd3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_c = smem;                         // C tile: D/64 panels of 128 rows x 128 B (K-major A of GEMM-1' / 3')
+  uint8_t* s_q = smem + p.off_q;               // Q tile: D/64 panels of nw_rows x 128 B
+  uint8_t* s_v = smem + p.off_v;               // Wu tile: D/8 planes of nw_rows x 16 B (no swizzle); 1 KB of zeros follows
+  uint8_t* misc = smem + p.off_misc;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
+  float* gab = reinterpret_cast<float*>(misc + 256);           // [2 (item parity)][2 (ga | gb)][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // two region tiles: CTAs (2k, 2k+1) share a range of units and take one tile each (the grid is even)
+  const int t = (p.n_tiles == 2) ? (int)(blockIdx.x & 1) : 0;
+  const int share = (p.n_tiles == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nshare = (p.n_tiles == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int u0 = (int)((int64_t)share * p.total_units / nshare);
+  const int u1 = (int)((int64_t)(share + 1) * p.total_units / nshare);
+  const int kchunks = p.D >> 6;
+  constexpr uint32_t kCPanel = 128 * 128;
+  constexpr int KS = (TP + 15) / 16;           // K steps of 16 words per caption in GEMM-5' / 6'
+
+  if (tid == 0) {
+    mbar_init(&bars[cCFull], 1);
+    mbar_init(&bars[cVFull], 1);
+    mbar_init(&bars[cQFull], 1);
+    mbar_init(&bars[cSxFull], 1);
+    mbar_init(&bars[cOpsFull], kB3EpiThreads);
+    mbar_init(&bars[cVFree], 1);
+    mbar_init(&bars[cAccDone], 1);
+    mbar_init(&bars[cDrained], kB3EpiThreads);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_c);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_dc);
+  }
+  // operand tiles are read a few rows beyond what TMA writes (K / N padding of the MMA shapes): keep them finite
+  for (uint32_t k = tid; k < (p.off_misc >> 4); k += kB3Threads) reinterpret_cast<uint4*>(smem)[k] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int prev_b = -1, n = 0, m = -1;
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G, g = u - b * p.G;
+        if (u + 1 < u1)                                             // the next Wu tile towards L2, one item ahead
+          for (int kc = 0; kc < kchunks; ++kc)
+            bulk_prefetch_l2(p.wu + (int64_t)(u + 1) * p.nw_rows * p.D + (int64_t)kc * (p.q_panel >> 1), p.q_panel);
+        const bool new_face = b != prev_b;
+        if (new_face) {
+          if (n > 0) mbar_wait(&bars[cAccDone], (n - 1) & 1);       // every MMA of the previous face has retired ...
+          if (m >= 0) mbar_wait(&bars[cDrained], m & 1);            // ... and its block is drained (the boxes overlay the tiles)
+          ++m;
+          mbar_arrive_expect_tx(&bars[cCFull], kchunks * kCPanel);
+          for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * kCPanel, &tm_c, &bars[cCFull], kc * 64, t * 128, b);
+          prev_b = b;
+        }
+        if (n > 0 && !new_face) mbar_wait(&bars[cVFree], (n - 1) & 1);   // GEMM-6' of the previous item has read the Wu tile
+        mbar_arrive_expect_tx(&bars[cVFull], kchunks * p.q_panel);
+        for (int kc = 0; kc < kchunks; ++kc)                        // the tile is one contiguous image: four bulk copies
+          bulk_load(s_v + kc * p.q_panel, p.wu + (int64_t)u * p.nw_rows * p.D + (int64_t)kc * (p.q_panel >> 1), p.q_panel,
+                    &bars[cVFull]);
+        if (n > 0 && !new_face) mbar_wait(&bars[cAccDone], (n - 1) & 1); // GEMM-5' of the previous item has read the Q tile
+        mbar_arrive_expect_tx(&bars[cQFull], kchunks * p.q_panel);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[cQFull], kc * 64, g * p.nw_rows, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);    // S, X
+      const uint32_t idesc5 = make_idesc_f16(128, p.D, false, true);     // d ctx block: A in TMEM, B MN-major
+      const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_v = smem_u32(s_v);
+      const uint32_t v_plane = (uint32_t)p.nw_rows * 16u;                // bytes between consecutive 8-feature planes of Wu
+      int prev_b = -1, n = 0, m = -1;
+      for (int u = u0; u < u1; ++u, ++n) {
+        const int b = u / p.G;
+        const bool first = b != prev_b;
+        if (first) {
+          ++m;
+          mbar_wait(&bars[cCFull], m & 1);
+          prev_b = b;
+        }
+        mbar_wait(&bars[cVFull], n & 1);
+        TGFR_TRACE(n, 17);
+        tc_fence_after();
+        for (int k16 = 0; k16 < (p.D >> 4); ++k16) {                     // GEMM-3': X = C_t Wu^T
+          const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * kCPanel + (k16 & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_ns(a_v + k16 * 2 * v_plane, v_plane, 128);   // K-major over d
+          umma_ss(tmem + 384, ad, bd, idesc1, k16 > 0);
+        }
+        mbar_wait(&bars[cQFull], n & 1);
+        tc_fence_after();
+        for (int k16 = 0; k16 < (p.D >> 4); ++k16) {                     // GEMM-1': S = C_t Q^T
+          const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * kCPanel + (k16 & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+          umma_ss(tmem + 256, ad, bd, idesc1, k16 > 0);
+        }
+        umma_commit(&bars[cSxFull]);
+        mbar_wait(&bars[cOpsFull], n & 1);
+        TGFR_TRACE(n, 18);
+        tc_fence_after();
+        bool acc = !first;
+        for (int c = 0; c < p.nc; ++c)                                   // GEMM-6': A_W . Wu  (the first MMA of a (b, t) range overwrites)
+          for (int j = 0; j < KS; ++j) {
+            const uint32_t row0 = (uint32_t)(c * TP + 16 * j);
+            const uint64_t bv = make_smem_desc_ns(a_v + row0 * 16u, 128, v_plane);        // MN-major over d, K = words
+            umma_ts(tmem, tmem + 384 + c * TP + 8 * j, bv, idesc5, acc);
+            acc = true;
+          }
+        umma_commit(&bars[cVFree]);
+        for (int c = 0; c < p.nc; ++c)                                   // GEMM-5': A_Q . Q
+          for (int j = 0; j < KS; ++j) {
+            const uint32_t row0 = (uint32_t)(c * TP + 16 * j);
+            const uint64_t bq = make_smem_desc(a_q + row0 * 128u, p.q_panel, 1024);
+            umma_ts(tmem, tmem + 256 + c * TP + 8 * j, bq, idesc5, true);
+          }
+        umma_commit(&bars[cAccDone]);
+        TGFR_TRACE(n, 19);
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int h = (warp - 2) >> 2;               // warp group 0..2: which captions in the epilogue (c = h, h + 3, ...);
+                                                 // groups 0 / 1 also drain one half of D each
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+    int prev_b = -1, n = 0;
+    float sigma = 1.f, inv_sigma = 1.f;
+    for (int u = u0; u < u1; ++u, ++n) {
+      const int b = u / p.G, g = u - b * p.G;
+      const bool last = (u + 1 == u1) || ((u + 1) / p.G != b);
+      if (b != prev_b) {                         // per-face power-of-two scale from the largest |d loss / d sim[b, :]|
+        float gmax = 0.f;
+        for (int i = lane; i < p.Bq; i += 32) gmax = fmaxf(gmax, fabsf(__ldg(p.gsim + (int64_t)b * p.Bq + i)));
+        gmax = warp_max(gmax);
+        // |A_Q| <~ G sigma alpha (1 + g1) with alpha <= g2 g3 / (|q| |Wu|): aim the largest entries at ~2^9
+        sigma = (gmax > 0.f) ? exp2f(floorf(log2f(16.f / gmax))) : 1.f;
+        inv_sigma = 1.f / sigma;
+        prev_b = b;
+      }
+      float* const ga = gab + (n & 1) * 256;
+      float* const gb = ga + 128;
+      if (h == 0) {
+        const int w = lrow, c = w / TP, i = g * p.nc + c;
+        float al = 0.f, be = 0.f;
+        if (w < p.nw_rows && i < p.Bq) {
+          const float gs = __ldg(p.gsim + (int64_t)b * p.Bq + i) * sigma;
+          al = __ldg(p.ab + (int64_t)u * 256 + w) * gs;
+          be = __ldg(p.ab + (int64_t)u * 256 + 128 + w) * gs;
+        }
+        ga[w] = al;
+        gb[w] = be;
+      }
+      const int r = t * 128 + lrow;
+      const bool warp_has_rows = (t * 128 + quarter * 32) < p.Rp;
+      const bool live_row = r < p.R;
+      b3_bar_sync();                             // ga / gb visible; the other buffer is free for the next item
+      mbar_wait(&bars[cSxFull], n & 1);          // GEMM-1' / 3' retired (and with them every MMA of the previous item)
+      if (tid == 64) TGFR_TRACE(n, 2);
+      tc_fence_after();
+      if (warp_has_rows) {
+        for (int c = h; c < p.nc; c += kB3NE) {
+          const int i = g * p.nc + c;
+          const uint32_t s_col = tmem + t_lane + 256 + c * TP, x_col = tmem + t_lane + 384 + c * TP;
+          uint32_t pq[TP / 2], pw[TP / 2];
+          if (i < p.Bq) {                    // warp-uniform: the TMEM loads / stores below are warp-collective
+            const int len = p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i);
+            uint32_t vs[TP], vx[TP];
+#pragma unroll
+            for (int j = 0; j < TP / 8; ++j) {
+              tmem_ld8(s_col + 8 * j, vs + 8 * j);
+              tmem_ld8(x_col + 8 * j, vx + 8 * j);
+            }
+            tmem_ld_wait();
+            float e[TP];
+            float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+            for (int tt = 0; tt < TP; ++tt) {
+              e[tt] = (tt < len) ? __uint_as_float(vs[tt]) : -INFINITY;
+              mxp[tt & 3] = fmaxf(mxp[tt & 3], e[tt]);
+            }
+            const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+            const float nmx = -mx * kLog2e;
+            float sump[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tt = 0; tt < TP; ++tt) {
+              e[tt] = fast_exp2(fmaf(e[tt], kLog2e, nmx));          // exp(S - max); 0 beyond the caption's length
+              sump[tt & 3] += e[tt];
+            }
+            const float inv = 1.f / ((sump[0] + sump[1]) + (sump[2] + sump[3]));
+            const float nk1 = -p.k1;
+            // with u = ga E, v = gb E, d = u S - v X (= dE E / g1):  dA1 = g1 d,  inner = sum_t A1 dA1 = g1 sum_t A1 d,
+            //   A_Q = A1 (dA1 - inner) + u = a1g d + u - a1g inner'   (a1g = g1 A1, inner' = sum_t A1 d),   A_W = -v
+            float innerp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tt = 0; tt < TP; tt += 2) {
+              const float2 gaw = *reinterpret_cast<const float2*>(ga + c * TP + tt);       // 0 for padding words
+              const float2 gbw = *reinterpret_cast<const float2*>(gb + c * TP + tt);
+              const float a0 = e[tt] * inv, a1 = e[tt + 1] * inv;
+              const float e0 = fast_exp2(fmaf(a0, p.k1, nk1)), e1 = fast_exp2(fmaf(a1, p.k1, nk1));   // E = exp(g1 (A1 - 1))
+              const float u0 = e0 * gaw.x, u1 = e1 * gaw.y, v0 = e0 * gbw.x, v1 = e1 * gbw.y;
+              const float d0 = fmaf(u0, __uint_as_float(vs[tt]), -(v0 * __uint_as_float(vx[tt])));
+              const float d1 = fmaf(u1, __uint_as_float(vs[tt + 1]), -(v1 * __uint_as_float(vx[tt + 1])));
+              innerp[tt & 2] = fmaf(a0, d0, innerp[tt & 2]);
+              innerp[(tt & 2) + 1] = fmaf(a1, d1, innerp[(tt & 2) + 1]);
+              const float g0 = a0 * p.g1, g1v = a1 * p.g1;
+              e[tt] = g0;
+              e[tt + 1] = g1v;
+              vs[tt] = __float_as_uint(fmaf(g0, d0, u0));
+              vs[tt + 1] = __float_as_uint(fmaf(g1v, d1, u1));
+              pw[tt >> 1] = live_row ? pack_half2(-v0, -v1) : 0u;
+            }
+            const float ninner = -((innerp[0] + innerp[1]) + (innerp[2] + innerp[3]));
+#pragma unroll
+            for (int tt = 0; tt < TP; tt += 2) {
+              const float q0 = fmaf(ninner, e[tt], __uint_as_float(vs[tt]));
+              const float q1 = fmaf(ninner, e[tt + 1], __uint_as_float(vs[tt + 1]));
+              pq[tt >> 1] = live_row ? pack_half2(q0, q1) : 0u;      // rows beyond R: zero operands
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TP / 2; ++j) pq[j] = pw[j] = 0u;     // missing captions: zero operands
+          }
+          // packed operands over the caption's own columns: TP / 2 columns of data, zero up to 8 KS
+#pragma unroll
+          for (int j = 0; j < 2 * KS; ++j) {
+            uint32_t a4[4], b4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              a4[k] = (4 * j + k < TP / 2) ? pq[(4 * j + k) < TP / 2 ? 4 * j + k : 0] : 0u;
+              b4[k] = (4 * j + k < TP / 2) ? pw[(4 * j + k) < TP / 2 ? 4 * j + k : 0] : 0u;
+            }
+            tmem_st4(s_col + 4 * j, a4[0], a4[1], a4[2], a4[3]);
+            tmem_st4(x_col + 4 * j, b4[0], b4[1], b4[2], b4[3]);
+          }
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[cOpsFull]);
+      if (tid == 64) TGFR_TRACE(n, 3);
+
+      if (last) {
+        // ---------------- drain: the (b, t) block / sigma -> per-warp 4 KB boxes -> TMA reduce-add into d ctx ----------------
+        mbar_wait(&bars[cAccDone], n & 1);
+        if (tid == 64) TGFR_TRACE(n, 8);
+        tc_fence_after();
+        const int row0 = t * 128 + quarter * 32;
+        const int dhalf = p.D >> 1;
+        if (row0 < p.R && h < 2) {
+          uint8_t* const stage = smem + (warp - 2) * 8192;           // every operand tile is dead by now
+          int cur = 0;
+#pragma unroll 1
+          for (int ch = 0; ch < (dhalf >> 5); ++ch) {
+            const int col0 = h * dhalf + 32 * ch;
+            uint32_t v[32];
+            tmem_ld32(tmem + t_lane + col0, v);
+            tmem_ld_wait();
+            uint8_t* const buf = stage + cur * 4096;
+            if (lane == 0) tma_wait_group_read<1>();                 // the box written two stores ago has been read
+            __syncwarp();
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * c16 + 0]) * inv_sigma;
+              o.y = __uint_as_float(v[4 * c16 + 1]) * inv_sigma;
+              o.z = __uint_as_float(v[4 * c16 + 2]) * inv_sigma;
+              o.w = __uint_as_float(v[4 * c16 + 3]) * inv_sigma;
+              *reinterpret_cast<float4*>(buf + sw128_offset(lane, c16)) = o;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_3d(&tm_dc, buf, col0, row0, b);
+              tma_commit_group();
+            }
+            cur ^= 1;
+          }
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[cDrained]);
+        if (tid == 64) TGFR_TRACE(n, 9);
+      }
+    }
+    if (lane == 0) tma_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+struct TcPlan {
+  int Tp, Rp, nc, G, nw_rows, n_tiles;
+  uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
+  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_dq, ws_total;
+};
+
+int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
+  TGFR_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "wordregion(tc): D=%d must be 64, 128, 192 or 256", D);
+  TGFR_REQUIRE(R >= 1 && R <= 256, "wordregion(tc): R=%d regions (max 256)", R);
+  TGFR_REQUIRE(T >= 1 && T <= 32, "wordregion(tc): T=%d words (max 32)", T);
+  pl->Tp = (T + 7) & ~7;
+  pl->Rp = (R + 15) & ~15;
+  pl->n_tiles = (pl->Rp + 127) / 128;
+  pl->nc = 128 / pl->Tp;
+  pl->nw_rows = pl->nc * pl->Tp;
+  pl->G = (Bq + pl->nc - 1) / pl->nc;
+  const int kch = D / 64;
+  pl->c_panel = (uint32_t)pl->Rp * 128u;
+  pl->q_panel = (uint32_t)pl->nw_rows * 128u;
+  pl->e_panel = (uint32_t)pl->Rp * 128u;
+  pl->off_q = kch * pl->c_panel;
+  pl->off_e = pl->off_q + kch * pl->q_panel;
+  pl->off_misc = pl->off_e + 2 * pl->e_panel;
+  pl->smem_bytes = pl->off_misc + 6144 + 1024;        // misc + alignment slack
+  TGFR_REQUIRE(pl->smem_bytes <= 232448, "wordregion(tc): shared memory plan needs %u bytes", pl->smem_bytes);
+  pl->ws_c16 = 0;
+  pl->ws_q16 = align_up((size_t)Bc * R * D * 2, 256);
+  pl->ws_qnorm = pl->ws_q16 + align_up((size_t)Bq * pl->Tp * D * 2, 256);
+  pl->ws_lens = pl->ws_qnorm + align_up((size_t)Bq * pl->Tp * 4, 256);
+  pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4, 256);                       // padded fp32 d words [Bq*Tp, D]
+  pl->ws_total = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);
+  return TGFR_OK;
+}
+
+// =============================================================================================
+// namespace rec: the RECORD-BASED variant of the saved state (TGFR_WORDREGION_SAVE=records, the default).
+// The forward additionally writes, per unit, the word softmax and E = exp(g1 (A1 - 1)) as fp16 rows (A1 | E records)
+// and V_w = kSV p_w (q^_w - cos_w w^_w) instead of Wu_w; the backward (wr_tc_bwd2_kernel) then needs no score product
+// and no exponential.  It is the faster of the two backward paths at the price of HBM traffic and memory
+// (B x B x T x R fp16 x 2); the record-free path (wr_tc_fwd3_kernel<.., true> + wr_tc_bwd3_kernel, TGFR_WORDREGION_SAVE=wu)
+// writes nothing of that size.  Both are parity-tested (tests/test_gpu_tc.py, bwd_mode fixture).
+// =============================================================================================
+namespace rec {
+
+constexpr float kSV = 256.f;   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
+
+struct TcParams {
+  const __half* q16;     // [Bq*Tp, D]
+  const float* qnorm;    // [Bq*Tp]
+  const int* lens;       // [Bq]
+  float* sim;            // [Bc, Bq]
+  // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
+  __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
+  uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
+  float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
+  uint32_t rec_stride;   // bytes of one unit's records
+  int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
+  int uniform_len;       // > 0: every caption has this many words (no cap_lens given); else read `lens`
+  uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
+  float k1, k2, g3;
+};
+
+
+template <int TP, bool SAVE>
+__global__ void __launch_bounds__(kF3Threads, 1)
+wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_c = smem;
+  uint8_t* s_q = smem + p.off_q;
+  uint8_t* s_e = smem + p.off_e;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_misc + 128);
+  float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 256);   // [kF3NB][128]
+  float* part_n = part_d + kF3NB * 128;                                // [kF3NB][128]
+  float* exs = part_n + kF3NB * 128;                                   // [128]
+  float* cosw = exs + 128;                                             // [128] SAVE: cos_w
+  float* inww = cosw + 128;                                            // [128] SAVE: 1 / |Wu_w|
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
+  const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.total_units / gridDim.x);
+  const int kchunks = p.D >> 6;
+
+  if (tid == 0) {
+    mbar_init(&bars[f3CFull], 1);
+    mbar_init(&bars[f3QFull], 1);
+    mbar_init(&bars[f3QEmpty], 1);
+    mbar_init(&bars[f3SFull0], 1);
+    mbar_init(&bars[f3SFull1], 1);
+    mbar_init(&bars[f3E0Full], kF3ThreadsA);
+    mbar_init(&bars[f3E1Full], kF3ThreadsA);
+    mbar_init(&bars[f3E0Free], 1);
+    mbar_init(&bars[f3WuFull], 1);
+    mbar_init(&bars[f3WuEmpty], kF3ThreadsB);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_c);
+    tma_prefetch_desc(&tm_q);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      // ===================================== TMA producer =====================================
+      if (lane == 0) {
+        int prev_b = -1, n = 0;
+        for (int u = u0; u < u1; ++u, ++n) {
+          const int b = u / p.G, g = u - b * p.G;
+          mbar_wait_lazy(&bars[f3QEmpty], (n & 1) ^ 1);               // GEMM-1(n-1) has read the Q tile
+          if (b != prev_b) {
+            if (n > 0) mbar_wait_lazy(&bars[f3WuFull], (n - 1) & 1);  // every MMA reading the old C_b has retired
+            mbar_arrive_expect_tx(&bars[f3CFull], kchunks * p.c_panel);
+            for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[f3CFull], kc * 64, 0, b);
+            prev_b = b;
+          }
+          mbar_arrive_expect_tx(&bars[f3QFull], kchunks * p.q_panel);
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[f3QFull], kc * 64, g * p.nw_rows, 0);
+        }
+      }
+    } else if (warp == 1) {
+      // ====================================== MMA issuer ======================================
+      if (lane == 0 && u0 < u1) {
+        const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);
+        const uint32_t idesc2 = make_idesc_f16(128, p.D, true, true);
+        const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_e = smem_u32(s_e);
+        const int j0 = min(p.Rp >> 4, 8), j1 = p.Rp >> 4;
+        auto gemm1 = [&](int t) {                                   // S_t = C_t . Q^T
+          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
+            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
+            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
+          }
+        };
+        auto gemm2 = [&](int ja, int jb) {                          // Wu (+)= E^T . C over K steps [ja, jb)
+          for (int j = ja; j < jb; ++j) {
+            const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
+            const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
+            umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
+          }
+        };
+        int m = 0;
+        mbar_wait(&bars[f3CFull], 0);
+        mbar_wait(&bars[f3QFull], 0);
+        tc_fence_after();
+        gemm1(0);
+        umma_commit(&bars[f3SFull0]);
+        if (p.n_tiles == 2) gemm1(1);
+        umma_commit(&bars[f3SFull1]);
+        umma_commit(&bars[f3QEmpty]);
+        int n = 0;
+        for (int u = u0; u < u1; ++u, ++n) {
+          const int b = u / p.G;
+          const bool has_next = u + 1 < u1;
+          const bool boundary = has_next && ((u + 1) / p.G != b);
+          mbar_wait_lazy(&bars[f3E0Full], n & 1);                    // E tile 0 of unit n written, S tile 0 read
+          TGFR_TRACE(n, 17);
+          bool g1_pending = has_next && !boundary, g2_pending = true;
+          while (g1_pending || g2_pending) {
+            if (g2_pending && mbar_test(&bars[f3WuEmpty], (n & 1) ^ 1)) {        // group B has drained Wu(n-1)
+              tc_fence_after();
+              gemm2(0, j0);
+              umma_commit(&bars[f3E0Free]);
+              g2_pending = false;
+            } else if (g1_pending && mbar_test(&bars[f3QFull], (n + 1) & 1)) {    // Q(n+1) has landed
+              tc_fence_after();
+              gemm1(0);
+              umma_commit(&bars[f3SFull0]);
+              g1_pending = false;
+            } else {
+              asm volatile("nanosleep.u32 64;" ::: "memory");
+            }
+          }
+          TGFR_TRACE(n, 18);
+          mbar_wait_lazy(&bars[f3E1Full], n & 1);                    // E tile 1 written, S tile 1 read
+          tc_fence_after();
+          gemm2(j0, j1);
+          umma_commit(&bars[f3WuFull]);
+          TGFR_TRACE(n, 19);
+          if (has_next) {
+            if (boundary) {                                          // new face: the C tile is reloaded once Wu(n) is complete
+              ++m;
+              mbar_wait(&bars[f3CFull], m & 1);
+              mbar_wait(&bars[f3QFull], (n + 1) & 1);
+              tc_fence_after();
+              gemm1(0);
+              umma_commit(&bars[f3SFull0]);
+            }
+            if (p.n_tiles == 2) gemm1(1);
+            umma_commit(&bars[f3SFull1]);
+            umma_commit(&bars[f3QEmpty]);
+          }
+        }
+      }
+    }
+  } else if (warp < 4 + 4 * kF3NA) {
+    // ======================================= group A: epi-1 =======================================
+    reg_alloc<104>();
+    const int grp = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+    const uint32_t rx = (uint32_t)(lrow & 7);
+    int n = 0;
+    for (int u = u0; u < u1; ++u, ++n) {
+      const int g = u % p.G;
+      for (int tile = 0; tile < 2; ++tile) {
+        // every thread follows both tile barriers (even without rows there): an arrival may never run a phase ahead
+        mbar_wait_lazy(&bars[tile ? f3SFull1 : f3SFull0], n & 1);
+        const bool has = tile < p.n_tiles && (tile * 128 + quarter * 32) < p.Rp;
+        if (has) {
+          tc_fence_after();
+          // GEMM-2(n-1)'s instalment over this tile's rows of E has retired
+          mbar_wait_lazy(&bars[tile ? f3WuFull : f3E0Free], (n & 1) ^ 1);
+          if (tid == 128 && tile == 0) TGFR_TRACE(n, 2);
+          const int r = tile * 128 + lrow;
+          uint8_t* const e_row = s_e + (uint32_t)r * 128u;
+          for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
+            const int i = g * p.nc + c;
+            if (i >= p.Bq) {
+              if constexpr (SAVE) {                               // missing captions: zero records for the backward
+                if (r < p.Rp) {
+                  uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
+#pragma unroll
+                  for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
+                }
+              }
+              continue;
+            }
+            const int len = p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i);
+            uint32_t v[TP];
+            const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
+#pragma unroll
+            for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
+            tmem_ld_wait();
+            float e[TP];
+#pragma unroll
+            for (int t = 0; t < TP; ++t) e[t] = __uint_as_float(v[t]);
+            if (len < TP) {                                       // padding words: the last 8 columns, or a ragged caption
+              if (len > TP - 8) {
+#pragma unroll
+                for (int t = TP - 8; t < TP; ++t) e[t] = (t < len) ? e[t] : -INFINITY;
+              } else {
+#pragma unroll
+                for (int t = 0; t < TP; ++t) e[t] = (t < len) ? e[t] : -INFINITY;
+              }
+            }
+            float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+            for (int t = 0; t < TP; ++t) mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
+            const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+            const float nmx = -mx * kLog2e;
+            float sump[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < TP; ++t) {
+              e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
+              sump[t & 3] += e[t];
+            }
+            const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
+            const float nk1 = -p.k1;
+            uint32_t pe[TP / 2];
+            uint32_t pa[SAVE ? TP / 2 : 1];
+            if constexpr (SAVE) {
+              const bool live_row = r < p.R;
+              const float inv = live_row ? 1.f / sum : 0.f;
+#pragma unroll
+              for (int t = 0; t < TP; t += 2) {
+                const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
+                pa[t >> 1] = pack_half2(a0, a1);
+                const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
+                pe[t >> 1] = live_row ? pk : 0u;
+              }
+            } else {
+              const float kinv = p.k1 / sum;
+#pragma unroll
+              for (int t = 0; t < TP; t += 2)
+                pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
+            }
+            if (r < p.Rp) {
+              // E first: GEMM-2 waits for it; the records (global stores, LSU bound) follow
+              const uint32_t w0 = (uint32_t)(c * TP);
+#pragma unroll
+              for (int j = 0; j < TP / 8; ++j) {
+                const uint32_t ww = w0 + 8u * j;
+                *reinterpret_cast<uint4*>(e_row + (ww >> 6) * p.e_panel + ((((ww & 63u) >> 3) ^ rx) << 4)) =
+                    make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+              }
+              if constexpr (SAVE) {
+                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
+#pragma unroll
+                for (int j = 0; j < TP / 8; ++j) {
+                  rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+                  rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+                }
+              }
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+        }
+        mbar_arrive(&bars[tile ? f3E1Full : f3E0Full]);
+        if (tid == 128) TGFR_TRACE(n, 3 + tile);
+      }
+    }
+  } else {
+    // ======================================= group B: epi-2 =======================================
+    reg_dealloc<64>();
+    const int grp = (warp - 4 - 4 * kF3NA) >> 2;         // which slice of the features
+    const int quarter = warp & 3;
+    const int w = quarter * 32 + lane;                    // word row = TMEM lane
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+    const int dq = p.D / kF3NB;                           // features per thread (16 .. 64)
+    const int nch = dq >> 3;                              // 8-column TMEM loads per pass (2 .. 8)
+    const int c = w / TP, t = w - c * TP;
+    const uint32_t wu_col = tmem + t_lane + 256 + grp * dq;
+    int n = 0;
+    for (int u = u0; u < u1; ++u, ++n) {
+      const int b = u / p.G, g = u - b * p.G;
+      const int i = g * p.nc + c;
+      const int len = (i < p.Bq) ? (p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i)) : 0;
+      const bool valid = (w < p.nw_rows) && (t < len);
+      const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
+      // this thread's slice of q_w is fetched before the wait: its latency hides under GEMM-2, and it serves both passes
+      uint4 qreg[8];
+      {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + grp * dq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) qreg[k] = (valid && k < nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
+      }
+      const float nq = valid ? fmaxf(__ldg(p.qnorm + qrow), 1e-30f) : 1.f;
+      mbar_wait_lazy(&bars[f3WuFull], n & 1);
+      if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 5);
+      tc_fence_after();
+      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
+      uint32_t vb[2][8];                          // the next 8 columns load while the current ones are consumed
+      tmem_ld8(wu_col, vb[0]);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        if (ch < nch) {
+          tmem_ld_wait();
+          if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
+          const uint32_t(&v)[8] = vb[ch & 1];
+          const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 qf = __half22float2(qh[k]);
+            const float w0 = __uint_as_float(v[2 * k]), w1 = __uint_as_float(v[2 * k + 1]);
+            dot = fmaf(qf.x, w0, dot);
+            dot1 = fmaf(qf.y, w1, dot1);
+            n2 = fmaf(w0, w0, n2);
+            n21 = fmaf(w1, w1, n21);
+          }
+        }
+      }
+      dot += dot1;
+      n2 += n21;
+      if constexpr (!SAVE) {
+        tc_fence_before();
+        mbar_arrive(&bars[f3WuEmpty]);
+      }
+      if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 6);
+      part_d[grp * 128 + w] = dot;
+      part_n[grp * 128 + w] = n2;
+      f3b_bar_sync();
+      if (grp == 0) {
+        float ex = 0.f, cs = 0.f, inw = 0.f;
+        if (valid) {
+          float dd = 0.f, nn = 0.f;
+#pragma unroll
+          for (int k = 0; k < kF3NB; ++k) {
+            dd += part_d[k * 128 + w];
+            nn += part_n[k * 128 + w];
+          }
+          const float nW = fmaxf(sqrtf(nn), 1e-30f);
+          cs = dd / (nq * nW);
+          ex = fast_exp2(p.k2 * cs);
+          inw = 1.f / nW;
+        }
+        exs[w] = ex;
+        if constexpr (SAVE) {
+          cosw[w] = cs;
+          inww[w] = inw;
+          p.sv_inw[(int64_t)u * 128 + w] = inw;
+        }
+      }
+      f3b_bar_sync();
+      if constexpr (SAVE) {
+        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 planes of the saved V tile
+        float c1 = 0.f, c2 = 0.f;
+        if (valid) {
+          float ssum = 0.f;
+#pragma unroll
+          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
+          const float pw = kSV * exs[w] / ssum;
+          c1 = pw / nq;
+          c2 = pw * cosw[w] * inww[w];
+        }
+        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
+                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
+        const int64_t vstep = p.nw_rows;
+        tmem_ld8(wu_col, vb[0]);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          if (ch < nch) {
+            tmem_ld_wait();
+            if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
+            const uint32_t(&v)[8] = vb[ch & 1];
+            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 qf = __half22float2(qh[k]);
+              // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
+              o[k] = valid ? pack_half2(fmaf(-c2, __uint_as_float(v[2 * k]), c1 * qf.x),
+                                        fmaf(-c2, __uint_as_float(v[2 * k + 1]), c1 * qf.y))
+                           : 0u;
+            }
+            if (w < p.nw_rows) vdst[ch * vstep] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[f3WuEmpty]);
+        if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 7);
+      }
+      if (grp == 0 && w < p.nc) {
+        const int ii = g * p.nc + w;
+        if (ii < p.Bq) {
+          float sacc = 0.f;
+          for (int tt = 0; tt < TP; ++tt) sacc += exs[w * TP + tt];
+          p.sim[(int64_t)b * p.Bq + ii] = p.g3 * logf(sacc);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // backward (d ctx) from the forward's records: wr_tc_bwd2_kernel
 //
 // The forward (SAVE) leaves, per unit (face b, caption group g): A1 and E as fp16 rows, 1/|Wu_w|, and the tile
@@ -1844,39 +2231,6 @@ wr_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
   }
 }
 
-struct TcPlan {
-  int Tp, Rp, nc, G, nw_rows, n_tiles;
-  uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
-  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_dq, ws_total;
-};
-
-int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
-  TGFR_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "wordregion(tc): D=%d must be 64, 128, 192 or 256", D);
-  TGFR_REQUIRE(R >= 1 && R <= 256, "wordregion(tc): R=%d regions (max 256)", R);
-  TGFR_REQUIRE(T >= 1 && T <= 32, "wordregion(tc): T=%d words (max 32)", T);
-  pl->Tp = (T + 7) & ~7;
-  pl->Rp = (R + 15) & ~15;
-  pl->n_tiles = (pl->Rp + 127) / 128;
-  pl->nc = 128 / pl->Tp;
-  pl->nw_rows = pl->nc * pl->Tp;
-  pl->G = (Bq + pl->nc - 1) / pl->nc;
-  const int kch = D / 64;
-  pl->c_panel = (uint32_t)pl->Rp * 128u;
-  pl->q_panel = (uint32_t)pl->nw_rows * 128u;
-  pl->e_panel = (uint32_t)pl->Rp * 128u;
-  pl->off_q = kch * pl->c_panel;
-  pl->off_e = pl->off_q + kch * pl->q_panel;
-  pl->off_misc = pl->off_e + 2 * pl->e_panel;
-  pl->smem_bytes = pl->off_misc + 6144 + 1024;        // misc + alignment slack
-  TGFR_REQUIRE(pl->smem_bytes <= 232448, "wordregion(tc): shared memory plan needs %u bytes", pl->smem_bytes);
-  pl->ws_c16 = 0;
-  pl->ws_q16 = align_up((size_t)Bc * R * D * 2, 256);
-  pl->ws_qnorm = pl->ws_q16 + align_up((size_t)Bq * pl->Tp * D * 2, 256);
-  pl->ws_lens = pl->ws_qnorm + align_up((size_t)Bq * pl->Tp * 4, 256);
-  pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4, 256);                       // padded fp32 d words [Bq*Tp, D]
-  pl->ws_total = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);
-  return TGFR_OK;
-}
 
 // what the forward leaves for wr_tc_bwd2_kernel, in one caller-owned buffer:
 //   [V tiles: total_units x (D/8 planes x nw_rows x 8 fp16)][records: total_units x (nc x Tp/4 chunks x Rp x 16 B)]
@@ -1901,18 +2255,50 @@ SavedLayout saved_layout(const TcPlan& pl, int Bc, int Bq, int R, int D) {
   return L;
 }
 
-// shared-memory plan of wr_tc_bwd2_kernel: one 128-row C tile, the Q and V tiles, 1 KB of zeros, misc
-struct TcBwd2Plan {
+
+}  // namespace rec
+
+// what the forward leaves for wr_tc_bwd3_kernel, in one caller-owned buffer:
+//   [Wu tiles: total_units x (D/8 planes x nw_rows x 8 fp16)][alpha | beta: total_units x 2 x 128 fp32]
+//   [the fp16 operand copies of ctx and words, word norms, caption lengths]
+// (the last group is what wr_tc_prep_kernel produces: the backward then skips its own conversion pass)
+struct SavedLayout {
+  size_t off_wu, off_ab, off_c16, off_q16, off_qnorm, off_lens, total;
+};
+SavedLayout saved_layout(const TcPlan& pl, int Bc, int Bq, int R, int D) {
+  SavedLayout L;
+  const size_t units = (size_t)Bc * pl.G;
+  L.off_wu = 0;
+  L.off_ab = align_up(units * pl.nw_rows * D * 2, 1024);
+  L.off_c16 = L.off_ab + align_up(units * 256 * 4, 256);
+  L.off_q16 = L.off_c16 + align_up((size_t)Bc * R * D * 2, 256);
+  L.off_qnorm = L.off_q16 + align_up((size_t)Bq * pl.Tp * D * 2, 256);
+  L.off_lens = L.off_qnorm + align_up((size_t)Bq * pl.Tp * 4, 256);
+  L.total = L.off_lens + align_up((size_t)Bq * 4, 256);
+  return L;
+}
+
+enum { kSavedNone = 0, kSavedRecords = 1, kSavedWu = 2 };
+// the record layout is strictly larger than the Wu layout, so the size of the caller's buffer names the layout
+inline int saved_mode_of(const void* saved, size_t saved_bytes, size_t wu_total, size_t rec_total) {
+  if (saved == nullptr) return kSavedNone;
+  if (saved_bytes >= rec_total) return kSavedRecords;
+  if (saved_bytes >= wu_total) return kSavedWu;
+  return kSavedNone;
+}
+
+// shared-memory plan of wr_tc_bwd2_kernel / wr_tc_bwd3_kernel: one 128-row C tile, the Q and V tiles, 1 KB of zeros, misc
+struct TcBwd3Plan {
   uint32_t q_panel, off_q, off_v, off_misc, smem_bytes;
 };
-int make_bwd2_plan(const TcPlan& fp, int D, TcBwd2Plan* pl) {
+int make_bwd3_plan(const TcPlan& fp, int D, TcBwd3Plan* pl) {
   const int kch = D / 64;
   pl->q_panel = fp.q_panel;
   pl->off_q = kch * 128u * 128u;
   pl->off_v = pl->off_q + kch * pl->q_panel;
   pl->off_misc = pl->off_v + kch * pl->q_panel + 1024;
   if (pl->off_misc < 65536) pl->off_misc = 65536;               // the drain boxes (8 warps x 8 KB) overlay the tiles
-  pl->smem_bytes = pl->off_misc + 2048 + 1024;                  // misc + alignment slack
+  pl->smem_bytes = pl->off_misc + 4096 + 1024;                  // misc (barriers, ga | gb double buffer) + alignment slack
   TGFR_REQUIRE(pl->smem_bytes <= 232448, "wordregion(tc): backward shared memory plan needs %u bytes", pl->smem_bytes);
   return TGFR_OK;
 }
@@ -1973,7 +2359,10 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
                       const void* saved, size_t saved_bytes, cudaStream_t st) {
   TcPlan fp;
   if (int rc = make_plan(Bc, Bq, T, R, D, &fp)) return rc;     // workspace layout is shared with the forward
-  const bool saved_ok = saved != nullptr && saved_bytes >= saved_layout(fp, Bc, Bq, R, D).total;
+  const SavedLayout L = saved_layout(fp, Bc, Bq, R, D);
+  const rec::SavedLayout LR = rec::saved_layout(fp, Bc, Bq, R, D);
+  const int sv_mode = saved_mode_of(saved, saved_bytes, L.total, LR.total);
+  const bool saved_ok = sv_mode != kSavedNone;
   TcBwdPlan pl{};
   pl.Tp = fp.Tp;
   if ((dctx && !saved_ok) || dwords) {                          // the recompute kernel has its own shared-memory plan
@@ -1992,15 +2381,15 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   int* lens = reinterpret_cast<int*>(base + fp.ws_lens);
   float* dq_pad = reinterpret_cast<float*>(base + fp.ws_dq);
 
-  const SavedLayout L = saved_layout(fp, Bc, Bq, R, D);
-  const bool have_saved = saved != nullptr && saved_bytes >= L.total;
+  const bool have_saved = saved_ok;
   if (have_saved) {
-    // the forward kept its fp16 operand copies next to the records: no second conversion pass
+    // the forward kept its fp16 operand copies next to its saved state: no second conversion pass
     uint8_t* sv = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(saved));
-    c16 = reinterpret_cast<__half*>(sv + L.off_c16);
-    q16 = reinterpret_cast<__half*>(sv + L.off_q16);
-    qnorm = reinterpret_cast<float*>(sv + L.off_qnorm);
-    lens = reinterpret_cast<int*>(sv + L.off_lens);
+    const bool r = sv_mode == kSavedRecords;
+    c16 = reinterpret_cast<__half*>(sv + (r ? LR.off_c16 : L.off_c16));
+    q16 = reinterpret_cast<__half*>(sv + (r ? LR.off_q16 : L.off_q16));
+    qnorm = reinterpret_cast<float*>(sv + (r ? LR.off_qnorm : L.off_qnorm));
+    lens = reinterpret_cast<int*>(sv + (r ? LR.off_lens : L.off_lens));
   } else {
     const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
     wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc,
@@ -2047,48 +2436,82 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     static bool attr_done[64] = {};                                                                               \
     bool& attr_set = attr_done[dev & 63];                                                                         \
     if (!attr_set) {                                                                                              \
-      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd2_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(rec::wr_tc_bwd2_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         232448));                                                                 \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    wr_tc_bwd2_kernel<TPV><<<grid2, kThreadsTC, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_dc, p2);                    \
+    rec::wr_tc_bwd2_kernel<TPV><<<grid2, kThreadsTC, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_dc, p2);               \
+  } break;
+#define TGFR_LAUNCH_BWD3(TPV)                                                                                     \
+  case TPV: {                                                                                                     \
+    static bool attr_done[64] = {};                                                                               \
+    bool& attr_set = attr_done[dev & 63];                                                                         \
+    if (!attr_set) {                                                                                              \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_bwd3_kernel<TPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        232448));                                                                 \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    wr_tc_bwd3_kernel<TPV><<<grid2, kB3Threads, pl2.smem_bytes, st>>>(tm_c2, tm_q2, tm_dc, p2);                     \
   } break;
   if (dctx) {
     CUtensorMap tm_dc;
     TGFR_CUDA_OK(cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)Bc * R * D, st));
     if (int rc = make_tmap_3d(&tm_dc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dctx, D, R, Bc, 32, 32, 1)) return rc;
     if (have_saved) {
-      // the forward left its records: (b, tile, caption group) items, d ctx accumulated in TMEM
-      TcBwd2Plan pl2;
-      if (int rc = make_bwd2_plan(fp, D, &pl2)) return rc;
+      // (b, tile, caption group) items, d ctx accumulated in TMEM -- from the forward's records (wr_tc_bwd2_kernel)
+      // or from its Wu tiles and the S it recomputes (wr_tc_bwd3_kernel); both share one shared-memory plan
+      TcBwd3Plan pl2;
+      if (int rc = make_bwd3_plan(fp, D, &pl2)) return rc;
       const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
       CUtensorMap tm_c2, tm_q2;
       if (int rc = make_tmap_3d(&tm_c2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, D, R, Bc, 64, 128, 1)) return rc;
       if (int rc = make_tmap_3d(&tm_q2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q16, D, (uint64_t)Bq * fp.Tp, 1, 64, fp.nw_rows, 1))
         return rc;
-      TcBwd2Params p2{};
-      p2.v = reinterpret_cast<const __half*>(sv + L.off_v);
-      p2.rec = sv + L.off_rec;
-      p2.inw = reinterpret_cast<const float*>(sv + L.off_inw);
-      p2.gsim = gsim;
-      p2.rec_stride = L.rec_stride;
-      p2.Bc = Bc; p2.Bq = Bq; p2.R = R; p2.Rp = fp.Rp; p2.D = D; p2.nc = fp.nc; p2.G = fp.G;
-      p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_units = Bc * fp.G;
-      p2.q_panel = pl2.q_panel; p2.off_q = pl2.off_q; p2.off_v = pl2.off_v; p2.off_misc = pl2.off_misc;
-      p2.g1 = g1; p2.g23 = g2 * g3;
       // one CTA per SM; with two region tiles CTAs (2k, 2k+1) share a unit range, one tile each
       int shares = fp.n_tiles == 2 ? sms / 2 : sms;
       if (grid_dbg > 0 && grid_dbg < shares) shares = grid_dbg;
-      if (shares > p2.total_units) shares = p2.total_units;
+      if (shares > Bc * fp.G) shares = Bc * fp.G;
       const int grid2 = shares * fp.n_tiles;
+      if (sv_mode == kSavedRecords) {
+        rec::TcBwd2Params p2{};
+        p2.v = reinterpret_cast<const __half*>(sv + LR.off_v);
+        p2.rec = sv + LR.off_rec;
+        p2.inw = reinterpret_cast<const float*>(sv + LR.off_inw);
+        p2.gsim = gsim;
+        p2.rec_stride = LR.rec_stride;
+        p2.Bc = Bc; p2.Bq = Bq; p2.R = R; p2.Rp = fp.Rp; p2.D = D; p2.nc = fp.nc; p2.G = fp.G;
+        p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_units = Bc * fp.G;
+        p2.q_panel = pl2.q_panel; p2.off_q = pl2.off_q; p2.off_v = pl2.off_v; p2.off_misc = pl2.off_misc;
+        p2.g1 = g1; p2.g23 = g2 * g3;
+        switch (fp.Tp) {
+          TGFR_LAUNCH_BWD2(8)
+          TGFR_LAUNCH_BWD2(16)
+          TGFR_LAUNCH_BWD2(24)
+          TGFR_LAUNCH_BWD2(32)
+          default:
+            set_error("wordregion(tc): unsupported padded caption length %d", fp.Tp);
+            return TGFR_E_INVALID;
+        }
+      } else {
+      TcBwd3Params p2{};
+      p2.wu = reinterpret_cast<const __half*>(sv + L.off_wu);
+      p2.ab = reinterpret_cast<const float*>(sv + L.off_ab);
+      p2.gsim = gsim;
+      p2.lens = lens;
+      p2.Bc = Bc; p2.Bq = Bq; p2.R = R; p2.Rp = fp.Rp; p2.D = D; p2.nc = fp.nc; p2.G = fp.G;
+      p2.nw_rows = fp.nw_rows; p2.n_tiles = fp.n_tiles; p2.total_units = Bc * fp.G;
+      p2.uniform_len = cap_lens ? 0 : T;
+      p2.q_panel = pl2.q_panel; p2.off_q = pl2.off_q; p2.off_v = pl2.off_v; p2.off_misc = pl2.off_misc;
+      p2.k1 = g1 * kLog2e; p2.g1 = g1;
       switch (fp.Tp) {
-        TGFR_LAUNCH_BWD2(8)
-        TGFR_LAUNCH_BWD2(16)
-        TGFR_LAUNCH_BWD2(24)
-        TGFR_LAUNCH_BWD2(32)
+        TGFR_LAUNCH_BWD3(8)
+        TGFR_LAUNCH_BWD3(16)
+        TGFR_LAUNCH_BWD3(24)
+        TGFR_LAUNCH_BWD3(32)
         default:
           set_error("wordregion(tc): unsupported padded caption length %d", fp.Tp);
           return TGFR_E_INVALID;
+      }
       }
     } else {
       switch (pl.Tp) {
@@ -2124,6 +2547,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     TGFR_LAUNCH_OK();
   }
 #undef TGFR_LAUNCH_BWD
+#undef TGFR_LAUNCH_BWD3
 #undef TGFR_LAUNCH_BWD2
   return TGFR_OK;
 }
@@ -2142,11 +2566,22 @@ int wordregion_tc_set_trace(void* dev_buf) {
   return TGFR_OK;
 }
 
-// bytes of the forward -> backward records: one per unit (0 if the shape has no plan)
+// bytes of the forward -> backward state (0 if the shape has no plan).  Two layouts, told apart by their size:
+//   records (default)              A1 | E per (caption, word, region) + V tiles: the backward runs no exponential
+//   TGFR_WORDREGION_SAVE=wu        Wu tiles + alpha | beta per word: ~9x fewer bytes, the backward recomputes S and E
 size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D) {
   TcPlan pl;
   if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return 0;
-  return saved_layout(pl, Bc, Bq, R, D).total;
+  const char* m = getenv("TGFR_WORDREGION_SAVE");
+  if (m && (strcmp(m, "wu") == 0 || strcmp(m, "WU") == 0)) return saved_layout(pl, Bc, Bq, R, D).total;
+  return rec::saved_layout(pl, Bc, Bq, R, D).total;
+}
+
+// which layout a buffer of `saved_bytes` holds: 0 none / too small, 1 records, 2 Wu tiles
+int wordregion_tc_saved_mode(int Bc, int Bq, int T, int R, int D, const void* saved, size_t saved_bytes) {
+  TcPlan pl;
+  if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return kSavedNone;
+  return saved_mode_of(saved, saved_bytes, saved_layout(pl, Bc, Bq, R, D).total, rec::saved_layout(pl, Bc, Bq, R, D).total);
 }
 
 size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
@@ -2172,14 +2607,17 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   int* lens = reinterpret_cast<int*>(base + pl.ws_lens);
   const bool save = saved != nullptr;
   const SavedLayout L = saved_layout(pl, Bc, Bq, R, D);
+  const rec::SavedLayout LR = rec::saved_layout(pl, Bc, Bq, R, D);
+  const int sv_mode = saved_mode_of(saved, saved_bytes, L.total, LR.total);
+  const bool records = sv_mode == kSavedRecords;
   if (save) {
-    TGFR_REQUIRE(saved_bytes >= L.total, "wordregion(tc): saved buffer too small (%zu < %zu)", saved_bytes, L.total);
+    TGFR_REQUIRE(sv_mode != kSavedNone, "wordregion(tc): saved buffer too small (%zu < %zu)", saved_bytes, L.total);
     TGFR_REQUIRE((reinterpret_cast<uintptr_t>(saved) & 255) == 0, "wordregion(tc): saved buffer must be 256-byte aligned");
-    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);     // the operand copies live with the records: the backward reuses them
-    c16 = reinterpret_cast<__half*>(sv + L.off_c16);
-    q16 = reinterpret_cast<__half*>(sv + L.off_q16);
-    qnorm = reinterpret_cast<float*>(sv + L.off_qnorm);
-    lens = reinterpret_cast<int*>(sv + L.off_lens);
+    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);     // the operand copies live with the saved state: the backward reuses them
+    c16 = reinterpret_cast<__half*>(sv + (records ? LR.off_c16 : L.off_c16));
+    q16 = reinterpret_cast<__half*>(sv + (records ? LR.off_q16 : L.off_q16));
+    qnorm = reinterpret_cast<float*>(sv + (records ? LR.off_qnorm : L.off_qnorm));
+    lens = reinterpret_cast<int*>(sv + (records ? LR.off_lens : L.off_lens));
   }
 
   const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
@@ -2198,14 +2636,12 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.nw_rows = pl.nw_rows; p.n_tiles = pl.n_tiles; p.total_units = Bc * pl.G;
   p.c_panel = pl.c_panel; p.q_panel = pl.q_panel; p.e_panel = pl.e_panel;
   p.off_q = pl.off_q; p.off_e = pl.off_e; p.off_misc = pl.off_misc;
-  p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3;
+  p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3; p.g23 = g2 * g3;
   p.uniform_len = cap_lens ? 0 : T;
   if (save) {
     uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
-    p.sv_v = reinterpret_cast<__half*>(sv + L.off_v);
-    p.sv_rec = sv + L.off_rec;
-    p.sv_inw = reinterpret_cast<float*>(sv + L.off_inw);
-    p.rec_stride = L.rec_stride;
+    p.sv_wu = reinterpret_cast<__half*>(sv + L.off_wu);
+    p.sv_ab = reinterpret_cast<float*>(sv + L.off_ab);
   }
 
   int dev = 0, sms = 0;
@@ -2216,26 +2652,47 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     const int v = atoi(dg);
     if (v > 0 && v < grid) grid = v;
   }
-  // TGFR_WR_FWD=2 selects the previous (unpipelined, 18-warp) forward kernel for A/B comparisons
-  bool pipelined = true;
-  if (const char* fv = getenv("TGFR_WR_FWD")) pipelined = atoi(fv) != 2;
+  rec::TcParams pr{};
+  if (records) {
+    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
+    pr.q16 = q16; pr.qnorm = qnorm; pr.lens = lens; pr.sim = sim;
+    pr.sv_v = reinterpret_cast<__half*>(sv + LR.off_v);
+    pr.sv_rec = sv + LR.off_rec;
+    pr.sv_inw = reinterpret_cast<float*>(sv + LR.off_inw);
+    pr.rec_stride = LR.rec_stride;
+    pr.Bc = Bc; pr.Bq = Bq; pr.Tp = pl.Tp; pr.R = R; pr.Rp = pl.Rp; pr.D = D; pr.nc = pl.nc; pr.G = pl.G;
+    pr.nw_rows = pl.nw_rows; pr.n_tiles = pl.n_tiles; pr.total_units = Bc * pl.G;
+    pr.c_panel = pl.c_panel; pr.q_panel = pl.q_panel; pr.e_panel = pl.e_panel;
+    pr.off_q = pl.off_q; pr.off_e = pl.off_e; pr.off_misc = pl.off_misc;
+    pr.k1 = p.k1; pr.k2 = p.k2; pr.g3 = g3;
+    pr.uniform_len = p.uniform_len;
+  }
+#define TGFR_LAUNCH_FWDR(TPV)                                                                                   \
+  {                                                                                                            \
+    static bool attr_done[64] = {};                                                                            \
+    bool& attr_set = attr_done[dev & 63];                                                                      \
+    if (!attr_set) {                                                                                           \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(rec::wr_tc_fwd3_kernel<TPV, true>,                                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));                 \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    rec::wr_tc_fwd3_kernel<TPV, true><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, pr);                  \
+  }
 #define TGFR_LAUNCH_FWD1(TPV, SV)                                                                               \
   {                                                                                                            \
     static bool attr_done[64] = {};                                                                            \
     bool& attr_set = attr_done[dev & 63];                                                                      \
     if (!attr_set) {                                                                                           \
-      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        232448));                                                              \
       TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd3_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         232448));                                                              \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    if (pipelined) wr_tc_fwd3_kernel<TPV, SV><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, p);           \
-    else wr_tc_fwd_kernel<TPV, SV><<<grid, kFwdThreads, pl.smem_bytes, st>>>(tm_c, tm_q, p);                      \
+    wr_tc_fwd3_kernel<TPV, SV><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, p);                          \
   }
 #define TGFR_LAUNCH_FWD(TPV)                  \
   case TPV:                                   \
-    if (save) TGFR_LAUNCH_FWD1(TPV, true)     \
+    if (records) TGFR_LAUNCH_FWDR(TPV)        \
+    else if (save) TGFR_LAUNCH_FWD1(TPV, true) \
     else TGFR_LAUNCH_FWD1(TPV, false)         \
     break;
   switch (pl.Tp) {
@@ -2249,6 +2706,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   }
 #undef TGFR_LAUNCH_FWD
 #undef TGFR_LAUNCH_FWD1
+#undef TGFR_LAUNCH_FWDR
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }

@@ -88,8 +88,10 @@ class _WordRegionSim(torch.autograd.Function):
         lib = _lib.load()
         wsb = lib.tgfr_wordregion_workspace_bytes(Bc, Bq, T, R, D, precision)
         ws = _workspace(wsb, feats.device)
-        # forward -> backward image of the word softmax / attention (fp16): the backward then skips the score
-        # GEMM and every exponential.  TGFR_WORDREGION_SAVE=0 (or a buffer above the cap) selects recomputation.
+        # forward -> backward image of the word softmax / attention (fp16 records): the backward then skips the score
+        # GEMM and every exponential.  TGFR_WORDREGION_SAVE=wu keeps only the Wu tiles (9x fewer bytes; the backward
+        # recomputes the scores), TGFR_WORDREGION_SAVE=0 (or a buffer above the cap) selects full recomputation.
+        # The library sizes the buffer for the selected layout and recognises the layout by that size.
         saved, svb = None, 0
         if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _save_enabled():
             svb = lib.tgfr_wordregion_saved_bytes(Bc, Bq, T, R, D, precision)

@@ -16,8 +16,8 @@ names = {
     # pipelined forward (wr_tc_fwd3_kernel): A = word-softmax warps, B = cosine / V warps
     'fwd': {2: 'A:tile0 start', 3: 'A:tile0 done', 4: 'A:tile1 done', 5: 'B:Wu ready', 6: 'B:pass1 done', 7: 'B:V pass done',
             17: 'mma:E0 ready', 18: 'mma:G2a+G1 issued', 19: 'mma:G2b issued'},
-    # record-based backward (wr_tc_bwd2_kernel): one line per (face, tile, caption group) item
-    'bwd': {2: 'dE ready', 3: 'ops written', 8: 'acc done', 9: 'drained', 17: 'mma:V ready', 18: 'mma:ops ready',
+    # record-free backward (wr_tc_bwd3_kernel): one line per (face, tile, caption group) item
+    'bwd': {2: 'S|X ready', 3: 'ops written', 8: 'acc done', 9: 'drained', 17: 'mma:Wu ready', 18: 'mma:ops ready',
             19: 'mma:G5 issued'},
 }
 for which in ('fwd', 'bwd'):
