@@ -320,6 +320,19 @@ int tgfr_imim_bwd(const float* gout, const float* out, const float* x, int64_t x
                   size_t saved_bytes, void* const* dparams, float* dx, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* The contraction IMIM's layers run on (csrc/gemm_tc.cu gemm_tc_pair), with fp32 operands: every 1x1 convolution /
+ * nn.Linear / torch.bmm of models/models.py:380-405 and models/fusion_nets.py:97-115 is one of these three shapes.
+ *   mode 0  C = A B^T  (A [M,K], B [N,K])    mode 1  C = A B  (A [M,K], B [K,N])    mode 2  C = A^T B  (A [K,M], B [K,N])
+ *   C [batch, M, ldc] = relu?( alpha * product + bias[col] )
+ * Both operands are split into fp16 hi + lo with one power-of-two scale each and the tensor cores accumulate
+ * A_hi B_lo + A_lo B_hi + A_hi B_hi in fp32 (nterms = 3, ~22 significant bits) or A_hi B_hi only (nterms = 1).
+ * batch > 1: densely packed samples (lda / ldb = the row length), no split-K.  splits > 1: split-K over `splits` CTAs
+ * per tile (no bias / relu).  workspace: tgfr_matmul_split_workspace_bytes, 256-byte aligned. */
+size_t tgfr_matmul_split_workspace_bytes(int mode, int M, int N, int K, int batch);
+int tgfr_matmul_split(int mode, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int M,
+                      int N, int K, int batch, float alpha, const float* bias, int relu, int splits, int nterms,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ProjectionHead (models/models.py:96-119), the global branch of ImageHeading: out [M,N] = normalize(x W^T + b) for
  * x [M,K] (row stride x_sr), weight [N,K], bias [N] (NULL = none); znorm [M] = |x W^T + b| for the backward, which
  * writes dweight [N,K], dbias [N] and, if not NULL, dx [M,K]; dz_scratch is [M,N] floats. */

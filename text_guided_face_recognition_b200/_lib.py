@@ -72,6 +72,8 @@ SIGNATURES = {
     "tgfr_imim_num_params": (I, []),
     "tgfr_imim_fwd": (I, [P, L, L, L, P, I, I, I, I, F, F, P, P, P, P, Z, P]),
     "tgfr_imim_bwd": (I, [P, P, P, L, L, L, P, I, I, I, I, P, Z, P, P, P, Z, P]),
+    "tgfr_matmul_split_workspace_bytes": (Z, [I, I, I, I, I]),
+    "tgfr_matmul_split": (I, [I, P, L, P, L, P, L, I, I, I, I, F, P, I, I, I, P, Z, P]),
     "tgfr_proj_head_fwd": (I, [P, L, P, P, I, I, I, P, P, P]),
     "tgfr_proj_head_bwd": (I, [P, P, P, P, L, P, I, I, I, P, P, P, P, P]),
     "tgfr_fcfm_train_saved_bytes": (Z, [I, I]),

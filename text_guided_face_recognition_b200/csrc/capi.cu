@@ -89,6 +89,10 @@ int texthead_bwd(const float*, const float*, const float*, int, int, int, int, i
                  size_t, const void*, size_t, cudaStream_t);
 
 // imim.cu
+size_t matmul_split_workspace_bytes(int mode, int M, int N, int K, int batch);
+int matmul_split(int mode, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
 size_t imim_saved_bytes(int, int);
 size_t imim_workspace_bytes(int, int);
 int imim_fwd(const float*, int64_t, int64_t, int64_t, const float* const*, int, int, int, float, float, float*, float*, float*,
@@ -359,6 +363,17 @@ int tgfr_mag_ce_stats(const float* cos_s, const float* cos_m, int64_t sr, const 
 int tgfr_mag_ce_bwd(const float* cos_s, const float* cos_m, int64_t sr, const int64_t* labels, const float* lse,
                     const float* gout, int B, int C, float* g_cos, float* g_cosm, void* stream) {
   return mag_ce_bwd(cos_s, cos_m, sr, labels, lse, gout, B, C, g_cos, g_cosm, ST(stream));
+}
+
+size_t tgfr_matmul_split_workspace_bytes(int mode, int M, int N, int K, int batch) {
+  return matmul_split_workspace_bytes(mode, M, N, K, batch);
+}
+int tgfr_matmul_split(int mode, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int M, int N,
+                      int K, int batch, float alpha, const float* bias, int relu, int splits, int nterms, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  TGFR_REQUIRE(a && b && c, "matmul_split: NULL tensor");
+  return matmul_split(mode, a, lda, b, ldb, c, ldc, M, N, K, batch, alpha, bias, relu, splits, nterms, workspace,
+                      workspace_bytes, ST(stream));
 }
 
 size_t tgfr_imim_saved_bytes(int B, int P) { return imim_saved_bytes(B, P); }

@@ -89,6 +89,9 @@ struct GemmTcParams {
   int nterms;            // 1 or 3
   // batched = 1: blockIdx.z selects one of up to three independent products (own maps, shapes and outputs; no split-K)
   int batched;
+  // strided = 1: blockIdx.z is the sample of a strided batch (third tensor-map coordinate; C advances by c_bs; no split-K)
+  int strided;
+  int64_t c_bs;
   struct Z {
     float* C;
     const float* bias;
@@ -119,13 +122,14 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
   const int zi = p.batched ? (int)blockIdx.z : 0;
   const int Mz = p.batched ? p.z[zi].M : p.M, Nz = p.batched ? p.z[zi].N : p.N, Kz = p.batched ? p.z[zi].K : p.K;
-  float* const Cz = p.batched ? p.z[zi].C : p.C;
+  const int zc = p.strided ? (int)blockIdx.z : 0;
+  float* const Cz = (p.batched ? p.z[zi].C : p.C) + (p.strided ? (int64_t)blockIdx.z * p.c_bs : 0);
   const int64_t ldcz = p.batched ? p.z[zi].ldc : p.ldc;
   const float* const biasz = p.batched ? p.z[zi].bias : p.bias;
   if (m0 >= Mz || n0 >= Nz) return;                        // batched products share one grid: tiles outside this one
   const int kt_total = (Kz + kBK - 1) / kBK;
-  const int kt0 = p.batched ? 0 : blockIdx.z * p.kt_per_split;
-  const int kt1 = p.batched ? kt_total : min(kt_total, kt0 + p.kt_per_split);
+  const int kt0 = (p.batched || p.strided) ? 0 : blockIdx.z * p.kt_per_split;
+  const int kt1 = (p.batched || p.strided) ? kt_total : min(kt_total, kt0 + p.kt_per_split);
   const int nk1 = kt1 - kt0;                               // >= 1 by construction of the grid
   const int nkt = nk1 * (p.nterms == 3 ? 3 : 1);
 
@@ -153,22 +157,27 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kTileBytes;
-        const int term = it / nk1;                           // 0: hi hi, 1: hi lo, 2: lo hi
+        // three terms: hi lo, lo hi, then hi hi.  The tensor core truncates (toward -inf) when it adds into the fp32
+        // accumulator, a bias proportional to the accumulator's magnitude per step: the two small cross terms go first,
+        // while the accumulator is 2^-11 of its final size, so only the K / 16 hi hi steps pay it (measured on the
+        // K = 25 088 column sums of IMIM's backward: 3e-4 -> 1e-4 relative).
+        const int term = it / nk1;
         const int k0 = (kt0 + it - term * nk1) * kBK;
-        const CUtensorMap* const ta = &maps.a[zi][term == 2 ? 1 : 0];
-        const CUtensorMap* const tb = &maps.b[zi][term == 1 ? 1 : 0];
+        const bool three = p.nterms == 3;
+        const CUtensorMap* const ta = &maps.a[zi][three && term == 1 ? 1 : 0];
+        const CUtensorMap* const tb = &maps.b[zi][three && term == 0 ? 1 : 0];
         mbar_arrive_expect_tx(&full[s], kStageBytes);
         if (p.a_mn) {                                        // memory [K, M]: two panels of 64 M-elements x 64 K-rows
-          tma_load_3d(sa, ta, &full[s], m0, k0, 0);
-          tma_load_3d(sa + 8192, ta, &full[s], m0 + 64, k0, 0);
+          tma_load_3d(sa, ta, &full[s], m0, k0, zc);
+          tma_load_3d(sa + 8192, ta, &full[s], m0 + 64, k0, zc);
         } else {                                             // memory [M, K]: 128 rows x 64 K-elements
-          tma_load_3d(sa, ta, &full[s], k0, m0, 0);
+          tma_load_3d(sa, ta, &full[s], k0, m0, zc);
         }
         if (p.b_mn) {
-          tma_load_3d(sb, tb, &full[s], n0, k0, 0);
-          tma_load_3d(sb + 8192, tb, &full[s], n0 + 64, k0, 0);
+          tma_load_3d(sb, tb, &full[s], n0, k0, zc);
+          tma_load_3d(sb + 8192, tb, &full[s], n0 + 64, k0, zc);
         } else {
-          tma_load_3d(sb, tb, &full[s], k0, n0, 0);
+          tma_load_3d(sb, tb, &full[s], k0, n0, zc);
         }
       }
     }
@@ -514,6 +523,46 @@ __global__ void split_f16_kernel(const float* __restrict__ g, int64_t ld, int ro
   }
 }
 
+// 16-byte variants for densely aligned matrices (cols, ld multiples of 4; ld_out a multiple of 8): one float4 per thread
+// and step, a grid that fills the machine whatever the row length
+__global__ void __launch_bounds__(256) maxabs4_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float scratch[32];
+  const int q = cols >> 2;
+  const int64_t n = (int64_t)rows * q;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / q;
+    const int c = (int)(i - r * q) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + r * ld + c));
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = block_max(m, scratch);
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+__global__ void __launch_bounds__(256) split4_f16_kernel(const float* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ scale,
+                                                         __half* __restrict__ hi, __half* __restrict__ lo, int ld_out) {
+  const float mx = scale[0];
+  const float sc = (mx > 0.f) ? exp2f(floorf(log2f(4096.f / mx))) : 1.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[1] = 1.f / sc;
+  const int q = ld_out >> 2;
+  const int64_t n = (int64_t)rows * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / q;
+    const int c = (int)(i - r * q) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cols) v = __ldg(reinterpret_cast<const float4*>(g + r * ld + c));       // cols % 4 == 0: whole quads only
+    const float x[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+    __half h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      h[u] = __float2half_rn(x[u]);
+      l[u] = __float2half_rn(x[u] - __half2float(h[u]));
+    }
+    *reinterpret_cast<uint2*>(hi + r * ld_out + c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + r * ld_out + c) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 // merge the per-tile online-softmax partials of a row: (max, sum exp(. - max)) over nt column tiles
 __global__ void ce_merge_partials_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int rows, int nt,
                                          float* __restrict__ rowmax, float* __restrict__ rowsum) {
@@ -543,12 +592,13 @@ int launch_norms(const float* x, int64_t s_vec, int64_t s_elem, int nvec, int le
 bool head_tc_supported(int B, int C, int Din) { return B >= 1 && C >= 1 && Din >= 8; }
 
 // fp16 operand: `mn` = 0: memory [rows, K] (K contiguous, pitch ld);  1: memory [K, rows] (rows contiguous, pitch ld)
+// `batch` samples lie ld * (mn ? K : rows) elements apart (contiguous samples)
 static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int K, int64_t ld, int box_rows = 128,
-                       bool overlap = false) {
+                       bool overlap = false, int batch = 1) {
   if (mn)
-    return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, 1, 64, 64, 1, 128, (uint64_t)ld,
-                        overlap);
-  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, 1, 64, box_rows, 1, 128,
+    return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)batch, 64, 64, 1, 128,
+                        (uint64_t)ld, overlap);
+  return make_tmap_3d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, (uint64_t)K, (uint64_t)rows, (uint64_t)batch, 64, box_rows, 1, 128,
                       (uint64_t)ld, overlap);
 }
 
@@ -717,21 +767,38 @@ int head_normalize_bwd_pair(const float* gx, const float* x, int64_t x_sr, const
 int head_split_f16(int nblocks, const float* const* src, const int64_t* ld, const int* rows, const int* cols, float* scale,
                    __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st) {
   TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
+  auto vec_ok = [&](int k) {
+    return (cols[k] & 3) == 0 && (ld[k] & 3) == 0 && (ld_out[k] & 7) == 0 && (reinterpret_cast<uintptr_t>(src[k]) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(hi[k]) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo[k]) & 7) == 0;
+  };
+  auto blocks_for = [](int64_t quads) { return (int)(quads + 255) / 256 < 148 * 8 ? (int)((quads + 255) / 256) : 148 * 8; };
   for (int k = 0; k < nblocks; ++k) {
-    maxabs_kernel<<<rows[k] < 1184 ? rows[k] : 1184, 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale);
+    if (vec_ok(k))
+      maxabs4_kernel<<<blocks_for((int64_t)rows[k] * (cols[k] >> 2)), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale);
+    else
+      maxabs_kernel<<<rows[k] < 1184 ? rows[k] : 1184, 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale);
     TGFR_LAUNCH_OK();
   }
   for (int k = 0; k < nblocks; ++k) {
-    split_f16_kernel<<<dim3((ld_out[k] + 1023) / 1024, rows[k] < 32768 ? rows[k] : 32768), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale, hi[k], lo[k],
-                                                                              ld_out[k]);
+    if (vec_ok(k))
+      split4_f16_kernel<<<blocks_for((int64_t)rows[k] * (ld_out[k] >> 2)), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale, hi[k],
+                                                                                        lo[k], ld_out[k]);
+    else
+      split_f16_kernel<<<dim3((ld_out[k] + 1023) / 1024, rows[k] < 32768 ? rows[k] : 32768), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k],
+                                                                                                          scale, hi[k], lo[k], ld_out[k]);
     TGFR_LAUNCH_OK();
   }
   return TGFR_OK;
 }
 
 // up to three independent error-compensated products in one launch (blockIdx.z = product):
-//   C_z [M_z, N_z] = relu?( alpha dscale[1] dscale2[1] (A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T) + bias_z )
+//   C_z [M_z, N_z] = relu?( alpha dscale[1] dscale2[1] (A_hi B_lo^T + A_lo B_hi^T + A_hi B_hi^T) + bias_z )
 // a_mn / b_mn as in gemm_tc; a_overlap / b_overlap: the operand's rows share memory (pitch < row length)
+struct TcOperand {          // an fp32 matrix as fp16 hi / lo (gemm_tc_split_operand); lo may be NULL for nterms == 1
+  const __half *hi, *lo;
+  int64_t ld;               // row pitch of the fp16 copies (multiple of 8)
+  const float* scale;       // device float[2]: scale[1] = 2^-e undoes the power-of-two scaling of the copies
+};
 struct Split3Product {
   const __half *a_hi, *a_lo, *b_hi, *b_lo;
   int64_t lda, ldb, ldc;
@@ -759,6 +826,92 @@ int gemm_tc_split3_batched(const Split3Product* prods, int n, int a_mn, int a_ov
     nt = nt > (q.N + 127) / 128 ? nt : (q.N + 127) / 128;
   }
   return launch_gemm<kEpiStore, 128, 3, 2>(dim3(nt, mt, n), maps, p, st);
+}
+
+// General error-compensated product on fp16 hi / lo operand pairs (the contractions of IMIM, csrc/imim.cu):
+//   mode 0  C = A B^T   A [M, K], B [N, K]          mode 1  C = A B   A [M, K], B [K, N]
+//   mode 2  C = A^T B   A [K, M], B [K, N]
+//   C [M, N] (pitch ldc) = relu?( alpha A.scale[1] B.scale[1] (sum of nterms products) + bias[col] )
+// batch > 1: contiguous samples of both operands (ld x rows-in-memory apart), C advances by c_bs per sample, no split-K.
+// splits > 1: split-K with vector reductions into a zeroed C (no bias / relu).
+int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int64_t c_bs, int M, int N, int K,
+                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, cudaStream_t st) {
+  TGFR_REQUIRE(mode >= 0 && mode <= 2 && (nterms == 1 || nterms == 3), "gemm_tc_pair: bad mode / nterms");
+  TGFR_REQUIRE(batch >= 1 && (batch == 1 || splits <= 1), "gemm_tc_pair: a strided batch cannot split K");
+  TGFR_REQUIRE(splits <= 1 || (!bias && !relu), "gemm_tc_pair: split-K has no bias / relu epilogue");
+  const int a_mn = mode == 2, b_mn = mode != 0;
+  const int kt_total = (K + kBK - 1) / kBK;
+  if (splits < 1) splits = 1;
+  if (splits > kt_total) splits = kt_total;
+  const int per = (kt_total + splits - 1) / splits;
+  splits = (kt_total + per - 1) / per;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (int rc = operand_map(&maps.a[0][0], A.hi, a_mn, M, K, A.ld, 128, false, batch)) return rc;
+  if (int rc = operand_map(&maps.b[0][0], B.hi, b_mn, N, K, B.ld, 128, false, batch)) return rc;
+  if (nterms == 3) {
+    if (int rc = operand_map(&maps.a[0][1], A.lo, a_mn, M, K, A.ld, 128, false, batch)) return rc;
+    if (int rc = operand_map(&maps.b[0][1], B.lo, b_mn, N, K, B.ld, 128, false, batch)) return rc;
+  }
+  GemmTcParams p{};
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.kt_per_split = per; p.alpha = alpha;
+  p.dscale = A.scale; p.dscale2 = B.scale; p.bias = bias; p.relu = relu;
+  p.atomic = splits > 1; p.a_mn = a_mn; p.b_mn = b_mn; p.nterms = nterms;
+  p.strided = batch > 1; p.c_bs = c_bs;
+  if (splits > 1) TGFR_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st));
+  const dim3 grid((N + 127) / 128, (M + kBM - 1) / kBM, batch > 1 ? batch : splits);
+  const int tiles = (int)(grid.x * grid.y * grid.z);
+  if (tiles > 2 * sm_count() && tiles <= 3 * sm_count()) return launch_gemm<kEpiStore, 128, 2, 3>(grid, maps, p, st);
+  return launch_gemm<kEpiStore, 128, 3, 2>(grid, maps, p, st);
+}
+
+// x [rows, cols] fp32 (pitch ld) -> hi / lo fp16 [rows, ld_out] with one power-of-two scale: scale[0] = max|x|, scale[1] = 2^-e
+int gemm_tc_split_operand(const float* src, int64_t ld, int rows, int cols, float* scale, __half* hi, __half* lo, int ld_out,
+                          cudaStream_t st) {
+  const float* srcs[1] = {src};
+  const int64_t lds[1] = {ld};
+  const int rws[1] = {rows}, cls[1] = {cols}, ldo[1] = {ld_out};
+  __half* his[1] = {hi};
+  __half* los[1] = {lo};
+  return head_split_f16(1, srcs, lds, rws, cls, scale, his, los, ldo, st);
+}
+
+// fp32 front end of gemm_tc_pair (C ABI tgfr_matmul_split): splits both operands into the workspace, then one product.
+// Memory shapes per sample: A [M, K] (modes 0, 1) or [K, M] (mode 2); B [N, K] (mode 0) or [K, N] (modes 1, 2); samples of a
+// batch are contiguous (pitch x rows apart).  C [batch, M, ldc].
+static size_t matmul_split_plan(int mode, int M, int N, int K, int batch, int* ra, int* ca, int* rb, int* cb) {
+  *ra = mode == 2 ? K : M; *ca = mode == 2 ? M : K;
+  *rb = mode == 0 ? N : K; *cb = mode == 0 ? K : N;
+  const size_t a = ((size_t)batch * *ra * ((*ca + 7) & ~7) * sizeof(__half) + 255) / 256 * 256;
+  const size_t b = ((size_t)batch * *rb * ((*cb + 7) & ~7) * sizeof(__half) + 255) / 256 * 256;
+  return 256 + 2 * a + 2 * b;
+}
+size_t matmul_split_workspace_bytes(int mode, int M, int N, int K, int batch) {
+  int ra, ca, rb, cb;
+  return matmul_split_plan(mode, M, N, K, batch, &ra, &ca, &rb, &cb);
+}
+int matmul_split(int mode, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  TGFR_REQUIRE(mode >= 0 && mode <= 2 && M >= 1 && N >= 1 && K >= 1 && batch >= 1, "matmul_split: bad shape / mode");
+  int ra, ca, rb, cb;
+  const size_t need = matmul_split_plan(mode, M, N, K, batch, &ra, &ca, &rb, &cb);
+  TGFR_REQUIRE(ws && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
+               "matmul_split: workspace too small or not 256-byte aligned (%zu < %zu)", ws_bytes, need);
+  const int lda16 = (ca + 7) & ~7, ldb16 = (cb + 7) & ~7;
+  const size_t a = ((size_t)batch * ra * lda16 * sizeof(__half) + 255) / 256 * 256;
+  const size_t b = ((size_t)batch * rb * ldb16 * sizeof(__half) + 255) / 256 * 256;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  float* scales = reinterpret_cast<float*>(base);
+  __half* ahi = reinterpret_cast<__half*>(base + 256);
+  __half* alo = reinterpret_cast<__half*>(base + 256 + a);
+  __half* bhi = reinterpret_cast<__half*>(base + 256 + 2 * a);
+  __half* blo = reinterpret_cast<__half*>(base + 256 + 2 * a + b);
+  TGFR_REQUIRE(batch == 1 || (lda == ca && ldb == cb), "matmul_split: a batch needs densely packed operands");
+  if (int rc = gemm_tc_split_operand(A, lda, batch * ra, ca, scales, ahi, alo, lda16, st)) return rc;
+  if (int rc = gemm_tc_split_operand(Bm, ldb, batch * rb, cb, scales + 2, bhi, blo, ldb16, st)) return rc;
+  const TcOperand oa{ahi, alo, lda16, scales}, ob{bhi, blo, ldb16, scales + 2};
+  return gemm_tc_pair(mode, oa, ob, C, ldc, (int64_t)M * ldc, M, N, K, batch, alpha, bias, relu, splits, nterms, st);
 }
 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e

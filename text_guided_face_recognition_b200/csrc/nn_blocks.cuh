@@ -406,11 +406,264 @@ __global__ void colsum_kernel(const float* __restrict__ g, int64_t ld, int M, in
   atomicAdd(&out[c], s);
 }
 
+// the same with 16-byte loads: a warp reads 128 consecutive columns of a row, the block's 8 warps take every 8th row of a
+// 128-row slab (16 loads in flight per thread), one atomic per column and block
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ g, int64_t ld, int M, int C, float* __restrict__ out) {
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + 4 * lane;
+  const int m0 = blockIdx.y * 128, m1 = min(M, m0 + 128);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll 8
+    for (int m = m0 + w; m < m1; m += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + (int64_t)m * ld + c));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = part[k][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    atomicAdd(&out[c], s.x); atomicAdd(&out[c + 1], s.y); atomicAdd(&out[c + 2], s.z); atomicAdd(&out[c + 3], s.w);
+  }
+}
 int colsum(const float* g, int64_t ld, int M, int C, float* out, cudaStream_t st) {
   TGFR_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-  colsum_kernel<<<dim3(ceil_div(C, 128), ceil_div(M, 256)), 128, 0, st>>>(g, ld, M, C, out);
+  if ((C & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0)
+    colsum4_kernel<<<dim3(ceil_div(C, 128), ceil_div(M, 128)), 256, 0, st>>>(g, ld, M, C, out);
+  else
+    colsum_kernel<<<dim3(ceil_div(C, 128), ceil_div(M, 256)), 128, 0, st>>>(g, ld, M, C, out);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Many-block variants of the per-channel / per-sample statistics for large batches (IMIM at B = 128: 25 MB per tensor).
+// The kernels above give a whole channel or sample to ONE block (256 / 128 blocks on 148 SMs, strided reads); these split
+// the reduction over blockIdx.y / .z, keep (mean, M2) partials in a small scratch vector and merge them in a fixed order
+// (Chan's update), so the result does not depend on scheduling.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kBnSplit = 16;     // sample groups per channel
+constexpr int kLnSplit = 8;      // chunks per sample
+
+// part[(c * kBnSplit + s) * 2 + {0,1}] = mean, M2 over samples b = s, s + kBnSplit, ...
+__global__ void bn_stats_part_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sp, int B, int P,
+                                     float* __restrict__ part) {
+  __shared__ float scratch[32];
+  const int c = blockIdx.x, s0 = blockIdx.y;
+  const int nb = s0 < B ? (B - s0 + kBnSplit - 1) / kBnSplit : 0;
+  const int n = nb * P;
+  const float* xc = x + c * sc;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += xc[(int64_t)(s0 + (k / P) * kBnSplit) * sb + (k % P) * sp];
+  const float mu = n ? block_sum(s, scratch) / (float)n : 0.f;
+  float v = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float d = xc[(int64_t)(s0 + (k / P) * kBnSplit) * sb + (k % P) * sp] - mu;
+    v = fmaf(d, d, v);
+  }
+  v = block_sum(v, scratch);
+  if (threadIdx.x == 0) {
+    part[(c * kBnSplit + s0) * 2] = mu;
+    part[(c * kBnSplit + s0) * 2 + 1] = v;
+  }
+}
+__global__ void bn_stats_merge_kernel(const float* __restrict__ part, int C, int B, int P, float eps, float momentum,
+                                      float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ mean,
+                                      float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float na = 0.f, ma = 0.f, m2a = 0.f;
+  for (int s0 = 0; s0 < kBnSplit; ++s0) {
+    const float nb = (float)((s0 < B ? (B - s0 + kBnSplit - 1) / kBnSplit : 0) * P);
+    if (nb == 0.f) continue;
+    const float mb = part[(c * kBnSplit + s0) * 2], m2b = part[(c * kBnSplit + s0) * 2 + 1];
+    const float d = mb - ma, nn = na + nb;
+    ma += d * (nb / nn);
+    m2a += m2b + d * d * (na * nb / nn);
+    na = nn;
+  }
+  const float var = m2a / na;                                   // biased variance normalises (as torch does)
+  mean[c] = ma;
+  invstd[c] = rsqrtf(var + eps);
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * ma;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (na / fmaxf(na - 1.f, 1.f));
+  }
+}
+
+// BatchNorm backward sums with coalesced reads of BOTH layouts: a 32-channel x 32-position tile of x (NCHW: positions
+// contiguous) goes through shared memory, dxn [B*P, C] is read along its channels.  dgamma / dbeta zeroed by the caller.
+__global__ void bn_bwd_sums_tile_kernel(const float* __restrict__ dxn, const float* __restrict__ x, int64_t sb, int64_t sc,
+                                        int64_t sp, int B, int C, int P, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float tile[32][33];
+  __shared__ float r1[8][32], r2[8][32];
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, pp = p0 + tx;
+      tile[j][tx] = (c < C && pp < P) ? (x[b * sb + c * sc + pp * sp] - mean[c]) * invstd[c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int pp = p0 + j, c = c0 + tx;
+      if (pp < P && c < C) {
+        const float g = dxn[((int64_t)b * P + pp) * C + c];
+        s1 += g;
+        s2 = fmaf(g, tile[tx][j], s2);
+      }
+    }
+    __syncthreads();
+  }
+  r1[ty][tx] = s1;
+  r2[ty][tx] = s2;
+  __syncthreads();
+  if (ty == 0 && c0 + tx < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s1 += r1[k][tx];
+      s2 += r2[k][tx];
+    }
+    atomicAdd(&dbeta[c0 + tx], s1);
+    atomicAdd(&dgamma[c0 + tx], s2);
+  }
+}
+
+// LayerNorm over a whole sample, split over kLnSplit blocks: part[(b * kLnSplit + s) * 2] = mean, M2 of chunk s
+__global__ void ln_stats_part_kernel(const float* __restrict__ o, int64_t o_stride, int n, float* __restrict__ part) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.y, s0 = blockIdx.x;
+  const int chunk = ((n + kLnSplit - 1) / kLnSplit + 3) & ~3;
+  const int k0 = s0 * chunk, k1 = min(n, k0 + chunk), cnt = max(k1 - k0, 0);
+  const float* src = o + (int64_t)b * o_stride;
+  float s = 0.f;
+  for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) s += src[k];
+  const float mu = cnt ? block_sum(s, scratch) / (float)cnt : 0.f;
+  float v = 0.f;
+  for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const float d = src[k] - mu;
+    v = fmaf(d, d, v);
+  }
+  v = block_sum(v, scratch);
+  if (threadIdx.x == 0) {
+    part[(b * kLnSplit + s0) * 2] = mu;
+    part[(b * kLnSplit + s0) * 2 + 1] = v;
+  }
+}
+__device__ __forceinline__ void ln_merge_parts(const float* __restrict__ part, int b, int n, float* mu, float* rstd) {
+  const int chunk = ((n + kLnSplit - 1) / kLnSplit + 3) & ~3;
+  float na = 0.f, ma = 0.f, m2a = 0.f;
+  for (int s0 = 0; s0 < kLnSplit; ++s0) {
+    const float nb = (float)max(min(n, (s0 + 1) * chunk) - s0 * chunk, 0);
+    if (nb == 0.f) continue;
+    const float mb = part[(b * kLnSplit + s0) * 2], m2b = part[(b * kLnSplit + s0) * 2 + 1];
+    const float d = mb - ma, nn = na + nb;
+    ma += d * (nb / nn);
+    m2a += m2b + d * d * (na * nb / nn);
+    na = nn;
+  }
+  *mu = ma;
+  *rstd = rsqrtf(m2a / na + kLnEps);
+}
+// y = (o - mu) rstd w + bias, one thread per element; every block merges its sample's partials itself
+__global__ void ln_apply_kernel(const float* __restrict__ o, int64_t o_stride, int P, int C, const float* __restrict__ w,
+                                const float* __restrict__ bia, int w_t, const float* __restrict__ part, float* __restrict__ y,
+                                int64_t y_stride, float* __restrict__ mu_out, float* __restrict__ rstd_out) {
+  // w_t != 0: w / bia are already position-major copies [p * C + c] (ln_affine_t_kernel), read along k
+  const int b = blockIdx.y, n = P * C;
+  float mu, rstd;
+  ln_merge_parts(part, b, n, &mu, &rstd);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    mu_out[b] = mu;
+    rstd_out[b] = rstd;
+  }
+  const float* src = o + (int64_t)b * o_stride;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    const int wi = w_t ? k : c * P + pp;
+    y[(int64_t)b * y_stride + k] = (src[k] - mu) * rstd * __ldg(w + wi) + __ldg(bia + wi);
+  }
+}
+// the reference's affine parameters are [c * P + p]; position-major copies [p * C + c] for the kernels below
+__global__ void ln_affine_t_kernel(const float* __restrict__ w, const float* __restrict__ bia, int P, int C, float* __restrict__ wt,
+                                   float* __restrict__ bt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P * C) return;
+  const int pp = k / C, c = k - pp * C;
+  wt[k] = w[c * P + pp];
+  bt[k] = bia[c * P + pp];
+}
+// backward: part[(b * kLnSplit + s) * 2] = sum dh, sum dh yhat over chunk s (dh = dY w), then the element-wise update
+__global__ void ln_bwd_part_kernel(const float* __restrict__ dy, int64_t dy_stride, const float* __restrict__ o, int64_t o_stride,
+                                   int P, int C, const float* __restrict__ w, int w_t, const float* __restrict__ mu_in,
+                                   const float* __restrict__ rstd_in, float* __restrict__ part) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.y, s0 = blockIdx.x, n = P * C;
+  const int chunk = ((n + kLnSplit - 1) / kLnSplit + 3) & ~3;
+  const int k0 = s0 * chunk, k1 = min(n, k0 + chunk);
+  const float mu = mu_in[b], rstd = rstd_in[b];
+  const float* g = dy + (int64_t)b * dy_stride;
+  const float* src = o + (int64_t)b * o_stride;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    const float dh = g[k] * __ldg(w + (w_t ? k : c * P + pp));
+    s1 += dh;
+    s2 = fmaf(dh, (src[k] - mu) * rstd, s2);
+  }
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  if (threadIdx.x == 0) {
+    part[(b * kLnSplit + s0) * 2] = s1;
+    part[(b * kLnSplit + s0) * 2 + 1] = s2;
+  }
+}
+__global__ void ln_bwd_apply_kernel(const float* dy, int64_t dy_stride, const float* __restrict__ o, int64_t o_stride, int P, int C,
+                                    const float* __restrict__ w, int w_t, const float* __restrict__ mu_in,
+                                    const float* __restrict__ rstd_in, const float* __restrict__ part, float* dx, int64_t dx_stride) {
+  const int b = blockIdx.y, n = P * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int s0 = 0; s0 < kLnSplit; ++s0) {
+    s1 += part[(b * kLnSplit + s0) * 2];
+    s2 += part[(b * kLnSplit + s0) * 2 + 1];
+  }
+  s1 /= (float)n;
+  s2 /= (float)n;
+  const float mu = mu_in[b], rstd = rstd_in[b];
+  const float* g = dy + (int64_t)b * dy_stride;
+  const float* src = o + (int64_t)b * o_stride;
+  float* out = dx + (int64_t)b * dx_stride;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int pp = k / C, c = k - pp * C;
+    const float dh = g[k] * __ldg(w + (w_t ? k : c * P + pp));
+    out[k] = rstd * (dh - s1 - (src[k] - mu) * rstd * s2);
+  }
+}
+// d ln.weight / d ln.bias with the batch split over blockIdx.y (atomics into vectors zeroed by the caller)
+__global__ void ln_bwd_params_split_kernel(const float* __restrict__ dy, int64_t dy_stride, const float* __restrict__ o,
+                                           int64_t o_stride, int B, int P, int C, const float* __restrict__ mu,
+                                           const float* __restrict__ rstd, float* __restrict__ dw, float* __restrict__ db) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, n = P * C;
+  if (k >= n) return;
+  const int pp = k / C, c = k - pp * C;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  float a = 0.f, s = 0.f;
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float g = dy[(int64_t)b * dy_stride + k];
+    a = fmaf(g, (o[(int64_t)b * o_stride + k] - mu[b]) * rstd[b], a);
+    s += g;
+  }
+  atomicAdd(&dw[c * P + pp], a);
+  atomicAdd(&db[c * P + pp], s);
 }
 
 }  // namespace

@@ -58,7 +58,7 @@ _KERNELS_PER_CALL = {
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
     "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_mag_ce_stats": 1, "tgfr_mag_ce_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
-    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 12, "tgfr_imim_bwd": 34,
+    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 34, "tgfr_imim_bwd": 39, "tgfr_matmul_split": 5,
     "tgfr_proj_head_fwd": 2, "tgfr_proj_head_bwd": 5, "tgfr_fcfm_train_fwd": 21, "tgfr_fcfm_train_bwd": 45,
 }
 
@@ -855,6 +855,28 @@ class _ProjHead(torch.autograd.Function):
         _call("tgfr_proj_head_bwd", ptr(g), ptr(out), ptr(znorm), ptr(x), x.stride(0), ptr(weight), M, N, K, ptr(dz), ptr(dx),
               ptr(dw), ptr(db), stream_ptr())
         return dx, dw, (db if ctx.has_bias else None)
+
+
+def matmul_split(a, b, mode=0, alpha=1.0, bias=None, relu=False, splits=1, nterms=3):
+    """The tensor-core contraction IMIM's layers run on (C ABI tgfr_matmul_split; no autograd): a, b fp32, 2-D or 3-D
+    (batch of densely packed samples).  mode 0: a [M,K] @ b [N,K].T; mode 1: a [M,K] @ b [K,N]; mode 2: a [K,M].T @ b [K,N].
+    nterms = 3 accumulates the fp16 hi / lo split products (fp32-class accuracy), nterms = 1 the hi parts only."""
+    _lib.ensure_device(a.device)
+    a, b = _f32(a).contiguous(), _f32(b).contiguous()
+    batch = a.shape[0] if a.dim() == 3 else 1
+    am, bm = a.shape[-2:], b.shape[-2:]
+    M, K = (am[1], am[0]) if mode == 2 else (am[0], am[1])
+    N = bm[0] if mode == 0 else bm[1]
+    if (bm[1] if mode == 0 else bm[0]) != K or (b.shape[0] if b.dim() == 3 else 1) != batch:
+        raise ValueError(f"matmul_split: shapes {tuple(a.shape)} / {tuple(b.shape)} do not contract in mode {mode}")
+    out = torch.empty((batch, M, N) if a.dim() == 3 else (M, N), dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    wsb = lib.tgfr_matmul_split_workspace_bytes(mode, M, N, K, batch)
+    ws = _workspace(wsb, a.device)
+    _call("tgfr_matmul_split", mode, a.data_ptr(), am[1], b.data_ptr(), bm[1], out.data_ptr(), N, M, N, K, batch,
+          float(alpha), ptr(None if bias is None else _f32(bias).contiguous()), int(relu), int(splits), int(nterms),
+          ptr(ws), wsb, stream_ptr())
+    return out
 
 
 def proj_head(x, weight, bias):
