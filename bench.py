@@ -889,17 +889,23 @@ def run_b200(args):
             ih.imim(ix).backward(ig)
         im_ms, _ = time_step(imim_step, flush, max(3, min(args.steps, 10)), use_graph)
         im_flops = 3 * 2 * 83.9e6 * B
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                      # FMA lanes x 2 x max SM clock: fp32 SIMT ceiling
+        im_mode = os.environ.get("TGFR_IMIM_PRECISION", "split")
+        if im_mode == "fp32":
+            im_peak, im_bound = 148 * 128 * 2 * 1.965e9 / 1e12, "fp32-simt"
+            im_note = ("TGFR_IMIM_PRECISION=fp32: register-blocked fp32 SIMT GEMMs; peak = 148 SMs x 128 FMA lanes x 2 x "
+                       "1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)")
+        else:
+            im_peak, im_bound = pk["tf_sus"], "tensor"
+            im_note = ("contractions on tcgen05 as fp16 hi/lo split products (3 MMA terms per algorithmic product, fp32-class "
+                       "accuracy): executed tensor flops = 3 x algorithmic; the rest of the step is the operand splits and "
+                       "the BatchNorm / LayerNorm / softmax passes (HBM bound)")
         line["image_head"] = {"metric": "imim_fwd_bwd_samples_per_sec", "value": B / (im_ms * 1e-3), "unit": "samples/s",
-                              "ms_per_step": im_ms, "dtype": "f32",
+                              "ms_per_step": im_ms, "dtype": "f32" if im_mode == "fp32" else "f16x3 split (f32 accumulate)",
                               "config": {"B": B, "positions": R, "channels": D, "mode": "training (batch statistics)"},
-                              "roofline": {"bound": "fp32-simt", "achieved": im_flops / (im_ms * 1e-3) / 1e12,
-                                           "peak": fp32_peak, "unit": "TFLOP/s", "frac": im_flops / (im_ms * 1e-3) / 1e12 / fp32_peak,
-                                           "peak_source": "148 SMs x 128 FMA lanes x 2 x 1.965 GHz (no measured fp32 peak in "
-                                                          "MEASURED_PEAKS.json)",
+                              "roofline": {"bound": im_bound, "achieved": im_flops / (im_ms * 1e-3) / 1e12,
+                                           "peak": im_peak, "unit": "TFLOP/s", "frac": im_flops / (im_ms * 1e-3) / 1e12 / im_peak,
                                            "algorithmic_flops_per_step": im_flops,
-                                           "note": "fp32 register-blocked GEMMs (not tensor cores): the contractions are "
-                                                   "83.9 M MACs per sample forward, x3 with the backward"}}
+                                           "note": im_note + "; 83.9 M MACs per sample forward, x3 with the backward"}}
         del ih, ix, ig
 
         # ---- configs[4]: FCFM fusion (eval kernel) + verification scoring in ONE timed call: 6 000 faces x 10 captions

@@ -36,8 +36,11 @@ def _shapes(mode, M, N, K, batch):
     (2, 768, 256, 5000, 0, 8),
     (0, 37, 50, 24, 0, 1),          # smaller than one tile / one K step
 ])
-def test_matmul_split_vs_float64(mode, M, N, K, batch, splits):
+@pytest.mark.parametrize("persistent", ["0", "1"])
+def test_matmul_split_vs_float64(mode, M, N, K, batch, splits, persistent, monkeypatch):
+    """persistent = 1: the one-CTA-per-SM kernel with double-buffered TMEM accumulators (TGFR_GEMM_PERSIST=1)."""
     from text_guided_face_recognition_b200 import ops
+    monkeypatch.setenv("TGFR_GEMM_PERSIST", persistent)
     rs = np.random.RandomState(M + 7 * N + 13 * K + mode)
     sa, sb = _shapes(mode, M, N, K, batch)
     a = (rs.randn(*sa) * np.exp(rs.randn(*sa))).astype(np.float32)      # heavy-tailed: exercises the lo parts

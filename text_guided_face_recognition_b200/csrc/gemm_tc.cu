@@ -105,6 +105,165 @@ struct GemmMaps {        // [product z][0 = hi (or the only operand), 1 = lo]
   CUtensorMap b[3][2];
 };
 
+// The epilogue of one 128 x BN tile whose accumulator sits at TMEM address `tmem`: warp quarter q owns rows
+// m0 + 32 q .. + 31.  `stage` is that warp's private 32 x 33 float transpose buffer; (bx, by) the tile's position in
+// the nx-wide tile grid.  Shared by the one-tile-per-CTA kernel and the persistent kernel.
+template <int EPI, int BN>
+__device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tmem, float* stage, int m0, int n0, int bx, int by,
+                                              int nx, int q, int lane, int warp, int Mz, int Nz, float* Cz, int64_t ldcz,
+                                              const float* biasz) {
+  const int row_base = m0 + q * 32;
+  const float alpha = p.alpha * (p.dscale ? __ldg(p.dscale + 1) : 1.f) * (p.dscale2 ? __ldg(p.dscale2 + 1) : 1.f);
+  if constexpr (EPI != kEpiStore) {
+    // a thread owns row (row_base + lane) of the tile: logits = s cos, phi on the label column
+    const int row = row_base + lane;
+    const bool row_ok = row < p.M;
+    const int64_t ycol = row_ok ? __ldg(p.ce.labels + row) - p.ce.class_off : -1;     // label column in this shard
+    float kscale = 0.f, lse = 0.f;
+    if constexpr (EPI == kEpiCeGrad) {
+      // power-of-two scale from the row-independent factor k: entries are k (p - onehot) phi', |.| <= k max(1, phi')
+      const float k = (p.ce.coef ? __ldg(p.ce.coef) : 1.f) * (p.ce.gout ? __ldg(p.ce.gout) : 1.f) / (float)p.M;
+      const float ak = fabsf(k);
+      const float sc = (ak > 0.f) ? exp2f(floorf(log2f(256.f / ak))) : 1.f;
+      kscale = k * sc;
+      if (bx == 0 && by == 0 && warp == 2 && lane == 0) p.ce.scale[1] = 1.f / sc;
+      lse = row_ok ? __ldg(p.ce.lse + row) : 0.f;
+    }
+    float mx = -INFINITY, sum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int c0 = n0 + 32 * ch;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);      // warp-collective even past the last column
+      tmem_ld_wait();
+      float lg[32];
+      float dph = 1.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float c = __uint_as_float(v[j]);
+        float l = c * p.alpha;
+        if ((int64_t)(c0 + j) == ycol && c0 + j < p.N) {   // a label of the NEXT class shard can fall into this tile's padding
+          l = p.alpha * arc_phi_tc(c, p.ce.cm, p.ce.sm, p.ce.th, p.ce.mm, p.ce.easy, &dph);
+          if constexpr (EPI == kEpiCeStats) {
+            p.ce.cos_t[row] = c;
+            p.ce.tgt[row] = l;
+          }
+        }
+        lg[j] = (c0 + j < p.N) ? l : -INFINITY;
+      }
+      if constexpr (EPI == kEpiCeStats) {
+        float cmx = lg[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) cmx = fmaxf(cmx, lg[j]);
+        if (cmx > mx) {
+          sum *= expf(mx - cmx);          // exp(-inf) = 0 on the first chunk
+          mx = cmx;
+        }
+        if (mx > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum += expf(lg[j] - mx);
+        }
+      } else {
+        // a thread owns 32 consecutive entries of ITS row: four 16-byte stores, no transpose (ld_g % 8 == 0)
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float g2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float g = 0.f;
+            if (c0 + j + u < p.N) {
+              const bool on = (int64_t)(c0 + j + u) == ycol;
+              g = kscale * (expf(lg[j + u] - lse) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
+              g = fminf(fmaxf(g, -65504.f), 65504.f);
+            }
+            g2[u] = g;
+          }
+          const __half2 h2 = __floats2half2_rn(g2[0], g2[1]);
+          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        if (row_ok) {
+          __half* dst = p.ce.g16 + (int64_t)row * p.ce.ld_g + c0;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (c0 + 8 * q4 < p.ce.ld_g)                           // columns [N, ld_g) are the zero K padding
+              *reinterpret_cast<uint4*>(dst + 8 * q4) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+      }
+    }
+    if constexpr (EPI == kEpiCeStats) {
+      if (row_ok) {
+        p.ce.pmax[(int64_t)row * nx + bx] = mx;
+        p.ce.psum[(int64_t)row * nx + bx] = sum;
+      }
+    }
+  } else {
+  const bool direct = (ldcz & 3) == 0 && (reinterpret_cast<uintptr_t>(Cz) & 15) == 0;
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    const int c0 = n0 + 32 * ch;
+    if (c0 >= Nz) break;
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);
+    tmem_ld_wait();
+    if (direct) {
+      // a thread owns 32 consecutive outputs of ITS row (128 contiguous bytes): 16-byte stores or vector reductions
+      const int row = row_base + lane;
+      if (row < Mz) {
+        float* dst = Cz + (int64_t)row * ldcz + c0;
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x = __uint_as_float(v[4 * g4 + u]);
+            if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
+            x *= alpha;
+            if (biasz && c0 + 4 * g4 + u < Nz) x += __ldg(biasz + c0 + 4 * g4 + u);
+            if (p.relu) x = fmaxf(x, 0.f);
+            o[u] = x;
+          }
+          const int c = c0 + 4 * g4;
+          if (c + 3 < Nz) {
+            if (p.atomic) red_add_v4(dst + 4 * g4, o[0], o[1], o[2], o[3]);
+            else *reinterpret_cast<float4*>(dst + 4 * g4) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c + u < Nz) {
+                if (p.atomic) atomicAdd(dst + 4 * g4 + u, o[u]);
+                else dst[4 * g4 + u] = o[u];
+              }
+          }
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]);
+      if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
+      x *= alpha;
+      if (biasz && c0 + j < Nz) x += __ldg(biasz + c0 + j);
+      if (p.relu) x = fmaxf(x, 0.f);
+      stage[lane * 33 + j] = x;
+    }
+    __syncwarp();
+    const int col = c0 + lane;
+    if (col < Nz) {
+      const int nrows = min(32, Mz - row_base);
+      for (int rr = 0; rr < nrows; ++rr) {
+        float* dst = Cz + (int64_t)(row_base + rr) * ldcz + col;
+        const float val = stage[rr * 33 + lane];
+        if (p.atomic) atomicAdd(dst, val);
+        else *dst = val;
+      }
+    }
+    __syncwarp();
+  }
+  }
+}
+
 template <int EPI, int BN, int STAGES, int MINB>
 __global__ void __launch_bounds__(kGemmThreads, MINB)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
@@ -205,163 +364,180 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
     mbar_wait(accum, 0);
     tc_fence_after();
     // the operand stages are dead now: warp-private 32 x 33 float transpose buffers live in stage 0
-    float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
-    const int row_base = m0 + q * 32;
-    const float alpha = p.alpha * (p.dscale ? __ldg(p.dscale + 1) : 1.f) * (p.dscale2 ? __ldg(p.dscale2 + 1) : 1.f);
-    if constexpr (EPI != kEpiStore) {
-      // a thread owns row (row_base + lane) of the tile: logits = s cos, phi on the label column
-      const int row = row_base + lane;
-      const bool row_ok = row < p.M;
-      const int64_t ycol = row_ok ? __ldg(p.ce.labels + row) - p.ce.class_off : -1;     // label column in this shard
-      float kscale = 0.f, lse = 0.f;
-      if constexpr (EPI == kEpiCeGrad) {
-        // power-of-two scale from the row-independent factor k: entries are k (p - onehot) phi', |.| <= k max(1, phi')
-        const float k = (p.ce.coef ? __ldg(p.ce.coef) : 1.f) * (p.ce.gout ? __ldg(p.ce.gout) : 1.f) / (float)p.M;
-        const float ak = fabsf(k);
-        const float sc = (ak > 0.f) ? exp2f(floorf(log2f(256.f / ak))) : 1.f;
-        kscale = k * sc;
-        if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) p.ce.scale[1] = 1.f / sc;
-        lse = row_ok ? __ldg(p.ce.lse + row) : 0.f;
-      }
-      float mx = -INFINITY, sum = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < kBN / 32; ++ch) {
-        const int c0 = n0 + 32 * ch;
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);      // warp-collective even past the last column
-        tmem_ld_wait();
-        float lg[32];
-        float dph = 1.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float c = __uint_as_float(v[j]);
-          float l = c * p.alpha;
-          if ((int64_t)(c0 + j) == ycol && c0 + j < p.N) {   // a label of the NEXT class shard can fall into this tile's padding
-            l = p.alpha * arc_phi_tc(c, p.ce.cm, p.ce.sm, p.ce.th, p.ce.mm, p.ce.easy, &dph);
-            if constexpr (EPI == kEpiCeStats) {
-              p.ce.cos_t[row] = c;
-              p.ce.tgt[row] = l;
-            }
-          }
-          lg[j] = (c0 + j < p.N) ? l : -INFINITY;
-        }
-        if constexpr (EPI == kEpiCeStats) {
-          float cmx = lg[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cmx = fmaxf(cmx, lg[j]);
-          if (cmx > mx) {
-            sum *= expf(mx - cmx);          // exp(-inf) = 0 on the first chunk
-            mx = cmx;
-          }
-          if (mx > -INFINITY) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum += expf(lg[j] - mx);
-          }
-        } else {
-          // a thread owns 32 consecutive entries of ITS row: four 16-byte stores, no transpose (ld_g % 8 == 0)
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float g2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float g = 0.f;
-              if (c0 + j + u < p.N) {
-                const bool on = (int64_t)(c0 + j + u) == ycol;
-                g = kscale * (expf(lg[j + u] - lse) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
-                g = fminf(fmaxf(g, -65504.f), 65504.f);
-              }
-              g2[u] = g;
-            }
-            const __half2 h2 = __floats2half2_rn(g2[0], g2[1]);
-            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-          }
-          if (row_ok) {
-            __half* dst = p.ce.g16 + (int64_t)row * p.ce.ld_g + c0;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              if (c0 + 8 * q4 < p.ce.ld_g)                           // columns [N, ld_g) are the zero K padding
-                *reinterpret_cast<uint4*>(dst + 8 * q4) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-          }
-        }
-      }
-      if constexpr (EPI == kEpiCeStats) {
-        if (row_ok) {
-          p.ce.pmax[(int64_t)row * gridDim.x + blockIdx.x] = mx;
-          p.ce.psum[(int64_t)row * gridDim.x + blockIdx.x] = sum;
-        }
-      }
-    } else {
-    const bool direct = (ldcz & 3) == 0 && (reinterpret_cast<uintptr_t>(Cz) & 15) == 0;
-#pragma unroll 1
-    for (int ch = 0; ch < kBN / 32; ++ch) {
-      const int c0 = n0 + 32 * ch;
-      if (c0 >= Nz) break;
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);
-      tmem_ld_wait();
-      if (direct) {
-        // a thread owns 32 consecutive outputs of ITS row (128 contiguous bytes): 16-byte stores or vector reductions
-        const int row = row_base + lane;
-        if (row < Mz) {
-          float* dst = Cz + (int64_t)row * ldcz + c0;
-#pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4) {
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float x = __uint_as_float(v[4 * g4 + u]);
-              if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
-              x *= alpha;
-              if (biasz && c0 + 4 * g4 + u < Nz) x += __ldg(biasz + c0 + 4 * g4 + u);
-              if (p.relu) x = fmaxf(x, 0.f);
-              o[u] = x;
-            }
-            const int c = c0 + 4 * g4;
-            if (c + 3 < Nz) {
-              if (p.atomic) red_add_v4(dst + 4 * g4, o[0], o[1], o[2], o[3]);
-              else *reinterpret_cast<float4*>(dst + 4 * g4) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (c + u < Nz) {
-                  if (p.atomic) atomicAdd(dst + 4 * g4 + u, o[u]);
-                  else dst[4 * g4 + u] = o[u];
-                }
-            }
-          }
-        }
-        continue;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.clamp) x = fminf(fmaxf(x, -1.f), 1.f);
-        x *= alpha;
-        if (biasz && c0 + j < Nz) x += __ldg(biasz + c0 + j);
-        if (p.relu) x = fmaxf(x, 0.f);
-        stage[lane * 33 + j] = x;
-      }
-      __syncwarp();
-      const int col = c0 + lane;
-      if (col < Nz) {
-        const int nrows = min(32, Mz - row_base);
-        for (int rr = 0; rr < nrows; ++rr) {
-          float* dst = Cz + (int64_t)(row_base + rr) * ldcz + col;
-          const float val = stage[rr * 33 + lane];
-          if (p.atomic) atomicAdd(dst, val);
-          else *dst = val;
-        }
-      }
-      __syncwarp();
-    }
-    }
+    gemm_epilogue<EPI, BN>(p, tmem, reinterpret_cast<float*>(smem) + q * (32 * 33), m0, n0, (int)blockIdx.x, (int)blockIdx.y,
+                           (int)gridDim.x, q, lane, warp, Mz, Nz, Cz, ldcz, biasz);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent form of the same GEMM: one CTA per SM walks the tile list (x fastest, so concurrently running CTAs share the
+// A rows and stream different B tiles), the TMA ring runs on across tile boundaries and the accumulator is double
+// buffered in TMEM -- tile i+1's main loop runs under tile i's epilogue, and the per-CTA set-up (TMEM allocation, barrier
+// initialisation, pipeline fill) is paid once per SM instead of once per tile.  Same roles, same epilogues
+// (gemm_epilogue), same split-K / multi-product / strided-batch meaning of the tile grid's z axis.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kEpiStageBytes = 4 * 32 * 33 * sizeof(float) + 512;      // warp-private transpose buffers, padded
+__host__ __device__ constexpr uint32_t gemm_persist_smem_bytes(int bn, int stages) {
+  return (uint32_t)stages * gemm_stage_bytes(bn) + 1024 /*barriers*/ + kEpiStageBytes + 1024 /*alignment*/;
+}
+
+struct TileInfo {
+  int bx, by, zi, zc, m0, n0, Mz, Nz, kt0, nk1, nkt;
+  bool skip;
+  float* Cz;
+  int64_t ldcz;
+  const float* biasz;
+};
+template <int BN>
+__device__ __forceinline__ TileInfo tile_info(const GemmTcParams& p, int t, int nx, int ny) {
+  TileInfo ti;
+  ti.bx = t % nx;
+  const int r = t / nx;
+  ti.by = r % ny;
+  const int bz = r / ny;
+  ti.zi = p.batched ? bz : 0;
+  ti.zc = p.strided ? bz : 0;
+  ti.Mz = p.batched ? p.z[ti.zi].M : p.M;
+  ti.Nz = p.batched ? p.z[ti.zi].N : p.N;
+  const int Kz = p.batched ? p.z[ti.zi].K : p.K;
+  ti.Cz = (p.batched ? p.z[ti.zi].C : p.C) + (p.strided ? (int64_t)bz * p.c_bs : 0);
+  ti.ldcz = p.batched ? p.z[ti.zi].ldc : p.ldc;
+  ti.biasz = p.batched ? p.z[ti.zi].bias : p.bias;
+  ti.m0 = ti.by * kBM;
+  ti.n0 = ti.bx * BN;
+  ti.skip = ti.m0 >= ti.Mz || ti.n0 >= ti.Nz;
+  const int kt_total = (Kz + kBK - 1) / kBK;
+  ti.kt0 = (p.batched || p.strided) ? 0 : bz * p.kt_per_split;
+  const int kt1 = (p.batched || p.strided) ? kt_total : min(kt_total, ti.kt0 + p.kt_per_split);
+  ti.nk1 = kt1 - ti.kt0;
+  ti.nkt = ti.nk1 * (p.nterms == 3 ? 3 : 1);
+  return ti;
+}
+
+template <int EPI, int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_persist_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p, const int nx, const int ny, const int nz) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t kStageBytes = gemm_stage_bytes(BN);
+  constexpr uint32_t kAccCols = BN <= 128 ? 128 : 256;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "tile width: whole 32-column epilogue chunks");
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;       // [2] accumulator buffer written (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;        // [2] accumulator buffer drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * kStageBytes + 1024);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = nx * ny * nz;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);           // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0][0]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                                         // ring position, running across tiles
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const TileInfo ti = tile_info<BN>(p, t, nx, ny);
+        if (ti.skip) continue;
+        const bool three = p.nterms == 3;
+        for (int k = 0; k < ti.nkt; ++k, ++it) {
+          const uint32_t s = it % STAGES, use = it / STAGES;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kTileBytes;
+          const int term = k / ti.nk1;                         // hi lo, lo hi, then hi hi (see gemm_tc_kernel)
+          const int k0 = (ti.kt0 + k - term * ti.nk1) * kBK;
+          const CUtensorMap* const ta = &maps.a[ti.zi][three && term == 1 ? 1 : 0];
+          const CUtensorMap* const tb = &maps.b[ti.zi][three && term == 0 ? 1 : 0];
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          if (p.a_mn) {
+            tma_load_3d(sa, ta, &full[s], ti.m0, k0, ti.zc);
+            tma_load_3d(sa + 8192, ta, &full[s], ti.m0 + 64, k0, ti.zc);
+          } else {
+            tma_load_3d(sa, ta, &full[s], k0, ti.m0, ti.zc);
+          }
+          if (p.b_mn) {
+            tma_load_3d(sb, tb, &full[s], ti.n0, k0, ti.zc);
+            tma_load_3d(sb + 8192, tb, &full[s], ti.n0 + 64, k0, ti.zc);
+          } else {
+            tma_load_3d(sb, tb, &full[s], k0, ti.n0, ti.zc);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBM, BN, p.a_mn != 0, p.b_mn != 0);
+      uint32_t it = 0, li = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const TileInfo ti = tile_info<BN>(p, t, nx, ny);
+        if (ti.skip) continue;
+        const uint32_t buf = li & 1, ub = li >> 1;
+        mbar_wait(&acc_empty[buf], (ub & 1) ^ 1);              // a fresh barrier passes the wait on parity 1 at once
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * kAccCols;
+        for (int k = 0; k < ti.nkt; ++k, ++it) {
+          const uint32_t s = it % STAGES, use = it / STAGES;
+          mbar_wait(&full[s], use & 1);
+          tc_fence_after();
+          const uint32_t a = smem_u32(smem + s * kStageBytes), b = a + kTileBytes;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t ad = p.a_mn ? make_smem_desc(a + k16 * 2048, 8192, 1024) : make_smem_desc(a + k16 * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? make_smem_desc(b + k16 * 2048, 8192, 1024) : make_smem_desc(b + k16 * 32, 16, 1024);
+            umma_ss(acc, ad, bd, idesc, (k | k16) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+        ++li;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t li = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const TileInfo ti = tile_info<BN>(p, t, nx, ny);
+      if (ti.skip) continue;
+      const uint32_t buf = li & 1, ub = li >> 1;
+      mbar_wait(&acc_full[buf], ub & 1);
+      tc_fence_after();
+      gemm_epilogue<EPI, BN>(p, tmem + buf * kAccCols, epi_stage + q * (32 * 33), ti.m0, ti.n0, ti.bx, ti.by, nx, q, lane, warp, ti.Mz,
+                             ti.Nz, ti.Cz, ti.ldcz, ti.biasz);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      ++li;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 2 * kAccCols);
   }
 }
 
@@ -605,8 +781,37 @@ static int operand_map(CUtensorMap* tm, const __half* ptr, int mn, int rows, int
 template <int EPI, int BN, int STAGES, int MINB>
 static int launch_gemm(dim3 grid, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmTcParams& p, cudaStream_t st);
 
+static int sm_count();
+// TGFR_GEMM_PERSIST=1 selects the persistent kernel.  Measured (B200, same runs, tools/time_head.py / time_imim.py):
+// fused head step 143 us vs 117 us, IMIM fwd+bwd 1.41 ms vs 1.35 ms for the one-tile-per-CTA kernel -- at 2-8 tiles per
+// SM these products are bound by their epilogues (160 exponentials per thread in the cross-entropy ones, 64 KB of
+// stores in the plain one), and two or three co-resident CTAs bring 8-12 epilogue warps per SM where one persistent
+// CTA has 4; the set-up it saves is smaller than that.  It stays selectable (and parity-tested) as the base for a
+// version with two epilogue warpgroups; the default is the co-resident plan.
+static bool gemm_persistent() {
+  const char* e = getenv("TGFR_GEMM_PERSIST");
+  return e && atoi(e) == 1;
+}
+template <int EPI, int BN, int STAGES>
+static int launch_gemm_persist(dim3 tiles, const GemmMaps& maps, const GemmTcParams& p, cudaStream_t st) {
+  constexpr uint32_t smem = gemm_persist_smem_bytes(BN, STAGES);
+  static_assert(smem <= 232448, "persistent GEMM: shared memory plan");
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_persist_kernel<EPI, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  const int n = (int)(tiles.x * tiles.y * tiles.z), sms = sm_count();
+  gemm_tc_persist_kernel<EPI, BN, STAGES><<<n < sms ? n : sms, kGemmThreads, smem, st>>>(maps, p, (int)tiles.x, (int)tiles.y, (int)tiles.z);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
 template <int EPI, int BN, int STAGES, int MINB>
 static int launch_gemm(dim3 grid, const GemmMaps& maps, const GemmTcParams& p, cudaStream_t st) {
+  if (gemm_persistent()) return launch_gemm_persist<EPI, BN, (BN <= 128 ? 6 : 5)>(grid, maps, p, st);
   constexpr uint32_t smem = gemm_smem_bytes(BN, STAGES);
   static bool attr_done[64] = {};
   int dev = 0;
