@@ -280,6 +280,16 @@ int tgfr_fcfm_working_fwd(const float* img, int64_t img_sb, int64_t img_sc, int6
                           int64_t word_sb, int64_t word_sd, int64_t word_st, const float* gl_img, int64_t gl_sr,
                           const float* sent, int64_t sent_sr, const float* const* params_host, int n_params, int B, int T,
                           float* out, int64_t out_sr, void* stream);
+/* The same forward with the 3x3 convolution (fusion_nets.py:235, 95 % of the arithmetic) on the tensor cores: one
+ * implicit GEMM per 4096 samples over fp16 hi / lo copies of the image (three split terms, fp32-class accuracy), the
+ * rest in the per-sample kernel.  For the large batches of verification (src/test.py: every pair of the list in one
+ * call).  workspace: tgfr_fcfm_working_workspace_bytes(B) bytes, 256-byte aligned; same results within 1e-5. */
+size_t tgfr_fcfm_working_workspace_bytes(int B);
+int tgfr_fcfm_working_fwd_tc(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw,
+                             const float* word, int64_t word_sb, int64_t word_sd, int64_t word_st, const float* gl_img,
+                             int64_t gl_sr, const float* sent, int64_t sent_sr, const float* const* params_host,
+                             int n_params, int B, int T, float* out, int64_t out_sr, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Self-tests of the tcgen05 / TMA building blocks (used by tests/test_gpu_tc.py only).

@@ -67,6 +67,8 @@ SIGNATURES = {
     "tgfr_row_argmax": (I, [P, L, I, I, P, P]),
     "tgfr_fcfm_working_num_params": (I, []),
     "tgfr_fcfm_working_fwd": (I, [P, L, L, L, L, P, L, L, L, P, L, P, L, P, I, I, I, P, L, P]),
+    "tgfr_fcfm_working_workspace_bytes": (Z, [I]),
+    "tgfr_fcfm_working_fwd_tc": (I, [P, L, L, L, L, P, L, L, L, P, L, P, L, P, I, I, I, P, L, P, Z, P]),
     "tgfr_imim_saved_bytes": (Z, [I, I]),
     "tgfr_imim_workspace_bytes": (Z, [I, I]),
     "tgfr_imim_num_params": (I, []),

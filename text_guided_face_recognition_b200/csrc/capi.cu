@@ -124,6 +124,9 @@ int roc_curve(const float*, const int64_t*, int64_t, int, float*, int64_t*, int6
 int fcfm_working_fwd(const float*, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const float*,
                      int64_t, const float*, int64_t, const float* const*, int, int, float*, int64_t, cudaStream_t);
 int fcfm_working_num_params();
+size_t fcfm_working_workspace_bytes(int B);
+int fcfm_working_fwd_tc(const float*, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const float*,
+                        int64_t, const float*, int64_t, const float* const*, int, int, float*, int64_t, void*, size_t, cudaStream_t);
 
 // tc_selftest.cu
 int debug_umma(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
@@ -466,6 +469,18 @@ int tgfr_fcfm_working_fwd(const float* img, int64_t img_sb, int64_t img_sc, int6
   TGFR_REQUIRE(B == 0 || (img && word && gl_img && sent && out), "fcfm_working_fwd: NULL tensor");
   return fcfm_working_fwd(img, img_sb, img_sc, img_sh, img_sw, word, word_sb, word_sd, word_st, gl_img, gl_sr, sent, sent_sr,
                           params_host, B, T, out, out_sr, ST(stream));
+}
+
+size_t tgfr_fcfm_working_workspace_bytes(int B) { return fcfm_working_workspace_bytes(B); }
+int tgfr_fcfm_working_fwd_tc(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw, const float* word,
+                             int64_t word_sb, int64_t word_sd, int64_t word_st, const float* gl_img, int64_t gl_sr,
+                             const float* sent, int64_t sent_sr, const float* const* params_host, int n_params, int B, int T,
+                             float* out, int64_t out_sr, void* workspace, size_t workspace_bytes, void* stream) {
+  TGFR_REQUIRE(params_host && n_params == fcfm_working_num_params(), "fcfm_working_fwd: expected %d parameter pointers, got %d",
+               fcfm_working_num_params(), n_params);
+  TGFR_REQUIRE(B == 0 || (img && word && gl_img && sent && out), "fcfm_working_fwd: NULL tensor");
+  return fcfm_working_fwd_tc(img, img_sb, img_sc, img_sh, img_sw, word, word_sb, word_sd, word_st, gl_img, gl_sr, sent, sent_sr,
+                             params_host, B, T, out, out_sr, workspace, workspace_bytes, ST(stream));
 }
 
 int tgfr_debug_umma(const void* a, const void* b, float* out, int N, int K, int a_mn, int b_mn, int manual_a,

@@ -92,6 +92,10 @@ struct GemmTcParams {
   // strided = 1: blockIdx.z is the sample of a strided batch (third tensor-map coordinate; C advances by c_bs; no split-K)
   int strided;
   int64_t c_bs;
+  // conv_c != 0: implicit 3x3 convolution over a channels-last image matrix A [rows = positions, conv_c channels]: K runs
+  // over 9 taps x conv_c channels, and tap (dy, dx) reads A shifted down by dy * conv_w + dx rows (valid convolution:
+  // the outputs of the anchors whose window leaves the image are garbage the caller ignores)
+  int conv_c, conv_w;
   struct Z {
     float* C;
     const float* bias;
@@ -329,6 +333,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
         if (p.a_mn) {                                        // memory [K, M]: two panels of 64 M-elements x 64 K-rows
           tma_load_3d(sa, ta, &full[s], m0, k0, zc);
           tma_load_3d(sa + 8192, ta, &full[s], m0 + 64, k0, zc);
+        } else if (p.conv_c) {                               // tap-shifted rows of the image matrix
+          const int tap = k0 / p.conv_c;
+          tma_load_3d(sa, ta, &full[s], k0 - tap * p.conv_c, m0 + (tap / 3) * p.conv_w + tap % 3, zc);
         } else {                                             // memory [M, K]: 128 rows x 64 K-elements
           tma_load_3d(sa, ta, &full[s], k0, m0, zc);
         }
@@ -476,6 +483,9 @@ gemm_tc_persist_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams
           if (p.a_mn) {
             tma_load_3d(sa, ta, &full[s], ti.m0, k0, ti.zc);
             tma_load_3d(sa + 8192, ta, &full[s], ti.m0 + 64, k0, ti.zc);
+          } else if (p.conv_c) {
+            const int tap = k0 / p.conv_c;
+            tma_load_3d(sa, ta, &full[s], k0 - tap * p.conv_c, ti.m0 + (tap / 3) * p.conv_w + tap % 3, ti.zc);
           } else {
             tma_load_3d(sa, ta, &full[s], k0, ti.m0, ti.zc);
           }
@@ -1079,6 +1089,39 @@ int gemm_tc_split_operand(const float* src, int64_t ld, int rows, int cols, floa
   __half* his[1] = {hi};
   __half* los[1] = {lo};
   return head_split_f16(1, srcs, lds, rws, cls, scale, his, los, ldo, st);
+}
+
+// Valid 3x3 convolution as ONE product (FCFM's conv, models/fusion_nets.py:235): img = channels-last hi / lo copies
+// [rows = B * H * W positions, Cin] (pitch img.ld), w = hi / lo copies of the weights re-laid as [N, 9 * Cin] (tap-major),
+// C [rows, N] (pitch ldc) = relu?(conv + bias) at every anchor position (the caller uses the anchors whose 3 x 3 window
+// fits).  No im2col matrix exists anywhere: a tap is a row offset of the TMA box.
+int gemm_tc_conv3x3(const TcOperand& img, const TcOperand& w, float* C, int64_t ldc, int rows, int N, int Cin, int width,
+                    const float* bias, int relu, int nterms, cudaStream_t st) {
+  TGFR_REQUIRE(Cin % kBK == 0 && N >= 1 && N <= 64 && (nterms == 1 || nterms == 3), "gemm_tc_conv3x3: Cin %% 64, N <= 64");
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (int rc = operand_map(&maps.a[0][0], img.hi, 0, rows, Cin, img.ld, 128)) return rc;
+  if (int rc = operand_map(&maps.b[0][0], w.hi, 0, N, 9 * Cin, w.ld, 64)) return rc;
+  if (nterms == 3) {
+    if (int rc = operand_map(&maps.a[0][1], img.lo, 0, rows, Cin, img.ld, 128)) return rc;
+    if (int rc = operand_map(&maps.b[0][1], w.lo, 0, N, 9 * Cin, w.ld, 64)) return rc;
+  }
+  GemmTcParams p{};
+  p.C = C; p.ldc = ldc; p.M = rows; p.N = N; p.K = 9 * Cin; p.kt_per_split = 9 * Cin / kBK; p.alpha = 1.f;
+  p.dscale = img.scale; p.dscale2 = w.scale; p.bias = bias; p.relu = relu; p.nterms = nterms;
+  p.conv_c = Cin; p.conv_w = width;
+  const dim3 grid(1, (rows + kBM - 1) / kBM, 1);
+  constexpr uint32_t smem = gemm_smem_bytes(64, 4);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TGFR_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TGFR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<kEpiStore, 64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  gemm_tc_kernel<kEpiStore, 64, 4, 2><<<grid, kGemmThreads, smem, st>>>(maps, p);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
 }
 
 // fp32 front end of gemm_tc_pair (C ABI tgfr_matmul_split): splits both operands into the workspace, then one product.

@@ -140,6 +140,8 @@ int sgemm(int mode, const float* A, int64_t lda, int64_t sa, const float* B, int
     TGFR_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
   }
   const dim3 grid(ceil_div(N, 128), ceil_div(M, 128), batch * p.splits);
+  TGFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "sgemm: %d row tiles x %d (batch x splits) exceed one launch grid", (int)grid.y,
+               (int)grid.z);
   if (mode == 0) sgemm_kernel<0><<<grid, 256, 0, st>>>(p);
   else if (mode == 1) sgemm_kernel<1><<<grid, 256, 0, st>>>(p);
   else sgemm_kernel<2><<<grid, 256, 0, st>>>(p);

@@ -58,7 +58,7 @@ _KERNELS_PER_CALL = {
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
     "tgfr_focal_finish": 1, "tgfr_ce_rows_bwd": 1, "tgfr_mag_ce_stats": 1, "tgfr_mag_ce_bwd": 1, "tgfr_arc_fused_fwd": 6, "tgfr_arc_fused_bwd": 5, "tgfr_texthead_fwd": 12, "tgfr_texthead_bwd": 5,
-    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 34, "tgfr_imim_bwd": 39, "tgfr_matmul_split": 5,
+    "tgfr_pair_cosine": 1, "tgfr_roc_curve": 20, "tgfr_row_argmax": 1, "tgfr_imim_fwd": 34, "tgfr_imim_bwd": 39, "tgfr_matmul_split": 5, "tgfr_fcfm_working_fwd_tc": 8,
     "tgfr_proj_head_fwd": 2, "tgfr_proj_head_bwd": 5, "tgfr_fcfm_train_fwd": 21, "tgfr_fcfm_train_bwd": 45,
 }
 
@@ -734,6 +734,15 @@ FCFM_PARAM_ORDER = (
 )
 
 
+def _fcfm_conv_on_tensor_cores(B) -> bool:
+    """TGFR_FCFM_CONV=tc|simt forces the convolution path; by default batches of 64 samples and more take the tensor cores
+    (below that the one-launch per-sample kernel wins on launch count)."""
+    mode = os.environ.get("TGFR_FCFM_CONV", "").lower()
+    if mode in ("tc", "simt"):
+        return mode == "tc"
+    return B >= 64
+
+
 def fcfm_working(img, word, gl_img, sent, state):
     """Working.forward in eval mode: img [B,256,14,14] (any strides), word [B,256,T], gl_img / sent [B,256] -> [B,640].
     `state` maps the reference module's state_dict names (FCFM_PARAM_ORDER) to CUDA tensors.  No autograd."""
@@ -756,9 +765,17 @@ def fcfm_working(img, word, gl_img, sent, state):
     arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
     out = torch.empty((B, 640), dtype=torch.float32, device=img.device)
     with torch.cuda.device(img.device):
-        _call("tgfr_fcfm_working_fwd", ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), ptr(word),
-              word.stride(0), word.stride(1), word.stride(2), ptr(gl_img), gl_img.stride(0), ptr(sent), sent.stride(0),
-              ctypes.cast(arr, ctypes.c_void_p), len(params), B, word.shape[2], ptr(out), out.stride(0), stream_ptr())
+        if B > 0 and _fcfm_conv_on_tensor_cores(B):
+            wsb = _lib.load().tgfr_fcfm_working_workspace_bytes(B)
+            ws = _workspace(wsb, img.device)
+            _call("tgfr_fcfm_working_fwd_tc", ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), ptr(word),
+                  word.stride(0), word.stride(1), word.stride(2), ptr(gl_img), gl_img.stride(0), ptr(sent), sent.stride(0),
+                  ctypes.cast(arr, ctypes.c_void_p), len(params), B, word.shape[2], ptr(out), out.stride(0), ptr(ws), wsb,
+                  stream_ptr())
+        else:
+            _call("tgfr_fcfm_working_fwd", ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), ptr(word),
+                  word.stride(0), word.stride(1), word.stride(2), ptr(gl_img), gl_img.stride(0), ptr(sent), sent.stride(0),
+                  ctypes.cast(arr, ctypes.c_void_p), len(params), B, word.shape[2], ptr(out), out.stride(0), stream_ptr())
     return out
 
 

@@ -3,6 +3,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from text_guided_face_recognition_b200.models.fusion_nets import Working
 torch.manual_seed(0)
+torch.set_grad_enabled(False)          # the verification path (utils/modules.py:129 runs under no_grad)
 net = Working(256).cuda().eval()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 for B in (6000, 60000):
