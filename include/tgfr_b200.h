@@ -56,7 +56,8 @@ int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
 
 /* Gradients of sum(gsim * sim): dctx [Bc,R,D] and dwords [Bq,T,D] (contiguous, OVERWRITTEN;
  * either may be NULL to skip it -- the reference's training scripts only need dctx because the
- * text side is detached, utils/dataset_utils.py:42-46).  Recomputes the attention on chip. */
+ * text side is detached, utils/dataset_utils.py:42-46).  With the forward's `saved` buffer the face-side gradient is
+ * computed from what the forward left there; without it (and for dwords) the attention is recomputed on chip. */
 int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
                         const float* words, int64_t w_sb, int64_t w_st, int64_t w_sd,
                         const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D,
@@ -67,10 +68,13 @@ int tgfr_wordregion_bwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
 
 /* Bytes of scratch the two calls above need for the given shape/precision (0 is possible). */
 size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int precision);
-/* Optional forward -> backward buffer (TGFR_PREC_TC): when `saved` (tgfr_wordregion_saved_bytes bytes, 16-byte
- * aligned) is given to the forward call it stores the fp16 word-softmax / attention image of every pair, and a
- * backward call that receives the same buffer reads it back instead of recomputing scores and exponentials.
- * saved = NULL on either side selects the recomputing (memory-lean) path; results agree to fp16 rounding. */
+/* Optional forward -> backward buffer (TGFR_PREC_TC): when `saved` (tgfr_wordregion_saved_bytes bytes, 256-byte
+ * aligned) is given to the forward call it stores, per pair, either the fp16 word-softmax / attention records (default:
+ * the backward then runs no score GEMM and no exponential) or, with the environment variable TGFR_WORDREGION_SAVE=wu
+ * set when the size is queried, only the fp16 attended-word tiles (9x fewer bytes; the backward recomputes the scores).
+ * The two layouts differ in size and both calls recognise the layout by `saved_bytes`, so pass exactly what
+ * tgfr_wordregion_saved_bytes returned.  saved = NULL on either side selects the fully recomputing (memory-lean) path;
+ * results agree to fp16 rounding. */
 size_t tgfr_wordregion_saved_bytes(int Bc, int Bq, int T, int R, int D, int precision);
 
 /* Stand-alone func_attention(query, context, gamma1) for B independent (query, context) pairs

@@ -16,10 +16,17 @@
 // Operands are fp16 (11-bit significand = TF32's) with fp32 accumulation; softmax / cosine /
 // log-sum-exp statistics stay in fp32.  C_b (<= 104 KB) stays resident in shared memory while the
 // CTA works on face b; Q_g is streamed by TMA and prefetched as soon as GEMM-1 has consumed it.
-// The B x B x T x R attention tensor never leaves the SM.
+// The fp32 B x B x T x R attention tensor of the reference is never formed in HBM.  What the forward leaves for the
+// backward is the caller's choice (TGFR_WORDREGION_SAVE; the layouts are told apart by the buffer size):
+//   records (default)   fp16 (A1 | E) per (face, caption, word, region) + V planes: the backward (rec::wr_tc_bwd2_kernel)
+//                       runs no score GEMM and no exponential                                  namespace rec below
+//   wu                  fp16 Wu planes + (alpha, beta) per word: 9x fewer bytes, the backward (wr_tc_bwd3_kernel)
+//                       recomputes S and E on the tensor cores / MUFU
+//   none                wr_tc_bwd_kernel recomputes everything (also the d words path)
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
-// warps 2-9 = epilogue (4 warps per 128-lane region tile; the two groups split D in epi-2).
+// Roles in the forward (wr_tc_fwd3_kernel, 896 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// thread) + TMEM allocator, warps 4-11 = group A (epi-1: word softmax, E), warps 12-27 = group B (epi-2: cosine,
+// log-sum, saved state); registers are re-dealt with setmaxnreg (40 / 104 / 64), group A runs one unit ahead of B.
 #include <stdlib.h>
 #include <string.h>
 
