@@ -240,3 +240,34 @@ def test_tc_grads_benchmarked_instances_vs_oracle(B, T, grads, bwd_mode):
         gw = wd.grad.cpu().numpy()
         errw = np.linalg.norm(gw - rw) / np.linalg.norm(rw)
         assert errw < TC_GRAD_RTOL, errw
+
+
+@pytest.mark.parametrize("save", ["1", "wu", "0"])
+def test_tc_operand_range_guard(save, monkeypatch):
+    """The fp16 operand copies carry no per-tensor scale (the reference's inputs are unit-norm rows, models/models.py:119,
+    403).  Inside the range fp16 holds well the result must not depend on how the magnitude is split between the two
+    operands (ctx x 64, words / 16 and a rescaled gamma give the same sim); outside it (largest entry above 65 504 or below
+    2^-9: x1e6, x1e-4) the tensor-core forward must fail LOUDLY -- every sim NaN -- while the fp32 path stays exact."""
+    from text_guided_face_recognition_b200 import _lib, ops
+    monkeypatch.setenv("TGFR_WORDREGION_SAVE", save)
+    B, T, R, D = 8, 22, 196, 256
+    ctx, words, _ = synth.wordregion_inputs(B, T, R, D, "BERT", seed=100)
+    f, w = torch.from_numpy(ctx).cuda(), torch.from_numpy(words).cuda()
+
+    def sim_of(ff, ww, prec, grad=False):
+        ff = ff.clone().requires_grad_(grad)
+        s, _ = ops.wordregion_sim(ff, ww, None, 4.0, 5.0, 10.0, precision=prec, want_attn=False)
+        return s
+
+    base = sim_of(f, w, _lib.PREC_TC, grad=True)
+    assert torch.isfinite(base).all()
+    # <c * 64, q / 64> = <c, q>: power-of-two rescaling is exact in fp16 while everything stays normal
+    moved = sim_of(f * 64.0, w / 64.0, _lib.PREC_TC, grad=True)
+    assert torch.isfinite(moved).all()
+    assert float((moved - base).detach().abs().max()) < 5e-3 * float(base.detach().abs().max())
+    for scale in (1e6, 1e-4):
+        for ff, ww in ((f * scale, w), (f, w * scale)):
+            bad = sim_of(ff, ww, _lib.PREC_TC, grad=True)
+            assert torch.isnan(bad).all(), scale
+            ok32 = sim_of(ff, ww, _lib.PREC_FP32)
+            assert torch.isfinite(ok32).all()

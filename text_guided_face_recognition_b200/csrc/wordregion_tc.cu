@@ -90,14 +90,25 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
                                   const int32_t* __restrict__ cap_lens, int Bc, int Bq, int T, int Tp, int R, int D,
                                   __half* __restrict__ c16, __half* __restrict__ q16, float* __restrict__ qnorm,
                                   int* __restrict__ lens) {
+  // range guard: lens[Bq] / lens[Bq + 1] collect max |ctx| / max |words| (float bits; zeroed by the host before the
+  // launch).  The fp16 copies carry no per-tensor scale, so the forward poisons `sim` with NaN when either tensor leaves
+  // the range fp16 holds well (range_bad below) instead of returning a silently degraded loss.
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int64_t n_ctx = (int64_t)Bc * R, n_w = (int64_t)Bq * Tp;
+  int* flags = lens + Bq;
   if (row < n_ctx) {
     const int b = (int)(row / R), r = (int)(row - (int64_t)b * R);
     const float* src = ctx + b * csb + r * csr;
     __half* dst = c16 + row * D;
-    for (int d = lane; d < D; d += 32) dst[d] = __float2half_rn(__ldg(src + (int64_t)d * csd));
+    float m = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = __ldg(src + (int64_t)d * csd);
+      m = fmaxf(m, fabsf(v));
+      dst[d] = __float2half_rn(v);
+    }
+    m = warp_max(m);
+    if (lane == 0 && __float_as_int(m) > __ldcg(flags)) atomicMax(flags, __float_as_int(m));
   } else if (row < n_ctx + n_w) {
     const int64_t wrow = row - n_ctx;
     const int i = (int)(wrow / Tp), t = (int)(wrow - (int64_t)i * Tp);
@@ -108,17 +119,27 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
     float acc = 0.f;
     if (t < len) {
       const float* src = words + i * wsb + t * wst;
+      float m = 0.f;
       for (int d = lane; d < D; d += 32) {
         const float v = __ldg(src + (int64_t)d * wsd);
         acc = fmaf(v, v, acc);
+        m = fmaxf(m, fabsf(v));
         dst[d] = __float2half_rn(v);
       }
+      m = warp_max(m);
+      if (lane == 0 && __float_as_int(m) > __ldcg(flags + 1)) atomicMax(flags + 1, __float_as_int(m));
     } else {
       for (int d = lane; d < D; d += 32) dst[d] = __float2half_rn(0.f);
     }
     acc = warp_sum(acc);
     if (lane == 0) qnorm[wrow] = sqrtf(acc);
   }
+}
+// largest entry of either operand outside [2^-9, 65504]: beyond fp16, or so small that typical entries are subnormal
+// (unit-norm rows of up to 256 features have a largest entry >= 1/16)
+__device__ __forceinline__ bool range_bad(const int* __restrict__ lens, int Bq) {
+  const float mc = __int_as_float(__ldg(lens + Bq)), mq = __int_as_float(__ldg(lens + Bq + 1));
+  return !(mc >= 0.001953125f && mc <= 65504.f && mq >= 0.001953125f && mq <= 65504.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -518,7 +539,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
         if (ii < p.Bq) {
           float sacc = 0.f;
           for (int tt = 0; tt < TP; ++tt) sacc += exs[w * TP + tt];
-          p.sim[(int64_t)b * p.Bq + ii] = p.g3 * logf(sacc);
+          p.sim[(int64_t)b * p.Bq + ii] = range_bad(p.lens, p.Bq) ? __int_as_float(0x7fc00000) : p.g3 * logf(sacc);
         }
       }
     }
@@ -1498,7 +1519,7 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   pl->ws_q16 = align_up((size_t)Bc * R * D * 2, 256);
   pl->ws_qnorm = pl->ws_q16 + align_up((size_t)Bq * pl->Tp * D * 2, 256);
   pl->ws_lens = pl->ws_qnorm + align_up((size_t)Bq * pl->Tp * 4, 256);
-  pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4, 256);                       // padded fp32 d words [Bq*Tp, D]
+  pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4 + 64, 256);                  // lens + the two range-guard words                       // padded fp32 d words [Bq*Tp, D]
   pl->ws_total = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);
   return TGFR_OK;
 }
@@ -1903,7 +1924,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
         if (ii < p.Bq) {
           float sacc = 0.f;
           for (int tt = 0; tt < TP; ++tt) sacc += exs[w * TP + tt];
-          p.sim[(int64_t)b * p.Bq + ii] = p.g3 * logf(sacc);
+          p.sim[(int64_t)b * p.Bq + ii] = range_bad(p.lens, p.Bq) ? __int_as_float(0x7fc00000) : p.g3 * logf(sacc);
         }
       }
     }
@@ -2258,7 +2279,7 @@ SavedLayout saved_layout(const TcPlan& pl, int Bc, int Bq, int R, int D) {
   L.off_q16 = L.off_c16 + align_up((size_t)Bc * R * D * 2, 256);
   L.off_qnorm = L.off_q16 + align_up((size_t)Bq * pl.Tp * D * 2, 256);
   L.off_lens = L.off_qnorm + align_up((size_t)Bq * pl.Tp * 4, 256);
-  L.total = L.off_lens + align_up((size_t)Bq * 4, 256);
+  L.total = L.off_lens + align_up((size_t)Bq * 4 + 64, 256);
   return L;
 }
 
@@ -2281,7 +2302,7 @@ SavedLayout saved_layout(const TcPlan& pl, int Bc, int Bq, int R, int D) {
   L.off_q16 = L.off_c16 + align_up((size_t)Bc * R * D * 2, 256);
   L.off_qnorm = L.off_q16 + align_up((size_t)Bq * pl.Tp * D * 2, 256);
   L.off_lens = L.off_qnorm + align_up((size_t)Bq * pl.Tp * 4, 256);
-  L.total = L.off_lens + align_up((size_t)Bq * 4, 256);
+  L.total = L.off_lens + align_up((size_t)Bq * 4 + 64, 256);
   return L;
 }
 
@@ -2399,6 +2420,7 @@ int wordregion_bwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     lens = reinterpret_cast<int*>(sv + (r ? LR.off_lens : L.off_lens));
   } else {
     const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
+    TGFR_CUDA_OK(cudaMemsetAsync(lens + Bq, 0, 2 * sizeof(int), st));
     wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc,
                                                                  Bq, T, pl.Tp, R, D, c16, q16, qnorm, lens);
     TGFR_LAUNCH_OK();
@@ -2628,6 +2650,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   }
 
   const int64_t rows = (int64_t)Bc * R + (int64_t)Bq * pl.Tp;
+  TGFR_CUDA_OK(cudaMemsetAsync(lens + Bq, 0, 2 * sizeof(int), st));
   wr_tc_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx, csb, csr, csd, words, wsb, wst, wsd, cap_lens, Bc, Bq,
                                                                T, pl.Tp, R, D, c16, q16, qnorm, lens);
   TGFR_LAUNCH_OK();
