@@ -44,7 +44,9 @@ int tgfr_device_check(void);
  *   sim[b, i] = gamma3 * log sum_t exp(gamma2 * cos(q_it, W_bit))           (losses.py:104-122)
  * cap_lens: int32 [Bq] (LSTM path, losses.py:82) or NULL (all captions use T words).
  * attn_diag: optional [Bc, T, R]; row b receives A2 of pair (b, b + diag_off) (losses.py:97),
- *            zero-filled beyond the caption's length; NULL to skip.
+ *            zero-filled beyond the caption's length; NULL to skip.  TGFR_PREC_TC emits it from the tensor-core
+ *            forward (fp16-operand scores: within 2e-3 of a map's largest entry); with the environment variable
+ *            TGFR_ATTN_MAPS=fp32 it comes from the exact fp32 kernel.
  * ------------------------------------------------------------------------------------------ */
 int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_t ctx_sd,
                         const float* words, int64_t w_sb, int64_t w_st, int64_t w_sd,

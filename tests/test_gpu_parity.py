@@ -68,7 +68,8 @@ def prec(request, monkeypatch):
     monkeypatch.setenv("TGFR_WORDREGION_PRECISION", request.param)
     tc = request.param == "tc"
     return types.SimpleNamespace(name=request.param, loss=LOSS_RTOL if tc else FP32_LOSS_RTOL,
-                                 grad=GRAD_RTOL if tc else FP32_GRAD_RTOL, sim_atol=5e-3 if tc else 2e-4)
+                                 grad=GRAD_RTOL if tc else FP32_GRAD_RTOL, sim_atol=5e-3 if tc else 2e-4,
+                                 att=2e-3 if tc else 1e-5)     # tc: the maps come out of the fp16-operand forward
 
 
 @pytest.fixture(params=["fp32", "tc"])
@@ -114,7 +115,7 @@ def test_words_loss_small_vs_golden(api, golden_dir, name, channels_last, prec):
     for i, a in enumerate(att):
         n = int(g["cap_lens"][i]) if g["cap_lens"].size else T
         assert tuple(a.shape) == (1, n, ih, iw)
-        assert rel(a.cpu().numpy().reshape(n, -1), g["att"][i, :n]) < 1e-5
+        assert rel(a.cpu().numpy().reshape(n, -1), g["att"][i, :n]) < prec.att
     (float(g["w0"]) * l0 + float(g["w1"]) * l1).backward()
     dctx, dwords = grads()
     assert rel(dctx, g["dctx"]) < prec.grad
@@ -134,7 +135,7 @@ def test_words_loss_full_width_vs_golden(api, golden_dir, name, prec):
     assert abs(l0.item() - float(g["loss0"])) < prec.loss * abs(float(g["loss0"]))
     assert abs(l1.item() - float(g["loss1"])) < prec.loss * abs(float(g["loss1"]))
     got = np.stack([a.cpu().numpy().reshape(T, -1) for a in att])
-    assert rel(got, g["att"]) < 1e-5
+    assert rel(got, g["att"]) < prec.att
     (l0 + l1).backward()
     dctx, dwords = grads()
     assert rel(dwords, g["dwords"]) < prec.grad
@@ -171,7 +172,7 @@ def test_words_loss_config2_size_vs_oracle(api, prec):
     sim, attn = ops.wordregion_sim(feats, wd, None, 4.0, 5.0, 10.0)
     ref, ref_att = O.wordregion_sim(ctx, words, None, 4.0, 5.0, 10.0)
     assert np.max(np.abs(sim.cpu().numpy() - ref)) < prec.sim_atol  # |sim| ~ 30
-    assert rel(attn.cpu().numpy(), np.stack(ref_att)) < 1e-5
+    assert rel(attn.cpu().numpy(), np.stack(ref_att)) < prec.att
     l0, l1 = ops.pair_ce(sim)
     r0, r1 = O.pair_ce(ref)
     assert abs(l0.item() - r0) < prec.loss * r0 and abs(l1.item() - r1) < prec.loss * r1

@@ -1,5 +1,6 @@
 // extern "C" surface of libtgfr_b200.so (declared in include/tgfr_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,8 +33,8 @@ size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D);
 int wordregion_tc_saved_mode(int Bc, int Bq, int T, int R, int D, const void* saved, size_t saved_bytes);
 bool wordregion_tc_recompute_ok(int Bq, int T, int R, int D);
 int wordregion_fwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
-                      const int32_t*, int, int, int, int, int, float, float, float, float, float*, void*, size_t, void*,
-                      size_t, cudaStream_t);
+                      const int32_t*, int, int, int, int, int, float, float, float, float, float*, float*, int, void*, size_t,
+                      void*, size_t, cudaStream_t);
 int wordregion_bwd_tc(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
                       const int32_t*, int, int, int, int, int, float, float, float, const float*, float*, float*, void*,
                       size_t, const void*, size_t, cudaStream_t);
@@ -171,14 +172,17 @@ int tgfr_wordregion_fwd(const float* ctx, int64_t ctx_sb, int64_t ctx_sr, int64_
                         void* saved, size_t saved_bytes, void* stream) {
   TGFR_REQUIRE(ctx && words && sim, "wordregion_fwd: NULL tensor");
   if (precision == TGFR_PREC_TC) {
+    // The B diagonal attention maps: emitted by the tensor-core forward itself (their scores are the fp16-operand ones,
+    // like the loss), or -- TGFR_ATTN_MAPS=fp32 -- by the exact fp32 kernel on the matching pairs only.
+    const char* am = getenv("TGFR_ATTN_MAPS");
+    const bool maps_fp32 = am && strcmp(am, "fp32") == 0;
+    TGFR_REQUIRE(!attn_diag || (diag_off >= 0 && diag_off + Bc <= Bq), "wordregion_fwd: diagonal outside the caption range");
     if (int rc = wordregion_fwd_tc(ctx, ctx_sb, ctx_sr, ctx_sd, words, w_sb, w_st, w_sd, cap_lens, Bc, Bq, T, R, D,
-                                   gamma1, gamma2, gamma3, eps, sim, workspace, workspace_bytes, saved, saved_bytes,
-                                   ST(stream)))
+                                   gamma1, gamma2, gamma3, eps, sim, maps_fp32 ? nullptr : attn_diag, diag_off, workspace,
+                                   workspace_bytes, saved, saved_bytes, ST(stream)))
       return rc;
-    if (!attn_diag) return TGFR_OK;
-    // the B diagonal attention maps are produced by the fp32 kernel on the matching pairs only
+    if (!attn_diag || !maps_fp32) return TGFR_OK;
     const int n = Bc;
-    TGFR_REQUIRE(diag_off >= 0 && diag_off + n <= Bq, "wordregion_fwd: diagonal outside the caption range");
     return attention_fwd_simt(ctx, ctx_sb, ctx_sr, ctx_sd, words + (int64_t)diag_off * w_sb, w_sb, w_st, w_sd,
                               cap_lens ? cap_lens + diag_off : nullptr, n, T, R, D, gamma1, nullptr, attn_diag,
                               ST(stream));

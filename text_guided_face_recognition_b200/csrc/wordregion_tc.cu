@@ -49,6 +49,9 @@ struct TcParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
+  float* attn_out;       // [Bc, T, R] diagonal attention maps (un-normalised here) or NULL
+  float* attn_z;         // [Bc, 32] their region sums
+  int diag_off, T;
   // SAVE: what the record-free backward (wr_tc_bwd3_kernel) needs beside its own recomputation of S, per unit u = b * G + g:
   __half* sv_wu;         // [total_units][D/8][nw_rows][8]  Wu_w as fp16 planes (the un-normalised context of word w)
   float* sv_ab;          // [total_units][2][128]  alpha_w = g2 g3 p_w / (|q_w| |Wu_w|), beta_w = g2 g3 p_w cos_w / |Wu_w|^2:
@@ -140,6 +143,38 @@ __global__ void wr_tc_prep_kernel(const float* __restrict__ ctx, int64_t csb, in
 __device__ __forceinline__ bool range_bad(const int* __restrict__ lens, int Bq) {
   const float mc = __int_as_float(__ldg(lens + Bq)), mq = __int_as_float(__ldg(lens + Bq + 1));
   return !(mc >= 0.001953125f && mc <= 65504.f && mq >= 0.001953125f && mq <= 65504.f);
+}
+
+// The diagonal pair's attention map (losses.py:97; the B maps words_loss returns) straight from epi-1: for the caption
+// i = b + diag_off of face b the un-normalised region-softmax numerators E[r, t] = exp(g1 (A1 - 1)) go to attn [b, t, r]
+// and their sums over the regions to z [b, t] (zeroed by the host); attn_normalize_kernel divides afterwards.  e[] holds
+// exp(s - max) of the word softmax, kinv = k1 / sum, nk1 = -k1.  One caption in Bq per face: the cost is nil, and the
+// separate attention-only kernel (36 us at B = 128) goes away.  The maps inherit the fp16-operand scores (TF32 class).
+// (not inlined: one caption in Bq takes this path, and inlined it costs the softmax loop registers -- spills)
+template <int TP>
+__device__ __noinline__ void emit_diag_attention(const float* e, float kinv, float nk1, int len, int T, int R, int r, int lane,
+                                                 float* __restrict__ attn_b, float* __restrict__ z_b) {
+  for (int t = 0; t < TP; ++t) {
+    if (t < len && t < T) {                                       // warp-uniform: len belongs to the caption
+      const float val = (r < R) ? fast_exp2(fmaf(e[t], kinv, nk1)) : 0.f;
+      if (r < R) attn_b[(int64_t)t * R + r] = val;
+      const float s = warp_sum(val);
+      if (lane == 0) atomicAdd(z_b + t, s);
+    }
+  }
+}
+// attn [b, t, r] /= z [b, t] for the words of caption b + diag_off, zeros beyond its length (and for a face without one)
+__global__ void attn_normalize_kernel(float* __restrict__ attn, const float* __restrict__ z, const int* __restrict__ lens, int Bc,
+                                      int Bq, int T, int R, int ztp, int diag_off, int uniform_len) {
+  const int64_t n = (int64_t)Bc * T * R;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = k / R;
+    const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
+    const int i = b + diag_off;
+    int len = 0;
+    if (i >= 0 && i < Bq) len = uniform_len > 0 ? uniform_len : __ldg(lens + i);
+    attn[k] = (t < len) ? attn[k] / __ldg(z + (int64_t)b * ztp + t) : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,6 +403,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           if (tid == 128 && tile == 0) TGFR_TRACE(n, 2);
           const int r = tile * 128 + lrow;
           uint8_t* const e_row = s_e + (uint32_t)r * 128u;
+          const int diag_i = p.attn_out != nullptr ? u / p.G + p.diag_off : -1;
           for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
             const int i = g * p.nc + c;
             if (i >= p.Bq) continue;                              // missing captions: their E columns are never read back
@@ -402,6 +438,13 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             }
             const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
             const float nk1 = -p.k1;
+            if (i == diag_i) {                                       // this face's own caption: its map is an output
+              float ecopy[TP];
+#pragma unroll
+              for (int t = 0; t < TP; ++t) ecopy[t] = e[t];
+              emit_diag_attention<TP>(ecopy, p.k1 / sum, nk1, len, p.T, p.R, r, lane, p.attn_out + (int64_t)(u / p.G) * p.T * p.R,
+                                      p.attn_z + (int64_t)(u / p.G) * 32);
+            }
             uint32_t pe[TP / 2];
             {
               // rows beyond R (K padding of GEMM-2) multiply zero rows of C: their E values only have to be finite
@@ -1493,7 +1536,7 @@ wr_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
 struct TcPlan {
   int Tp, Rp, nc, G, nw_rows, n_tiles;
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc, smem_bytes;
-  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_dq, ws_total;
+  size_t ws_c16, ws_q16, ws_qnorm, ws_lens, ws_dq, ws_attz, ws_total;
 };
 
 int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
@@ -1520,7 +1563,8 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
   pl->ws_qnorm = pl->ws_q16 + align_up((size_t)Bq * pl->Tp * D * 2, 256);
   pl->ws_lens = pl->ws_qnorm + align_up((size_t)Bq * pl->Tp * 4, 256);
   pl->ws_dq = pl->ws_lens + align_up((size_t)Bq * 4 + 64, 256);                  // lens + the two range-guard words                       // padded fp32 d words [Bq*Tp, D]
-  pl->ws_total = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);
+  pl->ws_attz = pl->ws_dq + align_up((size_t)Bq * pl->Tp * D * 4, 256);           // region sums of the diagonal attention maps
+  pl->ws_total = pl->ws_attz + align_up((size_t)Bc * 32 * 4, 256);
   return TGFR_OK;
 }
 
@@ -1541,6 +1585,9 @@ struct TcParams {
   const float* qnorm;    // [Bq*Tp]
   const int* lens;       // [Bq]
   float* sim;            // [Bc, Bq]
+  float* attn_out;       // [Bc, T, R] diagonal attention maps (un-normalised here) or NULL
+  float* attn_z;         // [Bc, 32] their region sums
+  int diag_off, T;
   // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
   __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
   uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
@@ -1712,6 +1759,7 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           if (tid == 128 && tile == 0) TGFR_TRACE(n, 2);
           const int r = tile * 128 + lrow;
           uint8_t* const e_row = s_e + (uint32_t)r * 128u;
+          const int diag_i = p.attn_out != nullptr ? u / p.G + p.diag_off : -1;
           for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
             const int i = g * p.nc + c;
             if (i >= p.Bq) {
@@ -1755,6 +1803,13 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             }
             const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
             const float nk1 = -p.k1;
+            if (i == diag_i) {                                       // this face's own caption: its map is an output
+              float ecopy[TP];
+#pragma unroll
+              for (int t = 0; t < TP; ++t) ecopy[t] = e[t];
+              emit_diag_attention<TP>(ecopy, p.k1 / sum, nk1, len, p.T, p.R, r, lane, p.attn_out + (int64_t)(u / p.G) * p.T * p.R,
+                                      p.attn_z + (int64_t)(u / p.G) * 32);
+            }
             uint32_t pe[TP / 2];
             uint32_t pa[SAVE ? TP / 2 : 1];
             if constexpr (SAVE) {
@@ -2619,10 +2674,11 @@ size_t wordregion_tc_workspace_bytes(int Bc, int Bq, int T, int R, int D) {
   return pl.ws_total;
 }
 
+// attn_diag != NULL: the forward also emits the attention map of every face's own caption (b, b + diag_off) -> [Bc, T, R]
 int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, const float* words, int64_t wsb,
                       int64_t wst, int64_t wsd, const int32_t* cap_lens, int Bc, int Bq, int T, int R, int D, float g1,
-                      float g2, float g3, float eps, float* sim, void* ws, size_t ws_bytes, void* saved, size_t saved_bytes,
-                      cudaStream_t st) {
+                      float g2, float g3, float eps, float* sim, float* attn_diag, int diag_off, void* ws, size_t ws_bytes,
+                      void* saved, size_t saved_bytes, cudaStream_t st) {
   (void)eps;
   TcPlan pl;
   if (int rc = make_plan(Bc, Bq, T, R, D, &pl)) return rc;
@@ -2668,6 +2724,12 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   p.off_q = pl.off_q; p.off_e = pl.off_e; p.off_misc = pl.off_misc;
   p.k1 = g1 * kLog2e; p.k2 = g2 * kLog2e; p.g3 = g3; p.g23 = g2 * g3;
   p.uniform_len = cap_lens ? 0 : T;
+  p.T = T; p.diag_off = diag_off;
+  if (attn_diag) {
+    p.attn_out = attn_diag;
+    p.attn_z = reinterpret_cast<float*>(base + pl.ws_attz);
+    TGFR_CUDA_OK(cudaMemsetAsync(p.attn_z, 0, sizeof(float) * (size_t)Bc * 32, st));
+  }
   if (save) {
     uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
     p.sv_wu = reinterpret_cast<__half*>(sv + L.off_wu);
@@ -2696,6 +2758,7 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     pr.off_q = pl.off_q; pr.off_e = pl.off_e; pr.off_misc = pl.off_misc;
     pr.k1 = p.k1; pr.k2 = p.k2; pr.g3 = g3;
     pr.uniform_len = p.uniform_len;
+    pr.T = T; pr.diag_off = diag_off; pr.attn_out = p.attn_out; pr.attn_z = p.attn_z;
   }
 #define TGFR_LAUNCH_FWDR(TPV)                                                                                   \
   {                                                                                                            \
@@ -2738,6 +2801,12 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
 #undef TGFR_LAUNCH_FWD1
 #undef TGFR_LAUNCH_FWDR
   TGFR_LAUNCH_OK();
+  if (attn_diag) {
+    const int64_t n = (int64_t)Bc * T * R;
+    attn_normalize_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(attn_diag, p.attn_z, lens, Bc, Bq, T,
+                                                                                                    R, 32, diag_off, p.uniform_len);
+    TGFR_LAUNCH_OK();
+  }
   return TGFR_OK;
 }
 
