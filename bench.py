@@ -978,19 +978,11 @@ def run_b200(args):
                 conv.weight.grad = conv.bias.grad = None
             wo, so = th(tok, None)
             torch.autograd.backward([wo, so], [gw_up, gs_up])
-        for _ in range(3):
-            th_step()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(10):
-            th_step()
-        e1.record()
-        torch.cuda.synchronize()
-        th_ms = e0.elapsed_time(e1) / 10
+        th_ms, _ = time_step(th_step, flush, 10, use_graph)           # one CUDA-graph replay per step, L2 flushed between
         th_flops = 2 * 2 * B * (bwn - 1) * (2 + 3 + 4) * 768 * D       # three products forward, three backward
         line["text_heading"] = {"metric": "text_heading_fwd_bwd_captions_per_sec", "value": B / (th_ms * 1e-3),
                                 "unit": "captions/s", "ms_per_step": th_ms, "dtype": "f16 hi+lo split operands (3 accumulated tcgen05 terms, ~22 bits) / f32 accumulate",
-                                "tflops": th_flops / (th_ms * 1e-3) / 1e12,
+                                "tflops": th_flops / (th_ms * 1e-3) / 1e12, "launch": "CUDA graph replay" if use_graph else "eager",
                                 "config": {"B": B, "bert_words_num": bwn, "E": 768, "F": D}}
 
         # ---- verification scoring (configs[4] in its pair-list form, utils/modules.py:150-166):

@@ -53,7 +53,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 # kernels launched by one call of each entry point (memsets not counted)
 _KERNELS_PER_CALL = {
-    "tgfr_wordregion_fwd": 1, "tgfr_wordregion_bwd": 1, "tgfr_attention_fwd": 1, "tgfr_attention_bwd": 1,
+    "tgfr_wordregion_fwd": 3, "tgfr_wordregion_bwd": 1, "tgfr_attention_fwd": 1, "tgfr_attention_bwd": 1,
     "tgfr_cosine_scores_fwd": 3, "tgfr_cosine_scores_bwd": 4, "tgfr_pair_ce_stats": 1, "tgfr_pair_ce_finish": 1,
     "tgfr_pair_ce_bwd": 1, "tgfr_cos_logits_fwd": 3, "tgfr_arc_margin_apply": 1, "tgfr_arc_margin_bwd": 5,
     "tgfr_mag_margin_fwd": 1, "tgfr_mag_margin_bwd": 1, "tgfr_cos_logits_bwd": 4, "tgfr_ce_rows_stats": 1,
