@@ -62,10 +62,19 @@ def main():
     for prec_name, prec, ltol, gtol in (("fp32", 0, 2e-5, 1e-4), ("tc", 1, 1e-4, 1e-3)):
         for t in (c, w, x, y):
             t.grad = None
-        l0, l1, _ = tdist.words_loss_sharded(c, w, lens, *G, precision=prec)
+        l0, l1, att = tdist.words_loss_sharded(c, w, lens, *G, precision=prec, want_attn=True)
         s0, s1 = tdist.sent_loss_sharded(x, y, ids, G[2])
         (l0 + l1 + s0 + s1).backward()
-        r0, r1, _, _ = O.words_loss(ctx, words, None, cap, *G)
+        r0, r1, r_att, _ = O.words_loss(ctx, words, None, cap, *G)
+        # this rank's diagonal attention maps (rows pair with captions rank * B_local + b): exact in fp32 mode, within
+        # 2e-3 of a map's largest entry when the tensor-core forward emits them
+        att_np = att.cpu().numpy()
+        for bl in range(att_np.shape[0]):
+            ref_map = r_att[sl.start + bl]
+            n_w = ref_map.shape[0]
+            tol_map = 1e-5 if prec_name == "fp32" else 2e-3 * float(np.max(ref_map))
+            assert np.max(np.abs(att_np[bl, :n_w] - ref_map)) < tol_map, (prec_name, "att", bl)
+            assert not att_np[bl, n_w:].any()
         q0, q1, _ = O.sent_loss(img, txt, None, cid, G[2])
         dctx, dwords = O.words_loss_grads(ctx, words, None, cap, *G)
         dimg, dtxt = O.sent_loss_grads(img, txt, None, cid, G[2])
