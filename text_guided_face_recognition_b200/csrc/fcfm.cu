@@ -32,7 +32,7 @@ struct TcOperand {          // gemm_tc.cu
 int gemm_tc_conv3x3(const TcOperand& img, const TcOperand& w, float* C, int64_t ldc, int rows, int N, int Cin, int width,
                     const float* bias, int relu, int nterms, cudaStream_t st);
 int gemm_tc_split_operand(const float* src, int64_t ld, int rows, int cols, float* scale, __half* hi, __half* lo, int ld_out,
-                          cudaStream_t st);
+                          cudaStream_t st, bool have_max);
 
 namespace {
 
@@ -455,7 +455,7 @@ int fcfm_working_fwd_tc(const float* img, int64_t isb, int64_t isc, int64_t ish,
   float* conv = reinterpret_cast<float*>(base + L.conv);
   fcfm_conv_w_taps_kernel<<<ceil_div(kC * 9 * kCin, 256), 256, 0, st>>>(P.p[P_CONV_W], wt);
   TGFR_LAUNCH_OK();
-  if (int rc = gemm_tc_split_operand(wt, 9 * kCin, kC, 9 * kCin, scales + 2, whi, wlo, 9 * kCin, st)) return rc;
+  if (int rc = gemm_tc_split_operand(wt, 9 * kCin, kC, 9 * kCin, scales + 2, whi, wlo, 9 * kCin, st, false)) return rc;
   const TcOperand ow{whi, wlo, 9 * kCin, scales + 2};
   for (int b0 = 0; b0 < B; b0 += kConvChunk) {
     const int nb = B - b0 < kConvChunk ? B - b0 : kConvChunk;

@@ -96,6 +96,9 @@ struct GemmTcParams {
   // over 9 taps x conv_c channels, and tap (dy, dx) reads A shifted down by dy * conv_w + dx rows (valid convolution:
   // the outputs of the anchors whose window leaves the image are garbage the caller ignores)
   int conv_c, conv_w;
+  // optional: max |output| over the whole product, as float bits via atomicMax (zeroed by the caller) -- the operand scale of
+  // the NEXT split product comes out of this product's epilogue instead of a separate pass over the result
+  float* amax;
   struct Z {
     float* C;
     const float* bias;
@@ -203,6 +206,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tm
     }
   } else {
   const bool direct = (ldcz & 3) == 0 && (reinterpret_cast<uintptr_t>(Cz) & 15) == 0;
+  float amax_t = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < BN / 32; ++ch) {
     const int c0 = n0 + 32 * ch;
@@ -226,6 +230,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tm
             if (biasz && c0 + 4 * g4 + u < Nz) x += __ldg(biasz + c0 + 4 * g4 + u);
             if (p.relu) x = fmaxf(x, 0.f);
             o[u] = x;
+            if (c0 + 4 * g4 + u < Nz) amax_t = fmaxf(amax_t, fabsf(x));
           }
           const int c = c0 + 4 * g4;
           if (c + 3 < Nz) {
@@ -251,6 +256,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tm
       if (biasz && c0 + j < Nz) x += __ldg(biasz + c0 + j);
       if (p.relu) x = fmaxf(x, 0.f);
       stage[lane * 33 + j] = x;
+      if (row_base + lane < Mz && c0 + j < Nz) amax_t = fmaxf(amax_t, fabsf(x));
     }
     __syncwarp();
     const int col = c0 + lane;
@@ -264,6 +270,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tm
       }
     }
     __syncwarp();
+  }
+  if (p.amax) {
+    amax_t = warp_max(amax_t);
+    if (lane == 0 && __float_as_int(amax_t) > __ldcg(reinterpret_cast<const int*>(p.amax)))
+      atomicMax(reinterpret_cast<int*>(p.amax), __float_as_int(amax_t));
   }
   }
 }
@@ -980,14 +991,14 @@ int head_normalize_bwd_pair(const float* gx, const float* x, int64_t x_sr, const
 
 // max|x| over several fp32 blocks into scale[0] (scale[0..1] zeroed first), then their hi / lo splits with ONE scale
 int head_split_f16(int nblocks, const float* const* src, const int64_t* ld, const int* rows, const int* cols, float* scale,
-                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st) {
-  TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
+                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st, bool have_max) {
+  if (!have_max) TGFR_CUDA_OK(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
   auto vec_ok = [&](int k) {
     return (cols[k] & 3) == 0 && (ld[k] & 3) == 0 && (ld_out[k] & 7) == 0 && (reinterpret_cast<uintptr_t>(src[k]) & 15) == 0 &&
            (reinterpret_cast<uintptr_t>(hi[k]) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo[k]) & 7) == 0;
   };
   auto blocks_for = [](int64_t quads) { return (int)(quads + 255) / 256 < 148 * 8 ? (int)((quads + 255) / 256) : 148 * 8; };
-  for (int k = 0; k < nblocks; ++k) {
+  for (int k = 0; k < nblocks && !have_max; ++k) {
     if (vec_ok(k))
       maxabs4_kernel<<<blocks_for((int64_t)rows[k] * (cols[k] >> 2)), 256, 0, st>>>(src[k], ld[k], rows[k], cols[k], scale);
     else
@@ -1050,7 +1061,7 @@ int gemm_tc_split3_batched(const Split3Product* prods, int n, int a_mn, int a_ov
 // batch > 1: contiguous samples of both operands (ld x rows-in-memory apart), C advances by c_bs per sample, no split-K.
 // splits > 1: split-K with vector reductions into a zeroed C (no bias / relu).
 int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int64_t c_bs, int M, int N, int K,
-                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, cudaStream_t st) {
+                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, cudaStream_t st, float* amax) {
   TGFR_REQUIRE(mode >= 0 && mode <= 2 && (nterms == 1 || nterms == 3), "gemm_tc_pair: bad mode / nterms");
   TGFR_REQUIRE(batch >= 1 && (batch == 1 || splits <= 1), "gemm_tc_pair: a strided batch cannot split K");
   TGFR_REQUIRE(splits <= 1 || (!bias && !relu), "gemm_tc_pair: split-K has no bias / relu epilogue");
@@ -1073,6 +1084,8 @@ int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int
   p.dscale = A.scale; p.dscale2 = B.scale; p.bias = bias; p.relu = relu;
   p.atomic = splits > 1; p.a_mn = a_mn; p.b_mn = b_mn; p.nterms = nterms;
   p.strided = batch > 1; p.c_bs = c_bs;
+  TGFR_REQUIRE(!amax || splits <= 1, "gemm_tc_pair: max |output| is not defined for split-K partial sums");
+  p.amax = amax;
   if (splits > 1) TGFR_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st));
   const dim3 grid((N + 127) / 128, (M + kBM - 1) / kBM, batch > 1 ? batch : splits);
   const int tiles = (int)(grid.x * grid.y * grid.z);
@@ -1081,14 +1094,16 @@ int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int
 }
 
 // x [rows, cols] fp32 (pitch ld) -> hi / lo fp16 [rows, ld_out] with one power-of-two scale: scale[0] = max|x|, scale[1] = 2^-e
+// have_max: scale[0] already holds max |x| (left there by the kernel that produced x: GemmTcParams::amax and the `amax`
+// arguments of the element-wise kernels in nn_blocks.cuh), so the max-abs pass is skipped
 int gemm_tc_split_operand(const float* src, int64_t ld, int rows, int cols, float* scale, __half* hi, __half* lo, int ld_out,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool have_max) {
   const float* srcs[1] = {src};
   const int64_t lds[1] = {ld};
   const int rws[1] = {rows}, cls[1] = {cols}, ldo[1] = {ld_out};
   __half* his[1] = {hi};
   __half* los[1] = {lo};
-  return head_split_f16(1, srcs, lds, rws, cls, scale, his, los, ldo, st);
+  return head_split_f16(1, srcs, lds, rws, cls, scale, his, los, ldo, st, have_max);
 }
 
 // Valid 3x3 convolution as ONE product (FCFM's conv, models/fusion_nets.py:235): img = channels-last hi / lo copies
@@ -1156,10 +1171,10 @@ int matmul_split(int mode, const float* A, int64_t lda, const float* Bm, int64_t
   __half* bhi = reinterpret_cast<__half*>(base + 256 + 2 * a);
   __half* blo = reinterpret_cast<__half*>(base + 256 + 2 * a + b);
   TGFR_REQUIRE(batch == 1 || (lda == ca && ldb == cb), "matmul_split: a batch needs densely packed operands");
-  if (int rc = gemm_tc_split_operand(A, lda, batch * ra, ca, scales, ahi, alo, lda16, st)) return rc;
-  if (int rc = gemm_tc_split_operand(Bm, ldb, batch * rb, cb, scales + 2, bhi, blo, ldb16, st)) return rc;
+  if (int rc = gemm_tc_split_operand(A, lda, batch * ra, ca, scales, ahi, alo, lda16, st, false)) return rc;
+  if (int rc = gemm_tc_split_operand(Bm, ldb, batch * rb, cb, scales + 2, bhi, blo, ldb16, st, false)) return rc;
   const TcOperand oa{ahi, alo, lda16, scales}, ob{bhi, blo, ldb16, scales + 2};
-  return gemm_tc_pair(mode, oa, ob, C, ldc, (int64_t)M * ldc, M, N, K, batch, alpha, bias, relu, splits, nterms, st);
+  return gemm_tc_pair(mode, oa, ob, C, ldc, (int64_t)M * ldc, M, N, K, batch, alpha, bias, relu, splits, nterms, st, nullptr);
 }
 
 // g [rows, cols] fp32 (pitch ld) -> g16 [rows, ld_out] fp16 scaled by a power of two; scale[0] = max|g|, scale[1] = 1/2^e

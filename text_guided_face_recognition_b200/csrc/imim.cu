@@ -37,9 +37,10 @@ struct TcOperand {          // gemm_tc.cu
   const float* scale;
 };
 int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int64_t c_bs, int M, int N, int K,
-                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, cudaStream_t st);
+                 int batch, float alpha, const float* bias, int relu, int splits, int nterms, cudaStream_t st,
+                 float* amax = nullptr);
 int gemm_tc_split_operand(const float* src, int64_t ld, int rows, int cols, float* scale, __half* hi, __half* lo, int ld_out,
-                          cudaStream_t st);
+                          cudaStream_t st, bool have_max = false);
 
 namespace {
 
@@ -79,6 +80,16 @@ struct HalfPool {            // bump allocator over a 256-byte aligned region; s
 };
 int split_into(const float* src, int64_t ld, int rows, int cols, const H16& h, cudaStream_t st) {
   return gemm_tc_split_operand(src, ld, rows, cols, h.scale, h.hi, h.lo, h.ld, st);
+}
+// The large activations / gradients skip the max-abs pass: the kernel that produces the tensor leaves max |x| in h.scale[0]
+// (zero_scale before it, split_ready after it).
+int zero_scale(const H16& h, cudaStream_t st) {
+  TGFR_CUDA_OK(cudaMemsetAsync(h.scale, 0, 2 * sizeof(float), st));
+  return TGFR_OK;
+}
+int split_ready(const float* src, int64_t ld, int rows, int cols, const H16& h, cudaStream_t st) {
+  static const bool fused = !(getenv("TGFR_IMIM_FUSED_MAX") && atoi(getenv("TGFR_IMIM_FUSED_MAX")) == 0);   // 0: A/B switch
+  return gemm_tc_split_operand(src, ld, rows, cols, h.scale, h.hi, h.lo, h.ld, st, fused);
 }
 constexpr int kScaleSlots = 32;
 
@@ -150,19 +161,19 @@ static size_t imim_ws_floats(int B, int P) {
 
 // LayerNorm([256,14,14]) forward / backward on position-major data, kLnSplit blocks per sample
 int ln_forward(const float* o, int B, int P, const float* w, const float* bia, float* wt, float* bt, float* part, float* y,
-               float* mu, float* rstd, cudaStream_t st) {
+               float* mu, float* rstd, cudaStream_t st, float* amax = nullptr) {
   const int n = P * kC;
   ln_affine_t_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w, bia, P, kC, wt, bt);
   TGFR_LAUNCH_OK();
   ln_stats_part_kernel<<<dim3(kLnSplit, B), 512, 0, st>>>(o, (int64_t)n, n, part);
   TGFR_LAUNCH_OK();
-  ln_apply_kernel<<<dim3(ceil_div(n, 1024), B), 256, 0, st>>>(o, (int64_t)n, P, kC, wt, bt, 1, part, y, (int64_t)n, mu, rstd);
+  ln_apply_kernel<<<dim3(ceil_div(n, 1024), B), 256, 0, st>>>(o, (int64_t)n, P, kC, wt, bt, 1, part, y, (int64_t)n, mu, rstd, amax);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
 // dY -> dO in place; d ln.weight / d ln.bias first (they need dY).  wt = the forward's position-major copy of ln.weight
 int ln_backward(float* dY, const float* o, int B, int P, const float* wt, const float* mu, const float* rstd, float* part,
-                float* dw, float* db, cudaStream_t st) {
+                float* dw, float* db, cudaStream_t st, float* amax = nullptr) {
   const int n = P * kC;
   TGFR_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * n, st));
   TGFR_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * n, st));
@@ -172,7 +183,7 @@ int ln_backward(float* dY, const float* o, int B, int P, const float* wt, const 
   ln_bwd_part_kernel<<<dim3(kLnSplit, B), 512, 0, st>>>(dY, (int64_t)n, o, (int64_t)n, P, kC, wt, 1, mu, rstd, part);
   TGFR_LAUNCH_OK();
   ln_bwd_apply_kernel<<<dim3(ceil_div(n, 1024), B), 256, 0, st>>>(dY, (int64_t)n, o, (int64_t)n, P, kC, wt, 1, mu, rstd, part, dY,
-                                                                 (int64_t)n);
+                                                                 (int64_t)n, amax);
   TGFR_LAUNCH_OK();
   return TGFR_OK;
 }
@@ -210,8 +221,9 @@ int imim_fwd(const float* x, int64_t sb, int64_t sc, int64_t sp, const float* co
     bn_stats_kernel<<<kC, 256, 0, st>>>(x, sb, sc, sp, B, P, eps, momentum, training, run_mean, run_var, S + L.mean, S + L.invstd);
   }
   TGFR_LAUNCH_OK();
+  if (nt) { if (int rc = zero_scale(H.xn, st)) return rc; }
   bn_apply_t_kernel<<<dim3(ceil_div(P, 32), kC / 32, B), dim3(32, 8), 0, st>>>(x, sb, sc, sp, kC, P, S + L.mean, S + L.invstd,
-                                                                              prm[0], prm[1], S + L.xn);
+                                                                              prm[0], prm[1], S + L.xn, nt ? H.xn.scale : nullptr);
   TGFR_LAUNCH_OK();
   // one product for the three projections: W_qkv [768,256] = [Wq; Wk; Wv]
   for (int k = 0; k < 3; ++k) {
@@ -220,27 +232,35 @@ int imim_fwd(const float* x, int64_t sb, int64_t sc, int64_t sp, const float* co
   }
   if (nt) {
     // the same graph on the tensor cores: split each operand once, products on the hi / lo pairs
-    if (int rc = split_into(S + L.xn, kC, M, kC, H.xn, st)) return rc;
+    if (int rc = split_ready(S + L.xn, kC, M, kC, H.xn, st)) return rc;
     if (int rc = split_into(S + L.wqkv, kC, 3 * kC, kC, H.wqkv, st)) return rc;
-    if (int rc = gemm_tc_pair(0, H.xn.op(), H.wqkv.op(), S + L.qkv, 3 * kC, 0, M, 3 * kC, kC, 1, 1.f, S + L.bqkv, 0, 1, nt, st)) return rc;
-    if (int rc = split_into(S + L.qkv, 3 * kC, M, 3 * kC, H.qkv, st)) return rc;
+    if (int rc = zero_scale(H.qkv, st)) return rc;
+    if (int rc = gemm_tc_pair(0, H.xn.op(), H.wqkv.op(), S + L.qkv, 3 * kC, 0, M, 3 * kC, kC, 1, 1.f, S + L.bqkv, 0, 1, nt, st, H.qkv.scale))
+      return rc;
+    if (int rc = split_ready(S + L.qkv, 3 * kC, M, 3 * kC, H.qkv, st)) return rc;
     // attention[b,i,j] = softmax_j(k_i . q_j / sqrt(256))      (fusion_nets.py:97-105)
     if (int rc = gemm_tc_pair(0, H.qkv.op(kC), H.qkv.op(0), S + L.prob, P, (int64_t)P * P, P, P, kC, B, 1.f / 16.f, nullptr, 0, 1, nt, st))
       return rc;
-    softmax_rows_kernel<<<ceil_div(B * P, 8), 256, 0, st>>>(S + L.prob, B * P, P);
+    if (int rc = zero_scale(H.prob, st)) return rc;
+    softmax_rows_kernel<<<ceil_div(B * P, 8), 256, 0, st>>>(S + L.prob, B * P, P, H.prob.scale);
     TGFR_LAUNCH_OK();
-    if (int rc = split_into(S + L.prob, P, M, P, H.prob, st)) return rc;
+    if (int rc = split_ready(S + L.prob, P, M, P, H.prob, st)) return rc;
     // response = attention . value                              (:115)
     if (int rc = gemm_tc_pair(1, H.prob.op(), H.qkv.op(2 * kC), S + L.o, kC, (int64_t)P * kC, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st))
       return rc;
-    if (int rc = ln_forward(S + L.o, B, P, prm[8], prm[9], S + L.ln_wt, S + L.ln_bt, S + L.ln_part, S + L.y, S + L.ln_mu, S + L.ln_rstd, st)) return rc;
-    if (int rc = split_into(S + L.y, kC, M, kC, H.y, st)) return rc;
+    if (int rc = zero_scale(H.y, st)) return rc;
+    if (int rc = ln_forward(S + L.o, B, P, prm[8], prm[9], S + L.ln_wt, S + L.ln_bt, S + L.ln_part, S + L.y, S + L.ln_mu, S + L.ln_rstd, st,
+                            H.y.scale))
+      return rc;
+    if (int rc = split_ready(S + L.y, kC, M, kC, H.y, st)) return rc;
     if (int rc = split_into(prm[10], kC, kC2, kC, H.w10, st)) return rc;
-    if (int rc = gemm_tc_pair(0, H.y.op(), H.w10.op(), S + L.h1, kC2, 0, M, kC2, kC, 1, 1.f, prm[11], 1, 1, nt, st)) return rc;
-    if (int rc = split_into(S + L.h1, kC2, M, kC2, H.h1, st)) return rc;
+    if (int rc = zero_scale(H.h1, st)) return rc;
+    if (int rc = gemm_tc_pair(0, H.y.op(), H.w10.op(), S + L.h1, kC2, 0, M, kC2, kC, 1, 1.f, prm[11], 1, 1, nt, st, H.h1.scale)) return rc;
+    if (int rc = split_ready(S + L.h1, kC2, M, kC2, H.h1, st)) return rc;
     if (int rc = split_into(prm[12], kC2, kC, kC2, H.w12, st)) return rc;
-    if (int rc = gemm_tc_pair(0, H.h1.op(), H.w12.op(), S + L.h2, kC, 0, M, kC, kC2, 1, 1.f, prm[13], 1, 1, nt, st)) return rc;
-    if (int rc = split_into(S + L.h2, kC, M, kC, H.h2, st)) return rc;
+    if (int rc = zero_scale(H.h2, st)) return rc;
+    if (int rc = gemm_tc_pair(0, H.h1.op(), H.w12.op(), S + L.h2, kC, 0, M, kC, kC2, 1, 1.f, prm[13], 1, 1, nt, st, H.h2.scale)) return rc;
+    if (int rc = split_ready(S + L.h2, kC, M, kC, H.h2, st)) return rc;
     if (int rc = split_into(prm[14], kC, kC, kC, H.w14, st)) return rc;
     if (int rc = gemm_tc_pair(0, H.h2.op(), H.w14.op(), out, kC, 0, M, kC, kC, 1, 1.f, prm[15], 0, 1, nt, st)) return rc;
     l2norm2_rows_kernel<<<ceil_div(M, 8), 256, 0, st>>>(out, M, kC, out, S + L.znorm);
@@ -297,43 +317,53 @@ int imim_bwd(const float* gout, const float* out, const float* x, int64_t sb, in
   float* dxn = dZ;                            // [M,256]  (dZ is dead by then)
   const int splits = M >= 4096 ? 32 : (M >= 512 ? 8 : 1);      // weight gradients: K = M rows
   // projection + L2 norm
-  l2norm_rows_bwd_kernel<<<ceil_div(M, 8), 256, 0, st>>>(gout, out, S + L.znorm, M, kC, dZ);
+  if (nt) { if (int rc = zero_scale(G.g256, st)) return rc; }
+  l2norm_rows_bwd_kernel<<<ceil_div(M, 8), 256, 0, st>>>(gout, out, S + L.znorm, M, kC, dZ, nt ? G.g256.scale : nullptr);
   TGFR_LAUNCH_OK();
   if (nt) {
     const int64_t sqh = (int64_t)P * 3 * kC;
     const int ks = M >= 8192 ? 37 : (M >= 512 ? 8 : 1);       // split-K of the weight gradients: 4 tiles x 37 = one wave
     H16 gz = G.g256;
-    if (int rc = split_into(dZ, kC, M, kC, gz, st)) return rc;
+    if (int rc = split_ready(dZ, kC, M, kC, gz, st)) return rc;
     if (int rc = gemm_tc_pair(2, gz.op(), H.h2.op(), dprm[14], kC, 0, kC, kC, M, 1, 1.f, nullptr, 0, ks, nt, st)) return rc;
     if (int rc = colsum(dZ, kC, M, kC, dprm[15], st)) return rc;
     if (int rc = gemm_tc_pair(1, gz.op(), H.w14.op(), dH2, kC, 0, M, kC, kC, 1, 1.f, nullptr, 0, 1, nt, st)) return rc;
-    relu_mask_kernel<<<1184, 256, 0, st>>>(dH2, S + L.h2, (int64_t)Mz * kC);
+    if (int rc = zero_scale(gz, st)) return rc;              // (the two products above have consumed gz and its scale)
+    relu_mask_kernel<<<1184, 256, 0, st>>>(dH2, S + L.h2, (int64_t)Mz * kC, gz.scale);
     TGFR_LAUNCH_OK();
     // conv1x1_2
-    if (int rc = split_into(dH2, kC, M, kC, gz, st)) return rc;
+    if (int rc = split_ready(dH2, kC, M, kC, gz, st)) return rc;
     if (int rc = gemm_tc_pair(2, gz.op(), H.h1.op(), dprm[12], kC2, 0, kC, kC2, M, 1, 1.f, nullptr, 0, ks, nt, st)) return rc;
     if (int rc = colsum(dH2, kC, M, kC, dprm[13], st)) return rc;
     if (int rc = gemm_tc_pair(1, gz.op(), H.w12.op(), dH1, kC2, 0, M, kC2, kC, 1, 1.f, nullptr, 0, 1, nt, st)) return rc;
-    relu_mask_kernel<<<1184, 256, 0, st>>>(dH1, S + L.h1, (int64_t)Mz * kC2);
+    if (int rc = zero_scale(G.g128, st)) return rc;
+    relu_mask_kernel<<<1184, 256, 0, st>>>(dH1, S + L.h1, (int64_t)Mz * kC2, G.g128.scale);
     TGFR_LAUNCH_OK();
     // conv1x1_1
-    if (int rc = split_into(dH1, kC2, M, kC2, G.g128, st)) return rc;
+    if (int rc = split_ready(dH1, kC2, M, kC2, G.g128, st)) return rc;
     if (int rc = gemm_tc_pair(2, G.g128.op(), H.y.op(), dprm[10], kC, 0, kC2, kC, M, 1, 1.f, nullptr, 0, ks, nt, st)) return rc;
     if (int rc = colsum(dH1, kC2, M, kC2, dprm[11], st)) return rc;
     if (int rc = gemm_tc_pair(1, G.g128.op(), H.w10.op(), dY, kC, 0, M, kC, kC2, 1, 1.f, nullptr, 0, 1, nt, st)) return rc;
     // LayerNorm
-    if (int rc = ln_backward(dY, S + L.o, B, P, S + L.ln_wt, S + L.ln_mu, S + L.ln_rstd, ln_part, dprm[8], dprm[9], st)) return rc;   // dY -> dO
+    if (int rc = zero_scale(gz, st)) return rc;
+    if (int rc = ln_backward(dY, S + L.o, B, P, S + L.ln_wt, S + L.ln_mu, S + L.ln_rstd, ln_part, dprm[8], dprm[9], st, gz.scale))
+      return rc;                                                                                    // dY -> dO
     // attention: O = P V;  S = K Q^T / 16
-    if (int rc = split_into(dY, kC, M, kC, gz, st)) return rc;                                     // dO
+    if (int rc = split_ready(dY, kC, M, kC, gz, st)) return rc;                                    // dO
     if (int rc = gemm_tc_pair(0, gz.op(), H.qkv.op(2 * kC), dP, P, (int64_t)P * P, P, P, kC, B, 1.f, nullptr, 0, 1, nt, st)) return rc;   // dP = dO V^T
-    if (int rc = gemm_tc_pair(2, H.prob.op(), gz.op(), dQKV + 2 * kC, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st)) return rc;   // dV = P^T dO
-    softmax_rows_bwd_kernel<<<ceil_div(B * P, 8), 256, 0, st>>>(S + L.prob, dP, B * P, P, 1.f / 16.f);          // dP -> dS
+    if (int rc = zero_scale(G.g768, st)) return rc;          // max |dQKV| is collected by the three products that write its slices
+    if (int rc = gemm_tc_pair(2, H.prob.op(), gz.op(), dQKV + 2 * kC, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st, G.g768.scale))
+      return rc;                                                                                    // dV = P^T dO
+    if (int rc = zero_scale(G.gp, st)) return rc;
+    softmax_rows_bwd_kernel<<<ceil_div(B * P, 8), 256, 0, st>>>(S + L.prob, dP, B * P, P, 1.f / 16.f, G.gp.scale);   // dP -> dS
     TGFR_LAUNCH_OK();
-    if (int rc = split_into(dP, P, M, P, G.gp, st)) return rc;
-    if (int rc = gemm_tc_pair(1, G.gp.op(), H.qkv.op(0), dQKV + kC, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st)) return rc;     // dK = dS Q
-    if (int rc = gemm_tc_pair(2, G.gp.op(), H.qkv.op(kC), dQKV, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st)) return rc;         // dQ = dS^T K
+    if (int rc = split_ready(dP, P, M, P, G.gp, st)) return rc;
+    if (int rc = gemm_tc_pair(1, G.gp.op(), H.qkv.op(0), dQKV + kC, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st, G.g768.scale))
+      return rc;                                                                                    // dK = dS Q
+    if (int rc = gemm_tc_pair(2, G.gp.op(), H.qkv.op(kC), dQKV, 3 * kC, sqh, P, kC, P, B, 1.f, nullptr, 0, 1, nt, st, G.g768.scale))
+      return rc;                                                                                    // dQ = dS^T K
     // projections: d W_qkv [768,256] = dQKV^T xn, biases, d xn = dQKV W_qkv
-    if (int rc = split_into(dQKV, 3 * kC, M, 3 * kC, G.g768, st)) return rc;
+    if (int rc = split_ready(dQKV, 3 * kC, M, 3 * kC, G.g768, st)) return rc;
     if (int rc = gemm_tc_pair(2, G.g768.op(), H.xn.op(), dwqkv, kC, 0, 3 * kC, kC, M, 1, 1.f, nullptr, 0, M >= 8192 ? 24 : ks, nt, st)) return rc;
     if (int rc = colsum(dQKV, 3 * kC, M, 3 * kC, dbqkv, st)) return rc;
     for (int k = 0; k < 3; ++k) {

@@ -149,6 +149,16 @@ int sgemm(int mode, const float* A, int64_t lda, int64_t sa, const float* B, int
   return TGFR_OK;
 }
 
+// Optional `amax` arguments below: max |output| of the kernel as float bits through atomicMax (zeroed by the caller).  The
+// consumer is gemm_tc_split_operand(have_max = true): the power-of-two operand scale of the next tensor-core product comes
+// out of the kernel that produced the tensor instead of a separate pass over it.  Every lane of the warp must call this.
+__device__ __forceinline__ void amax_commit(float m, float* amax) {
+  if (amax == nullptr) return;
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && __float_as_int(m) > __ldcg(reinterpret_cast<const int*>(amax)))
+    atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // BatchNorm2d over x [B, C, P] (element strides): per-channel statistics, apply + transpose to [B*P, C], backward
 // ------------------------------------------------------------------------------------------------------------
@@ -187,7 +197,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t sb, int64_t
 // xn[(b*P + p), c] = (x[b,c,p] - mean[c]) invstd[c] gamma[c] + beta[c]; a 32 x 32 tile transposed through shared memory
 __global__ void bn_apply_t_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sp, int C, int P,
                                   const float* __restrict__ mean, const float* __restrict__ invstd,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xn) {
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xn,
+                                  float* amax = nullptr) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -195,10 +206,16 @@ __global__ void bn_apply_t_kernel(const float* __restrict__ x, int64_t sb, int64
     tile[j][threadIdx.x] = (c < C && pp < P) ? x[b * sb + c * sc + pp * sp] : 0.f;
   }
   __syncthreads();
+  float am = 0.f;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int pp = p0 + j, c = c0 + threadIdx.x;
-    if (pp < P && c < C) xn[((int64_t)b * P + pp) * C + c] = (tile[threadIdx.x][j] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+    if (pp < P && c < C) {
+      const float v = (tile[threadIdx.x][j] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+      xn[((int64_t)b * P + pp) * C + c] = v;
+      am = fmaxf(am, fabsf(v));
+    }
   }
+  amax_commit(am, amax);
 }
 
 // per-channel sums for the BatchNorm backward: s1[c] = sum dxn, s2[c] = sum dxn * xhat  (xhat recomputed from x)
@@ -252,7 +269,7 @@ __global__ void bn_bwd_dx_kernel(const float* __restrict__ dxn, const float* __r
 // ------------------------------------------------------------------------------------------------------------
 // softmax over the last axis of [rows, n] in place, and its backward dS = scale * P (dP - sum_j P dP)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n) {
+__global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n, float* amax = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* p = s + (int64_t)row * n;
@@ -268,8 +285,10 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n) {
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
   for (int j = lane; j < n; j += 32) p[j] *= inv;
+  amax_commit(inv, amax);                                       // the row's largest probability is exp(0) / sum
 }
-__global__ void softmax_rows_bwd_kernel(const float* __restrict__ prob, float* __restrict__ dp, int rows, int n, float scale) {
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ prob, float* __restrict__ dp, int rows, int n, float scale,
+                                        float* amax = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* p = prob + (int64_t)row * n;
@@ -277,7 +296,13 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ prob, float* _
   float inner = 0.f;
   for (int j = lane; j < n; j += 32) inner = fmaf(p[j], d[j], inner);
   inner = warp_sum(inner);
-  for (int j = lane; j < n; j += 32) d[j] = scale * p[j] * (d[j] - inner);
+  float am = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float v = scale * p[j] * (d[j] - inner);
+    d[j] = v;
+    am = fmaxf(am, fabsf(v));
+  }
+  amax_commit(am, amax);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -383,7 +408,8 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ z, int M, int C, fl
 }
 // dZ = (g - (g . o) o) / |Z|   (o = the unit output rows)
 __global__ void l2norm_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ o,
-                                       const float* __restrict__ znorm, int M, int C, float* __restrict__ dz) {
+                                       const float* __restrict__ znorm, int M, int C, float* __restrict__ dz,
+                                       float* amax = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* gp = g + (int64_t)row * C;
@@ -392,11 +418,21 @@ __global__ void l2norm_rows_bwd_kernel(const float* __restrict__ g, const float*
   for (int c = lane; c < C; c += 32) d = fmaf(gp[c], op[c], d);
   d = warp_sum(d);
   const float inv = 1.f / znorm[row];
-  for (int c = lane; c < C; c += 32) dz[(int64_t)row * C + c] = (gp[c] - d * op[c]) * inv;
+  float am = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = (gp[c] - d * op[c]) * inv;
+    dz[(int64_t)row * C + c] = v;
+    am = fmaxf(am, fabsf(v));
+  }
+  amax_commit(am, amax);
 }
-__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t n) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t n, float* amax = nullptr) {
+  float am = 0.f;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     if (!(act[k] > 0.f)) g[k] = 0.f;
+    else if (amax) am = fmaxf(am, fabsf(g[k]));
+  }
+  amax_commit(am, amax);
 }
 // out[c] = sum_m g[m, ld*.. + c]: blocks of 256 rows, atomics into a zeroed vector
 __global__ void colsum_kernel(const float* __restrict__ g, int64_t ld, int M, int C, float* __restrict__ out) {
@@ -577,7 +613,7 @@ __device__ __forceinline__ void ln_merge_parts(const float* __restrict__ part, i
 // y = (o - mu) rstd w + bias, one thread per element; every block merges its sample's partials itself
 __global__ void ln_apply_kernel(const float* __restrict__ o, int64_t o_stride, int P, int C, const float* __restrict__ w,
                                 const float* __restrict__ bia, int w_t, const float* __restrict__ part, float* __restrict__ y,
-                                int64_t y_stride, float* __restrict__ mu_out, float* __restrict__ rstd_out) {
+                                int64_t y_stride, float* __restrict__ mu_out, float* __restrict__ rstd_out, float* amax = nullptr) {
   // w_t != 0: w / bia are already position-major copies [p * C + c] (ln_affine_t_kernel), read along k
   const int b = blockIdx.y, n = P * C;
   float mu, rstd;
@@ -587,11 +623,15 @@ __global__ void ln_apply_kernel(const float* __restrict__ o, int64_t o_stride, i
     rstd_out[b] = rstd;
   }
   const float* src = o + (int64_t)b * o_stride;
+  float am = 0.f;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int pp = k / C, c = k - pp * C;
     const int wi = w_t ? k : c * P + pp;
-    y[(int64_t)b * y_stride + k] = (src[k] - mu) * rstd * __ldg(w + wi) + __ldg(bia + wi);
+    const float v = (src[k] - mu) * rstd * __ldg(w + wi) + __ldg(bia + wi);
+    y[(int64_t)b * y_stride + k] = v;
+    am = fmaxf(am, fabsf(v));
   }
+  amax_commit(am, amax);
 }
 // the reference's affine parameters are [c * P + p]; position-major copies [p * C + c] for the kernels below
 __global__ void ln_affine_t_kernel(const float* __restrict__ w, const float* __restrict__ bia, int P, int C, float* __restrict__ wt,
@@ -629,7 +669,8 @@ __global__ void ln_bwd_part_kernel(const float* __restrict__ dy, int64_t dy_stri
 }
 __global__ void ln_bwd_apply_kernel(const float* dy, int64_t dy_stride, const float* __restrict__ o, int64_t o_stride, int P, int C,
                                     const float* __restrict__ w, int w_t, const float* __restrict__ mu_in,
-                                    const float* __restrict__ rstd_in, const float* __restrict__ part, float* dx, int64_t dx_stride) {
+                                    const float* __restrict__ rstd_in, const float* __restrict__ part, float* dx, int64_t dx_stride,
+                                    float* amax = nullptr) {
   const int b = blockIdx.y, n = P * C;
   float s1 = 0.f, s2 = 0.f;
   for (int s0 = 0; s0 < kLnSplit; ++s0) {
@@ -642,11 +683,15 @@ __global__ void ln_bwd_apply_kernel(const float* dy, int64_t dy_stride, const fl
   const float* g = dy + (int64_t)b * dy_stride;
   const float* src = o + (int64_t)b * o_stride;
   float* out = dx + (int64_t)b * dx_stride;
+  float am = 0.f;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int pp = k / C, c = k - pp * C;
     const float dh = g[k] * __ldg(w + (w_t ? k : c * P + pp));
-    out[k] = rstd * (dh - s1 - (src[k] - mu) * rstd * s2);
+    const float v = rstd * (dh - s1 - (src[k] - mu) * rstd * s2);
+    out[k] = v;
+    am = fmaxf(am, fabsf(v));
   }
+  amax_commit(am, amax);
 }
 // d ln.weight / d ln.bias with the batch split over blockIdx.y (atomics into vectors zeroed by the caller)
 __global__ void ln_bwd_params_split_kernel(const float* __restrict__ dy, int64_t dy_stride, const float* __restrict__ o,

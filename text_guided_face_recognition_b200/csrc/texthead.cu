@@ -46,7 +46,7 @@ struct Split3Product {
 int gemm_tc_split3_batched(const Split3Product* prods, int n, int a_mn, int a_overlap, int b_mn, int b_overlap, float alpha,
                            const float* dscale, const float* dscale2, int relu, cudaStream_t st);
 int head_split_f16(int nblocks, const float* const* src, const int64_t* ld, const int* rows, const int* cols, float* scale,
-                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st);
+                   __half* const* hi, __half* const* lo, const int* ld_out, cudaStream_t st, bool have_max = false);
 
 namespace {
 

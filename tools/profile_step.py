@@ -77,5 +77,11 @@ for _ in range(passes):
     fus = Working(channel_dim=256).cuda().train()
     fo = fus(li.detach(), w.transpose(1, 2), gi.detach(), b.detach())
     fo.square().sum().backward()
+    # the verification path of the fusion net: eval forward with the 3x3 convolution as an implicit tensor-core GEMM
+    with torch.no_grad():
+        fus.eval()
+        nb = 4096
+        fus(torch.randn(nb, 14, 14, 256, device="cuda").permute(0, 3, 1, 2), torch.randn(nb, T, 256, device="cuda").transpose(1, 2),
+            torch.randn(nb, 256, device="cuda"), torch.randn(nb, 256, device="cuda"))
 torch.cuda.synchronize()
 print("profile_step ok")
