@@ -19,7 +19,7 @@
 // The fp32 B x B x T x R attention tensor of the reference is never formed in HBM.  What the forward leaves for the
 // backward is the caller's choice (TGFR_WORDREGION_SAVE; the layouts are told apart by the buffer size):
 //   records (default)   fp16 (A1 | E) per (face, caption, word, region) + V planes: the backward (rec::wr_tc_bwd2_kernel)
-//                       runs no score GEMM and no exponential                                  namespace rec below
+//                       runs no score GEMM and no exponential                 (kLayRec; its kernels: namespace rec below)
 //   wu                  fp16 Wu planes + (alpha, beta) per word: 9x fewer bytes, the backward (wr_tc_bwd3_kernel)
 //                       recomputes S and E on the tensor cores / MUFU
 //   none                wr_tc_bwd_kernel recomputes everything (also the d words path)
@@ -44,6 +44,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 enum Bar { kCFull = 0, kQFull, kQEmpty, kSFull0, kSFull1, kEFull0, kEFull1, kWuFull, kWuEmpty, kNumBars };
 
+// what the forward leaves for the backward (TGFR_WORDREGION_SAVE; see the header of this file)
+enum { kLayNone = 0, kLayWu = 1, kLayRec = 2 };
+namespace rec { constexpr float kSV = 256.f; }   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
+
 struct TcParams {
   const __half* q16;     // [Bq*Tp, D]
   const float* qnorm;    // [Bq*Tp]
@@ -52,10 +56,15 @@ struct TcParams {
   float* attn_out;       // [Bc, T, R] diagonal attention maps (un-normalised here) or NULL
   float* attn_z;         // [Bc, 32] their region sums
   int diag_off, T;
-  // SAVE: what the record-free backward (wr_tc_bwd3_kernel) needs beside its own recomputation of S, per unit u = b * G + g:
+  // Wu layout: what the record-free backward (wr_tc_bwd3_kernel) needs beside its own recomputation of S, per unit u = b * G + g:
   __half* sv_wu;         // [total_units][D/8][nw_rows][8]  Wu_w as fp16 planes (the un-normalised context of word w)
   float* sv_ab;          // [total_units][2][128]  alpha_w = g2 g3 p_w / (|q_w| |Wu_w|), beta_w = g2 g3 p_w cos_w / |Wu_w|^2:
                          //   d sim[b,i] / d Wu_w = alpha_w q_w - beta_w Wu_w   (0 for padding words and missing captions)
+  // records layout (rec::wr_tc_bwd2_kernel reads these instead of recomputing), per unit u = b * G + g:
+  __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
+  uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
+  float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
+  uint32_t rec_stride;   // bytes of one unit's records
   int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
   int uniform_len;       // > 0: every caption has this many words (no cap_lens given); else read `lens`
   uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
@@ -244,7 +253,7 @@ __device__ __forceinline__ void f3b_bar_sync() { asm volatile("bar.sync 2, %0;" 
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int TP, bool SAVE>
+template <int TP, int LAY>
 __global__ void __launch_bounds__(kF3Threads, 1)
 wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -406,7 +415,16 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           const int diag_i = p.attn_out != nullptr ? u / p.G + p.diag_off : -1;
           for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
             const int i = g * p.nc + c;
-            if (i >= p.Bq) continue;                              // missing captions: their E columns are never read back
+            if (i >= p.Bq) {
+              if constexpr (LAY == kLayRec) {                               // missing captions: zero records for the backward
+                if (r < p.Rp) {
+                  uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
+#pragma unroll
+                  for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
+                }
+              }
+              continue;
+            }
             const int len = p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i);
             uint32_t v[TP];
             const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
@@ -446,20 +464,39 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
                                       p.attn_z + (int64_t)(u / p.G) * 32);
             }
             uint32_t pe[TP / 2];
-            {
-              // rows beyond R (K padding of GEMM-2) multiply zero rows of C: their E values only have to be finite
+            uint32_t pa[LAY == kLayRec ? TP / 2 : 1];
+            if constexpr (LAY == kLayRec) {
+              const bool live_row = r < p.R;
+              const float inv = live_row ? 1.f / sum : 0.f;
+#pragma unroll
+              for (int t = 0; t < TP; t += 2) {
+                const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
+                pa[t >> 1] = pack_half2(a0, a1);
+                const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
+                pe[t >> 1] = live_row ? pk : 0u;
+              }
+            } else {
               const float kinv = p.k1 / sum;
 #pragma unroll
               for (int t = 0; t < TP; t += 2)
                 pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
             }
             if (r < p.Rp) {
+              // E first: GEMM-2 waits for it; the records (global stores, LSU bound) follow
               const uint32_t w0 = (uint32_t)(c * TP);
 #pragma unroll
               for (int j = 0; j < TP / 8; ++j) {
                 const uint32_t ww = w0 + 8u * j;
                 *reinterpret_cast<uint4*>(e_row + (ww >> 6) * p.e_panel + ((((ww & 63u) >> 3) ^ rx) << 4)) =
                     make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+              }
+              if constexpr (LAY == kLayRec) {
+                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
+#pragma unroll
+                for (int j = 0; j < TP / 8; ++j) {
+                  rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+                  rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
+                }
               }
             }
           }
@@ -501,10 +538,10 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
       tc_fence_after();
       float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
       uint32_t vb[2][8];                          // the next 8 columns load while the current ones are consumed
-      // SAVE: Wu_w leaves for the backward as fp16 planes [d / 8][word][8 halfs] in this same pass (a warp's store covers
-      // 512 contiguous bytes; the tile is both a K-major and an MN-major no-swizzle UMMA operand, tc.cuh)
+      // Wu layout: Wu_w leaves for the backward as fp16 planes [d / 8][word][8 halfs] in this same pass (a warp's store
+      // covers 512 contiguous bytes; the tile is both a K-major and an MN-major no-swizzle UMMA operand, tc.cuh)
       uint4* wdst = nullptr;
-      if constexpr (SAVE)
+      if constexpr (LAY == kLayWu)
         wdst = reinterpret_cast<uint4*>(p.sv_wu + (int64_t)u * p.nw_rows * p.D) + (int64_t)(grp * (dq >> 3)) * p.nw_rows +
                min(w, p.nw_rows - 1);
       const int64_t wstep = p.nw_rows;
@@ -525,16 +562,18 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
             dot1 = fmaf(qf.y, w1, dot1);
             n2 = fmaf(w0, w0, n2);
             n21 = fmaf(w1, w1, n21);
-            if constexpr (SAVE) o[k] = valid ? pack_half2(w0, w1) : 0u;   // padding words / missing captions: exact zeros
+            if constexpr (LAY == kLayWu) o[k] = valid ? pack_half2(w0, w1) : 0u;   // padding words / missing captions: exact zeros
           }
-          if constexpr (SAVE)
+          if constexpr (LAY == kLayWu)
             if (w < p.nw_rows) wdst[ch * wstep] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       dot += dot1;
       n2 += n21;
-      tc_fence_before();
-      mbar_arrive(&bars[f3WuEmpty]);               // Wu is read once: the next unit's GEMM-2 may overwrite it
+      if constexpr (LAY != kLayRec) {
+        tc_fence_before();
+        mbar_arrive(&bars[f3WuEmpty]);
+      }
       if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 6);
       part_d[grp * 128 + w] = dot;
       part_n[grp * 128 + w] = n2;
@@ -554,13 +593,14 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           inw = 1.f / nW;
         }
         exs[w] = ex;
-        if constexpr (SAVE) {
+        if constexpr (LAY != kLayNone) {
           cosw[w] = cs;
           inww[w] = inw;
         }
+        if constexpr (LAY == kLayRec) p.sv_inw[(int64_t)u * 128 + w] = inw;
       }
       f3b_bar_sync();
-      if constexpr (SAVE) {
+      if constexpr (LAY == kLayWu) {
         if (grp == 1) {
           // d sim[b,i] / d Wu_w = alpha_w q_w - beta_w Wu_w with p_w = softmax over the caption's words of g2 cos
           float al = 0.f, be = 0.f;
@@ -575,6 +615,44 @@ wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constan
           p.sv_ab[(int64_t)u * 256 + w] = al;
           p.sv_ab[(int64_t)u * 256 + 128 + w] = be;
         }
+        if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 7);
+      }
+      if constexpr (LAY == kLayRec) {
+        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 planes of the saved V tile
+        float c1 = 0.f, c2 = 0.f;
+        if (valid) {
+          float ssum = 0.f;
+#pragma unroll
+          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
+          const float pw = rec::kSV * exs[w] / ssum;
+          c1 = pw / nq;
+          c2 = pw * cosw[w] * inww[w];
+        }
+        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
+                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
+        const int64_t vstep = p.nw_rows;
+        tmem_ld8(wu_col, vb[0]);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          if (ch < nch) {
+            tmem_ld_wait();
+            if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
+            const uint32_t(&v)[8] = vb[ch & 1];
+            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 qf = __half22float2(qh[k]);
+              // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
+              o[k] = valid ? pack_half2(fmaf(-c2, __uint_as_float(v[2 * k]), c1 * qf.x),
+                                        fmaf(-c2, __uint_as_float(v[2 * k + 1]), c1 * qf.y))
+                           : 0u;
+            }
+            if (w < p.nw_rows) vdst[ch * vstep] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[f3WuEmpty]);
         if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 7);
       }
       if (grp == 0 && w < p.nc) {
@@ -1578,419 +1656,10 @@ int make_plan(int Bc, int Bq, int T, int R, int D, TcPlan* pl) {
 // =============================================================================================
 namespace rec {
 
-constexpr float kSV = 256.f;   // power-of-two scale of the saved V tile (keeps small word weights in the fp16 normal range)
-
-struct TcParams {
-  const __half* q16;     // [Bq*Tp, D]
-  const float* qnorm;    // [Bq*Tp]
-  const int* lens;       // [Bq]
-  float* sim;            // [Bc, Bq]
-  float* attn_out;       // [Bc, T, R] diagonal attention maps (un-normalised here) or NULL
-  float* attn_z;         // [Bc, 32] their region sums
-  int diag_off, T;
-  // SAVE: what the backward (wr_tc_bwd2_kernel) reads instead of recomputing, per unit u = b * G + g:
-  __half* sv_v;          // [total_units][D/8][nw_rows][8]  V_w = kSV p_w (q^_w - cos_w w^_w): d sim / d Wu up to a per-caption scalar
-  uint8_t* sv_rec;       // [total_units][nc][Tp/4 chunks of 8 fp16: A1 x Tp | E x Tp][Rp]   word softmax, exp(g1 (A1 - 1))
-  float* sv_inw;         // [total_units][128]           1 / |Wu_w| (0 for padding words and missing captions)
-  uint32_t rec_stride;   // bytes of one unit's records
-  int Bc, Bq, Tp, R, Rp, D, nc, G, nw_rows, n_tiles, total_units;
-  int uniform_len;       // > 0: every caption has this many words (no cap_lens given); else read `lens`
-  uint32_t c_panel, q_panel, e_panel, off_q, off_e, off_misc;
-  float k1, k2, g3;
-};
 
 
-template <int TP, bool SAVE>
-__global__ void __launch_bounds__(kF3Threads, 1)
-wr_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_q, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_c = smem;
-  uint8_t* s_q = smem + p.off_q;
-  uint8_t* s_e = smem + p.off_e;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_misc);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_misc + 128);
-  float* part_d = reinterpret_cast<float*>(smem + p.off_misc + 256);   // [kF3NB][128]
-  float* part_n = part_d + kF3NB * 128;                                // [kF3NB][128]
-  float* exs = part_n + kF3NB * 128;                                   // [128]
-  float* cosw = exs + 128;                                             // [128] SAVE: cos_w
-  float* inww = cosw + 128;                                            // [128] SAVE: 1 / |Wu_w|
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int u0 = (int)((int64_t)blockIdx.x * p.total_units / gridDim.x);
-  const int u1 = (int)((int64_t)(blockIdx.x + 1) * p.total_units / gridDim.x);
-  const int kchunks = p.D >> 6;
 
-  if (tid == 0) {
-    mbar_init(&bars[f3CFull], 1);
-    mbar_init(&bars[f3QFull], 1);
-    mbar_init(&bars[f3QEmpty], 1);
-    mbar_init(&bars[f3SFull0], 1);
-    mbar_init(&bars[f3SFull1], 1);
-    mbar_init(&bars[f3E0Full], kF3ThreadsA);
-    mbar_init(&bars[f3E1Full], kF3ThreadsA);
-    mbar_init(&bars[f3E0Free], 1);
-    mbar_init(&bars[f3WuFull], 1);
-    mbar_init(&bars[f3WuEmpty], kF3ThreadsB);
-    fence_barrier_init();
-    tma_prefetch_desc(&tm_c);
-    tma_prefetch_desc(&tm_q);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp < 4) {
-    reg_dealloc<40>();
-    if (warp == 0) {
-      // ===================================== TMA producer =====================================
-      if (lane == 0) {
-        int prev_b = -1, n = 0;
-        for (int u = u0; u < u1; ++u, ++n) {
-          const int b = u / p.G, g = u - b * p.G;
-          mbar_wait_lazy(&bars[f3QEmpty], (n & 1) ^ 1);               // GEMM-1(n-1) has read the Q tile
-          if (b != prev_b) {
-            if (n > 0) mbar_wait_lazy(&bars[f3WuFull], (n - 1) & 1);  // every MMA reading the old C_b has retired
-            mbar_arrive_expect_tx(&bars[f3CFull], kchunks * p.c_panel);
-            for (int kc = 0; kc < kchunks; ++kc) tma_load_3d(s_c + kc * p.c_panel, &tm_c, &bars[f3CFull], kc * 64, 0, b);
-            prev_b = b;
-          }
-          mbar_arrive_expect_tx(&bars[f3QFull], kchunks * p.q_panel);
-          for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_3d(s_q + kc * p.q_panel, &tm_q, &bars[f3QFull], kc * 64, g * p.nw_rows, 0);
-        }
-      }
-    } else if (warp == 1) {
-      // ====================================== MMA issuer ======================================
-      if (lane == 0 && u0 < u1) {
-        const uint32_t idesc1 = make_idesc_f16(128, 128, false, false);
-        const uint32_t idesc2 = make_idesc_f16(128, p.D, true, true);
-        const uint32_t a_c = smem_u32(s_c), a_q = smem_u32(s_q), a_e = smem_u32(s_e);
-        const int j0 = min(p.Rp >> 4, 8), j1 = p.Rp >> 4;
-        auto gemm1 = [&](int t) {                                   // S_t = C_t . Q^T
-          for (int k16 = 0; k16 < (p.D >> 4); ++k16) {
-            const uint64_t ad = make_smem_desc(a_c + (k16 >> 2) * p.c_panel + t * (128 * 128) + (k16 & 3) * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(a_q + (k16 >> 2) * p.q_panel + (k16 & 3) * 32, 16, 1024);
-            umma_ss(tmem + t * 128, ad, bd, idesc1, k16 > 0);
-          }
-        };
-        auto gemm2 = [&](int ja, int jb) {                          // Wu (+)= E^T . C over K steps [ja, jb)
-          for (int j = ja; j < jb; ++j) {
-            const uint64_t ad = make_smem_desc(a_e + j * 2048, p.e_panel, 1024);
-            const uint64_t bd = make_smem_desc(a_c + j * 2048, p.c_panel, 1024);
-            umma_ss(tmem + 256, ad, bd, idesc2, j > 0);
-          }
-        };
-        int m = 0;
-        mbar_wait(&bars[f3CFull], 0);
-        mbar_wait(&bars[f3QFull], 0);
-        tc_fence_after();
-        gemm1(0);
-        umma_commit(&bars[f3SFull0]);
-        if (p.n_tiles == 2) gemm1(1);
-        umma_commit(&bars[f3SFull1]);
-        umma_commit(&bars[f3QEmpty]);
-        int n = 0;
-        for (int u = u0; u < u1; ++u, ++n) {
-          const int b = u / p.G;
-          const bool has_next = u + 1 < u1;
-          const bool boundary = has_next && ((u + 1) / p.G != b);
-          mbar_wait_lazy(&bars[f3E0Full], n & 1);                    // E tile 0 of unit n written, S tile 0 read
-          TGFR_TRACE(n, 17);
-          bool g1_pending = has_next && !boundary, g2_pending = true;
-          while (g1_pending || g2_pending) {
-            if (g2_pending && mbar_test(&bars[f3WuEmpty], (n & 1) ^ 1)) {        // group B has drained Wu(n-1)
-              tc_fence_after();
-              gemm2(0, j0);
-              umma_commit(&bars[f3E0Free]);
-              g2_pending = false;
-            } else if (g1_pending && mbar_test(&bars[f3QFull], (n + 1) & 1)) {    // Q(n+1) has landed
-              tc_fence_after();
-              gemm1(0);
-              umma_commit(&bars[f3SFull0]);
-              g1_pending = false;
-            } else {
-              asm volatile("nanosleep.u32 64;" ::: "memory");
-            }
-          }
-          TGFR_TRACE(n, 18);
-          mbar_wait_lazy(&bars[f3E1Full], n & 1);                    // E tile 1 written, S tile 1 read
-          tc_fence_after();
-          gemm2(j0, j1);
-          umma_commit(&bars[f3WuFull]);
-          TGFR_TRACE(n, 19);
-          if (has_next) {
-            if (boundary) {                                          // new face: the C tile is reloaded once Wu(n) is complete
-              ++m;
-              mbar_wait(&bars[f3CFull], m & 1);
-              mbar_wait(&bars[f3QFull], (n + 1) & 1);
-              tc_fence_after();
-              gemm1(0);
-              umma_commit(&bars[f3SFull0]);
-            }
-            if (p.n_tiles == 2) gemm1(1);
-            umma_commit(&bars[f3SFull1]);
-            umma_commit(&bars[f3QEmpty]);
-          }
-        }
-      }
-    }
-  } else if (warp < 4 + 4 * kF3NA) {
-    // ======================================= group A: epi-1 =======================================
-    reg_alloc<104>();
-    const int grp = (warp - 4) >> 2;
-    const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;
-    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-    const uint32_t rx = (uint32_t)(lrow & 7);
-    int n = 0;
-    for (int u = u0; u < u1; ++u, ++n) {
-      const int g = u % p.G;
-      for (int tile = 0; tile < 2; ++tile) {
-        // every thread follows both tile barriers (even without rows there): an arrival may never run a phase ahead
-        mbar_wait_lazy(&bars[tile ? f3SFull1 : f3SFull0], n & 1);
-        const bool has = tile < p.n_tiles && (tile * 128 + quarter * 32) < p.Rp;
-        if (has) {
-          tc_fence_after();
-          // GEMM-2(n-1)'s instalment over this tile's rows of E has retired
-          mbar_wait_lazy(&bars[tile ? f3WuFull : f3E0Free], (n & 1) ^ 1);
-          if (tid == 128 && tile == 0) TGFR_TRACE(n, 2);
-          const int r = tile * 128 + lrow;
-          uint8_t* const e_row = s_e + (uint32_t)r * 128u;
-          const int diag_i = p.attn_out != nullptr ? u / p.G + p.diag_off : -1;
-          for (int c = (grp + tile) % kF3NA; c < p.nc; c += kF3NA) {
-            const int i = g * p.nc + c;
-            if (i >= p.Bq) {
-              if constexpr (SAVE) {                               // missing captions: zero records for the backward
-                if (r < p.Rp) {
-                  uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-                  for (int j = 0; j < TP / 4; ++j) rdst[(int64_t)j * p.Rp] = make_uint4(0, 0, 0, 0);
-                }
-              }
-              continue;
-            }
-            const int len = p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i);
-            uint32_t v[TP];
-            const uint32_t col = tmem + t_lane + tile * 128 + c * TP;
-#pragma unroll
-            for (int j = 0; j < TP / 8; ++j) tmem_ld8(col + 8 * j, v + 8 * j);
-            tmem_ld_wait();
-            float e[TP];
-#pragma unroll
-            for (int t = 0; t < TP; ++t) e[t] = __uint_as_float(v[t]);
-            if (len < TP) {                                       // padding words: the last 8 columns, or a ragged caption
-              if (len > TP - 8) {
-#pragma unroll
-                for (int t = TP - 8; t < TP; ++t) e[t] = (t < len) ? e[t] : -INFINITY;
-              } else {
-#pragma unroll
-                for (int t = 0; t < TP; ++t) e[t] = (t < len) ? e[t] : -INFINITY;
-              }
-            }
-            float mxp[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
-#pragma unroll
-            for (int t = 0; t < TP; ++t) mxp[t & 3] = fmaxf(mxp[t & 3], e[t]);
-            const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-            const float nmx = -mx * kLog2e;
-            float sump[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int t = 0; t < TP; ++t) {
-              e[t] = fast_exp2(fmaf(e[t], kLog2e, nmx));
-              sump[t & 3] += e[t];
-            }
-            const float sum = (sump[0] + sump[1]) + (sump[2] + sump[3]);
-            const float nk1 = -p.k1;
-            if (i == diag_i) {                                       // this face's own caption: its map is an output
-              float ecopy[TP];
-#pragma unroll
-              for (int t = 0; t < TP; ++t) ecopy[t] = e[t];
-              emit_diag_attention<TP>(ecopy, p.k1 / sum, nk1, len, p.T, p.R, r, lane, p.attn_out + (int64_t)(u / p.G) * p.T * p.R,
-                                      p.attn_z + (int64_t)(u / p.G) * 32);
-            }
-            uint32_t pe[TP / 2];
-            uint32_t pa[SAVE ? TP / 2 : 1];
-            if constexpr (SAVE) {
-              const bool live_row = r < p.R;
-              const float inv = live_row ? 1.f / sum : 0.f;
-#pragma unroll
-              for (int t = 0; t < TP; t += 2) {
-                const float a0 = e[t] * inv, a1 = e[t + 1] * inv;
-                pa[t >> 1] = pack_half2(a0, a1);
-                const uint32_t pk = pack_half2(fast_exp2(fmaf(a0, p.k1, nk1)), fast_exp2(fmaf(a1, p.k1, nk1)));
-                pe[t >> 1] = live_row ? pk : 0u;
-              }
-            } else {
-              const float kinv = p.k1 / sum;
-#pragma unroll
-              for (int t = 0; t < TP; t += 2)
-                pe[t >> 1] = pack_half2(fast_exp2(fmaf(e[t], kinv, nk1)), fast_exp2(fmaf(e[t + 1], kinv, nk1)));
-            }
-            if (r < p.Rp) {
-              // E first: GEMM-2 waits for it; the records (global stores, LSU bound) follow
-              const uint32_t w0 = (uint32_t)(c * TP);
-#pragma unroll
-              for (int j = 0; j < TP / 8; ++j) {
-                const uint32_t ww = w0 + 8u * j;
-                *reinterpret_cast<uint4*>(e_row + (ww >> 6) * p.e_panel + ((((ww & 63u) >> 3) ^ rx) << 4)) =
-                    make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-              }
-              if constexpr (SAVE) {
-                uint4* rdst = reinterpret_cast<uint4*>(p.sv_rec + (int64_t)u * p.rec_stride) + (int64_t)c * (TP / 4) * p.Rp + r;
-#pragma unroll
-                for (int j = 0; j < TP / 8; ++j) {
-                  rdst[(int64_t)j * p.Rp] = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
-                  rdst[(int64_t)(TP / 8 + j) * p.Rp] = make_uint4(pe[4 * j], pe[4 * j + 1], pe[4 * j + 2], pe[4 * j + 3]);
-                }
-              }
-            }
-          }
-          fence_proxy_async();
-          tc_fence_before();
-        }
-        mbar_arrive(&bars[tile ? f3E1Full : f3E0Full]);
-        if (tid == 128) TGFR_TRACE(n, 3 + tile);
-      }
-    }
-  } else {
-    // ======================================= group B: epi-2 =======================================
-    reg_dealloc<64>();
-    const int grp = (warp - 4 - 4 * kF3NA) >> 2;         // which slice of the features
-    const int quarter = warp & 3;
-    const int w = quarter * 32 + lane;                    // word row = TMEM lane
-    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-    const int dq = p.D / kF3NB;                           // features per thread (16 .. 64)
-    const int nch = dq >> 3;                              // 8-column TMEM loads per pass (2 .. 8)
-    const int c = w / TP, t = w - c * TP;
-    const uint32_t wu_col = tmem + t_lane + 256 + grp * dq;
-    int n = 0;
-    for (int u = u0; u < u1; ++u, ++n) {
-      const int b = u / p.G, g = u - b * p.G;
-      const int i = g * p.nc + c;
-      const int len = (i < p.Bq) ? (p.uniform_len > 0 ? p.uniform_len : __ldg(p.lens + i)) : 0;
-      const bool valid = (w < p.nw_rows) && (t < len);
-      const int64_t qrow = (int64_t)min(i, p.Bq - 1) * p.Tp + t;
-      // this thread's slice of q_w is fetched before the wait: its latency hides under GEMM-2, and it serves both passes
-      uint4 qreg[8];
-      {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q16 + qrow * p.D + grp * dq);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) qreg[k] = (valid && k < nch) ? __ldg(qp + k) : make_uint4(0, 0, 0, 0);
-      }
-      const float nq = valid ? fmaxf(__ldg(p.qnorm + qrow), 1e-30f) : 1.f;
-      mbar_wait_lazy(&bars[f3WuFull], n & 1);
-      if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 5);
-      tc_fence_after();
-      float dot = 0.f, n2 = 0.f, dot1 = 0.f, n21 = 0.f;
-      uint32_t vb[2][8];                          // the next 8 columns load while the current ones are consumed
-      tmem_ld8(wu_col, vb[0]);
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        if (ch < nch) {
-          tmem_ld_wait();
-          if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
-          const uint32_t(&v)[8] = vb[ch & 1];
-          const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 qf = __half22float2(qh[k]);
-            const float w0 = __uint_as_float(v[2 * k]), w1 = __uint_as_float(v[2 * k + 1]);
-            dot = fmaf(qf.x, w0, dot);
-            dot1 = fmaf(qf.y, w1, dot1);
-            n2 = fmaf(w0, w0, n2);
-            n21 = fmaf(w1, w1, n21);
-          }
-        }
-      }
-      dot += dot1;
-      n2 += n21;
-      if constexpr (!SAVE) {
-        tc_fence_before();
-        mbar_arrive(&bars[f3WuEmpty]);
-      }
-      if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 6);
-      part_d[grp * 128 + w] = dot;
-      part_n[grp * 128 + w] = n2;
-      f3b_bar_sync();
-      if (grp == 0) {
-        float ex = 0.f, cs = 0.f, inw = 0.f;
-        if (valid) {
-          float dd = 0.f, nn = 0.f;
-#pragma unroll
-          for (int k = 0; k < kF3NB; ++k) {
-            dd += part_d[k * 128 + w];
-            nn += part_n[k * 128 + w];
-          }
-          const float nW = fmaxf(sqrtf(nn), 1e-30f);
-          cs = dd / (nq * nW);
-          ex = fast_exp2(p.k2 * cs);
-          inw = 1.f / nW;
-        }
-        exs[w] = ex;
-        if constexpr (SAVE) {
-          cosw[w] = cs;
-          inww[w] = inw;
-          p.sv_inw[(int64_t)u * 128 + w] = inw;
-        }
-      }
-      f3b_bar_sync();
-      if constexpr (SAVE) {
-        // second pass over Wu: V_w = kSV p_w (q_w / |q_w| - cos_w Wu_w / |Wu_w|) -> fp16 planes of the saved V tile
-        float c1 = 0.f, c2 = 0.f;
-        if (valid) {
-          float ssum = 0.f;
-#pragma unroll
-          for (int tt = 0; tt < TP; ++tt) ssum += exs[c * TP + tt];
-          const float pw = kSV * exs[w] / ssum;
-          c1 = pw / nq;
-          c2 = pw * cosw[w] * inww[w];
-        }
-        uint4* vdst = reinterpret_cast<uint4*>(p.sv_v + (int64_t)u * p.nw_rows * p.D) +
-                      (int64_t)(grp * (dq >> 3)) * p.nw_rows + min(w, p.nw_rows - 1);
-        const int64_t vstep = p.nw_rows;
-        tmem_ld8(wu_col, vb[0]);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          if (ch < nch) {
-            tmem_ld_wait();
-            if (ch + 1 < nch) tmem_ld8(wu_col + 8 * (ch + 1), vb[(ch + 1) & 1]);
-            const uint32_t(&v)[8] = vb[ch & 1];
-            const __half2* qh = reinterpret_cast<const __half2*>(&qreg[ch]);
-            uint32_t o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 qf = __half22float2(qh[k]);
-              // padding words / missing captions: exact zeros (their Wu rows come from unwritten E columns)
-              o[k] = valid ? pack_half2(fmaf(-c2, __uint_as_float(v[2 * k]), c1 * qf.x),
-                                        fmaf(-c2, __uint_as_float(v[2 * k + 1]), c1 * qf.y))
-                           : 0u;
-            }
-            if (w < p.nw_rows) vdst[ch * vstep] = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&bars[f3WuEmpty]);
-        if (tid == 128 + kF3ThreadsA) TGFR_TRACE(n, 7);
-      }
-      if (grp == 0 && w < p.nc) {
-        const int ii = g * p.nc + w;
-        if (ii < p.Bq) {
-          float sacc = 0.f;
-          for (int tt = 0; tt < TP; ++tt) sacc += exs[w * TP + tt];
-          p.sim[(int64_t)b * p.Bq + ii] = range_bad(p.lens, p.Bq) ? __int_as_float(0x7fc00000) : p.g3 * logf(sacc);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc(tmem, 512);
-  }
-}
 
 
 // ---------------------------------------------------------------------------------------------
@@ -2732,8 +2401,15 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   }
   if (save) {
     uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
-    p.sv_wu = reinterpret_cast<__half*>(sv + L.off_wu);
-    p.sv_ab = reinterpret_cast<float*>(sv + L.off_ab);
+    if (records) {
+      p.sv_v = reinterpret_cast<__half*>(sv + LR.off_v);
+      p.sv_rec = sv + LR.off_rec;
+      p.sv_inw = reinterpret_cast<float*>(sv + LR.off_inw);
+      p.rec_stride = LR.rec_stride;
+    } else {
+      p.sv_wu = reinterpret_cast<__half*>(sv + L.off_wu);
+      p.sv_ab = reinterpret_cast<float*>(sv + L.off_ab);
+    }
   }
 
   int dev = 0, sms = 0;
@@ -2744,49 +2420,22 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
     const int v = atoi(dg);
     if (v > 0 && v < grid) grid = v;
   }
-  rec::TcParams pr{};
-  if (records) {
-    uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
-    pr.q16 = q16; pr.qnorm = qnorm; pr.lens = lens; pr.sim = sim;
-    pr.sv_v = reinterpret_cast<__half*>(sv + LR.off_v);
-    pr.sv_rec = sv + LR.off_rec;
-    pr.sv_inw = reinterpret_cast<float*>(sv + LR.off_inw);
-    pr.rec_stride = LR.rec_stride;
-    pr.Bc = Bc; pr.Bq = Bq; pr.Tp = pl.Tp; pr.R = R; pr.Rp = pl.Rp; pr.D = D; pr.nc = pl.nc; pr.G = pl.G;
-    pr.nw_rows = pl.nw_rows; pr.n_tiles = pl.n_tiles; pr.total_units = Bc * pl.G;
-    pr.c_panel = pl.c_panel; pr.q_panel = pl.q_panel; pr.e_panel = pl.e_panel;
-    pr.off_q = pl.off_q; pr.off_e = pl.off_e; pr.off_misc = pl.off_misc;
-    pr.k1 = p.k1; pr.k2 = p.k2; pr.g3 = g3;
-    pr.uniform_len = p.uniform_len;
-    pr.T = T; pr.diag_off = diag_off; pr.attn_out = p.attn_out; pr.attn_z = p.attn_z;
+#define TGFR_LAUNCH_FWD1(TPV, LAYV)                                                                               \
+  {                                                                                                              \
+    static bool attr_done[64] = {};                                                                              \
+    bool& attr_set = attr_done[dev & 63];                                                                        \
+    if (!attr_set) {                                                                                             \
+      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd3_kernel<TPV, LAYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        232448));                                                                \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    wr_tc_fwd3_kernel<TPV, LAYV><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, p);                          \
   }
-#define TGFR_LAUNCH_FWDR(TPV)                                                                                   \
-  {                                                                                                            \
-    static bool attr_done[64] = {};                                                                            \
-    bool& attr_set = attr_done[dev & 63];                                                                      \
-    if (!attr_set) {                                                                                           \
-      TGFR_CUDA_OK(cudaFuncSetAttribute(rec::wr_tc_fwd3_kernel<TPV, true>,                                     \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));                 \
-      attr_set = true;                                                                                         \
-    }                                                                                                          \
-    rec::wr_tc_fwd3_kernel<TPV, true><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, pr);                  \
-  }
-#define TGFR_LAUNCH_FWD1(TPV, SV)                                                                               \
-  {                                                                                                            \
-    static bool attr_done[64] = {};                                                                            \
-    bool& attr_set = attr_done[dev & 63];                                                                      \
-    if (!attr_set) {                                                                                           \
-      TGFR_CUDA_OK(cudaFuncSetAttribute(wr_tc_fwd3_kernel<TPV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        232448));                                                              \
-      attr_set = true;                                                                                         \
-    }                                                                                                          \
-    wr_tc_fwd3_kernel<TPV, SV><<<grid, kF3Threads, pl.smem_bytes, st>>>(tm_c, tm_q, p);                          \
-  }
-#define TGFR_LAUNCH_FWD(TPV)                  \
-  case TPV:                                   \
-    if (records) TGFR_LAUNCH_FWDR(TPV)        \
-    else if (save) TGFR_LAUNCH_FWD1(TPV, true) \
-    else TGFR_LAUNCH_FWD1(TPV, false)         \
+#define TGFR_LAUNCH_FWD(TPV)                          \
+  case TPV:                                           \
+    if (records) TGFR_LAUNCH_FWD1(TPV, kLayRec)       \
+    else if (save) TGFR_LAUNCH_FWD1(TPV, kLayWu)      \
+    else TGFR_LAUNCH_FWD1(TPV, kLayNone)              \
     break;
   switch (pl.Tp) {
     TGFR_LAUNCH_FWD(8)
@@ -2799,7 +2448,6 @@ int wordregion_fwd_tc(const float* ctx, int64_t csb, int64_t csr, int64_t csd, c
   }
 #undef TGFR_LAUNCH_FWD
 #undef TGFR_LAUNCH_FWD1
-#undef TGFR_LAUNCH_FWDR
   TGFR_LAUNCH_OK();
   if (attn_diag) {
     const int64_t n = (int64_t)Bc * T * R;
