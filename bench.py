@@ -85,7 +85,7 @@ def ncu_traffic(kernel_substr):
         return None
 
 
-HEAD_STEP_KERNELS = ("norm_f16_pair", "gemm_tc_kernel", "normalize_bwd", "ce_merge_partials", "focal_finish")
+HEAD_STEP_KERNELS = ("norm_f16_pair", "gemm_tc_kernel", "ce_grad_from_cos", "normalize_bwd", "ce_merge_partials", "focal_finish")
 
 
 def ncu_traffic_sum(kernel_substrs, fname="r2_head_step_ncu_raw.txt"):

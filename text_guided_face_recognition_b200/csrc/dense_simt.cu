@@ -722,7 +722,10 @@ int head_prepare_operands(const float* x, int64_t x_sr, const float* w, int64_t 
 int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
                    int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
                    float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
-                   __half* g16, int ld_g, cudaStream_t st);
+                   __half* g16, int ld_g, cudaStream_t st, float* cos_out = nullptr, int ld_cos = 0);
+int arc_ce_grad_from_cos(const float* cosm, int ld_cos, int M, int N, float s, float m, int easy, const int64_t* labels,
+                         int class_off, const float* lse, const float* coef, const float* gout, float* scale, __half* g16,
+                         int ld_g, cudaStream_t st);
 
 namespace {
 struct HeadWs {   // workspace layout of the head calls (fp32 part first, everything 256-byte aligned)
@@ -859,7 +862,7 @@ int margin_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, int64
 // --------------------------------------------------------------------------------------------
 namespace {
 struct FusedWs {
-  size_t part, dxh, dwh, g16, scale, total, sv_x16, sv_w16, sv_total;
+  size_t part, dxh, dwh, g16, scale, total, sv_x16, sv_w16, sv_cos, sv_total;
   int Dp, Cp, nt;
 };
 FusedWs fused_ws(int B, int C, int Din) {
@@ -876,7 +879,8 @@ FusedWs fused_ws(int B, int C, int Din) {
   f.total = o;
   f.sv_x16 = 0;
   f.sv_w16 = align_up(2 * (size_t)B * f.Dp, 256);
-  f.sv_total = f.sv_w16 + align_up(2 * (size_t)C * f.Dp, 256);
+  f.sv_cos = f.sv_w16 + align_up(2 * (size_t)C * f.Dp, 256);                  // cos-theta [B, Cp] fp32 for the backward
+  f.sv_total = f.sv_cos + align_up(sizeof(float) * (size_t)B * f.Cp, 256);
   return f;
 }
 }  // namespace
@@ -902,7 +906,7 @@ int arc_fused_fwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
   if (int rc = head_prepare_operands(x, x_sr, w, w_sc, w_sk, B, C, Din, xnorm, wnorm, x16, w16, f.Dp, st)) return rc;
   return gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 0,
                         reinterpret_cast<float*>(base + f.part), rowmax, rowsum, tgt, cos_t, nullptr, nullptr, nullptr,
-                        nullptr, nullptr, 0, st);
+                        nullptr, nullptr, 0, st, reinterpret_cast<float*>(sv + f.sv_cos), f.Cp);
 }
 
 // per-device side stream + fork / join events of the head backward (TGFR_HEAD_OVERLAP=0 disables the overlap)
@@ -948,9 +952,18 @@ int arc_fused_bwd(const float* x, int64_t x_sr, const float* w, int64_t w_sc, in
   float* dwh = reinterpret_cast<float*>(base + f.dwh);
   __half* g16 = reinterpret_cast<__half*>(base + f.g16);
   float* scale = reinterpret_cast<float*>(base + f.scale);
-  if (int rc = gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 1, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, lse, coef, gout, scale, g16, f.Cp, st))
-    return rc;
+  // the softmax gradient (fp16 operand of the two gradient products) from the cos-theta matrix the forward kept: one
+  // element-wise pass over 21 MB that sit in L2 instead of a second cos-theta GEMM (TGFR_HEAD_RECOMPUTE=1: the GEMM)
+  static const bool recompute = getenv("TGFR_HEAD_RECOMPUTE") && atoi(getenv("TGFR_HEAD_RECOMPUTE")) == 1;
+  if (recompute) {
+    if (int rc = gemm_tc_arc_ce(x16, f.Dp, w16, f.Dp, B, C, f.Dp, s, m, easy, labels, class_off, 1, nullptr, nullptr,
+                                nullptr, nullptr, nullptr, lse, coef, gout, scale, g16, f.Cp, st))
+      return rc;
+  } else {
+    if (int rc = arc_ce_grad_from_cos(reinterpret_cast<const float*>(sv + f.sv_cos), f.Cp, B, C, s, m, easy, labels, class_off, lse,
+                                      coef, gout, scale, g16, f.Cp, st))
+      return rc;
+  }
   // dX^ = g w^ and dW^ = g^T x^ are independent given g16 and each is latency bound at this size (tensor pipe < 20 %):
   // the first runs on a per-device side stream beside the second (fork / join by events; capturable into a graph)
   cudaStream_t side = st;

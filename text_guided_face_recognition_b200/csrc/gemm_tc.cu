@@ -67,6 +67,10 @@ struct CeParams {            // fused ArcFace + cross-entropy epilogues (C = cos
   float* scale;              // scale[1] = 2^-e for the gradient GEMMs (written by block (0,0))
   __half* g16;               // [M, ld_g]
   int ld_g;
+  // kEpiCeStats, optional: the cos-theta tile itself, fp32 [M, ld_cos] (ld_cos % 4 == 0), so that the backward derives the
+  // softmax gradient with an element-wise pass (arc_ce_grad_from_cos) instead of a second GEMM
+  float* cos_out;
+  int ld_cos;
 };
 
 struct GemmTcParams {
@@ -143,6 +147,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTcParams& p, uint32_t tm
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch, v);      // warp-collective even past the last column
       tmem_ld_wait();
+      if constexpr (EPI == kEpiCeStats) {
+        if (p.ce.cos_out != nullptr && row_ok) {                         // a thread owns 32 consecutive columns of its row
+          float* cd = p.ce.cos_out + (int64_t)row * p.ce.ld_cos + c0;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            if (c0 + 4 * q4 < p.ce.ld_cos)
+              *reinterpret_cast<uint4*>(cd + 4 * q4) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+        }
+      }
       float lg[32];
       float dph = 1.f;
 #pragma unroll
@@ -902,6 +915,69 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
   return launch_gemm<kEpiStore, 128, 3, 2>(grid, tm_a, tm_b, p, st);
 }
 
+// g16[b, c] = fp16(2^e k (softmax - onehot) (phi' on the label column)) from the saved cos-theta matrix: the element-wise
+// twin of the kEpiCeGrad epilogue (same arithmetic), eight columns per thread
+__global__ void __launch_bounds__(256) ce_grad_from_cos_kernel(const float* __restrict__ cosm, int ld_cos, const int64_t* __restrict__ labels,
+                                                               int class_off, int M, int N, float alpha, float cm, float sm, float th,
+                                                               float mm, int easy, const float* __restrict__ lse,
+                                                               const float* __restrict__ coef, const float* __restrict__ gout,
+                                                               float* __restrict__ scale, __half* __restrict__ g16, int ld_g) {
+  const float k = (coef ? __ldg(coef) : 1.f) * (gout ? __ldg(gout) : 1.f) / (float)M;
+  const float ak = fabsf(k);
+  const float sc = (ak > 0.f) ? exp2f(floorf(log2f(256.f / ak))) : 1.f;
+  const float kscale = k * sc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[1] = 1.f / sc;
+  const int q = ld_g >> 3;
+  const int64_t n = (int64_t)M * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / q), c0 = (int)(i - (int64_t)row * q) << 3;
+    const int64_t ycol = __ldg(labels + row) - class_off;
+    const float ls = __ldg(lse + row);
+    float c[8];
+    if (c0 + 7 < ld_cos) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(cosm + (int64_t)row * ld_cos + c0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(cosm + (int64_t)row * ld_cos + c0 + 4));
+      c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c[u] = c0 + u < ld_cos ? __ldg(cosm + (int64_t)row * ld_cos + c0 + u) : 0.f;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      float g2[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        float g = 0.f;
+        const int col = c0 + u + v;
+        if (col < N) {
+          const bool on = (int64_t)col == ycol;
+          float dph = 1.f;
+          const float l = on ? alpha * arc_phi_tc(c[u + v], cm, sm, th, mm, easy, &dph) : alpha * c[u + v];
+          g = kscale * (expf(l - ls) - (on ? 1.f : 0.f)) * (on ? dph : 1.f);
+          g = fminf(fmaxf(g, -65504.f), 65504.f);
+        }
+        g2[v] = g;
+      }
+      const __half2 h2 = __floats2half2_rn(g2[0], g2[1]);
+      pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(g16 + (int64_t)row * ld_g + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+int arc_ce_grad_from_cos(const float* cosm, int ld_cos, int M, int N, float s, float m, int easy, const int64_t* labels,
+                         int class_off, const float* lse, const float* coef, const float* gout, float* scale, __half* g16,
+                         int ld_g, cudaStream_t st) {
+  TGFR_REQUIRE((ld_g & 7) == 0 && (ld_cos & 3) == 0, "arc_ce_grad_from_cos: pitches must be multiples of 8 / 4");
+  const float pi = 3.14159265358979323846f;
+  const int64_t n = (int64_t)M * (ld_g >> 3);
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  ce_grad_from_cos_kernel<<<blocks, 256, 0, st>>>(cosm, ld_cos, labels, class_off, M, N, s, cosf(m), sinf(m), cosf(pi - m),
+                                                  sinf(pi - m) * m, easy, lse, coef, gout, scale, g16, ld_g);
+  TGFR_LAUNCH_OK();
+  return TGFR_OK;
+}
+
 // cos-theta GEMM (x16 [M, K] . w16 [N, K]^T, alpha = s) with a fused ArcFace cross-entropy epilogue.
 //   grad == 0: rowmax / rowsum [M] (of this class shard), tgt, cos_t (owner rows only; others 0 / NaN);
 //              part = 2 * M * ceil(N / 128) floats of scratch
@@ -909,7 +985,7 @@ int gemm_tc(const __half* A, int a_mn, int64_t lda, const __half* Bm, int b_mn, 
 int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ldw, int M, int N, int K, float s, float m,
                    int easy, const int64_t* labels, int class_off, int grad, float* part, float* rowmax, float* rowsum,
                    float* tgt, float* cos_t, const float* lse, const float* coef, const float* gout, float* scale,
-                   __half* g16, int ld_g, cudaStream_t st) {
+                   __half* g16, int ld_g, cudaStream_t st, float* cos_out, int ld_cos) {
   const int plan = pick_tile_plan(M, N, 1, 0, grad ? ld_g : 0, false);
   const int bn = plan == 1 ? 160 : 128;
   CUtensorMap tm_a, tm_b;
@@ -923,6 +999,7 @@ int gemm_tc_arc_ce(const __half* x16, int64_t ldx, const __half* w16, int64_t ld
   p.ce.cm = cosf(m); p.ce.sm = sinf(m); p.ce.th = cosf(pi - m); p.ce.mm = sinf(pi - m) * m; p.ce.easy = easy;
   p.ce.pmax = part; p.ce.psum = part ? part + (size_t)M * nt : nullptr; p.ce.tgt = tgt; p.ce.cos_t = cos_t;
   p.ce.lse = lse; p.ce.coef = coef; p.ce.gout = gout; p.ce.scale = scale; p.ce.g16 = g16; p.ce.ld_g = ld_g;
+  p.ce.cos_out = grad ? nullptr : cos_out; p.ce.ld_cos = ld_cos;
   const dim3 grid(nt, (M + kBM - 1) / kBM, 1);
   if (!grad) {
     TGFR_CUDA_OK(cudaMemsetAsync(tgt, 0, sizeof(float) * M, st));
