@@ -881,7 +881,10 @@ def run_b200(args):
         from make_golden_imim_r2 import imim_inputs
         ih = ImageHeading(_types2.SimpleNamespace(aux_feat_dim_per_granularity=D)).to(dev).train()
         ix_np, ig_np, _, _, _, _ = imim_inputs(B, 100)
-        ix, ig = torch.from_numpy(ix_np).to(dev), torch.from_numpy(ig_np).to(dev)
+        # the upstream gradient in the layout the step produces it in: d ctx [B, R, D] of the word-region backward, i.e.
+        # channels-last memory behind the logical [B, 256, 14, 14] (an NCHW-contiguous one would add a 30 us transpose copy)
+        ix = torch.from_numpy(ix_np).to(dev)
+        ig = torch.from_numpy(ig_np).to(dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
         def imim_step():
             for p_ in ih.imim.parameters():

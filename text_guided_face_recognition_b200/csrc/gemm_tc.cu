@@ -1165,6 +1165,8 @@ int gemm_tc_pair(int mode, const TcOperand& A, const TcOperand& B, float* C, int
   p.amax = amax;
   if (splits > 1) TGFR_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st));
   const dim3 grid((N + 127) / 128, (M + kBM - 1) / kBM, batch > 1 ? batch : splits);
+  TGFR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_tc_pair: %u row tiles x %u samples / splits exceed one launch grid",
+               grid.y, grid.z);
   const int tiles = (int)(grid.x * grid.y * grid.z);
   if (tiles > 2 * sm_count() && tiles <= 3 * sm_count()) return launch_gemm<kEpiStore, 128, 2, 3>(grid, maps, p, st);
   return launch_gemm<kEpiStore, 128, 3, 2>(grid, maps, p, st);
@@ -1203,6 +1205,7 @@ int gemm_tc_conv3x3(const TcOperand& img, const TcOperand& w, float* C, int64_t 
   p.dscale = img.scale; p.dscale2 = w.scale; p.bias = bias; p.relu = relu; p.nterms = nterms;
   p.conv_c = Cin; p.conv_w = width;
   const dim3 grid(1, (rows + kBM - 1) / kBM, 1);
+  TGFR_REQUIRE(grid.y <= 65535, "gemm_tc_conv3x3: %u row tiles exceed one launch grid (chunk the batch)", grid.y);
   constexpr uint32_t smem = gemm_smem_bytes(64, 4);
   static bool attr_done[64] = {};
   int dev = 0;
