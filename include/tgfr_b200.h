@@ -73,7 +73,8 @@ size_t tgfr_wordregion_workspace_bytes(int Bc, int Bq, int T, int R, int D, int 
 /* Optional forward -> backward buffer (TGFR_PREC_TC): when `saved` (tgfr_wordregion_saved_bytes bytes, 256-byte
  * aligned) is given to the forward call it stores, per pair, either the fp16 word-softmax / attention records (default:
  * the backward then runs no score GEMM and no exponential) or, with the environment variable TGFR_WORDREGION_SAVE=wu
- * set when the size is queried, only the fp16 attended-word tiles (9x fewer bytes; the backward recomputes the scores).
+ * set when the size is queried, only the fp16 attended-word tiles (2.5x fewer bytes, nothing per (caption, word, region); the backward recomputes the
+ * scores).
  * The two layouts differ in size and both calls recognise the layout by `saved_bytes`, so pass exactly what
  * tgfr_wordregion_saved_bytes returned.  saved = NULL on either side selects the fully recomputing (memory-lean) path;
  * results agree to fp16 rounding. */

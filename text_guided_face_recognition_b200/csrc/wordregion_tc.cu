@@ -20,7 +20,7 @@
 // backward is the caller's choice (TGFR_WORDREGION_SAVE; the layouts are told apart by the buffer size):
 //   records (default)   fp16 (A1 | E) per (face, caption, word, region) + V planes: the backward (rec::wr_tc_bwd2_kernel)
 //                       runs no score GEMM and no exponential                 (kLayRec; its kernels: namespace rec below)
-//   wu                  fp16 Wu planes + (alpha, beta) per word: 9x fewer bytes, the backward (wr_tc_bwd3_kernel)
+//   wu                  fp16 Wu planes + (alpha, beta) per word: 2.5x fewer bytes, the backward (wr_tc_bwd3_kernel)
 //                       recomputes S and E on the tensor cores / MUFU
 //   none                wr_tc_bwd_kernel recomputes everything (also the d words path)
 //
@@ -2321,7 +2321,7 @@ int wordregion_tc_set_trace(void* dev_buf) {
 
 // bytes of the forward -> backward state (0 if the shape has no plan).  Two layouts, told apart by their size:
 //   records (default)              A1 | E per (caption, word, region) + V tiles: the backward runs no exponential
-//   TGFR_WORDREGION_SAVE=wu        Wu tiles + alpha | beta per word: ~9x fewer bytes, the backward recomputes S and E
+//   TGFR_WORDREGION_SAVE=wu        Wu tiles + alpha | beta per word: 2.5x fewer bytes, the backward recomputes S and E
 size_t wordregion_tc_saved_bytes(int Bc, int Bq, int T, int R, int D) {
   TcPlan pl;
   if (make_plan(Bc, Bq, T, R, D, &pl) != TGFR_OK) return 0;

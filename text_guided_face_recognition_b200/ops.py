@@ -89,7 +89,7 @@ class _WordRegionSim(torch.autograd.Function):
         wsb = lib.tgfr_wordregion_workspace_bytes(Bc, Bq, T, R, D, precision)
         ws = _workspace(wsb, feats.device)
         # forward -> backward image of the word softmax / attention (fp16 records): the backward then skips the score
-        # GEMM and every exponential.  TGFR_WORDREGION_SAVE=wu keeps only the Wu tiles (9x fewer bytes; the backward
+        # GEMM and every exponential.  TGFR_WORDREGION_SAVE=wu keeps only the Wu tiles (2.5x fewer bytes; the backward
         # recomputes the scores), TGFR_WORDREGION_SAVE=0 (or a buffer above the cap) selects full recomputation.
         # The library sizes the buffer for the selected layout and recognises the layout by that size.
         saved, svb = None, 0
