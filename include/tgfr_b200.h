@@ -280,7 +280,7 @@ int tgfr_row_argmax(const float* scores, int64_t sr, int rows, int cols, int64_t
  * bn_img.{weight,bias,running_mean,running_var}, projection.{weight,bias}, bn_word.{weight,bias,running_mean,
  * running_var}, sa.query_proj.{weight,bias}, sa.key_proj.{weight,bias}, sa.value_proj.{weight,bias}, ln.{weight,bias},
  * linear.{weight,bias}, ln_gl_image.{weight,bias}, ln_sent.{weight,bias} (all contiguous fp32).  BatchNorm uses the
- * running statistics (the evaluation path of utils/modules.py:141-147); training mode is not provided.
+ * running statistics (the evaluation path of utils/modules.py:141-147); training mode: tgfr_fcfm_train_fwd / _bwd below.
  * ------------------------------------------------------------------------------------------ */
 int tgfr_fcfm_working_num_params(void);
 int tgfr_fcfm_working_fwd(const float* img, int64_t img_sb, int64_t img_sc, int64_t img_sh, int64_t img_sw, const float* word,
