@@ -27,14 +27,33 @@ class _LaunchCounter:
 launch_counter = _LaunchCounter
 
 
+_noticed = set()
+
+
+def _notice_once(var: str, what: str) -> None:
+    """The drop-in mirrors default to fp16-operand tensor-core arithmetic, which is NOT what the reference computes bit
+    for bit (losses within 1e-4, gradients within 1e-3, logits within 1e-2; a `cos > th` margin switch can flip for a sample
+    sitting on the threshold).  A process that did not choose says so once, on stderr via `warnings` (TGFR_QUIET=1 silences)."""
+    if var in os.environ or var in _noticed or os.environ.get("TGFR_QUIET") == "1":
+        return
+    _noticed.add(var)
+    import warnings
+    warnings.warn(f"tgfr_b200: {what} run on the tensor cores with fp16 operands / fp32 accumulation (TF32-class: losses within "
+                  f"1e-4, gradients within 1e-3 of the reference's fp32). Set {var}=fp32 for the exact-fp32 kernels, or {var}=tc "
+                  f"to acknowledge this default.", stacklevel=3)
+
+
 def default_precision() -> int:
     """TGFR_WORDREGION_PRECISION = tc (default: tcgen05, fp16 operands / fp32 accumulate) | fp32 (SIMT)."""
+    _notice_once("TGFR_WORDREGION_PRECISION", "the word-region loss kernels")
     v = os.environ.get("TGFR_WORDREGION_PRECISION", "tc").lower()
     return PREC_FP32 if v in ("fp32", "simt", "0") else PREC_TC
 
 
 def head_precision(Din: int) -> int:
     """TGFR_HEAD_PRECISION = tc (default: tcgen05 cos-theta / gradient GEMMs, fp16 operands, fp32 accumulate) | fp32."""
+    if Din >= 8:
+        _notice_once("TGFR_HEAD_PRECISION", "the margin-head products (ArcMarginProduct / MagLinear)")
     v = os.environ.get("TGFR_HEAD_PRECISION", "tc").lower()
     if v in ("fp32", "simt", "0") or Din < 8:
         return PREC_FP32
